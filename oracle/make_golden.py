@@ -1,0 +1,223 @@
+"""Generate tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE (TEST INFRASTRUCTURE).
+
+Run in the build container (needs /root/reference):   python oracle/make_golden.py
+The reference ships no tests or golden vectors of its own, so every fixture here is
+the output of the reference's own code on seeded inputs:
+
+  step_f32.npz   TwoSeriesCSTREnv.step            twoseriescstr.py:394-454  (4096 single steps incl. edge rows)
+  traj_f32.npz   DummyVecEnv over 8 envs, 405 steps (auto-reset at 400)  dummy_vec_env.py:56-73
+  dyn_f64.npz    TwoSeriesCSTREnv._dynamics fed float64                   twoseriescstr.py:456-503
+  reset.npz      reset()/generate_initial_state, random + static modes    twoseriescstr.py:167-269
+  replay.npz     ReplayBuffer.add/sample under np.random.seed             core/common/buffers.py:247-325
+  td3_actor.npz  TD3Policy actor forward / predict / _sample_action maps  core/td3/policies.py:75-78,
+                                                                           core/common/off_policy_algorithm.py:364-411
+Host note: NumPy's float32 exp is a SIMD kernel whose code path depends on the CPU, so the fp32
+fixtures are bit-stable only on hosts taking the same path; tests re-check them with the ulp-level
+tolerance stated in tests/test_golden.py and bit-exactly in tests/test_oracle_vs_reference.py (live).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, _HERE)
+import refload  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(_HERE), "tests", "golden")
+
+
+def edge_rows(states: np.ndarray, actions: np.ndarray) -> None:
+    """Overwrite the first rows with the edge cases the reference handles specially."""
+    states[:16] = np.sign(states[:16])  # on the clip bounds
+    states[16] = [1.0, 1.0, 1.0, 1.0]
+    states[17] = [-1.0, -1.0, -1.0, -1.0]
+    states[18] = [1.5, -1.5, 2.0, -2.0]  # outside the Box: clipped by :406-410
+    actions[20] = [np.inf, -np.inf]
+    actions[21] = [np.nan, 0.1]  # NaN path :415-421
+    actions[22] = [0.2, np.nan]
+    actions[23] = [5.0, -5.0]
+    actions[24] = [1.0, -1.0]
+    actions[25] = [-1.0, 1.0]
+
+
+def gen_step(m) -> None:
+    rng = np.random.default_rng(20260101)
+    N = 4096
+    states = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
+    actions = rng.uniform(-1.25, 1.25, (N, 2)).astype(np.float32)
+    step_count = rng.integers(0, 402, N).astype(np.int32)
+    step_count[:8] = [398, 399, 400, 0, 1, 397, 399, 399]
+    edge_rows(states, actions)
+    env = m.TwoSeriesCSTREnv()
+    env.reset(seed=0)
+    obs = np.zeros((N, 4), np.float32)
+    rew = np.zeros(N, np.float32)
+    trunc = np.zeros(N, bool)
+    term = np.zeros(N, bool)
+    conc = np.zeros(N, np.float32)
+    tpen = np.zeros(N, np.float32)
+    for i in range(N):
+        env.state = states[i].copy()
+        env.current_step = int(step_count[i])
+        with contextlib.redirect_stdout(io.StringIO()):
+            o, r, te, tr, info = env.step(actions[i].copy())
+        obs[i], rew[i], term[i], trunc[i] = o, r, te, tr
+        conc[i] = info.get("concentration_reward", np.nan)
+        tpen[i] = info.get("temp_penalty", np.nan)
+    np.savez_compressed(os.path.join(OUT, "step_f32.npz"), states=states, actions=actions, step_count=step_count,
+                        obs=obs, reward=rew, terminated=term, truncated=trunc, conc_reward=conc, temp_penalty=tpen)
+
+
+def gen_traj(m, core) -> None:
+    from core.common.vec_env import DummyVecEnv
+
+    N, T, seed = 8, 405, 100
+    venv = DummyVecEnv([(lambda: m.TwoSeriesCSTREnv(init_mode="random")) for _ in range(N)])
+    venv.seed(seed)
+    obs0 = venv.reset()
+    rng = np.random.default_rng(7)
+    actions = rng.uniform(-1, 1, (T, N, 2)).astype(np.float32)
+    actions[:, 0] = [1.0, -1.0]  # T2 pins at 400 K under this tape
+    actions[:, 1] = [-1.0, 1.0]
+    obs = np.zeros((T, N, 4), np.float32)
+    rew = np.zeros((T, N), np.float32)
+    done = np.zeros((T, N), bool)
+    timeout = np.zeros((T, N), bool)
+    term_obs = np.zeros((T, N, 4), np.float32)
+    for t in range(T):
+        o, r, d, infos = venv.step(actions[t])
+        obs[t], rew[t], done[t] = o, r, d
+        for i, info in enumerate(infos):
+            timeout[t, i] = info.get("TimeLimit.truncated", False)
+            term_obs[t, i] = info["terminal_observation"] if d[i] else o[i]
+    np.savez_compressed(os.path.join(OUT, "traj_f32.npz"), seed=seed, obs0=obs0, actions=actions, obs=obs, reward=rew,
+                        done=done, timeout=timeout, terminal_obs=term_obs)
+
+
+def gen_dyn64(m) -> None:
+    rng = np.random.default_rng(5)
+    N = 2048
+    env = m.TwoSeriesCSTREnv()
+    lo, hi = env.raw_state_low.astype(np.float64), env.raw_state_high.astype(np.float64)
+    raw = lo + (hi - lo) * rng.random((N, 4))
+    raw[:8] = np.where(rng.random((8, 4)) < 0.5, lo, hi)
+    act = 30.0 + 220.0 * rng.random((N, 2))
+    out = np.zeros((N, 4), np.float64)
+    for i in range(N):
+        res = env._dynamics(state=raw[i].copy(), action=act[i].copy())
+        assert res.dtype == np.float64
+        out[i] = res
+    np.savez_compressed(os.path.join(OUT, "dyn_f64.npz"), raw_state=raw, raw_action=act, new_raw_state=out)
+
+
+def gen_reset(m) -> None:
+    seeds = np.array([0, 1, 7, 42, 123, 2**31 - 1, 99991, 5], np.int64)
+    E = 5
+    rnd = np.zeros((len(seeds), E, 4), np.float32)
+    rnd_raw = np.zeros((len(seeds), E, 4), np.float64)
+    sta = np.zeros((len(seeds), E, 4), np.float32)
+    for k, s in enumerate(seeds):
+        env = m.TwoSeriesCSTREnv(init_mode="random")
+        for e in range(E):
+            o, info = env.reset(seed=int(s) if e == 0 else None)
+            rnd[k, e] = o
+            rnd_raw[k, e] = [info["initial_concentration_1"], info["initial_temperature_1"],
+                             info["initial_concentration_2"], info["initial_temperature_2"]]
+        env = m.TwoSeriesCSTREnv(init_mode="static")
+        for e in range(E):
+            o, _ = env.reset(seed=int(s) if e == 0 else None)
+            sta[k, e] = o
+    np.savez_compressed(os.path.join(OUT, "reset.npz"), seeds=seeds, random_obs=rnd, random_raw=rnd_raw, static_obs=sta)
+
+
+def gen_replay(core) -> None:
+    from core.common.buffers import ReplayBuffer
+    from gymnasium import spaces
+
+    ospace = spaces.Box(-1, 1, (4,), np.float32)
+    aspace = spaces.Box(-1, 1, (2,), np.float32)
+    out = {}
+    for tag, (size, n_envs, n_add, batch) in {"a": (40, 4, 25, 32), "b": (50, 1, 30, 16), "c": (64, 8, 5, 64)}.items():
+        rng = np.random.default_rng(ord(tag) + 3)
+        buf = ReplayBuffer(size, ospace, aspace, device="cpu", n_envs=n_envs)
+        O_, NO, A, R_, D, TO = [], [], [], [], [], []
+        for _ in range(n_add):
+            o = rng.uniform(-1, 1, (n_envs, 4)).astype(np.float32)
+            no = rng.uniform(-1, 1, (n_envs, 4)).astype(np.float32)
+            a = rng.uniform(-1, 1, (n_envs, 2)).astype(np.float32)
+            r = rng.normal(size=n_envs).astype(np.float32)
+            d = rng.random(n_envs) < 0.3
+            to = d & (rng.random(n_envs) < 0.5)
+            buf.add(o, no, a, r, d, [{"TimeLimit.truncated": bool(x)} for x in to])
+            for lst, v in zip((O_, NO, A, R_, D, TO), (o, no, a, r, d, to)):
+                lst.append(v)
+        np.random.seed(11)
+        s = buf.sample(batch)
+        np.random.seed(11)
+        upper = buf.buffer_size if buf.full else buf.pos
+        bi = np.random.randint(0, upper, size=batch)
+        ei = np.random.randint(0, high=n_envs, size=(batch,))
+        out.update({
+            f"{tag}_cfg": np.array([size, n_envs, n_add, batch]),
+            f"{tag}_add_obs": np.stack(O_), f"{tag}_add_next_obs": np.stack(NO), f"{tag}_add_action": np.stack(A),
+            f"{tag}_add_reward": np.stack(R_), f"{tag}_add_done": np.stack(D), f"{tag}_add_timeout": np.stack(TO),
+            f"{tag}_store_observations": buf.observations, f"{tag}_store_next_observations": buf.next_observations,
+            f"{tag}_store_actions": buf.actions, f"{tag}_store_rewards": buf.rewards, f"{tag}_store_dones": buf.dones,
+            f"{tag}_store_timeouts": buf.timeouts, f"{tag}_pos": np.array(buf.pos), f"{tag}_full": np.array(buf.full),
+            f"{tag}_batch_inds": bi, f"{tag}_env_inds": ei,
+            f"{tag}_s_obs": s.observations.numpy(), f"{tag}_s_act": s.actions.numpy(),
+            f"{tag}_s_next_obs": s.next_observations.numpy(), f"{tag}_s_dones": s.dones.numpy(),
+            f"{tag}_s_rewards": s.rewards.numpy(),
+        })
+    np.savez_compressed(os.path.join(OUT, "replay.npz"), **out)
+
+
+def gen_actor(m, core) -> None:
+    import torch as th
+    from core.common.vec_env import DummyVecEnv
+
+    th.set_num_threads(1)
+    venv = DummyVecEnv([lambda: m.TwoSeriesCSTREnv(init_mode="random")])
+    model = core.TD3("MlpPolicy", venv, seed=0, device="cpu", buffer_size=1000, learning_starts=0)
+    actor = model.policy.actor
+    lin = [mod for mod in actor.mu if isinstance(mod, th.nn.Linear)]
+    W = {f"W{i + 1}": l.weight.detach().numpy().copy() for i, l in enumerate(lin)}
+    Bz = {f"b{i + 1}": l.bias.detach().numpy().copy() for i, l in enumerate(lin)}
+    rng = np.random.default_rng(3)
+    obs = rng.uniform(-1, 1, (256, 4)).astype(np.float32)
+    with th.no_grad():
+        mu = actor(th.as_tensor(obs)).numpy()
+    pred, _ = model.predict(obs, deterministic=False)
+    # _sample_action's maps with an injected noise callable (off_policy_algorithm.py:398-406)
+    noise = (0.1 * rng.standard_normal((256, 2))).astype(np.float32)
+    noise[:4] = [[3.0, -3.0], [0.0, 0.0], [-0.5, 0.5], [1.0, 1.0]]
+    model._last_obs = obs
+    model.num_timesteps = 10
+    action, buffer_action = model._sample_action(0, action_noise=lambda: noise, n_envs=256)
+    np.savez_compressed(os.path.join(OUT, "td3_actor.npz"), obs=obs, mu=mu, predict=pred, noise=noise,
+                        env_action=action, buffer_action=buffer_action, **W, **Bz)
+
+
+def main() -> None:
+    if not refload.available():
+        raise SystemExit("reference tree not found; fixtures can only be generated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    m = refload.load_env_module()
+    core = refload.load_core()
+    gen_step(m)
+    gen_traj(m, core)
+    gen_dyn64(m)
+    gen_reset(m)
+    gen_replay(core)
+    gen_actor(m, core)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+"""Oracle restatement vs the committed fixtures produced by the unmodified reference
+(oracle/make_golden.py).  CPU only.
+
+Tolerances: everything is bit-exact except float32 ``exp`` — NumPy's float32 exp is a SIMD kernel
+whose code path depends on the host CPU — so observations are allowed 1 raw-state
+ulp of drift per step (|Δobs| <= 6e-7 normalised) when the host differs from the one that generated
+the fixtures; on the generating host the comparison is bit-exact (asserted in
+test_oracle_vs_reference.py against the live reference).
+"""
+import numpy as np
+import pytest
+
+import cstr_oracle as O
+
+OBS_TOL = 6.0e-7  # 1 ulp of a raw temperature (3.05e-5 K) mapped to the normalised scale, rounded up
+REW_TOL = 1.0e-5
+
+
+def test_step_f32_matches_reference_fixture(golden):
+    g = golden("step_f32.npz")
+    out = O.step_f32(g["states"], g["actions"], g["step_count"])
+    assert np.array_equal(out.truncated, g["truncated"])
+    assert not g["terminated"].any()
+    assert np.array_equal(out.nan_row, np.isnan(g["conc_reward"]))
+    np.testing.assert_allclose(out.obs, g["obs"], rtol=0, atol=OBS_TOL)
+    np.testing.assert_allclose(out.reward, g["reward"], rtol=0, atol=REW_TOL)
+    # rows that did not go through exp-sensitive rounding must be identical; report the exact share
+    exact = (out.obs == g["obs"]).all(axis=1).mean()
+    assert exact > 0.95, exact
+
+
+def test_step_f32_edge_rows(golden):
+    g = golden("step_f32.npz")
+    out = O.step_f32(g["states"], g["actions"], g["step_count"])
+    # NaN action rows: state unchanged, reward -10, truncated (Q4)
+    for i in (21, 22):
+        assert out.nan_row[i]
+        assert np.array_equal(out.obs[i], g["states"][i])
+        assert out.reward[i] == np.float32(-10.0) and out.truncated[i]
+        assert out.step_count[i] == g["step_count"][i] + 1
+    # +-inf / out-of-range actions are clipped, not errors
+    assert not out.nan_row[20] and not out.nan_row[23]
+    assert np.isfinite(out.obs).all()
+
+
+def test_trajectory_with_autoreset(golden):
+    g = golden("traj_f32.npz")
+    T, N = g["reward"].shape
+    seed = int(g["seed"])
+    gens = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed + i))) for i in range(N)]
+
+    def fresh(idx):
+        u = np.stack([gens[i].random(8) for i in idx])
+        return O.obs_from_raw_f64(O.initial_state_from_uniforms(u))
+
+    obs0 = fresh(range(N))
+    assert np.array_equal(obs0, g["obs0"])
+    vec = O.VecOracle(obs0)
+    for t in range(T):
+        st = vec.step(g["actions"][t], reset_fn=fresh)
+        assert np.array_equal(st.done, g["done"][t]), t
+        assert np.array_equal(st.timeout, g["timeout"][t]), t
+        np.testing.assert_allclose(st.obs, g["obs"][t], rtol=0, atol=1e-5)  # <=1e-5 over 400 steps
+        np.testing.assert_allclose(st.terminal_obs, g["terminal_obs"][t], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(st.reward, g["reward"][t], rtol=0, atol=REW_TOL * 5)
+    assert g["done"][399].all() and g["done"].sum() == N  # exactly the step-400 truncation row
+
+
+def test_dynamics_f64(golden):
+    g = golden("dyn_f64.npz")
+    out = O.dynamics(g["raw_state"], g["raw_action"])
+    assert out.dtype == np.float64
+    np.testing.assert_allclose(out, g["new_raw_state"], rtol=1e-12, atol=0)
+
+
+def test_reset_random_and_static(golden):
+    g = golden("reset.npz")
+    for k, seed in enumerate(g["seeds"]):
+        E = g["random_obs"].shape[1]
+        u = O.pcg64_reset_uniforms(int(seed), E)
+        raw = O.initial_state_from_uniforms(u)
+        assert np.array_equal(raw, g["random_raw"][k])
+        assert np.array_equal(O.obs_from_raw_f64(raw), g["random_obs"][k])
+        gen = np.random.Generator(np.random.PCG64(np.random.SeedSequence(int(seed))))
+        base = np.array([[0.45, 310.0, 0.25, 290.0]])
+        for e in range(E):
+            raw_s = O.static_state_from_uniforms(base, gen.random((1, 4)))
+            assert np.array_equal(O.obs_from_raw_f64(raw_s)[0], g["static_obs"][k, e])  # Q2 drift
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_replay_buffer(golden, tag):
+    g = golden("replay.npz")
+    size, n_envs, n_add, batch = (int(v) for v in g[f"{tag}_cfg"])
+    buf = O.ReplayOracle(size, n_envs)
+    for i in range(n_add):
+        buf.add(g[f"{tag}_add_obs"][i], g[f"{tag}_add_next_obs"][i], g[f"{tag}_add_action"][i],
+                g[f"{tag}_add_reward"][i], g[f"{tag}_add_done"][i], g[f"{tag}_add_timeout"][i])
+    for name in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts"):
+        assert np.array_equal(getattr(buf, name), g[f"{tag}_store_{name}"]), name
+    assert buf.pos == int(g[f"{tag}_pos"]) and buf.full == bool(g[f"{tag}_full"])
+    np.random.seed(11)
+    bi, ei = buf.draw_indices(batch)
+    assert np.array_equal(bi, g[f"{tag}_batch_inds"]) and np.array_equal(ei, g[f"{tag}_env_inds"])
+    obs, act, nobs, dones, rew = buf.gather(bi, ei)
+    assert np.array_equal(obs, g[f"{tag}_s_obs"]) and np.array_equal(act, g[f"{tag}_s_act"])
+    assert np.array_equal(nobs, g[f"{tag}_s_next_obs"]) and np.array_equal(dones, g[f"{tag}_s_dones"])
+    assert np.array_equal(rew, g[f"{tag}_s_rewards"])
+
+
+def test_actor_and_action_maps(golden):
+    g = golden("td3_actor.npz")
+    w = [(g["W1"], g["b1"]), (g["W2"], g["b2"]), (g["W3"], g["b3"])]
+    assert g["W1"].shape == (400, 4) and g["W2"].shape == (300, 400) and g["W3"].shape == (2, 300)
+    mu = O.actor_forward(g["obs"], w)
+    np.testing.assert_allclose(mu, g["mu"], rtol=0, atol=2e-6)  # fp32 sgemm vs fp64 accumulate
+    # predict() = unscale(mu) for the squashed TD3 actor (policies.py:375)
+    a, s = O.sample_action_maps(g["mu"], g["noise"])
+    assert np.array_equal(a, g["env_action"]) and np.array_equal(s, g["buffer_action"])
+    a0, _ = O.sample_action_maps(g["mu"], np.zeros_like(g["noise"]))
+    np.testing.assert_allclose(a0, g["predict"], rtol=0, atol=1.2e-7)

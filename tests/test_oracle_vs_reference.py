@@ -1,0 +1,98 @@
+"""Pins the oracle against the UNMODIFIED reference, live (only where /root/reference exists —
+the build container; skipped on the GPU box, which re-checks the frozen fixtures instead)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+import cstr_oracle as O
+import refload
+
+pytestmark = pytest.mark.skipif(not refload.available(), reason="reference tree not present on this host")
+
+
+@pytest.fixture(scope="module")
+def ref_env_module():
+    return refload.load_env_module()
+
+
+def _ref_steps(m, states, actions, step_count):
+    env = m.TwoSeriesCSTREnv()
+    env.reset(seed=0)
+    N = len(states)
+    obs = np.zeros((N, 4), np.float32)
+    rew = np.zeros(N, np.float32)
+    tr = np.zeros(N, bool)
+    for i in range(N):
+        env.state = states[i].copy()
+        env.current_step = int(step_count[i])
+        with contextlib.redirect_stdout(io.StringIO()):
+            o, r, te, t, _ = env.step(actions[i].copy())
+        assert te is False
+        obs[i], rew[i], tr[i] = o, r, t
+    return obs, rew, tr
+
+
+def test_step_bit_exact(ref_env_module):
+    rng = np.random.default_rng(99)
+    N = 6000
+    states = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
+    states[:64] = np.sign(states[:64])
+    actions = rng.uniform(-1.5, 1.5, (N, 2)).astype(np.float32)
+    actions[70] = [np.nan, 0.0]
+    actions[71] = [np.inf, -np.inf]
+    sc = rng.integers(0, 402, N).astype(np.int32)
+    obs, rew, tr = _ref_steps(ref_env_module, states, actions, sc)
+    out = O.step_f32(states, actions, sc)
+    assert np.array_equal(out.obs, obs)
+    assert np.array_equal(out.reward, rew)
+    assert np.array_equal(out.truncated, tr)
+
+
+def test_dynamics_f64_bit_exact(ref_env_module):
+    rng = np.random.default_rng(5)
+    env = ref_env_module.TwoSeriesCSTREnv()
+    lo, hi = env.raw_state_low.astype(np.float64), env.raw_state_high.astype(np.float64)
+    raw = lo + (hi - lo) * rng.random((1500, 4))
+    act = 30.0 + 220.0 * rng.random((1500, 2))
+    ref = np.stack([env._dynamics(state=raw[i].copy(), action=act[i].copy()) for i in range(len(raw))])
+    assert np.array_equal(O.dynamics(raw, act), ref)
+
+
+def test_reset_stream(ref_env_module):
+    for seed in (3, 17):
+        env = ref_env_module.TwoSeriesCSTREnv(init_mode="random")
+        u = O.pcg64_reset_uniforms(seed, 3)
+        mine = O.obs_from_raw_f64(O.initial_state_from_uniforms(u))
+        for e in range(3):
+            o, _ = env.reset(seed=seed if e == 0 else None)
+            assert np.array_equal(o, mine[e])
+
+
+def test_replay_buffer_live():
+    refload.load_core()
+    from core.common.buffers import ReplayBuffer
+    from gymnasium import spaces
+
+    rng = np.random.default_rng(1)
+    n_envs, size = 3, 21
+    ref = ReplayBuffer(size, spaces.Box(-1, 1, (4,), np.float32), spaces.Box(-1, 1, (2,), np.float32), "cpu", n_envs)
+    mine = O.ReplayOracle(size, n_envs)
+    for _ in range(17):
+        o, no = rng.random((n_envs, 4), np.float32), rng.random((n_envs, 4), np.float32)
+        a, r = rng.random((n_envs, 2), np.float32), rng.random(n_envs, np.float32)
+        d = rng.random(n_envs) < 0.4
+        to = d & (rng.random(n_envs) < 0.5)
+        ref.add(o, no, a, r, d, [{"TimeLimit.truncated": bool(x)} for x in to])
+        mine.add(o, no, a, r, d, to)
+    for k in ("observations", "next_observations", "actions", "rewards", "dones", "timeouts"):
+        assert np.array_equal(getattr(ref, k), getattr(mine, k))
+    assert (ref.pos, ref.full) == (mine.pos, mine.full)
+    np.random.seed(4)
+    s = ref.sample(50)
+    np.random.seed(4)
+    obs, act, nobs, dones, rew = mine.sample(50)
+    assert np.array_equal(s.observations.numpy(), obs) and np.array_equal(s.actions.numpy(), act)
+    assert np.array_equal(s.next_observations.numpy(), nobs) and np.array_equal(s.dones.numpy(), dones)
+    assert np.array_equal(s.rewards.numpy(), rew)
