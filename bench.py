@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""bench.py — CSTR env-steps/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math strict|fast]
+
+Workload at N=1 = BASELINE.json configs[1]: "TwoSeriesCSTR step-only, 65,536 batched envs, random
+actions, fp32", one *step* = one pass of the hot path over one batch = ONE launch of the tape kernel
+integrating 400 control intervals (a full episode incl. the truncation/auto-reset row) for 65,536
+reactors = 26,214,400 env-steps, actions streamed from a (400, 65536, 2) float32 tape resident in HBM
+(210 MB > the 126 MB L2, so every step reads its inputs from DRAM; no L2 flush needed).
+N>1: one process per GPU (torchrun), every rank owns its own 65,536-reactor shard (weak scaling, no
+data-path collective — reactors are independent); time = max over ranks.
+
+Keys beyond the base contract:
+  roofline     dominant kernel (tape_f32) against the FP32 pipe peak MEASURED in this run by an FMA-chain
+               probe (MEASURED_PEAKS.json has no non-tensor peak): achieved = 176 flop/env-step
+               x env-steps per launch / CUDA-event duration.
+  cpu_baseline the oracle's C port (oracle/cstr_oracle.c, OpenMP, all host cores) on a bounded sample.
+  e2e          same metric through the C-ABI call with HOST (pinned) buffers: H2D of the action tape and
+               state, the kernel, D2H of rewards/dones/state, all inside the timed region.
+  extras       other variants (fast math, fp64, in-kernel Philox actions, VecEnv.step loop, replay GB/s,
+               fused rollout transitions/s) — reported, not the headline.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+N_ENVS = 65_536
+T_STEPS = 400
+FLOP_PER_ENV_STEP = 176  # 172 add/mul/div/min/max/abs/cmp + 4 exp, no FMA credit
+METRIC = "CSTR env-steps/sec (TwoSeriesCSTR step-only, 65,536 batched envs per GPU, random actions)"
+UNIT = "env-steps/s"
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.rows, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or [r for (_, r) in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        power = [float(r[3]) for r in rows if r[3].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's C port on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_port_rate(n_envs: int, target_seconds: float, seed: int = 0):
+    """env-steps/s of oracle/cstr_oracle.c (libm exp, powf: the faithful scalar port; OpenMP all cores)
+    on a bounded sample of the workload: n_envs reactors x T_cpu control intervals."""
+    import numpy as np
+
+    import build_oracle as B
+
+    rng = np.random.default_rng(seed)
+    st, sc, ep, _ = B.reset_f32(n_envs, 0, seed, 0)
+    cal_T = 8
+    acts = rng.uniform(-1, 1, (cal_T, n_envs, 2)).astype(np.float32)
+    B.tape_f32(st, sc, ep, acts, 0, seed, 0, want_rewards=False, want_dones=False)  # warm-up (page-in, thread pool)
+    t0 = time.perf_counter()
+    B.tape_f32(st, sc, ep, acts, 0, seed, 0, want_rewards=True, want_dones=True)
+    dt = time.perf_counter() - t0
+    rate = cal_T * n_envs / dt
+    T_cpu = int(max(16, min(T_STEPS, target_seconds * rate / n_envs)))
+    acts = rng.uniform(-1, 1, (T_cpu, n_envs, 2)).astype(np.float32)
+    t0 = time.perf_counter()
+    B.tape_f32(st, sc, ep, acts, 0, seed, 0, want_rewards=True, want_dones=True)
+    dt = time.perf_counter() - t0
+    return T_cpu * n_envs / dt, T_cpu, B.num_threads(), dt
+
+
+def run_reference_arm(args) -> None:
+    """--impl reference: the reference's CPU implementation of the path, timed on this box's host cores.
+    The reference is pure Python and cannot travel to the GPU box, so this is the oracle's C port of it
+    (kind "port", all host threads) — a much faster stand-in than the Python original (6.8 k steps/s/core)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    import build_oracle as B
+
+    rng = np.random.default_rng(0)
+    st, sc, ep, _ = B.reset_f32(N_ENVS, 0, 0, 0)
+    # size one step to ~2 s of CPU work so that K+W steps finish within a few minutes
+    cal = rng.uniform(-1, 1, (4, N_ENVS, 2)).astype(np.float32)
+    B.tape_f32(st, sc, ep, cal, 0, 0, 0)
+    t0 = time.perf_counter()
+    B.tape_f32(st, sc, ep, cal, 0, 0, 0)
+    rate = 4 * N_ENVS / (time.perf_counter() - t0)
+    per_step_budget = min(2.0, 150.0 / max(1, args.steps + args.warmup))
+    T_ref = int(max(4, min(T_STEPS, per_step_budget * rate / N_ENVS)))
+    acts = rng.uniform(-1, 1, (T_ref, N_ENVS, 2)).astype(np.float32)
+    state = dict(state=st, step_count=sc, episode=ep)
+
+    def one():
+        r = B.tape_f32(state["state"], state["step_count"], state["episode"], acts, 0, 0, 0, want_rewards=True, want_dones=True)
+        state.update(state=r["state"], step_count=r["step_count"], episode=r["episode"])
+
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    value = args.steps * T_ref * N_ENVS / dt
+    sample = f"{N_ENVS} reactors x {T_ref} control intervals per step (of the arm's 400), float32, libm expf/powf, OpenMP"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "TwoSeriesCSTR step-only, 65,536 batched envs, random actions, fp32", "n_envs": N_ENVS,
+                   "control_intervals_per_step": T_ref, "note": "reference is pure Python and absent on this box; timed: its C port (oracle/cstr_oracle.c)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": B.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def measure_pipe_peaks(pkg, torch, device) -> dict:
+    """FMA-chain probes (cstr_probe_pipe): fp32 FFMA, fp64 DFMA, fp32 FMUL+FADD pairs, MUFU.EX2."""
+    lib = pkg._lib.load()
+    info = [__import__("ctypes").c_int() for _ in range(4)]
+    lib.cstr_device_info(*[__import__("ctypes").byref(x) for x in info])
+    sms = info[0].value
+    grid, block, iters = sms * 16, 256, 4096
+    out = torch.empty(grid * block, dtype=torch.float32, device=device)
+    res = {"sm_count": sms}
+    stream = torch.cuda.current_stream(device).cuda_stream
+    for kind, name, flop in ((0, "fp32_ffma_tflops", 2), (1, "fp64_dfma_tflops", 2), (2, "fp32_fmul_fadd_tflops", 2), (3, "mufu_ex2_tops", 1)):
+        best = 0.0
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pkg._lib.check(lib.cstr_probe_pipe(kind, iters, grid, block, out.data_ptr(), stream), "probe")
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if rep:
+                best = max(best, grid * block * iters * 8 * flop / (ms * 1e-3) / 1e12)
+        res[name] = best
+    return res
+
+
+def time_launches(torch, fn, k: int):
+    """Run fn() k times, one CUDA-event pair per launch on the current stream; returns (total_ms, [ms])."""
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+    evs[0].record()
+    for i in range(k):
+        fn()
+        evs[i + 1].record()
+    evs[-1].synchronize()
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(k)]
+    return evs[0].elapsed_time(evs[-1]), per
+
+
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+
+    pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    lib = pkg._lib.load()
+    from ctypes import byref
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    n, T = N_ENVS, T_STEPS
+    seed = 20260101
+    env = pkg.GpuCSTRVecEnv(n, device=device, math=args.math, seed=seed, env_offset=rank * n, monitor=False)
+    env.reset()
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    tape = (torch.rand((T, n, 2), generator=gen, device=device, dtype=torch.float32) * 2 - 1).contiguous()  # 210 MB > L2
+    rewards = torch.empty((T, n), dtype=torch.float32, device=device)
+    dones = torch.empty((T, n), dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    mode = {"strict": 0, "fast": 1}[args.math]
+
+    def step():
+        pkg._lib.check(lib.cstr_tape_f32(byref(env._params), n, T, mode, tape.data_ptr(), 0, env.state.data_ptr(), env.step_count.data_ptr(),
+                                         env.episode.data_ptr(), None, rewards.data_ptr(), dones.data_ptr(), None, None, stream), "cstr_tape_f32")
+
+    peaks = measure_pipe_peaks(pkg, torch, device) if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    t_wall0 = time.time()
+    barrier()
+    total_ms, per = time_launches(torch, step, args.steps)
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = world * args.steps * n * T / (total_ms_max * 1e-3)
+    # sanity inside the bench: one truncation row per episode, rewards finite
+    assert int(dones.sum().item()) == n and bool(torch.isfinite(rewards).all().item())
+
+    # ---- e2e: the C-ABI call with HOST buffers (H2D tape + state, kernel, D2H rewards/dones/state) --------------
+    h_tape = torch.empty((T, n, 2), dtype=torch.float32).pin_memory()
+    h_tape.copy_(tape)
+    h_state = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    h_state.copy_(env.state)
+    h_sc = torch.zeros(n, dtype=torch.int32).pin_memory()
+    h_ep = torch.ones(n, dtype=torch.int32).pin_memory()
+    h_rew = torch.empty((T, n), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((T, n), dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        pkg._lib.check(lib.cstr_tape_f32_host(byref(env._params), n, T, mode, h_tape.data_ptr(), h_state.data_ptr(), h_sc.data_ptr(),
+                                              h_ep.data_ptr(), h_rew.data_ptr(), h_done.data_ptr(), stream), "cstr_tape_f32_host")
+
+    e2e_reps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_reps):
+        e2e_step()  # synchronises internally: results are on the host when it returns
+    torch.cuda.synchronize(device)
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_reps * n * T / float(e2e_dt.item())
+    h2d = T * n * 8 + n * (16 + 4 + 4)
+    d2h = T * n * (4 + 1) + n * (16 + 4 + 4)
+    assert int(h_done.sum().item()) == n
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- extras (rank 0, N=1 only: variants that explain the headline) ---------------------------------------------
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args)
+    # ---- CPU baseline on a bounded sample ----------------------------------------------------------------------------
+    cpu = None
+    if world == 1:
+        try:
+            rate, T_cpu, cores, dt = cpu_port_rate(n, target_seconds=12.0)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n} reactors x {T_cpu} control intervals, float32, libm expf/powf, OpenMP ({dt:.1f} s)"}
+        except Exception as exc:  # the baseline must never take the bench down
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+    kernel_ms = statistics.mean(per)
+    achieved = FLOP_PER_ENV_STEP * n * T / (kernel_ms * 1e-3) / 1e12
+    peak = peaks["fp32_ffma_tflops"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"tape_f32_{args.math}")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "TwoSeriesCSTR step-only, 65,536 batched envs, random actions, fp32 (BASELINE.json configs[1])",
+                   "n_envs_per_gpu": n, "control_intervals_per_step": T, "env_steps_per_step_per_gpu": n * T, "math": args.math,
+                   "actions": "U(-1,1) float32 tape (400,65536,2) streamed from HBM", "outputs_per_interval": "reward f32 + done u8",
+                   "l2": "inputs larger than L2 (210 MB tape vs 126 MB): no flush needed", "parallelism": f"env-shard x{world}"},
+        "roofline": {"bound": "fp32-pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     "traffic": traffic, "kernel": f"tape_f32_kernel<{args.math}>", "kernel_ms": kernel_ms,
+                     "flop_per_env_step": FLOP_PER_ENV_STEP, "peak_source": "measured in this run: cstr_probe_pipe FFMA chains (2 flop/FMA)",
+                     "other_peaks": peaks,
+                     "hbm_algorithmic_gbs": n * T * (8 + 4 + 1) / (kernel_ms * 1e-3) / 1e9},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "cstr_tape_f32_host (pinned host buffers -> H2D -> tape kernel -> D2H, synchronous)"},
+        "gpu_launches": args.steps, "clocks": clocks, "extras": extras,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict:
+    """Variants that explain the headline; each timed with CUDA events after its own warm-up."""
+    from ctypes import byref
+
+    import numpy as np
+
+    n, T = N_ENVS, T_STEPS
+    stream = torch.cuda.current_stream(device).cuda_stream
+    ex = {}
+
+    def rate_of(fn, env_steps, reps=5):
+        for _ in range(2):
+            fn()
+        ms, per = time_launches(torch, fn, reps)
+        return env_steps / (statistics.mean(per) * 1e-3)
+
+    try:
+        for math, mode in (("strict", 0), ("fast", 1)):
+            ex[f"tape_f32_{math}_hbm_actions"] = rate_of(lambda: lib.cstr_tape_f32(
+                byref(env._params), n, T, mode, tape.data_ptr(), 0, env.state.data_ptr(), env.step_count.data_ptr(), env.episode.data_ptr(),
+                None, rewards.data_ptr(), dones.data_ptr(), None, None, stream), n * T)
+            ex[f"tape_f32_{math}_philox_actions"] = rate_of(lambda: lib.cstr_tape_f32(
+                byref(env._params), n, T, mode, None, 0, env.state.data_ptr(), env.step_count.data_ptr(), env.episode.data_ptr(),
+                None, rewards.data_ptr(), dones.data_ptr(), None, None, stream), n * T)
+        # fp64 (north_star: fp64 vs fp32)
+        e64 = pkg.GpuCSTRVecEnv(n, device=device, dtype="fp64", seed=1, monitor=False)
+        e64.reset()
+        r64 = torch.empty((T, n), dtype=torch.float64, device=device)
+        ex["tape_f64_philox_actions"] = rate_of(lambda: lib.cstr_tape_f64(
+            byref(e64._params), n, T, None, 0, e64.state.data_ptr(), e64.step_count.data_ptr(), e64.episode.data_ptr(), None, r64.data_ptr(),
+            dones.data_ptr(), None, None, stream), n * T, reps=3)
+        del e64, r64
+        # 1,048,576 reactors (config #3 batch) — the chip is full at this size
+        nb, Tb = 1 << 20, 100
+        eb = pkg.GpuCSTRVecEnv(nb, device=device, math=args.math, seed=2, monitor=False)
+        eb.reset()
+        rb = torch.empty((Tb, nb), dtype=torch.float32, device=device)
+        db = torch.empty((Tb, nb), dtype=torch.uint8, device=device)
+        for math, mode in (("strict", 0), ("fast", 1)):
+            ex[f"tape_f32_{math}_philox_1M_envs"] = rate_of(lambda: lib.cstr_tape_f32(
+                byref(eb._params), nb, Tb, mode, None, 0, eb.state.data_ptr(), eb.step_count.data_ptr(), eb.episode.data_ptr(), None,
+                rb.data_ptr(), db.data_ptr(), None, None, stream), nb * Tb, reps=3)
+        # single VecEnv step kernel at 1M envs: HBM-bound (70 B/env-step)
+        ab = torch.rand((nb, 2), device=device) * 2 - 1
+        r1 = rate_of(lambda: eb.step_tensor(ab), nb, reps=20)
+        ex["vec_step_f32_1M_envs"] = r1
+        ex["vec_step_f32_1M_envs_hbm_gbs"] = r1 * 70 / 1e9
+        del eb, rb, db, ab
+        # VecEnv.step() through NumPy buffers (the reference-facing protocol call), 65,536 envs
+        ev = pkg.GpuCSTRVecEnv(n, device=device, math=args.math, seed=3, monitor=False)
+        ev.reset()
+        a_np = np.random.default_rng(0).uniform(-1, 1, (n, 2)).astype(np.float32)
+        for _ in range(3):
+            ev.step(a_np)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ev.step(a_np)
+        ex["vecenv_step_numpy_protocol"] = 20 * n / (time.perf_counter() - t0)
+        del ev
+        # replay buffer: add (52 B/transition algorithmic) and sample (116 B/sample algorithmic), HBM-bound
+        rows, ne = 64, 1 << 20
+        buf = pkg.GpuReplayBuffer(rows * ne, device=device, n_envs=ne, index_mode="philox")
+        o = torch.rand((ne, 4), device=device)
+        a2 = torch.rand((ne, 2), device=device)
+        r2 = torch.rand(ne, device=device)
+        d2 = torch.zeros(ne, dtype=torch.uint8, device=device)
+        add_rate = rate_of(lambda: buf.add(o, o, a2, r2, d2, None, timeouts=d2), ne, reps=64)
+        ex["replay_add_transitions_per_s"] = add_rate
+        ex["replay_add_algorithmic_gbs"] = add_rate * 52 / 1e9
+        B_ = 1 << 22
+        smp = rate_of(lambda: buf.sample(B_), B_, reps=10)
+        ex["replay_sample_philox_samples_per_s"] = smp
+        ex["replay_sample_algorithmic_gbs"] = smp * 116 / 1e9
+        # fused rollout (config #3 shape: TD3 actor 4-400-300-2, sigma 0.1), transitions/s
+        g = torch.Generator().manual_seed(0)
+        lin = [torch.nn.Linear(4, 400), torch.nn.Linear(400, 300), torch.nn.Linear(300, 2)]
+        actor = pkg.ActorWeights(lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias, device=device)
+        er = pkg.GpuCSTRVecEnv(ne, device=device, math=args.math, seed=4, monitor=False)
+        er.reset()
+        for mode_name in ("fp32", "tc"):
+            try:
+                roll = pkg.FusedRollout(er, buf, actor, sigma=0.1, actor_mode=mode_name)
+                Kr = 2 if mode_name == "fp32" else 16
+                ex[f"fused_rollout_{mode_name}_transitions_per_s"] = rate_of(lambda: roll.collect(Kr), ne * Kr, reps=3)
+            except Exception as exc:
+                ex[f"fused_rollout_{mode_name}_transitions_per_s"] = f"unavailable: {exc}"
+    except Exception as exc:  # extras must never take the headline down
+        ex["error"] = repr(exc)
+    torch.cuda.synchronize(device)
+    return ex
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--math", choices=["strict", "fast"], default="strict")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+/*
+ * cstr_b200.h — C ABI of the B200-native (sm_100a) two-series CSTR hot path.
+ *
+ * The reference (CHAINNEVERLIU/Pytorch-RL-EnhancedStableBaselines) is 100 % Python and has no
+ * FFI of its own; its boundary for this path is three Python protocols.  The
+ * entry points below are what a ctypes binding placed under those protocols calls; each one
+ * names the reference code it replaces.  INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - plain C, no torch types: raw DEVICE pointers + sizes + a CUDA stream handle (void*, the
+ *     cudaStream_t; NULL = legacy default stream).  The caller owns every buffer.
+ *   - every call is asynchronous and stream-ordered; nothing synchronises unless stated.
+ *   - return value: 0 = ok; > 0 = cudaError_t of the failed launch/copy; < 0 = argument error
+ *     (CSTR_EINVAL...).  cstr_last_error() returns a thread-local message for the last failure.
+ *     NaN actions are DATA, handled with the reference's semantics, not errors.
+ *   - layouts: state/obs (n,4) float32 (one float4 per reactor: C1,T1,C2,T2 normalised to [-1,1]),
+ *     actions (n,2) float32, step_count/episode (n,) int32, rewards (n,) float32,
+ *     done/timeout (n,) uint8.  The f64 entry points use double for state/action/reward.
+ *   - not re-entrant on the same buffers; one CUDA context per process (one process per GPU).
+ */
+#ifndef CSTR_B200_H
+#define CSTR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSTR_B200_ABI_VERSION 3
+
+#define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
+#define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
+
+/* math_mode */
+#define CSTR_MATH_STRICT 0 /* reference association, no FMA contraction, IEEE division, shared exp  */
+#define CSTR_MATH_FAST 1   /* FMA contraction, reciprocal multiplies, ex2.approx (documented tolerance) */
+
+/* init_mode (twoseriescstr.py:91-96) */
+#define CSTR_INIT_RANDOM 0
+#define CSTR_INIT_STATIC 1
+
+/* Environment parameters shared by all entry points (twoseriescstr.py:63-112). */
+typedef struct cstr_env_params {
+    uint64_t seed;       /* Philox4x32-10 key of the device RNG (reset draws, exploration noise)   */
+    int64_t env_offset;  /* global id of reactor 0 of this shard (multi-GPU: rank * n_per_rank)   */
+    float target_c2;     /* TwoSeriesCSTREnv.target_C2 (default 0.20)                             */
+    int32_t max_steps;   /* TwoSeriesCSTREnv.max_steps (400)                                      */
+    int32_t init_mode;   /* CSTR_INIT_RANDOM | CSTR_INIT_STATIC                                   */
+    int32_t reserved;
+} cstr_env_params;
+
+int cstr_b200_abi_version(void);
+const char *cstr_last_error(void);
+/* device properties the host needs for launch/roofline bookkeeping: SM count, SM clock (kHz) */
+int cstr_device_info(int *sm_count, int *sm_clock_khz, int *cc_major, int *cc_minor);
+
+/* ---- reset ------------------------------------------------------------------------------------
+ * Replaces TwoSeriesCSTREnv.reset / generate_initial_state (twoseriescstr.py:226-269,167-224) for
+ * the reactors whose mask byte is non-zero (mask == NULL: all).  Draws 8 unit doubles per reset
+ * from Philox (counter = env id, episode; DESIGN.md "RNG"), float64 arithmetic as in the reference,
+ * result stored normalised.  static_base: (n,4) double, required for CSTR_INIT_STATIC (quirk Q2:
+ * the base state random-walks), may be NULL otherwise.  is_f64: state is double (n,4).             */
+int cstr_reset(const cstr_env_params *p, int64_t n, const uint8_t *mask, void *state, int is_f64,
+               int32_t *step_count, int32_t *episode, double *static_base, void *stream);
+
+/* ---- one VecEnv step --------------------------------------------------------------------------
+ * Replaces DummyVecEnv.step_wait over N TwoSeriesCSTREnv.step calls
+ * (core/common/vec_env/dummy_vec_env.py:56-73; twoseriescstr.py:394-503,271-392).
+ *   state        in: current normalised state; out: the observation step_wait returns
+ *                (post-reset on done rows when auto_reset != 0, else the terminal observation)
+ *   terminal_obs out (nullable): the new state before any reset (info["terminal_observation"] /
+ *                the next_obs _store_transition stores)
+ *   done = terminated or truncated; timeout = truncated and not terminated ("TimeLimit.truncated")
+ * auto_reset == 0 leaves resetting to the caller (host PCG64 parity mode).
+ * Episode statistics (Monitor semantics, core/common/monitor.py:85-111), all nullable:
+ *   ep_return  (n,) double in/out running return; ep_final_return / ep_final_length (n,) out, written
+ *   on done rows only: the finished episode's return and length (info["episode"]["r"/"l"]).          */
+int cstr_vec_step_f32(const cstr_env_params *p, int64_t n, int math_mode, int auto_reset,
+                      const float *actions, float *state, int32_t *step_count, int32_t *episode,
+                      double *static_base, float *terminal_obs, float *reward, uint8_t *done,
+                      uint8_t *timeout, double *ep_return, double *ep_final_return,
+                      int32_t *ep_final_length, void *stream);
+int cstr_vec_step_f64(const cstr_env_params *p, int64_t n, int auto_reset, const double *actions,
+                      double *state, int32_t *step_count, int32_t *episode, double *static_base,
+                      double *terminal_obs, double *reward, uint8_t *done, uint8_t *timeout,
+                      double *ep_return, double *ep_final_return, int32_t *ep_final_length,
+                      void *stream);
+
+/* ---- T control intervals per launch, state held in registers ------------------------------------
+ * Same semantics as T successive cstr_vec_step calls with auto-reset.
+ *   actions  (T,n,2) tape, or NULL: actions are U(-1,1) from Philox (stream "action", counter
+ *            t_base + t) generated in-kernel
+ *   rewards (T,n), dones (T,n), obs_tape (T,n,4) = observation returned by each step: nullable
+ *   reward_sum: nullable device double[1], atomically accumulates the sum of all rewards
+ *   (size-independent checksum for large runs).                                                   */
+int cstr_tape_f32(const cstr_env_params *p, int64_t n, int64_t T, int math_mode,
+                  const float *actions, uint32_t t_base, float *state, int32_t *step_count,
+                  int32_t *episode, double *static_base, float *rewards, uint8_t *dones,
+                  float *obs_tape, double *reward_sum, void *stream);
+int cstr_tape_f64(const cstr_env_params *p, int64_t n, int64_t T, const double *actions,
+                  uint32_t t_base, double *state, int32_t *step_count, int32_t *episode,
+                  double *static_base, double *rewards, uint8_t *dones, double *obs_tape,
+                  double *reward_sum, void *stream);
+
+/* Same as cstr_tape_f32 but with HOST buffers (pinned recommended): copies state/step_count/episode
+ * and the action tape to scratch device memory owned by the library, runs the tape, copies state,
+ * rewards and dones back, and synchronises.  This is the end-to-end call bench.py times ("e2e").   */
+int cstr_tape_f32_host(const cstr_env_params *p, int64_t n, int64_t T, int math_mode,
+                       const float *h_actions, float *h_state, int32_t *h_step_count,
+                       int32_t *h_episode, float *h_rewards, uint8_t *h_dones, void *stream);
+
+/* ---- ring replay buffer -------------------------------------------------------------------------
+ * HBM layout: ONE 64-byte record per transition, records (rows, n_envs, 16) float32:
+ *   [0:4] obs   [4:8] next_obs   [8:10] action   [10] reward   [11] done   [12] timeout   [13:16] pad
+ * so that `add` is four coalesced 16-byte stores per reactor and a random-index `sample` reads two
+ * whole 32-byte sectors per transition instead of six partial ones.  The reference's six arrays
+ * (core/common/buffers.py:213-228: observations, next_observations, actions, rewards, dones,
+ * timeouts) are exposed by the Python host as strided views of this tensor.
+ *
+ * cstr_replay_add replaces ReplayBuffer.add (buffers.py:247-283): writes ring row `pos`; the caller
+ * advances pos/full (host ints, as in the reference).  done/timeout are uint8 device vectors
+ * (timeout may be NULL = all False, the handle_timeout_termination=False case).                    */
+#define CSTR_REC_FLOATS 16
+#define CSTR_REC_OBS 0
+#define CSTR_REC_NEXT_OBS 4
+#define CSTR_REC_ACTION 8
+#define CSTR_REC_REWARD 10
+#define CSTR_REC_DONE 11
+#define CSTR_REC_TIMEOUT 12
+
+int cstr_replay_add(int64_t n_envs, int64_t pos, const float *obs, const float *next_obs,
+                    const float *action, const float *reward, const uint8_t *done,
+                    const uint8_t *timeout, float *records, void *stream);
+
+/* cstr_replay_sample replaces ReplayBuffer._get_samples + to_torch (buffers.py:307-325,128-140):
+ * gathers `batch` transitions at (batch_inds[i], env_inds[i]) into contiguous outputs
+ * obs (B,4), act (B,2), next_obs (B,4), dones (B,1) = dones*(1-timeouts), rewards (B,1).
+ * Index pairs are int64 device vectors (bit-exact mode: drawn on the host with the reference's two
+ * np.random.randint calls).                                                                        */
+int cstr_replay_sample(int64_t n_envs, int64_t batch, const int64_t *batch_inds,
+                       const int64_t *env_inds, const float *records, float *out_obs,
+                       float *out_act, float *out_next_obs, float *out_dones, float *out_rewards,
+                       void *stream);
+
+/* Fast mode: indices drawn in-kernel from Philox (stream "sample", counter = (i, draw)): row uniform
+ * in [0, upper), env uniform in [0, n_envs) by 32x32->64 multiply-shift.  Optionally returns the
+ * drawn pairs (nullable).                                                                          */
+int cstr_replay_sample_philox(uint64_t seed, uint64_t draw, int64_t n_envs, int64_t upper,
+                              int64_t batch, const float *records, float *out_obs, float *out_act,
+                              float *out_next_obs, float *out_dones, float *out_rewards,
+                              int64_t *out_batch_inds, int64_t *out_env_inds, void *stream);
+
+/* ---- fused rollout --------------------------------------------------------------------------------
+ * Replaces, for K consecutive env steps of N reactors, OffPolicyAlgorithm._sample_action +
+ * policy.predict (TD3 Actor.forward) + env.step + _store_transition + ReplayBuffer.add
+ * (core/common/off_policy_algorithm.py:364-411,445-508,564; core/td3/policies.py:75-78;
+ *  core/common/policies.py:331-413; core/common/buffers.py:247-283).
+ * Actor = tanh(W3 relu(W2 relu(W1 x + b1) + b2) + b3), torch Linear layout (out,in), fp32.
+ *   actor_mode 0: fp32 CUDA-core actor (parity path)
+ *   actor_mode 1: bf16 tcgen05 tensor-core hidden layer, fp32 accumulate (throughput path);
+ *                 needs the packed weights from cstr_actor_pack_bf16.
+ * noise: sigma * N(0,1) from Philox (stream "noise") when noise == NULL, else the (K,n,2) tensor.
+ * warmup != 0: uniform random actions instead of the actor (learning_starts phase, :386-388).
+ * Each step writes ring row (pos0 + k) % rows of the replay records and leaves `state` at the
+ * observation to act on next.  rows = ring capacity in rows.                                       */
+typedef struct cstr_actor_f32 {
+    const float *W1, *b1; /* (H1,4), (H1) */
+    const float *W2, *b2; /* (H2,H1), (H2) */
+    const float *W3, *b3; /* (2,H2), (2)  */
+    int32_t H1, H2;
+} cstr_actor_f32;
+
+int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, int actor_mode,
+                       const cstr_actor_f32 *actor, const void *packed_bf16, float sigma,
+                       const float *noise, int warmup, uint32_t t_base, float *state,
+                       int32_t *step_count, int32_t *episode, double *static_base, int64_t rows,
+                       int64_t pos0, float *records, double *reward_sum, void *stream);
+
+/* Packs W2 (H2,H1) fp32 into the bf16 UMMA shared-memory image the tensor-core path streams with
+ * TMA-style bulk copies; returns the required size in bytes when dst == NULL.                      */
+int64_t cstr_actor_pack_bf16(const cstr_actor_f32 *actor, void *dst, void *stream);
+
+/* ---- measurement probes (bench.py roofline denominators) ------------------------------------------
+ * FMA-chain microbenchmarks: every thread runs `iters` iterations of 8 independent FMA chains.
+ * kind 0: fp32 FFMA, 1: fp64 DFMA, 2: fp32 separate FMUL+FADD (the non-contractible op mix),
+ * 3: MUFU.EX2.  out: one value per thread (keeps the chains live).  flops/launch =
+ * grid*block*iters*8*(2 for kinds 0,1,2; 1 for kind 3).                                            */
+int cstr_probe_pipe(int kind, int64_t iters, int grid, int block, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSTR_B200_H */

@@ -1,0 +1,32 @@
+"""B200-native (sm_100a) two-series CSTR hot path behind the reference's env / VecEnv / ReplayBuffer
+protocols.  See DESIGN.md and INTEGRATION.md at the repository root.
+
+The directory name contains a hyphen, so import it with
+``importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")`` or through the ``b200rl`` alias
+module at the repository root.  Importing the package does not need a GPU; constructing any of its
+classes does (the CUDA library has no CPU fallback).
+"""
+from . import _build, _lib
+from ._lib import CstrLibraryError
+from .buffer import GpuReplayBuffer, ReplayBufferSamples, bind_replay_buffer_class
+from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
+from .rollout import ActorWeights, FusedRollout
+
+__all__ = [
+    "ActorWeights",
+    "CstrLibraryError",
+    "FusedRollout",
+    "GpuCSTRVecEnv",
+    "GpuReplayBuffer",
+    "LazyInfos",
+    "ReplayBufferSamples",
+    "TwoSeriesCSTREnv",
+    "bind_replay_buffer_class",
+    "bind_vec_env_class",
+    "build",
+]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree (nvcc, sm_100a)."""
+    return _build.build(force=force, verbose=verbose)

@@ -1,0 +1,131 @@
+"""ctypes binding of include/cstr_b200.h.  There is NO fallback: if the CUDA library is missing or a
+call fails, a ``CstrLibraryError`` is raised (the product never routes through a CPU path)."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+from typing import Optional
+
+from . import _build
+
+ABI_VERSION = 3
+MATH_STRICT, MATH_FAST = 0, 1
+INIT_RANDOM, INIT_STATIC = 0, 1
+REC_FLOATS = 16
+
+
+class CstrLibraryError(RuntimeError):
+    pass
+
+
+class EnvParams(Structure):
+    """struct cstr_env_params"""
+
+    _fields_ = [
+        ("seed", c_uint64),
+        ("env_offset", c_int64),
+        ("target_c2", c_float),
+        ("max_steps", c_int32),
+        ("init_mode", c_int32),
+        ("reserved", c_int32),
+    ]
+
+
+class ActorF32(Structure):
+    """struct cstr_actor_f32"""
+
+    _fields_ = [
+        ("W1", c_void_p), ("b1", c_void_p),
+        ("W2", c_void_p), ("b2", c_void_p),
+        ("W3", c_void_p), ("b3", c_void_p),
+        ("H1", c_int32), ("H2", c_int32),
+    ]
+
+
+P = c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)  — mirrors include/cstr_b200.h one to one
+    "cstr_b200_abi_version": (c_int, []),
+    "cstr_last_error": (c_char_p, []),
+    "cstr_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "cstr_reset": (c_int, [POINTER(EnvParams), c_int64, P, P, c_int, P, P, P, P]),
+    "cstr_vec_step_f32": (c_int, [POINTER(EnvParams), c_int64, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "cstr_vec_step_f64": (c_int, [POINTER(EnvParams), c_int64, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "cstr_tape_f32": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, P, c_uint32, P, P, P, P, P, P, P, P, P]),
+    "cstr_tape_f64": (c_int, [POINTER(EnvParams), c_int64, c_int64, P, c_uint32, P, P, P, P, P, P, P, P, P]),
+    "cstr_tape_f32_host": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, P, P, P, P, P, P, P]),
+    "cstr_replay_add": (c_int, [c_int64, c_int64, P, P, P, P, P, P, P, P]),
+    "cstr_replay_sample": (c_int, [c_int64, c_int64, P, P, P, P, P, P, P, P, P]),
+    "cstr_replay_sample_philox": (c_int, [c_uint64, c_uint64, c_int64, c_int64, c_int64, P, P, P, P, P, P, P, P, P]),
+    "cstr_rollout_fused": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, c_int, POINTER(ActorF32), P, c_float, P, c_int,
+                                   c_uint32, P, P, P, P, c_int64, c_int64, P, P, P]),
+    "cstr_actor_pack_bf16": (c_int64, [POINTER(ActorF32), P, P]),
+    "cstr_probe_pipe": (c_int, [c_int, c_int64, c_int, c_int, P, P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """dlopen libcstr_b200.so (building it in-tree first if it is missing or stale and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build()
+        except Exception as exc:  # stale-but-present library is still usable; missing is fatal
+            if not os.path.exists(path):
+                raise CstrLibraryError(f"libcstr_b200.so is missing and could not be built: {exc}") from exc
+    if not os.path.exists(path):
+        raise CstrLibraryError(f"{path} not found — run `python __graft_entry__.py build` (no CPU fallback exists)")
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as exc:
+        raise CstrLibraryError(f"could not load {path}: {exc}") from exc
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise CstrLibraryError(f"{path} does not export {name} (stale build?)") from exc
+        fn.restype = restype
+        fn.argtypes = argtypes
+    got = lib.cstr_b200_abi_version()
+    if got != ABI_VERSION:
+        raise CstrLibraryError(f"ABI version mismatch: library {got}, binding {ABI_VERSION} — rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cstr_last_error()
+        raise CstrLibraryError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def require_cuda():
+    """Import torch and insist on a CUDA device — the product has no CPU path."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise CstrLibraryError("no CUDA device: the CSTR kernels are sm_100a-only and have no CPU fallback")
+    return torch
+
+
+def ptr(t) -> Optional[int]:
+    """data_ptr of a torch tensor (None passes NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle(torch_stream=None) -> int:
+    import torch
+
+    s = torch_stream if torch_stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream

@@ -1,0 +1,210 @@
+// K2 — fused rollout: actor MLP -> exploration noise -> action bounds -> CSTR step -> reward/done ->
+// replay record, K env steps per launch with the reactor state resident in registers (sm_100a).
+//
+// Replaces, per env step (reference file:line):
+//   OffPolicyAlgorithm._sample_action   core/common/off_policy_algorithm.py:364-411
+//   BasePolicy.predict / scale / unscale core/common/policies.py:331-413
+//   TD3 Actor.forward                   core/td3/policies.py:75-78 (create_mlp, torch_layers.py:110-183)
+//   VecEnv.step -> TwoSeriesCSTREnv.step core/common/vec_env/dummy_vec_env.py:56-73, twoseriescstr.py:394-454
+//   _store_transition + ReplayBuffer.add core/common/off_policy_algorithm.py:445-508, core/common/buffers.py:247-283
+//
+// actor_mode 0 (this file, fp32 CUDA cores): the parity path.  One CTA = 128 reactors, one thread
+// per reactor.  Layer 1 (K=4) is computed per thread and parked in shared memory k-major
+// (h1[k][m]: conflict-free); layer 2 is a register-tiled contraction, 12 outputs per pass with the
+// W2 rows fetched as warp-uniform 16-byte loads (L1-resident, 480 KB total streams from L2); layer 3
+// (N=2) and tanh are folded into the layer-2 epilogue so h2 never exists in memory.
+// actor_mode 1 (cstr_rollout_tc.cu): bf16 tcgen05 tensor-core hidden layer.
+#include "cstr_abi.cuh"
+#include "cstr_device.cuh"
+
+namespace cstr {
+
+constexpr int ROLL_M = 128;  // reactors per CTA
+constexpr int ROLL_NB = 12;  // layer-2 outputs per register pass
+
+// float32 action plumbing for a Box(-1,1) action space, same association as the reference:
+//   predict():        u = low + (0.5*(mu+1))*(high-low)                      policies.py:375,402-413
+//   _sample_action(): s = clip(2*((u-low)/(high-low)) - 1 + noise, -1, 1)    off_policy_algorithm.py:398-402
+//                     a = low + (0.5*(s+1))*(high-low)                       :405
+// (x+1)-1 is not the identity in float32, so the three maps are applied, not skipped.
+__device__ __forceinline__ void action_maps(float mu, float noise, float &env_action, float &buffer_action) {
+    const float u = __fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(mu, 1.0f)), 2.0f));
+    float s = __fadd_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn(u, 1.0f), 0.5f)), -1.0f);
+    s = clampf(__fadd_rn(s, noise), -1.0f, 1.0f);
+    buffer_action = s;
+    env_action = __fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(s, 1.0f)), 2.0f));
+}
+
+// N(0,1) pair by Box-Muller from one Philox call (stream "noise", counter = global step)
+__device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint64_t env, uint32_t g) {
+    const uint4 r = philox_env(seed, env, g, STREAM_NOISE, 0);
+    const float u1 = fmaf(u24(r.x), 1.0f, 5.9604644775390625e-08f);  // (0,1]
+    const float u2 = u24(r.y);
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+
+__device__ __forceinline__ void store_record(float4 *__restrict__ rec, float4 obs, float4 next_obs, float2 act, float reward, bool done) {
+    rec[0] = obs;
+    rec[1] = next_obs;
+    rec[2] = make_float4(act.x, act.y, reward, done ? 1.0f : 0.0f);
+    rec[3] = make_float4(done ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f);  // timeout == truncated (terminated is always False)
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ROLL_M)
+rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, float sigma, const float2 *__restrict__ noise, int warmup,
+                   uint32_t t_base, float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode,
+                   double *static_base, int64_t rows, int64_t pos0, float4 *__restrict__ records, double *reward_sum) {
+    extern __shared__ float h1[];  // [H1][ROLL_M]
+    const int m = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * ROLL_M + m;
+    const bool live = i < n;
+    const int H1 = actor.H1, H2 = actor.H2;
+    float4 s = live ? state[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int sc = live ? step_count[i] : 0, ep = live ? episode[i] : 0;
+    const uint64_t env = (uint64_t)(p.env_offset + i);
+    double acc_r = 0.0;
+    uint4 cache = make_uint4(0, 0, 0, 0);
+
+    for (int64_t k = 0; k < K; ++k) {
+        const uint32_t g = t_base + (uint32_t)k;
+        float2 env_a, buf_a;
+        if (warmup) {
+            // learning_starts phase: uniform action from the space (:386-388), then scale (:398)
+            const float2 a = philox_action(p.seed, env, g, cache, k == 0 || (g & 1u) == 0);
+            env_a = a;
+            buf_a = make_float2(__fadd_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn(a.x, 1.0f), 0.5f)), -1.0f),
+                                __fadd_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn(a.y, 1.0f), 0.5f)), -1.0f));
+            env_a = make_float2(__fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(buf_a.x, 1.0f)), 2.0f)),
+                                __fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(buf_a.y, 1.0f)), 2.0f)));
+        } else {
+            // ---- layer 1: h1 = relu(W1 s + b1), parked k-major in shared memory (column m is private to thread m: no barrier)
+            for (int j = 0; j < H1; ++j) {
+                const float4 w = __ldg(reinterpret_cast<const float4 *>(actor.W1) + j);
+                float v = __ldg(actor.b1 + j);
+                v = fmaf(w.x, s.x, v);
+                v = fmaf(w.y, s.y, v);
+                v = fmaf(w.z, s.z, v);
+                v = fmaf(w.w, s.w, v);
+                h1[j * ROLL_M + m] = fmaxf(v, 0.0f);
+            }
+            // each thread only reads back its own column m: no barrier needed between layers
+            // ---- layer 2 + 3: out = W3 relu(W2 h1 + b2) + b3, 12 hidden units per pass
+            float o0 = __ldg(actor.b3), o1 = __ldg(actor.b3 + 1);
+            for (int nb = 0; nb < H2; nb += ROLL_NB) {
+                float acc[ROLL_NB];
+#pragma unroll
+                for (int q = 0; q < ROLL_NB; ++q) acc[q] = 0.0f;
+                const int H1v = H1 & ~3;
+                for (int kk = 0; kk < H1v; kk += 4) {
+                    const float a0 = h1[(kk + 0) * ROLL_M + m], a1 = h1[(kk + 1) * ROLL_M + m];
+                    const float a2 = h1[(kk + 2) * ROLL_M + m], a3 = h1[(kk + 3) * ROLL_M + m];
+#pragma unroll
+                    for (int q = 0; q < ROLL_NB; ++q) {
+                        const int row = min(nb + q, H2 - 1);  // clamp: tail lanes recompute the last row, discarded below
+                        const float4 w = __ldg(reinterpret_cast<const float4 *>(actor.W2 + (size_t)row * H1 + kk));
+                        acc[q] = fmaf(w.x, a0, acc[q]);
+                        acc[q] = fmaf(w.y, a1, acc[q]);
+                        acc[q] = fmaf(w.z, a2, acc[q]);
+                        acc[q] = fmaf(w.w, a3, acc[q]);
+                    }
+                }
+                for (int kk = H1v; kk < H1; ++kk) {
+                    const float a0 = h1[kk * ROLL_M + m];
+#pragma unroll
+                    for (int q = 0; q < ROLL_NB; ++q) acc[q] = fmaf(__ldg(actor.W2 + (size_t)min(nb + q, H2 - 1) * H1 + kk), a0, acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < ROLL_NB; ++q) {
+                    if (nb + q < H2) {
+                        const float h = fmaxf(acc[q] + __ldg(actor.b2 + nb + q), 0.0f);
+                        o0 = fmaf(__ldg(actor.W3 + nb + q), h, o0);
+                        o1 = fmaf(__ldg(actor.W3 + H2 + nb + q), h, o1);
+                    }
+                }
+            }
+            const float mu0 = tanhf(o0), mu1 = tanhf(o1);
+            float2 nz;
+            if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
+            else if (sigma != 0.0f) { nz = philox_normal2(p.seed, env, g); nz.x *= sigma; nz.y *= sigma; }
+            else nz = make_float2(0.f, 0.f);
+            action_maps(mu0, nz.x, env_a.x, buf_a.x);
+            action_maps(mu1, nz.y, env_a.y, buf_a.y);
+        }
+        // ---- env step + transition record
+        const float4 obs = s;
+        const StepResult r = (MODE == CSTR_MATH_STRICT) ? step_strict_f32(s, env_a, sc, p.target_c2, p.max_steps)
+                                                        : step_fast_f32(s, env_a, sc, p.target_c2, p.max_steps);
+        if (live) {
+            const int64_t row = (pos0 + k) % rows;
+            store_record(records + ((size_t)row * n + i) * 4, obs, s, buf_a, r.reward, r.truncated);
+            acc_r += (double)r.reward;
+        }
+        if (r.truncated) {
+            if (live) s = reset_f32_env(p, i, ep, static_base);
+            sc = 0;
+        }
+    }
+    if (live) {
+        state[i] = s;
+        step_count[i] = sc;
+        episode[i] = ep;
+    }
+    if (reward_sum) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc_r += __shfl_down_sync(0xffffffffu, acc_r, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(reward_sum, acc_r);
+    }
+}
+
+}  // namespace cstr
+
+using namespace cstr;
+
+// tensor-core path lives in cstr_rollout_tc.cu
+int cstr_rollout_tc_launch(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, const cstr_actor_f32 *actor,
+                           const void *packed_bf16, float sigma, const float *noise, int warmup, uint32_t t_base, float *state,
+                           int32_t *step_count, int32_t *episode, double *static_base, int64_t rows, int64_t pos0, float *records,
+                           double *reward_sum, void *stream);
+
+extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, int actor_mode,
+                                  const cstr_actor_f32 *actor, const void *packed_bf16, float sigma, const float *noise, int warmup,
+                                  uint32_t t_base, float *state, int32_t *step_count, int32_t *episode, double *static_base,
+                                  int64_t rows, int64_t pos0, float *records, double *reward_sum, void *stream) {
+    if (!p || n < 0 || K < 0 || !state || !step_count || !episode || !records || rows <= 0 || pos0 < 0)
+        return fail_arg(CSTR_EINVAL, "rollout: null pointer or bad size");
+    if (p->init_mode == CSTR_INIT_STATIC && !static_base) return fail_arg(CSTR_EINVAL, "static init_mode needs static_base");
+    if (math_mode != CSTR_MATH_STRICT && math_mode != CSTR_MATH_FAST) return fail_arg(CSTR_EINVAL, "unknown math_mode");
+    if (!aligned(state, 16) || !aligned(records, 16) || (noise && !aligned(noise, 8))) return fail_arg(CSTR_EALIGN, "rollout: alignment");
+    if (!warmup) {
+        if (!actor || !actor->W1 || !actor->b1 || !actor->W2 || !actor->b2 || !actor->W3 || !actor->b3)
+            return fail_arg(CSTR_EINVAL, "rollout: actor weights missing");
+        if (actor->H1 <= 0 || actor->H2 <= 0 || (actor->H1 & 3)) return fail_arg(CSTR_EINVAL, "rollout: H1 must be a positive multiple of 4");
+        if (!aligned(actor->W1, 16) || !aligned(actor->W2, 16)) return fail_arg(CSTR_EALIGN, "rollout: W1/W2 16 B alignment");
+    }
+    if (n == 0 || K == 0) return 0;
+    if (actor_mode == 1 && !warmup)
+        return cstr_rollout_tc_launch(p, n, K, math_mode, actor, packed_bf16, sigma, noise, warmup, t_base, state, step_count, episode,
+                                      static_base, rows, pos0, records, reward_sum, stream);
+    if (actor_mode != 0 && actor_mode != 1) return fail_arg(CSTR_EINVAL, "rollout: unknown actor_mode");
+    cstr_actor_f32 a = {};
+    if (actor) a = *actor;
+    const size_t smem = warmup ? 0 : (size_t)a.H1 * ROLL_M * sizeof(float);
+    if (smem > 227 * 1024) return fail_arg(CSTR_EINVAL, "rollout: H1 too large for the fp32 path (max 452)");
+    const int grid = (int)((n + ROLL_M - 1) / ROLL_M);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (math_mode == CSTR_MATH_STRICT) {
+        if ((rc = check_cuda(cudaFuncSetAttribute(rollout_f32_kernel<CSTR_MATH_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))) return rc;
+        rollout_f32_kernel<CSTR_MATH_STRICT><<<grid, ROLL_M, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state,
+                                                                         step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum);
+    } else {
+        if ((rc = check_cuda(cudaFuncSetAttribute(rollout_f32_kernel<CSTR_MATH_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))) return rc;
+        rollout_f32_kernel<CSTR_MATH_FAST><<<grid, ROLL_M, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state,
+                                                                       step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum);
+    }
+    return check_launch("rollout_f32_kernel");
+}

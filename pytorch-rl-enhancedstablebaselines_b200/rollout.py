@@ -1,0 +1,128 @@
+"""Fast-mode rollout driver: K env steps per launch of the fused kernel ``cstr_rollout_fused``
+(actor MLP -> noise -> bounds -> CSTR step -> reward/done -> replay record), nothing leaves the GPU.
+
+Semantics per step = the reference's ``collect_rollouts`` body for a deterministic-actor algorithm
+(TD3/DDPG): ``_sample_action`` (off_policy_algorithm.py:364-411) + ``env.step`` (:564) +
+``_store_transition`` (:445-508) + ``ReplayBuffer.add`` (buffers.py:247-283), without the O(n_envs)
+Python loops of SURVEY.md H1.  ``train()`` of the unchanged algorithm then samples from the buffer.
+"""
+from __future__ import annotations
+
+from ctypes import byref
+from typing import Optional
+
+from . import _lib
+from .buffer import GpuReplayBuffer
+from .env import _MATH, GpuCSTRVecEnv
+
+
+class ActorWeights:
+    """fp32 weights of ``tanh(W3 relu(W2 relu(W1 x + b1) + b2) + b3)`` on the device, torch Linear layout
+    (out,in) — the ``mu`` Sequential of the TD3 ``Actor`` (core/td3/policies.py:20-83)."""
+
+    def __init__(self, W1, b1, W2, b2, W3, b3, device="cuda"):
+        torch = _lib.require_cuda()
+        dev = torch.device(device)
+
+        def put(x):
+            return torch.as_tensor(x).detach().to(device=dev, dtype=torch.float32).contiguous()
+
+        self.W1, self.b1, self.W2, self.b2, self.W3, self.b3 = (put(x) for x in (W1, b1, W2, b2, W3, b3))
+        self.H1, self.H2 = int(self.W1.shape[0]), int(self.W2.shape[0])
+        if tuple(self.W1.shape) != (self.H1, 4) or tuple(self.W2.shape) != (self.H2, self.H1) or tuple(self.W3.shape) != (2, self.H2):
+            raise ValueError("actor must be 4 -> H1 -> H2 -> 2")
+        if self.H1 % 4:
+            raise ValueError("H1 must be a multiple of 4")
+        self.device = dev
+        self.packed_bf16 = None
+        self._struct = _lib.ActorF32(W1=self.W1.data_ptr(), b1=self.b1.data_ptr(), W2=self.W2.data_ptr(), b2=self.b2.data_ptr(),
+                                     W3=self.W3.data_ptr(), b3=self.b3.data_ptr(), H1=self.H1, H2=self.H2)
+
+    @classmethod
+    def from_module(cls, mu_sequential, device="cuda") -> "ActorWeights":
+        """From the reference actor's ``mu`` ``nn.Sequential`` (Linear, ReLU, Linear, ReLU, Linear, Tanh)."""
+        lin = [m for m in mu_sequential if hasattr(m, "weight")]
+        if len(lin) != 3:
+            raise ValueError("expected three Linear layers")
+        return cls(lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias, device=device)
+
+    def refresh_from_module(self, mu_sequential) -> None:
+        """Copy updated parameters in place (device-to-device) after an optimiser step."""
+        lin = [m for m in mu_sequential if hasattr(m, "weight")]
+        for dst, src in zip((self.W1, self.b1, self.W2, self.b2, self.W3, self.b3),
+                            (lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)):
+            dst.copy_(src.detach(), non_blocking=True)
+        if self.packed_bf16 is not None:
+            self.pack_bf16()
+
+    def pack_bf16(self):
+        """Build the bf16 UMMA image of W2 for the tensor-core path (cstr_actor_pack_bf16)."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            nbytes = lib.cstr_actor_pack_bf16(byref(self._struct), None, None)
+            if nbytes <= 0:
+                _lib.check(-1, "cstr_actor_pack_bf16")
+            if self.packed_bf16 is None or self.packed_bf16.numel() != nbytes:
+                self.packed_bf16 = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            rc = lib.cstr_actor_pack_bf16(byref(self._struct), self.packed_bf16.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+            if rc < 0:
+                _lib.check(int(rc), "cstr_actor_pack_bf16")
+        return self.packed_bf16
+
+
+class FusedRollout:
+    """Collects transitions from ``env`` straight into ``buffer`` with the fused kernel.
+
+    :param actor_mode: ``"fp32"`` (CUDA-core parity path) or ``"tc"`` (bf16 tcgen05 hidden layer).
+    :param sigma: std of the Gaussian exploration noise (``NormalActionNoise``, noise.py:29-48).
+    """
+
+    def __init__(self, env: GpuCSTRVecEnv, buffer: GpuReplayBuffer, actor: Optional[ActorWeights] = None, sigma: float = 0.1,
+                 actor_mode: str = "fp32"):
+        if env.dtype != "fp32":
+            raise ValueError("the fused rollout is fp32 (the actor and the replay records are float32)")
+        if env.reset_rng != "philox":
+            raise ValueError("the fused rollout needs reset_rng='philox'")
+        if buffer.n_envs != env.num_envs:
+            raise ValueError("buffer.n_envs must equal env.num_envs")
+        if buffer.device != env.device:
+            raise ValueError("env and buffer must live on the same device")
+        if actor_mode not in ("fp32", "tc"):
+            raise ValueError("actor_mode must be 'fp32' or 'tc'")
+        self.env, self.buffer, self.actor, self.sigma = env, buffer, actor, float(sigma)
+        self.actor_mode = actor_mode
+        self.t = 0  # global step counter: the Philox counter of the noise / warm-up action streams
+        self._lib = _lib.load()
+        self.launches = 0
+        if actor_mode == "tc" and actor is not None and actor.packed_bf16 is None:
+            actor.pack_bf16()
+
+    def collect(self, K: int, warmup: bool = False, noise=None, reward_sum=None) -> None:
+        """K env steps for every reactor; K ring rows are appended to the buffer.
+
+        :param warmup: uniform random actions instead of the actor (``learning_starts`` phase).
+        :param noise: optional device tensor (K,N,2) float32 added instead of Philox noise (parity tests).
+        :param reward_sum: optional device float64[1] accumulating the sum of rewards.
+        """
+        env, buf = self.env, self.buffer
+        torch = env._torch
+        if env._needs_reset:
+            raise ValueError("Please call env.reset() to reset the env first!")
+        if not warmup and self.actor is None:
+            raise ValueError("an ActorWeights is required unless warmup=True")
+        if noise is not None and (tuple(noise.shape) != (K, env.num_envs, 2) or noise.dtype != torch.float32 or not noise.is_contiguous()):
+            raise ValueError("noise must be a contiguous float32 tensor of shape (K, N, 2)")
+        packed = None
+        if self.actor_mode == "tc" and not warmup:
+            packed = self.actor.packed_bf16 if self.actor.packed_bf16 is not None else self.actor.pack_bf16()
+        with torch.cuda.device(env.device):
+            rc = self._lib.cstr_rollout_fused(
+                byref(env._params), env.num_envs, K, _MATH[env.math], int(self.actor_mode == "tc"),
+                byref(self.actor._struct) if self.actor is not None else None, _lib.ptr(packed), self.sigma, _lib.ptr(noise), int(warmup),
+                self.t & 0xFFFFFFFF, _lib.ptr(env.state), _lib.ptr(env.step_count), _lib.ptr(env.episode), env._sb_ptr(),
+                buf.buffer_size, buf.pos, _lib.ptr(buf.records), _lib.ptr(reward_sum), env._stream())
+        _lib.check(rc, "cstr_rollout_fused")
+        self.launches += 1
+        self.t += K
+        buf.advance(K)

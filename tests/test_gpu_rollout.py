@@ -1,0 +1,99 @@
+"""-m gpu: fused rollout kernel (actor -> noise -> bounds -> step -> record) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import build_oracle as B
+import cstr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _actor(golden):
+    g = golden("td3_actor.npz")
+    return g, [(g["W1"], g["b1"]), (g["W2"], g["b2"]), (g["W3"], g["b3"])]
+
+
+def _env_action_from_buffer_action(b):
+    f = np.float32
+    return (f(-1.0) + (f(0.5) * (b + f(1.0)) * f(2.0))).astype(f)
+
+
+@pytest.mark.parametrize("actor_mode,atol", [("fp32", 3e-6)])
+def test_rollout_matches_oracle_composition(pkg, golden, actor_mode, atol):
+    g, w = _actor(golden)
+    n, K, seed = 256, 3, 11
+    env = pkg.GpuCSTRVecEnv(n, seed=seed, monitor=False)
+    env.reset()
+    env.set_state(g["obs"], np.zeros(n, np.int32))  # the fixture's 256 observations
+    buf = pkg.GpuReplayBuffer(8 * n, device="cuda", n_envs=n)
+    actor = pkg.ActorWeights(g["W1"], g["b1"], g["W2"], g["b2"], g["W3"], g["b3"])
+    roll = pkg.FusedRollout(env, buf, actor, sigma=0.1, actor_mode=actor_mode)
+    rng = np.random.default_rng(0)
+    noise = (0.1 * rng.standard_normal((K, n, 2))).astype(np.float32)
+    noise[0, :4] = g["noise"][:4]  # saturating rows
+    noise[0, 4:] = g["noise"][4:]
+    roll.collect(K, noise=torch.as_tensor(noise, device="cuda"))
+    rec = buf.records.cpu().numpy()
+    assert buf.pos == K and not buf.full
+    state = g["obs"].copy()
+    sc = np.zeros(n, np.int32)
+    for k in range(K):
+        # (1) the record's obs is the state the actor saw
+        assert np.array_equal(rec[k, :, 0:4], state)
+        # (2) actor + action maps: reference torch forward (fixture) for k=0, fp64 oracle otherwise
+        mu = g["mu"] if k == 0 else O.actor_forward(state, w).astype(np.float32)
+        a_env, a_buf = O.sample_action_maps(mu, noise[k])
+        np.testing.assert_allclose(rec[k, :, 8:10], a_buf, rtol=0, atol=atol)
+        if k == 0:
+            np.testing.assert_allclose(rec[k, :, 8:10], g["buffer_action"], rtol=0, atol=atol)
+        assert np.abs(rec[k, :, 8:10]).max() <= 1.0
+        # (3) given the action it stored, the env step is the strict kernel bit for bit
+        s, r, tr, sc, _ = B.step_f32(state, _env_action_from_buffer_action(rec[k, :, 8:10]), sc, exp_mode=B.EXP_SHARED, sq_mode=B.SQ_MUL)
+        assert np.array_equal(rec[k, :, 4:8], s) and np.array_equal(rec[k, :, 10], r)
+        assert np.array_equal(rec[k, :, 11], tr.astype(np.float32)) and np.array_equal(rec[k, :, 12], tr.astype(np.float32))
+        state = s
+    assert np.array_equal(env.state.cpu().numpy(), state) and np.array_equal(env.step_count.cpu().numpy(), sc)
+
+
+def test_rollout_warmup_autoreset_and_ring(pkg):
+    n, seed = 640, 5  # 5 CTAs of 128
+    env = pkg.GpuCSTRVecEnv(n, seed=seed, monitor=False)
+    env.reset()
+    env.step_count.fill_(398)
+    buf = pkg.GpuReplayBuffer(4 * n, device="cuda", n_envs=n)  # 4-row ring
+    roll = pkg.FusedRollout(env, buf, None, sigma=0.1)
+    rs = torch.zeros(1, dtype=torch.float64, device="cuda")
+    st0 = env.state.cpu().numpy().copy()
+    roll.collect(3, warmup=True, reward_sum=rs)
+    rec = buf.records.cpu().numpy()
+    assert buf.pos == 3 and roll.t == 3
+    assert np.array_equal(rec[0, :, 0:4], st0)
+    assert np.abs(rec[:3, :, 8:10]).max() <= 1.0 and abs(rec[:3, :, 8:10].mean()) < 0.05  # U(-1,1) warm-up actions
+    assert (rec[1, :, 11] == 1).all() and (rec[0, :, 11] == 0).all() and (rec[1, :, 12] == 1).all()  # step 400: done+timeout
+    # row 2 starts from the post-reset state (episode 1 of the Philox reset stream), not from the terminal obs
+    st_reset, _, _, _ = B.reset_f32(n, 0, seed, 0, episode=np.ones(n, np.int32))
+    assert np.array_equal(rec[2, :, 0:4], st_reset) and not np.array_equal(rec[2, :, 0:4], rec[1, :, 4:8])
+    assert abs(rs.item() - rec[:3, :, 10].astype(np.float64).sum()) < 1e-6 * abs(rs.item())
+    roll.collect(2, warmup=True)  # wraps
+    assert buf.pos == 1 and buf.full
+    rec2 = buf.records.cpu().numpy()
+    assert np.array_equal(rec2[3, :, 0:4], rec[2, :, 4:8]) and np.array_equal(rec2[0, :, 0:4], rec2[3, :, 4:8])
+    s = buf.sample(128)
+    assert s.observations.shape == (128, 4)
+
+
+def test_rollout_philox_noise_statistics(pkg, golden):
+    g, w = _actor(golden)
+    n = 128 * 64
+    env = pkg.GpuCSTRVecEnv(n, seed=1, monitor=False)
+    env.reset()
+    st = env.state.cpu().numpy().copy()
+    buf = pkg.GpuReplayBuffer(2 * n, device="cuda", n_envs=n)
+    actor = pkg.ActorWeights(g["W1"], g["b1"], g["W2"], g["b2"], g["W3"], g["b3"])
+    pkg.FusedRollout(env, buf, actor, sigma=0.1).collect(1)
+    a = buf.records[0, :, 8:10].cpu().numpy()
+    mu = O.actor_forward(st, w)
+    _, base = O.sample_action_maps(mu.astype(np.float32), np.zeros_like(a))
+    d = (a - base)[np.abs(a) < 0.999]
+    assert abs(d.mean()) < 5e-3 and abs(d.std() - 0.1) < 5e-3  # N(0, 0.1^2) exploration noise
