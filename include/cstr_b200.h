@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 3
+#define CSTR_B200_ABI_VERSION 5
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -44,10 +44,9 @@ extern "C" {
 typedef struct cstr_env_params {
     uint64_t seed;       /* Philox4x32-10 key of the device RNG (reset draws, exploration noise)   */
     int64_t env_offset;  /* global id of reactor 0 of this shard (multi-GPU: rank * n_per_rank)   */
-    float target_c2;     /* TwoSeriesCSTREnv.target_C2 (default 0.20)                             */
+    double target_c2;    /* TwoSeriesCSTREnv.target_C2 (default 0.20); rounded to float in fp32 mode */
     int32_t max_steps;   /* TwoSeriesCSTREnv.max_steps (400)                                      */
     int32_t init_mode;   /* CSTR_INIT_RANDOM | CSTR_INIT_STATIC                                   */
-    int32_t reserved;
 } cstr_env_params;
 
 int cstr_b200_abi_version(void);
@@ -187,6 +186,11 @@ int64_t cstr_actor_pack_bf16(const cstr_actor_f32 *actor, void *dst, void *strea
  * 3: MUFU.EX2.  out: one value per thread (keeps the chains live).  flops/launch =
  * grid*block*iters*8*(2 for kinds 0,1,2; 1 for kind 3).                                            */
 int cstr_probe_pipe(int kind, int64_t iters, int grid, int block, float *out, void *stream);
+
+/* Exhaustive device self-tests of the strict kernels' arithmetic shortcuts against the plain IEEE
+ * operations they replace (0: -E/(R T) division, 1: normal-range exp scaling, 2: x/const Markstein
+ * sequences for every constant divisor).  *mismatches (device uint64, caller-zeroed) must stay 0.  */
+int cstr_selftest(int which, unsigned long long *mismatches, void *stream);
 
 #ifdef __cplusplus
 }

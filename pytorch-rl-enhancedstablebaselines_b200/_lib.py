@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 3
+ABI_VERSION = 5
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -25,10 +25,9 @@ class EnvParams(Structure):
     _fields_ = [
         ("seed", c_uint64),
         ("env_offset", c_int64),
-        ("target_c2", c_float),
+        ("target_c2", c_double),
         ("max_steps", c_int32),
         ("init_mode", c_int32),
-        ("reserved", c_int32),
     ]
 
 
@@ -62,6 +61,7 @@ _SIGNATURES = {
                                    c_uint32, P, P, P, P, c_int64, c_int64, P, P, P]),
     "cstr_actor_pack_bf16": (c_int64, [POINTER(ActorF32), P, P]),
     "cstr_probe_pipe": (c_int, [c_int, c_int64, c_int, c_int, P, P]),
+    "cstr_selftest": (c_int, [c_int, P, P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -102,12 +102,18 @@ __device__ __forceinline__ void reset_draw(uint64_t seed, uint64_t env, uint32_t
 }
 
 // ---- reset / random-action helpers shared by the step, tape and rollout kernels -----------------------
-__device__ __forceinline__ float4 reset_f32_env(const cstr_env_params &p, int64_t i, int &episode, double *static_base) {
+// rare path (once per 400 steps): kept out of line so the unrolled step loops stay inside the I-cache
+// (all arguments by value: nothing of the caller's register state has to live on the stack)
+static __device__ __noinline__ float4 reset_f32_call(uint64_t seed, uint64_t env, uint32_t episode, int init_mode, double *base) {
     double o[4];
-    reset_draw(p.seed, (uint64_t)(p.env_offset + i), (uint32_t)episode, p.init_mode,
-               static_base ? static_base + 4 * i : nullptr, o);
-    episode += 1;
+    reset_draw(seed, env, episode, init_mode, base, o);
     return make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+}
+__device__ __forceinline__ float4 reset_f32_env(const cstr_env_params &p, int64_t i, int &episode, double *static_base) {
+    const float4 s = reset_f32_call(p.seed, (uint64_t)(p.env_offset + i), (uint32_t)episode, p.init_mode,
+                                    static_base ? static_base + 4 * i : nullptr);
+    episode += 1;
+    return s;
 }
 
 // U(-1,1) action pair for global step g of reactor `env`: one Philox call serves two steps.
@@ -155,29 +161,81 @@ __device__ __forceinline__ float expf_shared(float x) {
 struct StepResult {
     float reward;
     bool truncated;  // == done (terminated is always False, twoseriescstr.py:435)
+    bool bad;        // NaN input row: the reference's "Dynamics calculation error" path (:413-421)
 };
 
+// half ranges: (s+1)*(hi-lo)/2 == (s+1)*((hi-lo)/2) and 2*(x-lo)/(hi-lo) == (x-lo)/((hi-lo)/2) bit for bit,
+// because scaling by a power of two commutes with round-to-nearest (no underflow in these ranges)
+#define CSTR_HALF_C 0.3499999940395355224609375f  // 0.7f / 2
+#define CSTR_HALF_T 63.4250030517578125f          // 126.850006103515625f / 2
+#define CSTR_HALF_A 110.0f                        // 220 / 2
+
+// -E / y for y = R*T, T in [273.15, 400] K (y in [2270.9, 3325.6]): IEEE-correct quotient without the
+// generic division's range check and slow path.  rcp.approx + one Newton step gives the reciprocal
+// to < 1 ulp; the Markstein correction then yields the correctly rounded quotient.  Verified against
+// __fdiv_rn for EVERY float32 in the range by cstr_selftest(0) (tests/test_gpu_selftest.py).
+__device__ __forceinline__ float rcp_approx_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float div_neg_e(float y) {
+    const float NE = -83140.0f;
+    float r = rcp_approx_ftz(y);
+    r = __fmaf_rn(r, __fmaf_rn(-y, r, 1.0f), r);
+    const float q = __fmul_rn(NE, r);
+    return __fmaf_rn(__fmaf_rn(-y, q, NE), r, q);
+}
+
+// shared exp restricted to results in the normal range (|n| <= 100 and p*2^n normal): the two exact
+// power-of-two multiplies collapse into one integer add on the exponent field — same bits.
+// (bits(t) << 23 == n << 23 because 0x4B400000 << 23 == 0 mod 2^32.)
+__device__ __forceinline__ float expf_shared_normal(float x) {
+    const float MAGIC = 12582912.0f;
+    const float t = __fadd_rn(__fmul_rn(x, 1.44269504088896341f), MAGIC);
+    const float n = __fadd_rn(t, -MAGIC);
+    float r = __fmaf_rn(n, -0.693145751953125f, x);
+    r = __fmaf_rn(n, -1.42860682030941723212e-6f, r);
+    float q = 0.00019891989359166473f;
+    q = __fmaf_rn(q, r, 0.001393454847857356f);
+    q = __fmaf_rn(q, r, 0.008333309553563595f);
+    q = __fmaf_rn(q, r, 0.04166645556688309f);
+    q = __fmaf_rn(q, r, 0.1666666716337204f);
+    q = __fmaf_rn(q, r, 0.5f);
+    const float p = __fadd_rn(__fmaf_rn(__fmul_rn(r, r), q, r), 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+__device__ __forceinline__ float4 clamp_unit4(float4 s) {
+    return make_float4(clampf(s.x, -1.0f, 1.0f), clampf(s.y, -1.0f, 1.0f), clampf(s.z, -1.0f, 1.0f), clampf(s.w, -1.0f, 1.0f));
+}
+__device__ __forceinline__ bool any_nan4(float4 s) { return (s.x != s.x) | (s.y != s.y) | (s.z != s.z) | (s.w != s.w); }
+
 // ---- StrictF32 -------------------------------------------------------------------------------------------
-// s: normalised state in/out.  a: the action handed to env.step (clipped here, :399).
-__device__ __forceinline__ StepResult step_strict_f32(float4 &s, float2 a, int &step_count, float target, int max_steps) {
+// Core of one control interval.  sx = the normalised state with every component inside [-1,1]
+// (clip(denorm(s)) == denorm(clamp(s,-1,1)) exactly, and states produced by this function or by
+// reset are always inside, so the tape/rollout loops skip the clamp after their first step).
+// s is overwritten with the new state unless the row is "bad" (NaN input -> :413-421 path).
+template <bool CHECK_ACTION>
+__device__ __forceinline__ StepResult step_strict_core(float4 &s, const float4 sx, float2 a, bool bad_state, int &step_count,
+                                                       float target, int max_steps) {
     StepResult out;
     step_count += 1;  // :396
-    // NaN anywhere -> the reference's "Dynamics calculation error" path (:413-421): state unchanged,
-    // reward -10, truncated.  (fminf/fmaxf drop NaNs, so test the inputs; +-inf is clipped, not NaN.)
-    const bool bad = (a.x != a.x) | (a.y != a.y) | (s.x != s.x) | (s.y != s.y) | (s.z != s.z) | (s.w != s.w);
+    bool bad = bad_state;
+    if (CHECK_ACTION) bad |= (a.x != a.x) | (a.y != a.y);
     // :399-400  F = lo + (clip(a)+1)*(hi-lo)/2
-    const float F1 = __fadd_rn(CSTR_ALO, __fmul_rn(__fmul_rn(__fadd_rn(clampf(a.x, -1.0f, 1.0f), 1.0f), CSTR_ARNG), 0.5f));
-    const float F2 = __fadd_rn(CSTR_ALO, __fmul_rn(__fmul_rn(__fadd_rn(clampf(a.y, -1.0f, 1.0f), 1.0f), CSTR_ARNG), 0.5f));
-    // :404-410  raw = clip(lo + (s+1)*(hi-lo)/2)   (x/2 == x*0.5 exactly)
-    const float C1 = clampf(__fadd_rn(CSTR_SLO_C, __fmul_rn(__fmul_rn(__fadd_rn(s.x, 1.0f), CSTR_RNG_C), 0.5f)), CSTR_SLO_C, CSTR_SHI_C);
-    const float T1 = clampf(__fadd_rn(CSTR_SLO_T, __fmul_rn(__fmul_rn(__fadd_rn(s.y, 1.0f), CSTR_RNG_T), 0.5f)), CSTR_SLO_T, CSTR_SHI_T);
-    const float C2 = clampf(__fadd_rn(CSTR_SLO_C, __fmul_rn(__fmul_rn(__fadd_rn(s.z, 1.0f), CSTR_RNG_C), 0.5f)), CSTR_SLO_C, CSTR_SHI_C);
-    const float T2 = clampf(__fadd_rn(CSTR_SLO_T, __fmul_rn(__fmul_rn(__fadd_rn(s.w, 1.0f), CSTR_RNG_T), 0.5f)), CSTR_SLO_T, CSTR_SHI_T);
-    // :470-473 are no-ops here: T >= 273.15f after the clip, F in [30,250] inside [1e-5,1e5].
-    // :476-477,479-491  folded constants as in SURVEY App. A
-    const float NE = -83140.0f, RG = 8.314f, K0 = 7.2e10f, HK = 4.8816e15f, RC = 239.0f, KC = 0.01f;
-    const float k1 = expf_shared(clampf(__fdiv_rn(NE, __fmul_rn(RG, T1)), -100.0f, 100.0f));
-    const float k2 = expf_shared(clampf(__fdiv_rn(NE, __fmul_rn(RG, T2)), -100.0f, 100.0f));
+    const float F1 = __fadd_rn(CSTR_ALO, __fmul_rn(__fadd_rn(CHECK_ACTION ? clampf(a.x, -1.0f, 1.0f) : a.x, 1.0f), CSTR_HALF_A));
+    const float F2 = __fadd_rn(CSTR_ALO, __fmul_rn(__fadd_rn(CHECK_ACTION ? clampf(a.y, -1.0f, 1.0f) : a.y, 1.0f), CSTR_HALF_A));
+    // :404-410  raw = lo + (s+1)*(hi-lo)/2  (already inside the bounds, see above; lo_C = 0)
+    const float C1 = __fmul_rn(__fadd_rn(sx.x, 1.0f), CSTR_HALF_C);
+    const float T1 = __fadd_rn(CSTR_SLO_T, __fmul_rn(__fadd_rn(sx.y, 1.0f), CSTR_HALF_T));
+    const float C2 = __fmul_rn(__fadd_rn(sx.z, 1.0f), CSTR_HALF_C);
+    const float T2 = __fadd_rn(CSTR_SLO_T, __fmul_rn(__fadd_rn(sx.w, 1.0f), CSTR_HALF_T));
+    // :470-477 are no-ops here: T >= 273.15f, F in [30,250], and -E/(R T) in [-36.7,-24.9] needs no +-100 clip.
+    // :479-491  folded constants as in SURVEY App. A
+    const float RG = 8.314f, K0 = 7.2e10f, HK = 4.8816e15f, RC = 239.0f, KC = 0.01f;
+    const float k1 = expf_shared_normal(div_neg_e(__fmul_rn(RG, T1)));
+    const float k2 = expf_shared_normal(div_neg_e(__fmul_rn(RG, T2)));
     // cooling term: 1 - exp(clip(-UA/(F*rho_c*cpc))) with F in [30,250] -> exp <= e^-98.9 < 2^-126,
     // so (1 - c) == 1.0f exactly and (KC*F)*1.0f == KC*F: constant-folded, result-identical.
     const float dC1 = __fsub_rn(__fmul_rn(0.5f, __fsub_rn(0.5f, C1)), __fmul_rn(__fmul_rn(K0, C1), k1));
@@ -194,31 +252,31 @@ __device__ __forceinline__ StepResult step_strict_f32(float4 &s, float2 a, int &
     const float nT2 = clampf(__fadd_rn(T2, __fmul_rn(dT2, DT)), CSTR_SLO_T, CSTR_SHI_T);
     // :429,131  obs = 2*(x-lo)/(hi-lo) - 1
     float4 o;
-    o.x = __fadd_rn(CSTR_DIV_CONST(__fmul_rn(2.0f, __fsub_rn(nC1, CSTR_SLO_C)), CSTR_RNG_C), -1.0f);
-    o.y = __fadd_rn(CSTR_DIV_CONST(__fmul_rn(2.0f, __fsub_rn(nT1, CSTR_SLO_T)), CSTR_RNG_T), -1.0f);
-    o.z = __fadd_rn(CSTR_DIV_CONST(__fmul_rn(2.0f, __fsub_rn(nC2, CSTR_SLO_C)), CSTR_RNG_C), -1.0f);
-    o.w = __fadd_rn(CSTR_DIV_CONST(__fmul_rn(2.0f, __fsub_rn(nT2, CSTR_SLO_T)), CSTR_RNG_T), -1.0f);
+    o.x = __fadd_rn(CSTR_DIV_CONST(nC1, CSTR_HALF_C), -1.0f);
+    o.y = __fadd_rn(CSTR_DIV_CONST(__fsub_rn(nT1, CSTR_SLO_T), CSTR_HALF_T), -1.0f);
+    o.z = __fadd_rn(CSTR_DIV_CONST(nC2, CSTR_HALF_C), -1.0f);
+    o.w = __fadd_rn(CSTR_DIV_CONST(__fsub_rn(nT2, CSTR_SLO_T), CSTR_HALF_T), -1.0f);
     // compute_reward on the round-tripped state (Q12; :283-291,331-341,369-377)
-    const float rT1 = __fadd_rn(CSTR_SLO_T, __fmul_rn(__fmul_rn(__fadd_rn(o.y, 1.0f), CSTR_RNG_T), 0.5f));
-    const float rC2 = __fadd_rn(CSTR_SLO_C, __fmul_rn(__fmul_rn(__fadd_rn(o.z, 1.0f), CSTR_RNG_C), 0.5f));
-    const float rT2 = __fadd_rn(CSTR_SLO_T, __fmul_rn(__fmul_rn(__fadd_rn(o.w, 1.0f), CSTR_RNG_T), 0.5f));
+    const float rT1 = __fadd_rn(CSTR_SLO_T, __fmul_rn(__fadd_rn(o.y, 1.0f), CSTR_HALF_T));
+    const float rC2 = __fmul_rn(__fadd_rn(o.z, 1.0f), CSTR_HALF_C);
+    const float rT2 = __fadd_rn(CSTR_SLO_T, __fmul_rn(__fadd_rn(o.w, 1.0f), CSTR_HALF_T));
     const float nerr = CSTR_DIV_CONST(fabsf(__fsub_rn(rC2, target)), 0.4f);
     const float conc = __fsub_rn(__fmul_rn(-5.0f, __fmul_rn(nerr, nerr)), __fmul_rn(2.0f, nerr));
     float tp = 0.0f;
-    {
-        const float lo_pen = __fmul_rn(0.2f, CSTR_DIV_CONST(__fsub_rn(280.0f, rT1), 280.0f));
-        const float hi_pen = __fmul_rn(0.5f, CSTR_DIV_CONST(__fsub_rn(rT1, 350.0f), 350.0f));
-        tp = rT1 < 280.0f ? __fsub_rn(tp, lo_pen) : (rT1 > 350.0f ? __fsub_rn(tp, hi_pen) : tp);
-    }
-    {
-        const float lo_pen = __fmul_rn(0.2f, CSTR_DIV_CONST(__fsub_rn(280.0f, rT2), 280.0f));
-        const float hi_pen = __fmul_rn(0.5f, CSTR_DIV_CONST(__fsub_rn(rT2, 350.0f), 350.0f));
-        tp = rT2 < 280.0f ? __fsub_rn(tp, lo_pen) : (rT2 > 350.0f ? __fsub_rn(tp, hi_pen) : tp);
-    }
+    if (rT1 < 280.0f) tp = __fsub_rn(tp, __fmul_rn(0.2f, CSTR_DIV_CONST(__fsub_rn(280.0f, rT1), 280.0f)));
+    else if (rT1 > 350.0f) tp = __fsub_rn(tp, __fmul_rn(0.5f, CSTR_DIV_CONST(__fsub_rn(rT1, 350.0f), 350.0f)));
+    if (rT2 < 280.0f) tp = __fsub_rn(tp, __fmul_rn(0.2f, CSTR_DIV_CONST(__fsub_rn(280.0f, rT2), 280.0f)));
+    else if (rT2 > 350.0f) tp = __fsub_rn(tp, __fmul_rn(0.5f, CSTR_DIV_CONST(__fsub_rn(rT2, 350.0f), 350.0f)));
     out.reward = bad ? -10.0f : __fadd_rn(conc, __fmul_rn(0.5f, tp));
     out.truncated = bad | (step_count >= max_steps);  // :438, :418
+    out.bad = bad;
     if (!bad) s = o;
     return out;
+}
+
+// General entry: any input state (out-of-box values are clipped, NaN -> bad row), any action.
+__device__ __forceinline__ StepResult step_strict_f32(float4 &s, float2 a, int &step_count, float target, int max_steps) {
+    return step_strict_core<true>(s, clamp_unit4(s), a, any_nan4(s), step_count, target, max_steps);
 }
 
 // ---- FastF32 -----------------------------------------------------------------------------------------------
@@ -227,49 +285,51 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+
+// raw <-> normalised maps of the fast path
+__device__ __forceinline__ float4 fast_denorm(float4 s) {
+    return make_float4(clampf(fmaf(s.x, CSTR_HALF_C, CSTR_HALF_C), CSTR_SLO_C, CSTR_SHI_C),
+                       clampf(fmaf(s.y, CSTR_HALF_T, CSTR_SLO_T + CSTR_HALF_T), CSTR_SLO_T, CSTR_SHI_T),
+                       clampf(fmaf(s.z, CSTR_HALF_C, CSTR_HALF_C), CSTR_SLO_C, CSTR_SHI_C),
+                       clampf(fmaf(s.w, CSTR_HALF_T, CSTR_SLO_T + CSTR_HALF_T), CSTR_SLO_T, CSTR_SHI_T));
+}
+__device__ __forceinline__ float4 fast_norm(float4 x) {
+    const float IC = (float)(1.0 / 0.3499999940395355224609375), IT = (float)(1.0 / 63.4250030517578125);
+    return make_float4(fmaf(x.x, IC, -1.0f), fmaf(x.y - CSTR_SLO_T, IT, -1.0f), fmaf(x.z, IC, -1.0f), fmaf(x.w - CSTR_SLO_T, IT, -1.0f));
 }
 
-__device__ __forceinline__ StepResult step_fast_f32(float4 &s, float2 a, int &step_count, float target, int max_steps) {
+// One control interval on the RAW state x = (C1,T1,C2,T2) held in registers (the tape / rollout loops
+// keep it raw across steps and only normalise what they store).  FMA contraction, reciprocal
+// multiplies, MUFU.RCP (+1 Newton step) and MUFU.EX2; reward from the raw new state.
+template <bool CHECK_ACTION>
+__device__ __forceinline__ StepResult step_fast_raw(float4 &x, float2 a, bool bad_state, int &step_count, float target, int max_steps) {
     StepResult out;
     step_count += 1;
-    const bool bad = (a.x != a.x) | (a.y != a.y) | (s.x != s.x) | (s.y != s.y) | (s.z != s.z) | (s.w != s.w);
-    const float F1 = fmaf(clampf(a.x, -1.0f, 1.0f), 110.0f, 140.0f);
-    const float F2 = fmaf(clampf(a.y, -1.0f, 1.0f), 110.0f, 140.0f);
-    const float HC = 0.5f * CSTR_RNG_C, HT = 0.5f * CSTR_RNG_T;
-    const float C1 = clampf(fmaf(s.x, HC, HC), CSTR_SLO_C, CSTR_SHI_C);
-    const float T1 = clampf(fmaf(s.y, HT, CSTR_SLO_T + HT), CSTR_SLO_T, CSTR_SHI_T);
-    const float C2 = clampf(fmaf(s.z, HC, HC), CSTR_SLO_C, CSTR_SHI_C);
-    const float T2 = clampf(fmaf(s.w, HT, CSTR_SLO_T + HT), CSTR_SLO_T, CSTR_SHI_T);
-    // k0*exp(-E/(R T)) = 2^(log2(k0) - (E/R)*log2(e)/T): one MUFU.RCP + one MUFU.EX2 per reactor
+    bool bad = bad_state;
+    if (CHECK_ACTION) bad |= (a.x != a.x) | (a.y != a.y);
+    const float a1 = CHECK_ACTION ? clampf(a.x, -1.0f, 1.0f) : a.x, a2 = CHECK_ACTION ? clampf(a.y, -1.0f, 1.0f) : a.y;
+    const float C1 = x.x, T1 = x.y, C2 = x.z, T2 = x.w;
+    // k0*C*exp(-E/(R T)) = C * 2^(log2(k0) - (E/R)*log2(e)/T)
     // (rcp.approx is refined by one Newton step: its 1-ulp error would be amplified ~50x by |E/(R T)|)
     const float A = -(float)(83140.0 / 8.314 * 1.4426950408889634);
     const float LK0 = 36.06727785542857f;  // log2(7.2e10)
-    float i1 = rcp_approx(T1), i2 = rcp_approx(T2);
+    float i1 = rcp_approx_ftz(T1), i2 = rcp_approx_ftz(T2);
     i1 = fmaf(i1, fmaf(-T1, i1, 1.0f), i1);
     i2 = fmaf(i2, fmaf(-T2, i2, 1.0f), i2);
-    const float r1 = ex2_approx(fmaf(A, i1, LK0)) * C1;  // k0*C1*k1
+    const float r1 = ex2_approx(fmaf(A, i1, LK0)) * C1;
     const float r2 = ex2_approx(fmaf(A, i2, LK0)) * C2;
     const float HR = (float)(6.78e4 / 239.0);  // (-dH)/(rho*cp)
     const float DT = 0.1f;
-    const float dC1 = fmaf(0.5f, 0.5f - C1, -r1);
-    const float dT1 = fmaf(0.01f * F1, 370.0f - T1, fmaf(HR, r1, 0.5f * (320.0f - T1)));
+    // KC*F = 0.01*(140 + 110 a) = 1.4 + 1.1 a
+    const float g1 = fmaf(a1, 1.1f, 1.4f), g2 = fmaf(a2, 1.1f, 1.4f);
+    const float dC1 = fmaf(-0.5f, C1, 0.25f) - r1;
+    const float dT1 = fmaf(g1, 370.0f - T1, fmaf(HR, r1, fmaf(-0.5f, T1, 160.0f)));
     const float dC2 = fmaf(0.5f, C1 - C2, -r2);
-    const float dT2 = fmaf(0.01f * F2, 370.0f - T2, fmaf(HR, r2, 0.5f * (T1 - T2)));
+    const float dT2 = fmaf(g2, 370.0f - T2, fmaf(HR, r2, 0.5f * (T1 - T2)));
     const float nC1 = clampf(fmaf(dC1, DT, C1), CSTR_SLO_C, CSTR_SHI_C);
     const float nT1 = clampf(fmaf(dT1, DT, T1), CSTR_SLO_T, CSTR_SHI_T);
     const float nC2 = clampf(fmaf(dC2, DT, C2), CSTR_SLO_C, CSTR_SHI_C);
     const float nT2 = clampf(fmaf(dT2, DT, T2), CSTR_SLO_T, CSTR_SHI_T);
-    const float IC = 2.0f / CSTR_RNG_C, IT = (float)(2.0 / 126.850006103515625);
-    float4 o;
-    o.x = fmaf(nC1, IC, -1.0f);
-    o.y = fmaf(nT1 - CSTR_SLO_T, IT, -1.0f);
-    o.z = fmaf(nC2, IC, -1.0f);
-    o.w = fmaf(nT2 - CSTR_SLO_T, IT, -1.0f);
-    // reward straight from the raw new state (skips the normalise/denormalise round trip: <= 1 ulp)
     const float nerr = fabsf(nC2 - target) * 2.5f;
     const float conc = nerr * fmaf(-5.0f, nerr, -2.0f);
     float tp = 0.0f;
@@ -277,8 +337,17 @@ __device__ __forceinline__ StepResult step_fast_f32(float4 &s, float2 a, int &st
     tp -= nT2 < 280.0f ? (280.0f - nT2) * (0.2f / 280.0f) : (nT2 > 350.0f ? (nT2 - 350.0f) * (0.5f / 350.0f) : 0.0f);
     out.reward = bad ? -10.0f : fmaf(0.5f, tp, conc);
     out.truncated = bad | (step_count >= max_steps);
-    if (!bad) s = o;
+    out.bad = bad;
+    if (!bad) x = make_float4(nC1, nT1, nC2, nT2);
     return out;
+}
+
+// General entry on the normalised state (single VecEnv step)
+__device__ __forceinline__ StepResult step_fast_f32(float4 &s, float2 a, int &step_count, float target, int max_steps) {
+    float4 x = fast_denorm(s);
+    const StepResult r = step_fast_raw<true>(x, a, any_nan4(s), step_count, target, max_steps);
+    if (!r.bad) s = fast_norm(x);  // bad rows keep the input state untouched (:418)
+    return r;
 }
 
 // ---- F64 ------------------------------------------------------------------------------------------------------
@@ -298,7 +367,9 @@ __device__ __forceinline__ StepResult64 step_f64(double s[4], double a0, double 
     double x[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) x[j] = clipd(slo[j] + (s[j] + 1.0) * (shi[j] - slo[j]) / 2.0, slo[j], shi[j]);
-    const double C1 = x[0], T1 = x[1], C2 = x[2], T2 = x[3];
+    // :470-471 T = max(T, 273.15): NOT a no-op in double — the clip bound is the float32 constant widened
+    // (273.1499938964844) while this literal is the double 273.15
+    const double C1 = x[0], T1 = fmax(x[1], 273.15), C2 = x[2], T2 = fmax(x[3], 273.15);
     const double NE = -8.314e4, RG = 8.314, K0 = 7.2e10, HK = 6.78e4 * 7.2e10, RC = 1000 * 0.239;
     const double KC = (1000 * 0.239) / (1000 * 0.239 * 100);
     const double k1 = exp(clipd(NE / (RG * T1), -100.0, 100.0));

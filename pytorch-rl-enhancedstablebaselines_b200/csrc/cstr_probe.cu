@@ -1,5 +1,7 @@
 // Pipe-peak microbenchmarks: the roofline denominators bench.py reports K1 against are MEASURED in
 // the same run (MEASURED_PEAKS.json has no non-tensor peak).
+#include <string.h>
+
 #include "cstr_abi.cuh"
 
 namespace cstr {
@@ -53,4 +55,72 @@ extern "C" int cstr_probe_pipe(int kind, int64_t iters, int grid, int block, flo
         default: return fail_arg(CSTR_EINVAL, "probe: unknown kind");
     }
     return check_launch("probe_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Exhaustive self-tests of the strict kernel's arithmetic shortcuts (each must be bit-identical to the
+// plain IEEE operation it replaces).  Results: number of mismatching inputs, must be 0.
+//   0  div_neg_e(y) == __fdiv_rn(-83140, y)        for EVERY float32 y in [2200, 3400]  (R*T, T in [273.15,400])
+//   1  expf_shared_normal(x) == expf_shared(x)     for EVERY float32 x in [-40, -20]     (-E/(R T) range)
+//   2  CSTR_DIV_CONST(x, c) == __fdiv_rn(x, c)      for EVERY float32 x with |x| in [2^-100, 2^100] and every
+//      constant divisor c the step uses
+// ---------------------------------------------------------------------------------------------------
+#include "cstr_device.cuh"
+
+namespace cstr {
+
+template <typename F>
+__global__ void sweep_kernel(uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches, F f) {
+    unsigned long long bad = 0;
+    for (uint64_t b = (uint64_t)lo_bits + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= hi_bits;
+         b += (uint64_t)gridDim.x * blockDim.x)
+        bad += f(__uint_as_float((uint32_t)b)) ? 0ull : 1ull;
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+struct CheckDivNegE {
+    __device__ bool operator()(float y) const { return __float_as_uint(div_neg_e(y)) == __float_as_uint(__fdiv_rn(-83140.0f, y)); }
+};
+struct CheckExpNormal {
+    __device__ bool operator()(float x) const { return __float_as_uint(expf_shared_normal(x)) == __float_as_uint(expf_shared(x)); }
+};
+template <int WHICH>
+struct CheckDivConst {
+    __device__ bool operator()(float x) const {
+        float a, b;
+        switch (WHICH) {
+            case 0: a = CSTR_DIV_CONST(x, 239.0f); b = __fdiv_rn(x, 239.0f); break;
+            case 1: a = CSTR_DIV_CONST(x, CSTR_HALF_C); b = __fdiv_rn(x, CSTR_HALF_C); break;
+            case 2: a = CSTR_DIV_CONST(x, CSTR_HALF_T); b = __fdiv_rn(x, CSTR_HALF_T); break;
+            case 3: a = CSTR_DIV_CONST(x, 0.4f); b = __fdiv_rn(x, 0.4f); break;
+            case 4: a = CSTR_DIV_CONST(x, 280.0f); b = __fdiv_rn(x, 280.0f); break;
+            default: a = CSTR_DIV_CONST(x, 350.0f); b = __fdiv_rn(x, 350.0f); break;
+        }
+        return __float_as_uint(a) == __float_as_uint(b) && __float_as_uint(CSTR_DIV_CONST(-x, 239.0f)) == __float_as_uint(__fdiv_rn(-x, 239.0f));
+    }
+};
+
+}  // namespace cstr
+
+extern "C" int cstr_selftest(int which, unsigned long long *mismatches, void *stream) {
+    if (!mismatches) return fail_arg(CSTR_EINVAL, "selftest: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = sm_count() * 8, block = 256;
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    switch (which) {
+        case 0: sweep_kernel<<<grid, block, 0, st>>>(bits(2200.0f), bits(3400.0f), mismatches, CheckDivNegE()); break;
+        case 1: sweep_kernel<<<grid, block, 0, st>>>(bits(20.0f) | 0x80000000u, bits(40.0f) | 0x80000000u, mismatches, CheckExpNormal()); break;
+        case 2: {
+            const uint32_t lo = bits(7.888609052210118e-31f) /* 2^-100 */, hi = bits(1.2676506002282294e30f) /* 2^100 */;
+            sweep_kernel<<<grid, block, 0, st>>>(lo, hi, mismatches, CheckDivConst<0>());
+            sweep_kernel<<<grid, block, 0, st>>>(lo, hi, mismatches, CheckDivConst<1>());
+            sweep_kernel<<<grid, block, 0, st>>>(lo, hi, mismatches, CheckDivConst<2>());
+            sweep_kernel<<<grid, block, 0, st>>>(lo, hi, mismatches, CheckDivConst<3>());
+            sweep_kernel<<<grid, block, 0, st>>>(lo, hi, mismatches, CheckDivConst<4>());
+            sweep_kernel<<<grid, block, 0, st>>>(lo, hi, mismatches, CheckDivConst<5>());
+            break;
+        }
+        default: return fail_arg(CSTR_EINVAL, "selftest: unknown test");
+    }
+    return check_launch("selftest");
 }

@@ -136,8 +136,8 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
         }
         // ---- env step + transition record
         const float4 obs = s;
-        const StepResult r = (MODE == CSTR_MATH_STRICT) ? step_strict_f32(s, env_a, sc, p.target_c2, p.max_steps)
-                                                        : step_fast_f32(s, env_a, sc, p.target_c2, p.max_steps);
+        const StepResult r = (MODE == CSTR_MATH_STRICT) ? step_strict_f32(s, env_a, sc, (float)p.target_c2, p.max_steps)
+                                                        : step_fast_f32(s, env_a, sc, (float)p.target_c2, p.max_steps);
         if (live) {
             const int64_t row = (pos0 + k) % rows;
             store_record(records + ((size_t)row * n + i) * 4, obs, s, buf_a, r.reward, r.truncated);

@@ -89,7 +89,7 @@ vec_step_f32_kernel(cstr_env_params p, int64_t n, int auto_reset, const float2 *
     float4 s = state[i];
     const float2 a = actions[i];
     int sc = step_count[i];
-    const StepResult r = step_f32<MODE>(s, a, sc, p.target_c2, p.max_steps);
+    const StepResult r = step_f32<MODE>(s, a, sc, (float)p.target_c2, p.max_steps);
     if (terminal_obs) terminal_obs[i] = s;
     reward[i] = r.reward;
     done[i] = (uint8_t)r.truncated;
@@ -117,7 +117,7 @@ vec_step_f64_kernel(cstr_env_params p, int64_t n, int auto_reset, const double2 
     double s[4] = {s01.x, s01.y, s23.x, s23.y};
     const double2 a = actions[i];
     int sc = step_count[i];
-    const StepResult64 r = step_f64(s, a.x, a.y, sc, (double)p.target_c2, p.max_steps);
+    const StepResult64 r = step_f64(s, a.x, a.y, sc, p.target_c2, p.max_steps);
     if (terminal_obs) {
         terminal_obs[2 * i] = make_double2(s[0], s[1]);
         terminal_obs[2 * i + 1] = make_double2(s[2], s[3]);
@@ -147,7 +147,22 @@ __device__ __forceinline__ void block_sum_to(double v, double *dst) {
     if ((threadIdx.x & 31) == 0) atomicAdd(dst, v);
 }
 
-template <int MODE, bool PHILOX>
+// SUM / OBS are compile-time so the common launch (rewards + dones only) carries no dead work.
+// After the first step the register state is always "in the box" (it is either this kernel's own
+// output or a fresh reset: a bad/NaN row truncates and is reset at once), so the loop runs the
+// clamp-free cores; strict keeps the normalised state, fast keeps the RAW state across steps.
+constexpr int TAPE_PF = 8;  // actions in flight per thread (cp.async depth)
+
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int MODE, bool PHILOX, bool SUM, bool OBS>
 __global__ void __launch_bounds__(256)
 tape_f32_kernel(cstr_env_params p, int64_t n, int64_t T, const float2 *__restrict__ actions, uint32_t t_base,
                 float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode, double *static_base,
@@ -157,35 +172,73 @@ tape_f32_kernel(cstr_env_params p, int64_t n, int64_t T, const float2 *__restric
     double acc = 0.0;
     if (live) {
         float4 s = state[i];
+        bool bad_state = any_nan4(s);
+        if (MODE != MODE_STRICT) s = fast_denorm(s);  // fast: RAW state in registers (clipped); strict: normalised
+        // strict: a state that did not come out of step_strict_core may lie outside the box (caller-injected, or a
+        // static-mode reset, which the reference does not clip: twoseriescstr.py:245-253) -> clamp it on first use
+        bool unboxed = true;
         int sc = step_count[i], ep = episode[i];
         const uint64_t env = (uint64_t)(p.env_offset + i);
+        const float target = (float)p.target_c2;
         uint4 cache = make_uint4(0, 0, 0, 0);
-        float2 a_next = make_float2(0.f, 0.f);
-        if (!PHILOX) a_next = actions[i];
+        // Action staging: each thread cp.async's its own 8-byte action of step t+TAPE_PF into a private
+        // shared-memory slot (LDGSTS: no registers tied up, no dependent MOV), so TAPE_PF loads per thread
+        // are always in flight.  A step is only ~110-230 instructions and a scheduler holds 3-4 warps at
+        // 65,536 reactors, so without this every step would expose the ~800-cycle HBM latency
+        // (measured: 70 % of stall samples were long-scoreboard on the register-ring variant).
+        // The slot being refilled (t+TAPE_PF) is never the one being read (ring of TAPE_PF+1): no WAR hazard,
+        // and every slot is private to its thread: no barrier.
+        extern __shared__ float2 stage[];
+        const int tid = threadIdx.x, bdim = blockDim.x;
+        if (!PHILOX) {
+#pragma unroll
+            for (int d = 0; d < TAPE_PF; ++d) {
+                if (d < T) cp_async_8(&stage[d * bdim + tid], &actions[(int64_t)d * n + i]);
+                cp_async_commit();
+            }
+        }
+        int slot_rd = 0, slot_wr = TAPE_PF;
         for (int64_t t = 0; t < T; ++t) {
             float2 a;
             if (PHILOX) {
                 const uint32_t g = t_base + (uint32_t)t;
                 a = philox_action(p.seed, env, g, cache, t == 0 || (g & 1u) == 0);
             } else {
-                a = a_next;
-                if (t + 1 < T) a_next = actions[(t + 1) * n + i];  // prefetch: the load overlaps this step's math
+                cp_async_wait<TAPE_PF - 1>();
+                a = stage[slot_rd * bdim + tid];
+                if (t + TAPE_PF < T) cp_async_8(&stage[slot_wr * bdim + tid], &actions[(t + TAPE_PF) * n + i]);
+                cp_async_commit();
+                slot_rd = (slot_rd == TAPE_PF) ? 0 : slot_rd + 1;
+                slot_wr = (slot_wr == TAPE_PF) ? 0 : slot_wr + 1;
             }
-            const StepResult r = step_f32<MODE>(s, a, sc, p.target_c2, p.max_steps);
+            StepResult r;
+            if (MODE == MODE_STRICT) {
+                float4 sx = s;
+                if (unboxed) sx = clamp_unit4(s);
+                r = step_strict_core<!PHILOX>(s, sx, a, bad_state, sc, target, p.max_steps);
+                unboxed = r.bad;  // a bad row keeps its (possibly unboxed) state
+            } else {
+                r = step_fast_raw<!PHILOX>(s, a, bad_state, sc, target, p.max_steps);
+            }
+            bad_state = false;
             if (rewards) rewards[t * n + i] = r.reward;
             if (dones) dones[t * n + i] = (uint8_t)r.truncated;
-            if (reward_sum) acc += (double)r.reward;
+            if (SUM) acc += (double)r.reward;
             if (r.truncated) {
                 s = reset_f32_env(p, i, ep, static_base);
+                if (OBS && MODE != MODE_STRICT) obs_tape[t * n + i] = s;
+                if (MODE != MODE_STRICT) s = fast_denorm(s);
+                unboxed = p.init_mode != CSTR_INIT_RANDOM;
                 sc = 0;
+                if (OBS && MODE != MODE_STRICT) continue;
             }
-            if (obs_tape) obs_tape[t * n + i] = s;
+            if (OBS) obs_tape[t * n + i] = (MODE == MODE_STRICT) ? s : fast_norm(s);
         }
-        state[i] = s;
+        state[i] = (MODE == MODE_STRICT) ? s : fast_norm(s);
         step_count[i] = sc;
         episode[i] = ep;
     }
-    if (reward_sum) block_sum_to(acc, reward_sum);
+    if (SUM) block_sum_to(acc, reward_sum);
 }
 
 template <bool PHILOX>
@@ -214,7 +267,7 @@ tape_f64_kernel(cstr_env_params p, int64_t n, int64_t T, const double2 *__restri
                 a0 = a.x;
                 a1 = a.y;
             }
-            const StepResult64 r = step_f64(s, a0, a1, sc, (double)p.target_c2, p.max_steps);
+            const StepResult64 r = step_f64(s, a0, a1, sc, p.target_c2, p.max_steps);
             if (rewards) rewards[t * n + i] = r.reward;
             if (dones) dones[t * n + i] = (uint8_t)r.truncated;
             if (reward_sum) acc += r.reward;
@@ -353,14 +406,25 @@ int cstr_tape_f32(const cstr_env_params *p, int64_t n, int64_t T, int math_mode,
     int grid, block;
     env_launch_geometry(n, grid, block);
     cudaStream_t st = (cudaStream_t)stream;
-#define CSTR_LAUNCH_TAPE(MODE, PH)                                                                                              \
-    tape_f32_kernel<MODE, PH><<<grid, block, 0, st>>>(*p, n, T, (const float2 *)actions, t_base, (float4 *)state, step_count, episode, \
-                                                      static_base, rewards, dones, (float4 *)obs_tape, reward_sum)
+#define CSTR_LAUNCH_TAPE(MODE, PH, SUM, OBS)                                                                                     \
+    tape_f32_kernel<MODE, PH, SUM, OBS><<<grid, block, PH ? 0 : (TAPE_PF + 1) * block * sizeof(float2), st>>>(*p, n, T, (const float2 *)actions, t_base, (float4 *)state, step_count, \
+                                                                episode, static_base, rewards, dones, (float4 *)obs_tape, reward_sum)
+#define CSTR_TAPE_FLAGS(MODE, PH)                                         \
+    do {                                                                  \
+        if (reward_sum) {                                                 \
+            if (obs_tape) CSTR_LAUNCH_TAPE(MODE, PH, true, true);         \
+            else CSTR_LAUNCH_TAPE(MODE, PH, true, false);                 \
+        } else {                                                          \
+            if (obs_tape) CSTR_LAUNCH_TAPE(MODE, PH, false, true);        \
+            else CSTR_LAUNCH_TAPE(MODE, PH, false, false);                \
+        }                                                                 \
+    } while (0)
     if (math_mode == CSTR_MATH_STRICT) {
-        if (actions) CSTR_LAUNCH_TAPE(MODE_STRICT, false); else CSTR_LAUNCH_TAPE(MODE_STRICT, true);
+        if (actions) CSTR_TAPE_FLAGS(MODE_STRICT, false); else CSTR_TAPE_FLAGS(MODE_STRICT, true);
     } else {
-        if (actions) CSTR_LAUNCH_TAPE(MODE_FAST, false); else CSTR_LAUNCH_TAPE(MODE_FAST, true);
+        if (actions) CSTR_TAPE_FLAGS(MODE_FAST, false); else CSTR_TAPE_FLAGS(MODE_FAST, true);
     }
+#undef CSTR_TAPE_FLAGS
 #undef CSTR_LAUNCH_TAPE
     return check_launch("tape_f32_kernel");
 }
@@ -390,28 +454,50 @@ int cstr_tape_f32_host(const cstr_env_params *p, int64_t n, int64_t T, int math_
         return fail_arg(CSTR_EINVAL, "null pointer or negative size");
     if (p->init_mode != CSTR_INIT_RANDOM) return fail_arg(CSTR_EINVAL, "host tape supports init_mode=random only");
     if (n == 0 || T == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    // scratch layout: state | step_count | episode | actions | rewards | dones  (256 B aligned sections)
-    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t o_state = 0, o_sc = up(o_state + (size_t)n * 16), o_ep = up(o_sc + (size_t)n * 4), o_act = up(o_ep + (size_t)n * 4);
-    const size_t o_rew = up(o_act + (size_t)T * n * 8), o_done = up(o_rew + (size_t)T * n * 4), total = up(o_done + (size_t)T * n);
-    if (int rc = g_scratch.ensure(total)) return rc;
-    char *d = (char *)g_scratch.buf;
+    // Reactors are independent, so the batch is cut into chunks that flow through a 3-stream pipeline:
+    // while chunk c computes, chunk c+1's action tape is on its way down (H2D) and chunk c-1's rewards are
+    // on their way up (D2H) — PCIe is full duplex, so the end-to-end time approaches max(H2D, D2H) instead
+    // of H2D + kernel + D2H.  2-D copies cut the (T, n, .) host arrays into per-chunk compact device tiles.
+    static cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     int rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(d + o_state, h_state, (size_t)n * 16, cudaMemcpyHostToDevice, st), "H2D state"))) return rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(d + o_sc, h_step_count, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D step_count"))) return rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(d + o_ep, h_episode, (size_t)n * 4, cudaMemcpyHostToDevice, st), "H2D episode"))) return rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(d + o_act, h_actions, (size_t)T * n * 8, cudaMemcpyHostToDevice, st), "H2D actions"))) return rc;
-    rc = cstr_tape_f32(p, n, T, math_mode, (const float *)(d + o_act), 0u, (float *)(d + o_state), (int32_t *)(d + o_sc),
-                       (int32_t *)(d + o_ep), nullptr, h_rewards ? (float *)(d + o_rew) : nullptr,
-                       h_dones ? (uint8_t *)(d + o_done) : nullptr, nullptr, nullptr, stream);
-    if (rc) return rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(h_state, d + o_state, (size_t)n * 16, cudaMemcpyDeviceToHost, st), "D2H state"))) return rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(h_step_count, d + o_sc, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H step_count"))) return rc;
-    if ((rc = check_cuda(cudaMemcpyAsync(h_episode, d + o_ep, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H episode"))) return rc;
-    if (h_rewards && (rc = check_cuda(cudaMemcpyAsync(h_rewards, d + o_rew, (size_t)T * n * 4, cudaMemcpyDeviceToHost, st), "D2H rewards"))) return rc;
-    if (h_dones && (rc = check_cuda(cudaMemcpyAsync(h_dones, d + o_done, (size_t)T * n, cudaMemcpyDeviceToHost, st), "D2H dones"))) return rc;
-    return check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    for (int k = 0; k < 3; ++k)
+        if (!streams[k] && (rc = check_cuda(cudaStreamCreateWithFlags(&streams[k], cudaStreamNonBlocking), "cudaStreamCreate"))) return rc;
+    if ((rc = check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize(caller)"))) return rc;
+    int64_t chunk = (n + 7) / 8;
+    chunk = (chunk + 63) & ~(int64_t)63;
+    if (chunk < 4096) chunk = n < 4096 ? n : 4096;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t per_chunk = up((size_t)chunk * 16) + 2 * up((size_t)chunk * 4) + up((size_t)T * chunk * 8) + up((size_t)T * chunk * 4) +
+                             up((size_t)T * chunk);
+    if ((rc = g_scratch.ensure(per_chunk * (size_t)nchunks))) return rc;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t c0 = c * chunk, cnt = (c0 + chunk <= n) ? chunk : n - c0;
+        cudaStream_t st = streams[c % 3];
+        char *d = (char *)g_scratch.buf + per_chunk * (size_t)c;
+        char *d_state = d, *d_sc = d_state + up((size_t)chunk * 16), *d_ep = d_sc + up((size_t)chunk * 4);
+        char *d_act = d_ep + up((size_t)chunk * 4), *d_rew = d_act + up((size_t)T * chunk * 8), *d_done = d_rew + up((size_t)T * chunk * 4);
+        if ((rc = check_cuda(cudaMemcpyAsync(d_state, h_state + 4 * c0, (size_t)cnt * 16, cudaMemcpyHostToDevice, st), "H2D state"))) return rc;
+        if ((rc = check_cuda(cudaMemcpyAsync(d_sc, h_step_count + c0, (size_t)cnt * 4, cudaMemcpyHostToDevice, st), "H2D step_count"))) return rc;
+        if ((rc = check_cuda(cudaMemcpyAsync(d_ep, h_episode + c0, (size_t)cnt * 4, cudaMemcpyHostToDevice, st), "H2D episode"))) return rc;
+        if ((rc = check_cuda(cudaMemcpy2DAsync(d_act, (size_t)cnt * 8, h_actions + 2 * c0, (size_t)n * 8, (size_t)cnt * 8, (size_t)T,
+                                               cudaMemcpyHostToDevice, st), "H2D actions"))) return rc;
+        cstr_env_params pc = *p;
+        pc.env_offset = p->env_offset + c0;
+        rc = cstr_tape_f32(&pc, cnt, T, math_mode, (const float *)d_act, 0u, (float *)d_state, (int32_t *)d_sc, (int32_t *)d_ep, nullptr,
+                           h_rewards ? (float *)d_rew : nullptr, h_dones ? (uint8_t *)d_done : nullptr, nullptr, nullptr, (void *)st);
+        if (rc) return rc;
+        if (h_rewards && (rc = check_cuda(cudaMemcpy2DAsync(h_rewards + c0, (size_t)n * 4, d_rew, (size_t)cnt * 4, (size_t)cnt * 4, (size_t)T,
+                                                            cudaMemcpyDeviceToHost, st), "D2H rewards"))) return rc;
+        if (h_dones && (rc = check_cuda(cudaMemcpy2DAsync(h_dones + c0, (size_t)n, d_done, (size_t)cnt, (size_t)cnt, (size_t)T,
+                                                          cudaMemcpyDeviceToHost, st), "D2H dones"))) return rc;
+        if ((rc = check_cuda(cudaMemcpyAsync(h_state + 4 * c0, d_state, (size_t)cnt * 16, cudaMemcpyDeviceToHost, st), "D2H state"))) return rc;
+        if ((rc = check_cuda(cudaMemcpyAsync(h_step_count + c0, d_sc, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st), "D2H step_count"))) return rc;
+        if ((rc = check_cuda(cudaMemcpyAsync(h_episode + c0, d_ep, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st), "D2H episode"))) return rc;
+    }
+    for (int k = 0; k < 3; ++k)
+        if ((rc = check_cuda(cudaStreamSynchronize(streams[k]), "cudaStreamSynchronize"))) return rc;
+    return 0;
 }
 
 }  // extern "C"

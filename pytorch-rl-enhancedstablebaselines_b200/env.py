@@ -209,6 +209,8 @@ class GpuCSTRVecEnv:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.CstrLibraryError("GpuCSTRVecEnv needs a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
         self.observation_space = _observation_space()
         self.action_space = _action_space()
@@ -225,7 +227,7 @@ class GpuCSTRVecEnv:
         self.max_steps = MAX_STEPS
         self.monitor = monitor
         self._params = _lib.EnvParams(seed=int(seed) & (2**64 - 1), env_offset=int(env_offset), target_c2=self.target_C2,
-                                      max_steps=MAX_STEPS, init_mode=_INIT[init_mode], reserved=0)
+                                      max_steps=MAX_STEPS, init_mode=_INIT[init_mode])
         fdt = torch.float32 if dtype == "fp32" else torch.float64
         self._fdt = fdt
         n = self.num_envs

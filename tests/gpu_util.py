@@ -10,7 +10,7 @@ L = PKG._lib
 
 
 def params(seed=0, env_offset=0, target=0.2, init_mode=0):
-    return L.EnvParams(seed=seed, env_offset=env_offset, target_c2=target, max_steps=400, init_mode=init_mode, reserved=0)
+    return L.EnvParams(seed=seed, env_offset=env_offset, target_c2=target, max_steps=400, init_mode=init_mode)
 
 
 def dev(x, dtype=None):

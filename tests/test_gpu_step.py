@@ -293,3 +293,32 @@ def test_abi_argument_errors(G):
     p.init_mode = 1
     assert lib.cstr_reset(byref(p), 2, None, s.data_ptr(), 0, sc.data_ptr(), sc.data_ptr(), None, None) == -1  # static w/o base
     assert lib.cstr_tape_f32(byref(G.params()), 0, 5, 0, None, 0, s.data_ptr(), sc.data_ptr(), sc.data_ptr(), None, None, None, None, None, None) == 0
+
+
+def test_host_tape_entry_matches_device_tape(G, pkg):
+    """cstr_tape_f32_host (chunked 3-stream H2D/compute/D2H pipeline over pinned host buffers) must return
+    exactly what the device-resident tape returns, for a batch that is not a multiple of the chunk size."""
+    from ctypes import byref
+
+    n, T, seed = 40_000 + 37, 50, 3
+    rng = np.random.default_rng(1)
+    env = pkg.GpuCSTRVecEnv(n, seed=seed, monitor=False)
+    obs0 = env.reset()
+    env.step_count.fill_(370)
+    acts = rng.uniform(-1, 1, (T, n, 2)).astype(np.float32)
+    res = env.tape(T, torch.as_tensor(acts, device="cuda"))
+    h_act = torch.as_tensor(acts).pin_memory()
+    h_state = torch.as_tensor(obs0).pin_memory()
+    h_sc = torch.full((n,), 370, dtype=torch.int32).pin_memory()
+    h_ep = torch.ones(n, dtype=torch.int32).pin_memory()
+    h_rew = torch.zeros((T, n), dtype=torch.float32).pin_memory()
+    h_done = torch.zeros((T, n), dtype=torch.uint8).pin_memory()
+    lib = G.L.load()
+    p = G.params(seed=seed)
+    G.L.check(lib.cstr_tape_f32_host(byref(p), n, T, 0, h_act.data_ptr(), h_state.data_ptr(), h_sc.data_ptr(), h_ep.data_ptr(),
+                                     h_rew.data_ptr(), h_done.data_ptr(), None), "cstr_tape_f32_host")
+    assert np.array_equal(h_rew.numpy(), res["rewards"].cpu().numpy())
+    assert np.array_equal(h_done.numpy(), res["dones"].cpu().numpy())
+    assert np.array_equal(h_state.numpy(), env.state.cpu().numpy())
+    assert np.array_equal(h_sc.numpy(), env.step_count.cpu().numpy()) and np.array_equal(h_ep.numpy(), env.episode.cpu().numpy())
+    assert h_done.numpy()[29].all()  # 370 + 30 = 400: the truncation row
