@@ -1,14 +1,417 @@
-// K2, tensor-core actor path (placeholder until the tcgen05 kernel lands in this file).
+// K2, tensor-core path — fused rollout with the actor's hidden layer on tcgen05 (sm_100a only).
+//
+//   obs (4) --W1,b1,relu--> h1 (H1) ==W2 on tcgen05.mma, bf16 x bf16 -> fp32 in TMEM==> (H2) --b2,relu,W3,b3,tanh--> mu (2)
+//   -> exploration noise -> action maps -> CSTR step -> reward/done -> replay record        (same tail as the fp32 path)
+//
+// One CTA owns a tile of 128 reactors for the K steps of the launch; the reactor state never leaves
+// registers.  Warp roles (10 warps):
+//   warps 0-7  "env" warps: thread t serves reactor m = t % 128, half h = t / 128.  Each step they
+//              (a) compute layer 1 in fp32 on the CUDA cores, K-chunk by K-chunk, and write it as bf16 straight
+//                  into the UMMA A-operand image in shared memory (no-swizzle K-major: 16-byte st.shared,
+//                  conflict-free), (b) read the accumulator row of their reactor out of TMEM (tcgen05.ld),
+//                  apply b2/relu and contract with W3 (half of the columns per thread), (c) run the env step.
+//   warp 8     W2 loader: streams the pre-packed bf16 K-chunks of W2 (L2-resident, 243 KB) into a 3-deep
+//              shared-memory ring with cp.async.bulk + mbarrier complete_tx (TMA bulk engine).
+//   warp 9     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=160+144, K=16) accumulating over the
+//              K-chunks in TMEM, and tcgen05.commit's to the mbarriers that free the operand buffers.
+// Layer-1 compute of chunk c+1 overlaps the MMAs of chunk c (A is double-buffered); the accumulators
+// (128 lanes x N_pad fp32 columns) live in TMEM and are only read once per step.
+//
+// Reference replaced: same as cstr_rollout.cu (off_policy_algorithm.py:364-411,445-508,564; td3/policies.py:75-78;
+// policies.py:331-413; buffers.py:247-283).  bf16 operands => the action differs from the fp32 actor by
+// ~1e-2 relative in the pre-activation (documented tolerance, tests/test_gpu_rollout.py); everything
+// after the actor (maps, step, reward, record) is the strict fp32 arithmetic.
+#include <cuda_bf16.h>
+
 #include "cstr_abi.cuh"
+#include "cstr_device.cuh"
+#include "cstr_rollout_common.cuh"
+
+namespace cstr {
+
+constexpr int TC_M = 128;             // reactors per CTA = UMMA M
+constexpr int TC_ENV_THREADS = 256;   // two threads per reactor
+constexpr int TC_THREADS = 320;       // + loader warp + MMA warp
+constexpr int TC_WSTAGES = 3;
+constexpr int TC_ASTAGES = 2;
+
+struct TcGeometry {
+    int H1, H2;      // actor hidden sizes
+    int KC;          // K-chunk (multiple of 16, divides H1)
+    int NKC;         // H1 / KC
+    int NP;          // H2 padded to a multiple of 16
+    int N0, N1;      // MMA instruction widths: N0 + N1 == NP, each a multiple of 16 and <= 256 (N1 may be 0)
+    int tmem_cols;   // power of two >= NP
+    uint32_t a_chunk_bytes, w_chunk_bytes;
+    uint32_t off_w1, off_ep, off_part, off_a, off_w, smem_bytes;
+};
+
+static bool make_geometry(int H1, int H2, TcGeometry &g) {
+    g.H1 = H1; g.H2 = H2;
+    if (H1 <= 0 || H2 <= 0 || (H1 % 16) || H1 > 1024) return false;
+    g.NP = (H2 + 15) & ~15;
+    if (g.NP > 512) return false;
+    const int cands[] = {80, 64, 48, 32, 16};
+    g.KC = 0;
+    for (int c : cands)
+        if (H1 % c == 0) { g.KC = c; break; }
+    if (!g.KC) return false;
+    g.NKC = H1 / g.KC;
+    if (g.NP <= 256) { g.N0 = g.NP; g.N1 = 0; }
+    else { g.N0 = ((g.NP / 2) + 15) & ~15; g.N1 = g.NP - g.N0; }
+    g.tmem_cols = 32;
+    while (g.tmem_cols < g.NP) g.tmem_cols <<= 1;
+    auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
+    g.a_chunk_bytes = (uint32_t)(g.KC / 8) * TC_M * 16;
+    g.w_chunk_bytes = (uint32_t)(g.KC / 8) * g.NP * 16;
+    g.off_w1 = 256;                                             // [0,256): mbarriers + tmem base
+    g.off_ep = up(g.off_w1 + 5u * H1 * 4);                      // w0,w1,w2,w3,b1 arrays
+    g.off_part = up(g.off_ep + 3u * g.NP * 4);                  // b2, W3[0], W3[1] (zero padded)
+    g.off_a = up(g.off_part + 2 * 2 * TC_M * 2 * 4);            // layer-3 partial sums [step parity][half][m]
+    g.off_w = up(g.off_a + TC_ASTAGES * g.a_chunk_bytes);
+    g.smem_bytes = up(g.off_w + TC_WSTAGES * g.w_chunk_bytes);
+    return g.smem_bytes <= 227u * 1024u;
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 8 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1):
+// canonical layout ((8,n),2):((16 B, SBO), LBO) — 8x16-byte core matrices, SBO between 8-row groups,
+// LBO between the two 8-element K halves of one K=16 instruction.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, dense
+__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// barrier slots inside the first 256 bytes of shared memory
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_FULL = 6, BAR_A_EMPTY = 8, BAR_D_FULL = 10, BAR_COUNT = 11 };
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, const uint8_t *__restrict__ packed_w2, TcGeometry g,
+                  float sigma, const float2 *__restrict__ noise, uint32_t t_base, float4 *__restrict__ state,
+                  int32_t *__restrict__ step_count, int32_t *__restrict__ episode, double *static_base, int64_t rows, int64_t pos0,
+                  float4 *__restrict__ records, double *reward_sum) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bars = smem_base;  // BAR_COUNT x 8 bytes
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 128);
+    float *sw1 = reinterpret_cast<float *>(smem + g.off_w1);     // [5][H1]: W1 columns 0..3, b1
+    float *sep = reinterpret_cast<float *>(smem + g.off_ep);     // [3][NP]: b2, W3 row 0, W3 row 1
+    float2 *spart = reinterpret_cast<float2 *>(smem + g.off_part);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H1 = g.H1, NP = g.NP;
+
+    // ---- one-time setup ---------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int b = 0; b < TC_WSTAGES; ++b) { mbar_init(bars + 8 * (BAR_W_FULL + b), 1); mbar_init(bars + 8 * (BAR_W_EMPTY + b), 1); }
+        for (int b = 0; b < TC_ASTAGES; ++b) { mbar_init(bars + 8 * (BAR_A_FULL + b), TC_ENV_THREADS); mbar_init(bars + 8 * (BAR_A_EMPTY + b), 1); }
+        mbar_init(bars + 8 * BAR_D_FULL, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {  // TMEM allocation is warp-collective; the same warp frees it at the end
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                     "r"((uint32_t)g.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int j = tid; j < H1; j += TC_THREADS) {
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(actor.W1) + j);
+        sw1[0 * H1 + j] = w.x; sw1[1 * H1 + j] = w.y; sw1[2 * H1 + j] = w.z; sw1[3 * H1 + j] = w.w;
+        sw1[4 * H1 + j] = __ldg(actor.b1 + j);
+    }
+    for (int j = tid; j < NP; j += TC_THREADS) {
+        const bool in = j < g.H2;
+        sep[0 * NP + j] = in ? __ldg(actor.b2 + j) : 0.0f;
+        sep[1 * NP + j] = in ? __ldg(actor.W3 + j) : 0.0f;
+        sep[2 * NP + j] = in ? __ldg(actor.W3 + g.H2 + j) : 0.0f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kgroups = g.KC / 8;  // 16-byte K groups per chunk
+
+    if (warp < 8) {
+        // =========================== env warps ===========================================================
+        const int m = tid & (TC_M - 1), half = tid >> 7;
+        const int64_t i = (int64_t)blockIdx.x * TC_M + m;
+        const bool live = i < n;
+        float4 s = live ? state[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        int sc = live ? step_count[i] : 0, ep = live ? episode[i] : 0;
+        const uint64_t env = (uint64_t)(p.env_offset + i);
+        const float b3x = __ldg(actor.b3), b3y = __ldg(actor.b3 + 1);
+        double acc_r = 0.0;
+        double sb[4] = {0.0, 0.0, 0.0, 0.0};
+        if (static_base && live) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sb[q] = static_base[4 * i + q];
+        }
+        uint32_t gchunk = 0;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int cols_per_half = NP / 2;
+
+        for (int64_t k = 0; k < K; ++k) {
+            // ---- (a) layer 1, chunk by chunk, into the A-operand ring ------------------------------------
+            for (int kc = 0; kc < g.NKC; ++kc, ++gchunk) {
+                const uint32_t ab = gchunk & 1u, use = gchunk >> 1;
+                mbar_wait(bars + 8 * (BAR_A_EMPTY + ab), (use & 1u) ^ 1u);
+                uint8_t *abuf = smem + g.off_a + ab * g.a_chunk_bytes;
+                for (int kg = half; kg < kgroups; kg += 2) {
+                    const int j0 = kc * g.KC + kg * 8;
+                    float v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q += 4) {
+                        const float4 w0 = *reinterpret_cast<const float4 *>(sw1 + 0 * H1 + j0 + q);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(sw1 + 1 * H1 + j0 + q);
+                        const float4 w2 = *reinterpret_cast<const float4 *>(sw1 + 2 * H1 + j0 + q);
+                        const float4 w3 = *reinterpret_cast<const float4 *>(sw1 + 3 * H1 + j0 + q);
+                        const float4 bb = *reinterpret_cast<const float4 *>(sw1 + 4 * H1 + j0 + q);
+                        v[q + 0] = fmaxf(fmaf(w3.x, s.w, fmaf(w2.x, s.z, fmaf(w1.x, s.y, fmaf(w0.x, s.x, bb.x)))), 0.0f);
+                        v[q + 1] = fmaxf(fmaf(w3.y, s.w, fmaf(w2.y, s.z, fmaf(w1.y, s.y, fmaf(w0.y, s.x, bb.y)))), 0.0f);
+                        v[q + 2] = fmaxf(fmaf(w3.z, s.w, fmaf(w2.z, s.z, fmaf(w1.z, s.y, fmaf(w0.z, s.x, bb.z)))), 0.0f);
+                        v[q + 3] = fmaxf(fmaf(w3.w, s.w, fmaf(w2.w, s.z, fmaf(w1.w, s.y, fmaf(w0.w, s.x, bb.w)))), 0.0f);
+                    }
+                    __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+                    __nv_bfloat162 h45 = __floats2bfloat162_rn(v[4], v[5]), h67 = __floats2bfloat162_rn(v[6], v[7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t *>(&h01); pk.y = *reinterpret_cast<uint32_t *>(&h23);
+                    pk.z = *reinterpret_cast<uint32_t *>(&h45); pk.w = *reinterpret_cast<uint32_t *>(&h67);
+                    *reinterpret_cast<uint4 *>(abuf + (size_t)kg * (TC_M * 16) + m * 16) = pk;  // [kg][m][8 x bf16]
+                }
+                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                mbar_arrive(bars + 8 * (BAR_A_FULL + ab));
+            }
+            // ---- (b) epilogue: TMEM row -> b2, relu, W3 --------------------------------------------------
+            mbar_wait(bars + 8 * BAR_D_FULL, (uint32_t)(k & 1));
+            tc_fence_after();
+            float o0 = 0.0f, o1 = 0.0f;
+            const int c_begin = half * cols_per_half;
+            for (int c = 0; c < cols_per_half; c += 8) {
+                float v[8];
+                tmem_ld8(tmem_base + lane_base + (uint32_t)(c_begin + c), v);
+                tmem_ld_wait();
+                const float *b2p = sep + c_begin + c;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float h = fmaxf(v[q] + b2p[q], 0.0f);
+                    o0 = fmaf(b2p[NP + q], h, o0);
+                    o1 = fmaf(b2p[2 * NP + q], h, o1);
+                }
+            }
+            tc_fence_before();  // TMEM reads are complete before anybody re-arms the accumulator
+            float2 *sp = spart + (size_t)(k & 1) * (2 * TC_M);  // double-buffered by step parity: one barrier per step
+            sp[half * TC_M + m] = make_float2(o0, o1);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float2 p0 = sp[m], p1 = sp[TC_M + m];
+            const float mu0 = tanhf((p0.x + p1.x) + b3x), mu1 = tanhf((p0.y + p1.y) + b3y);  // same order in both threads
+            // ---- (c) noise, action maps, env step, record (both threads of a pair compute, half 0 stores) ---
+            const uint32_t gstep = t_base + (uint32_t)k;
+            float2 nz;
+            if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
+            else if (sigma != 0.0f) { nz = philox_normal2(p.seed, env, gstep); nz.x *= sigma; nz.y *= sigma; }
+            else nz = make_float2(0.f, 0.f);
+            float2 env_a, buf_a;
+            action_maps(mu0, nz.x, env_a.x, buf_a.x);
+            action_maps(mu1, nz.y, env_a.y, buf_a.y);
+            const float4 obs = s;
+            const StepResult r = (MODE == CSTR_MATH_STRICT) ? step_strict_f32(s, env_a, sc, (float)p.target_c2, p.max_steps)
+                                                            : step_fast_f32(s, env_a, sc, (float)p.target_c2, p.max_steps);
+            if (live && half == 0) {
+                const int64_t row = (pos0 + k) % rows;
+                store_record(records + ((size_t)row * n + i) * 4, obs, s, buf_a, r.reward, r.truncated);
+                acc_r += (double)r.reward;
+            }
+            if (r.truncated) {
+                // both threads of a pair draw the same reset from the same Philox counter; in static mode each keeps its own
+                // copy of the drifting base state (Q2) and only half 0 writes it back at the end of the launch
+                s = reset_f32_call(p.seed, env, (uint32_t)ep, p.init_mode, static_base ? sb : nullptr);
+                ep += 1;
+                sc = 0;
+            }
+        }
+        if (live && half == 0) {
+            state[i] = s;
+            step_count[i] = sc;
+            episode[i] = ep;
+            if (static_base) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) static_base[4 * i + q] = sb[q];
+            }
+        }
+        if (reward_sum) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc_r += __shfl_down_sync(0xffffffffu, acc_r, o);
+            if (lane == 0 && half == 0) atomicAdd(reward_sum, acc_r);
+        }
+    } else if (warp == 8) {
+        // =========================== W2 loader ===========================================================
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)(K * g.NKC);
+            for (uint32_t gc = 0; gc < total; ++gc) {
+                const uint32_t wb = gc % TC_WSTAGES, use = gc / TC_WSTAGES;
+                mbar_wait(bars + 8 * (BAR_W_EMPTY + wb), (use & 1u) ^ 1u);
+                mbar_expect_tx(bars + 8 * (BAR_W_FULL + wb), g.w_chunk_bytes);
+                bulk_g2s(smem_base + g.off_w + wb * g.w_chunk_bytes, packed_w2 + (size_t)(gc % g.NKC) * g.w_chunk_bytes, g.w_chunk_bytes,
+                         bars + 8 * (BAR_W_FULL + wb));
+            }
+        }
+    } else {
+        // =========================== MMA issuer ==========================================================
+        if (lane == 0) {
+            const uint32_t idesc0 = umma_idesc_bf16(TC_M, g.N0), idesc1 = g.N1 ? umma_idesc_bf16(TC_M, g.N1) : 0;
+            const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)NP * 16, sbo = 128;
+            uint32_t gc = 0;
+            for (int64_t k = 0; k < K; ++k) {
+                for (int kc = 0; kc < g.NKC; ++kc, ++gc) {
+                    const uint32_t wb = gc % TC_WSTAGES, wuse = gc / TC_WSTAGES, ab = gc & 1u, ause = gc >> 1;
+                    mbar_wait(bars + 8 * (BAR_W_FULL + wb), wuse & 1u);
+                    mbar_wait(bars + 8 * (BAR_A_FULL + ab), ause & 1u);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + g.off_a + ab * g.a_chunk_bytes;
+                    const uint32_t b_addr = smem_base + g.off_w + wb * g.w_chunk_bytes;
+                    for (int j = 0; j < g.KC / 16; ++j) {
+                        const uint32_t acc = (kc > 0 || j > 0) ? 1u : 0u;
+                        const uint64_t da = umma_desc(a_addr + (uint32_t)(2 * j) * lbo_a, lbo_a, sbo);
+                        const uint64_t db0 = umma_desc(b_addr + (uint32_t)(2 * j) * lbo_b, lbo_b, sbo);
+                        tc_mma_bf16(tmem_base, da, db0, idesc0, acc);
+                        if (g.N1) {
+                            const uint64_t db1 = umma_desc(b_addr + (uint32_t)(2 * j) * lbo_b + (uint32_t)g.N0 * 16, lbo_b, sbo);
+                            tc_mma_bf16(tmem_base + (uint32_t)g.N0, da, db1, idesc1, acc);
+                        }
+                    }
+                    tc_commit(bars + 8 * (BAR_W_EMPTY + wb));  // operand buffers are free once these MMAs retire
+                    tc_commit(bars + 8 * (BAR_A_EMPTY + ab));
+                    if (kc == g.NKC - 1) tc_commit(bars + 8 * BAR_D_FULL);
+                }
+            }
+        }
+    }
+    // ---- teardown ---------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+}
+
+// W2 (H2,H1) fp32 -> bf16 UMMA image: [kc][kg][n (NP, zero padded)][8 x bf16], one contiguous chunk per kc
+__global__ void pack_w2_kernel(const float *__restrict__ W2, int H1, int H2, int KC, int NP, __nv_bfloat16 *__restrict__ out) {
+    const int64_t total = (int64_t)(H1 / 8) * NP * 8;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx & 7);
+        const int64_t t = idx >> 3;
+        const int nrow = (int)(t % NP);
+        const int kgg = (int)(t / NP);  // global K group = kc * (KC/8) + kg
+        const int kcol = kgg * 8 + e;
+        out[idx] = __float2bfloat16_rn(nrow < H2 ? W2[(size_t)nrow * H1 + kcol] : 0.0f);
+    }
+    (void)KC;
+}
+
+}  // namespace cstr
 
 using namespace cstr;
 
-int cstr_rollout_tc_launch(const cstr_env_params *, int64_t, int64_t, int, const cstr_actor_f32 *, const void *, float, const float *, int,
-                           uint32_t, float *, int32_t *, int32_t *, double *, int64_t, int64_t, float *, double *, void *) {
-    return fail_arg(CSTR_EINVAL, "rollout: actor_mode 1 (tcgen05) is not available in this build");
+int cstr_rollout_tc_launch(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, const cstr_actor_f32 *actor,
+                           const void *packed_bf16, float sigma, const float *noise, int warmup, uint32_t t_base, float *state,
+                           int32_t *step_count, int32_t *episode, double *static_base, int64_t rows, int64_t pos0, float *records,
+                           double *reward_sum, void *stream) {
+    (void)warmup;
+    TcGeometry g;
+    if (!make_geometry(actor->H1, actor->H2, g)) return fail_arg(CSTR_EINVAL, "rollout(tc): H1 must be a multiple of 16 (<=1024), H2 <= 512, and fit in shared memory");
+    if (!packed_bf16) return fail_arg(CSTR_EINVAL, "rollout(tc): packed bf16 weights missing (cstr_actor_pack_bf16)");
+    if (!aligned(packed_bf16, 16)) return fail_arg(CSTR_EALIGN, "rollout(tc): packed weights must be 16-byte aligned");
+    if ((int64_t)K * g.NKC >= (int64_t)1 << 31) return fail_arg(CSTR_EINVAL, "rollout(tc): K too large");
+    const int grid = (int)((n + TC_M - 1) / TC_M);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (math_mode == CSTR_MATH_STRICT) {
+        if ((rc = check_cuda(cudaFuncSetAttribute(rollout_tc_kernel<CSTR_MATH_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes), "smem attr"))) return rc;
+        rollout_tc_kernel<CSTR_MATH_STRICT><<<grid, TC_THREADS, g.smem_bytes, st>>>(*p, n, K, *actor, (const uint8_t *)packed_bf16, g, sigma, (const float2 *)noise,
+                                                                                    t_base, (float4 *)state, step_count, episode, static_base, rows, pos0,
+                                                                                    (float4 *)records, reward_sum);
+    } else {
+        if ((rc = check_cuda(cudaFuncSetAttribute(rollout_tc_kernel<CSTR_MATH_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes), "smem attr"))) return rc;
+        rollout_tc_kernel<CSTR_MATH_FAST><<<grid, TC_THREADS, g.smem_bytes, st>>>(*p, n, K, *actor, (const uint8_t *)packed_bf16, g, sigma, (const float2 *)noise,
+                                                                                  t_base, (float4 *)state, step_count, episode, static_base, rows, pos0,
+                                                                                  (float4 *)records, reward_sum);
+    }
+    return check_launch("rollout_tc_kernel");
 }
 
-extern "C" int64_t cstr_actor_pack_bf16(const cstr_actor_f32 *, void *, void *) {
-    fail_arg(CSTR_EINVAL, "actor_pack_bf16: not available in this build");
-    return -1;
+extern "C" int64_t cstr_actor_pack_bf16(const cstr_actor_f32 *actor, void *dst, void *stream) {
+    if (!actor || !actor->W2) { fail_arg(CSTR_EINVAL, "actor_pack_bf16: null actor"); return -1; }
+    TcGeometry g;
+    if (!make_geometry(actor->H1, actor->H2, g)) { fail_arg(CSTR_EINVAL, "actor_pack_bf16: unsupported actor shape"); return -1; }
+    const int64_t bytes = (int64_t)g.NKC * g.w_chunk_bytes;
+    if (!dst) return bytes;
+    if (!aligned(dst, 16)) { fail_arg(CSTR_EALIGN, "actor_pack_bf16: dst must be 16-byte aligned"); return -2; }
+    pack_w2_kernel<<<256, 256, 0, (cudaStream_t)stream>>>(actor->W2, g.H1, g.H2, g.KC, g.NP, (__nv_bfloat16 *)dst);
+    if (check_launch("pack_w2_kernel")) return -3;
+    return bytes;
 }

@@ -19,7 +19,10 @@ def _env_action_from_buffer_action(b):
     return (f(-1.0) + (f(0.5) * (b + f(1.0)) * f(2.0))).astype(f)
 
 
-@pytest.mark.parametrize("actor_mode,atol", [("fp32", 3e-6)])
+# fp32 path: fp32 accumulation order differs from torch/NumPy -> 3e-6.  tc path: h1 and W2 are rounded to bf16
+# (8-bit mantissa) before the tcgen05 MMA, fp32 accumulate -> |Δaction| <= 5e-3 (measured 7e-4), the env step
+# on the action it stored stays bit-exact.
+@pytest.mark.parametrize("actor_mode,atol", [("fp32", 3e-6), ("tc", 5e-3)])
 def test_rollout_matches_oracle_composition(pkg, golden, actor_mode, atol):
     g, w = _actor(golden)
     n, K, seed = 256, 3, 11
@@ -45,6 +48,8 @@ def test_rollout_matches_oracle_composition(pkg, golden, actor_mode, atol):
         mu = g["mu"] if k == 0 else O.actor_forward(state, w).astype(np.float32)
         a_env, a_buf = O.sample_action_maps(mu, noise[k])
         np.testing.assert_allclose(rec[k, :, 8:10], a_buf, rtol=0, atol=atol)
+        if actor_mode == "tc":
+            print("tc actor |Δaction| max", float(np.abs(rec[k, :, 8:10] - a_buf).max()))
         if k == 0:
             np.testing.assert_allclose(rec[k, :, 8:10], g["buffer_action"], rtol=0, atol=atol)
         assert np.abs(rec[k, :, 8:10]).max() <= 1.0
@@ -97,3 +102,32 @@ def test_rollout_philox_noise_statistics(pkg, golden):
     _, base = O.sample_action_maps(mu.astype(np.float32), np.zeros_like(a))
     d = (a - base)[np.abs(a) < 0.999]
     assert abs(d.mean()) < 5e-3 and abs(d.std() - 0.1) < 5e-3  # N(0, 0.1^2) exploration noise
+
+
+def test_tc_rollout_multi_tile_many_steps(pkg, golden):
+    """tcgen05 path over several CTAs, a ragged last tile and enough steps to wrap every mbarrier phase many times;
+    compared with the fp32-actor kernel run on identical inputs (same Philox noise stream)."""
+    g, w = _actor(golden)
+    n, K = 128 * 5 + 37, 23
+    outs = {}
+    for mode in ("fp32", "tc"):
+        env = pkg.GpuCSTRVecEnv(n, seed=4, monitor=False)
+        env.reset()
+        env.step_count.fill_(390)  # crosses the truncation row inside the launch
+        buf = pkg.GpuReplayBuffer(32 * n, device="cuda", n_envs=n)
+        actor = pkg.ActorWeights(g["W1"], g["b1"], g["W2"], g["b2"], g["W3"], g["b3"])
+        rs = torch.zeros(1, dtype=torch.float64, device="cuda")
+        pkg.FusedRollout(env, buf, actor, sigma=0.1, actor_mode=mode).collect(K, reward_sum=rs)
+        torch.cuda.synchronize()
+        outs[mode] = (buf.records.cpu().numpy()[:K], env.state.cpu().numpy(), env.step_count.cpu().numpy(), env.episode.cpu().numpy(), rs.item())
+    a, b = outs["fp32"], outs["tc"]
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])  # counters / episodes identical
+    assert np.array_equal(a[0][:, :, 11], b[0][:, :, 11])  # dones
+    assert (a[0][9, :, 11] == 1).all()  # 390 + 10 = 400
+    # first step: same observation, actions within the bf16 tolerance
+    assert np.array_equal(a[0][0, :, 0:4], b[0][0, :, 0:4])
+    assert np.abs(a[0][0, :, 8:10] - b[0][0, :, 8:10]).max() < 2e-2
+    # trajectories stay close (contractive dynamics) and the step after the reset starts from identical states
+    assert np.array_equal(a[0][10, :, 0:4], b[0][10, :, 0:4])
+    assert np.abs(a[0][:, :, 0:4] - b[0][:, :, 0:4]).max() < 5e-2
+    assert abs(a[4] - b[4]) < 1e-2 * abs(a[4])
