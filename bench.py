@@ -319,11 +319,12 @@ def run_ours(args) -> None:
     kernel_ms = statistics.mean(per)
     achieved = FLOP_PER_ENV_STEP * n * T / (kernel_ms * 1e-3) / 1e12
     peak = peaks["fp32_ffma_tflops"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = None  # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(f"tape_f32_{args.math}")
+            key = "tape_f32_kernel<0, 0, 0, 0>" if args.math == "strict" else "tape_f32_kernel<1, 0, 0, 0>"
+            traffic = json.load(open(tpath)).get(key, {}).get("dram_bytes")
         except Exception:
             traffic = None
     line = {

@@ -6,7 +6,7 @@ The directory name contains a hyphen, so import it with
 module at the repository root.  Importing the package does not need a GPU; constructing any of its
 classes does (the CUDA library has no CPU fallback).
 """
-from . import _build, _lib
+from . import _build, _lib, dist
 from ._lib import CstrLibraryError
 from .buffer import GpuReplayBuffer, ReplayBufferSamples, bind_replay_buffer_class
 from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
@@ -24,6 +24,7 @@ __all__ = [
     "bind_replay_buffer_class",
     "bind_vec_env_class",
     "build",
+    "dist",
 ]
 
 
