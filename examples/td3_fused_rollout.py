@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""TD3 end to end on the GPU-resident rollout path (config #3 shape, any number of GPUs).
+
+    python examples/td3_fused_rollout.py --n-envs 131072 --iters 40
+    torchrun --nproc-per-node 8 examples/td3_fused_rollout.py --n-envs 1048576 --iters 40   # env shards, DP update
+
+Per iteration, on every rank:
+  1. ``FusedRollout.collect(K)``   — actor inference (tcgen05) + noise + bounds + CSTR step + reward/done + replay
+                                     records for this rank's reactor shard, ONE kernel launch, nothing leaves the GPU;
+  2. ``GpuReplayBuffer.sample(B)`` — Philox-index gather straight into the update's float32 tensors;
+  3. TD3 update with the reference's semantics (``core/td3/td3.py:154-211``: target policy smoothing, twin-min
+     target, delayed actor, polyak) in plain torch — the update kernels are the "next" row, the
+     hot path here is 1–2; gradients are all-reduced with ONE flat NCCL bucket (``dist.allreduce_gradients``);
+  4. the fresh actor weights are handed back to the rollout kernel device-to-device.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def mlp(i, hs, o, squash=False):
+    layers, last = [], i
+    for h in hs:
+        layers += [nn.Linear(last, h), nn.ReLU()]
+        last = h
+    layers.append(nn.Linear(last, o))
+    if squash:
+        layers.append(nn.Tanh())
+    return nn.Sequential(*layers)
+
+
+def polyak(src, dst, tau):
+    with torch.no_grad():
+        ps, pt = list(src.parameters()), list(dst.parameters())
+        torch._foreach_mul_(pt, 1.0 - tau)
+        torch._foreach_add_(pt, ps, alpha=tau)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-envs", type=int, default=131072, help="total reactors over all ranks")
+    ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--steps-per-iter", type=int, default=8, help="env steps per fused launch")
+    ap.add_argument("--updates-per-iter", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=4096, help="per-rank batch")
+    ap.add_argument("--rows", type=int, default=64, help="ring rows per rank")
+    ap.add_argument("--actor-mode", default="tc", choices=["tc", "fp32"])
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+
+    pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(args.seed)  # same initial weights on every rank (+ broadcast below)
+
+    env = pkg.dist.make_sharded_env(args.n_envs, rank, world, device=dev, seed=args.seed, monitor=False)
+    n = env.num_envs
+    buf = pkg.GpuReplayBuffer(args.rows * n, device=dev, n_envs=n, index_mode="philox", seed=args.seed * 1000 + rank)
+    actor, actor_t = mlp(4, [400, 300], 2, squash=True).to(dev), mlp(4, [400, 300], 2, squash=True).to(dev)
+    critics = nn.ModuleList([mlp(6, [400, 300], 1) for _ in range(2)]).to(dev)
+    critics_t = nn.ModuleList([mlp(6, [400, 300], 1) for _ in range(2)]).to(dev)
+    pkg.dist.broadcast_parameters(list(actor.parameters()) + list(critics.parameters()))
+    actor_t.load_state_dict(actor.state_dict())
+    critics_t.load_state_dict(critics.state_dict())
+    opt_a = torch.optim.Adam(actor.parameters(), lr=3e-4)
+    opt_c = torch.optim.Adam(critics.parameters(), lr=3e-4)
+    weights = pkg.ActorWeights.from_module(actor, device=dev)
+    roll = pkg.FusedRollout(env, buf, weights, sigma=0.1, actor_mode=args.actor_mode)
+    gamma, tau, tnoise, tclip, delay = 0.99, 0.005, 0.2, 0.5, 2
+
+    env.reset()
+    roll.collect(args.steps_per_iter, warmup=True)  # learning_starts phase: uniform random actions
+    rsum = torch.zeros(1, dtype=torch.float64, device=dev)
+    bucket_c = bucket_a = None
+    n_updates, log = 0, []
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for it in range(args.iters):
+        rsum.zero_()
+        roll.collect(args.steps_per_iter, reward_sum=rsum)
+        for _ in range(args.updates_per_iter):
+            b = buf.sample(args.batch)
+            with torch.no_grad():
+                noise = (torch.randn_like(b.actions) * tnoise).clamp(-tclip, tclip)
+                na = (actor_t(b.next_observations) + noise).clamp(-1, 1)
+                q_next = torch.min(*[c(torch.cat([b.next_observations, na], 1)) for c in critics_t])
+                target = b.rewards + (1 - b.dones) * gamma * q_next
+            qs = [c(torch.cat([b.observations, b.actions], 1)) for c in critics]
+            loss_c = sum(F.mse_loss(q, target) for q in qs)
+            opt_c.zero_grad(set_to_none=False)
+            loss_c.backward()
+            bucket_c = pkg.dist.allreduce_gradients(list(critics.parameters()), bucket=bucket_c)
+            opt_c.step()
+            n_updates += 1
+            if n_updates % delay == 0:
+                loss_a = -critics[0](torch.cat([b.observations, actor(b.observations)], 1)).mean()
+                opt_a.zero_grad(set_to_none=False)
+                loss_a.backward()
+                bucket_a = pkg.dist.allreduce_gradients(list(actor.parameters()), bucket=bucket_a)
+                opt_a.step()
+                polyak(actor, actor_t, tau)
+                polyak(critics, critics_t, tau)
+        weights.refresh_from_module(actor)  # device-to-device; repacks the bf16 UMMA image of W2
+        mean_r = pkg.dist.global_sum(float(rsum.item()), device=dev) / (args.n_envs * args.steps_per_iter)
+        log.append(mean_r)
+        if rank == 0 and (it % 5 == 0 or it == args.iters - 1):
+            print(f"iter {it:3d}  mean reward/step {mean_r:8.4f}  critic loss {float(loss_c.detach()):.4f}", flush=True)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    if rank == 0:
+        transitions = args.iters * args.steps_per_iter * args.n_envs
+        print(json.dumps({"world_size": world, "n_envs": args.n_envs, "transitions": transitions, "seconds": dt,
+                          "transitions_per_s_incl_updates": transitions / dt, "updates": n_updates,
+                          "mean_reward_first": log[0], "mean_reward_last": log[-1], "actor_mode": args.actor_mode}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return log
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,8 @@ def load() -> ctypes.CDLL:
     lib.cstr_oracle_tape_f32.argtypes = [P, P, P, P, P, c.c_int64, c.c_int64, c.c_int64, c.c_uint64, c.c_int,
                                          c.c_float, c.c_int, c.c_int, P, P, P, P, P]
     lib.cstr_oracle_num_threads.restype = c.c_int
+    lib.cstr_oracle_set_threads.argtypes = [c.c_int]
+    lib.cstr_oracle_set_threads.restype = None
     for name in ("cstr_expf_shared_array", "cstr_powf2_array", "cstr_philox_array", "cstr_oracle_reset_uniforms",
                  "cstr_oracle_step_f32", "cstr_oracle_step_f64", "cstr_oracle_reset_f32", "cstr_oracle_tape_f32"):
         getattr(lib, name).restype = None
@@ -160,6 +162,13 @@ def tape_f32(state, step_count, episode, actions, env0=0, seed=0, init_mode=0, s
 
 def num_threads() -> int:
     return int(load().cstr_oracle_num_threads())
+
+
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().cstr_oracle_set_threads(n)
+    return num_threads()
 
 
 if __name__ == "__main__":

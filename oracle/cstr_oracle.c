@@ -351,6 +351,14 @@ void cstr_oracle_tape_f32(float *state, int32_t *step_count, int32_t *episode, d
     if (reward_sum) *reward_sum = total;
 }
 
+void cstr_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int cstr_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
