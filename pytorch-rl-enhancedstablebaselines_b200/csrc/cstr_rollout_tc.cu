@@ -43,7 +43,8 @@ struct TcGeometry {
     int N0, N1;      // MMA instruction widths: N0 + N1 == NP, each a multiple of 16 and <= 256 (N1 may be 0)
     int tmem_cols;   // power of two >= NP
     uint32_t a_chunk_bytes, w_chunk_bytes;
-    uint32_t off_w1, off_ep, off_part, off_a, off_w, smem_bytes;
+    uint32_t off_w1, off_a1, off_ep, off_part, off_a, off_w, smem_bytes;
+    int d1_col;      // first TMEM column of the two layer-1 accumulator buffers (KC columns each)
 };
 
 static bool make_geometry(int H1, int H2, TcGeometry &g) {
@@ -59,13 +60,16 @@ static bool make_geometry(int H1, int H2, TcGeometry &g) {
     g.NKC = H1 / g.KC;
     if (g.NP <= 256) { g.N0 = g.NP; g.N1 = 0; }
     else { g.N0 = ((g.NP / 2) + 15) & ~15; g.N1 = g.NP - g.N0; }
+    g.d1_col = g.NP;
+    if (g.NP + 2 * g.KC > 512) return false;  // layer-2 accumulator + two layer-1 chunk accumulators must fit in TMEM
     g.tmem_cols = 32;
-    while (g.tmem_cols < g.NP) g.tmem_cols <<= 1;
+    while (g.tmem_cols < g.NP + 2 * g.KC) g.tmem_cols <<= 1;
     auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
     g.a_chunk_bytes = (uint32_t)(g.KC / 8) * TC_M * 16;
     g.w_chunk_bytes = (uint32_t)(g.KC / 8) * g.NP * 16;
     g.off_w1 = 256;                                             // [0,256): mbarriers + tmem base
-    g.off_ep = up(g.off_w1 + 5u * H1 * 4);                      // w0,w1,w2,w3,b1 arrays
+    g.off_a1 = up(g.off_w1 + 2u * H1 * 16);                     // W1 split-bf16 UMMA image [2][H1][8 x bf16]
+    g.off_ep = up(g.off_a1 + 2u * TC_M * 16);                   // layer-1 A operand [2][128][8 x bf16]
     g.off_part = up(g.off_ep + 3u * g.NP * 4);                  // b2, W3[0], W3[1] (zero padded)
     g.off_a = up(g.off_part + 2 * 2 * TC_M * 2 * 4);            // layer-3 partial sums [step parity][half][m]
     g.off_w = up(g.off_a + TC_ASTAGES * g.a_chunk_bytes);
@@ -129,6 +133,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 8 hidden units of the layer-2/3 epilogue: h = relu(acc + b2); o += W3 * h
+__device__ __forceinline__ void epi8(const float v[8], float4 ba, float4 bb, float4 w0a, float4 w0b, float4 w1a, float4 w1b, float &o0, float &o1) {
+    const float b[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    const float w0[8] = {w0a.x, w0a.y, w0a.z, w0a.w, w0b.x, w0b.y, w0b.z, w0b.w};
+    const float w1[8] = {w1a.x, w1a.y, w1a.z, w1a.w, w1b.x, w1b.y, w1b.z, w1b.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float h = fmaxf(v[q] + b[q], 0.0f);
+        o0 = fmaf(w0[q], h, o0);
+        o1 = fmaf(w1[q], h, o1);
+    }
+}
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor, version 1):
 // canonical layout ((8,n),2):((16 B, SBO), LBO) — 8x16-byte core matrices, SBO between 8-row groups,
 // LBO between the two 8-element K halves of one K=16 instruction.
@@ -146,7 +163,7 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // barrier slots inside the first 256 bytes of shared memory
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_FULL = 6, BAR_A_EMPTY = 8, BAR_D_FULL = 10, BAR_COUNT = 11 };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_FULL = 6, BAR_A_EMPTY = 8, BAR_D_FULL = 10, BAR_A1_FULL = 11, BAR_D1_FULL = 12, BAR_D1_EMPTY = 14, BAR_COUNT = 16 };
 
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -158,7 +175,6 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bars = smem_base;  // BAR_COUNT x 8 bytes
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 128);
-    float *sw1 = reinterpret_cast<float *>(smem + g.off_w1);     // [5][H1]: W1 columns 0..3, b1
     float *sep = reinterpret_cast<float *>(smem + g.off_ep);     // [3][NP]: b2, W3 row 0, W3 row 1
     float2 *spart = reinterpret_cast<float2 *>(smem + g.off_part);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -169,6 +185,8 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         for (int b = 0; b < TC_WSTAGES; ++b) { mbar_init(bars + 8 * (BAR_W_FULL + b), 1); mbar_init(bars + 8 * (BAR_W_EMPTY + b), 1); }
         for (int b = 0; b < TC_ASTAGES; ++b) { mbar_init(bars + 8 * (BAR_A_FULL + b), TC_ENV_THREADS); mbar_init(bars + 8 * (BAR_A_EMPTY + b), 1); }
         mbar_init(bars + 8 * BAR_D_FULL, 1);
+        mbar_init(bars + 8 * BAR_A1_FULL, TC_ENV_THREADS);
+        for (int b = 0; b < 2; ++b) { mbar_init(bars + 8 * (BAR_D1_FULL + b), 1); mbar_init(bars + 8 * (BAR_D1_EMPTY + b), TC_ENV_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {  // TMEM allocation is warp-collective; the same warp frees it at the end
@@ -177,10 +195,22 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // Layer 1 (K=4 + bias) as ONE K=16 bf16 MMA with fp32-grade accuracy: x = x_hi + x_lo (two bf16 each), and
+    //   W.s + b ~= W_hi.s_hi + W_hi.s_lo + W_lo.s_hi + b_hi + b_lo          (the dropped W_lo.s_lo term is ~2^-18 relative)
+    // B1 row j = [W_hi(4) | W_hi(4)] [W_lo(4) | b_hi b_lo 0 0]   against   A1 row m = [s_hi(4) | s_lo(4)] [s_hi(4) | 1 1 0 0]
     for (int j = tid; j < H1; j += TC_THREADS) {
         const float4 w = __ldg(reinterpret_cast<const float4 *>(actor.W1) + j);
-        sw1[0 * H1 + j] = w.x; sw1[1 * H1 + j] = w.y; sw1[2 * H1 + j] = w.z; sw1[3 * H1 + j] = w.w;
-        sw1[4 * H1 + j] = __ldg(actor.b1 + j);
+        const float b = __ldg(actor.b1 + j);
+        const float wf[4] = {w.x, w.y, w.z, w.w};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { hi[q] = __float2bfloat16_rn(wf[q]); lo[q] = __float2bfloat16_rn(wf[q] - __bfloat162float(hi[q])); }
+        const __nv_bfloat16 bhi = __float2bfloat16_rn(b), blo = __float2bfloat16_rn(b - __bfloat162float(bhi)), z = __float2bfloat16_rn(0.0f);
+        __nv_bfloat16 *g0 = reinterpret_cast<__nv_bfloat16 *>(smem + g.off_w1 + (size_t)j * 16);
+        __nv_bfloat16 *g1 = reinterpret_cast<__nv_bfloat16 *>(smem + g.off_w1 + (size_t)(H1 + j) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { g0[q] = hi[q]; g0[4 + q] = hi[q]; g1[q] = lo[q]; }
+        g1[4] = bhi; g1[5] = blo; g1[6] = z; g1[7] = z;
     }
     for (int j = tid; j < NP; j += TC_THREADS) {
         const bool in = j < g.H2;
@@ -188,6 +218,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         sep[1 * NP + j] = in ? __ldg(actor.W3 + j) : 0.0f;
         sep[2 * NP + j] = in ? __ldg(actor.W3 + g.H2 + j) : 0.0f;
     }
+    fence_proxy_async();  // the W1 image above is read by the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -215,32 +246,59 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         const int cols_per_half = NP / 2;
 
         for (int64_t k = 0; k < K; ++k) {
-            // ---- (a) layer 1, chunk by chunk, into the A-operand ring ------------------------------------
+            // ---- (a) layer 1 on the tensor core: publish this step's split-bf16 observation row (A1) ... -------------
+            const uint32_t gstep = t_base + (uint32_t)k;
+            {
+                const float sf[4] = {s.x, s.y, s.z, s.w};
+                __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { hi[q] = __float2bfloat16_rn(sf[q]); lo[q] = __float2bfloat16_rn(sf[q] - __bfloat162float(hi[q])); }
+                const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), z = __float2bfloat16_rn(0.0f);
+                __nv_bfloat162 p0 = __halves2bfloat162(hi[0], hi[1]), p1 = __halves2bfloat162(hi[2], hi[3]);
+                __nv_bfloat162 p2 = half == 0 ? __halves2bfloat162(lo[0], lo[1]) : __halves2bfloat162(one, one);
+                __nv_bfloat162 p3 = half == 0 ? __halves2bfloat162(lo[2], lo[3]) : __halves2bfloat162(z, z);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&p0); pk.y = *reinterpret_cast<uint32_t *>(&p1);
+                pk.z = *reinterpret_cast<uint32_t *>(&p2); pk.w = *reinterpret_cast<uint32_t *>(&p3);
+                *reinterpret_cast<uint4 *>(smem + g.off_a1 + (size_t)half * (TC_M * 16) + m * 16) = pk;  // K group = half
+                fence_proxy_async();
+                mbar_arrive(bars + 8 * BAR_A1_FULL);
+            }
+            float2 nz;  // exploration noise does not depend on the actor: drawn here, while the first MMAs are in flight
+            if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
+            else if (sigma != 0.0f) { nz = philox_normal2(p.seed, env, gstep); nz.x *= sigma; nz.y *= sigma; }
+            else nz = make_float2(0.f, 0.f);
+            // ---- ... then turn each layer-1 accumulator chunk (TMEM) into the bf16 A operand of layer 2 (relu + pack) ---
             for (int kc = 0; kc < g.NKC; ++kc, ++gchunk) {
                 const uint32_t ab = gchunk & 1u, use = gchunk >> 1;
+                const uint32_t db = (uint32_t)kc & 1u, duse = (uint32_t)(k * ((g.NKC + 1 - (int)db) / 2) + (kc >> 1));
+                mbar_wait(bars + 8 * (BAR_D1_FULL + db), duse & 1u);
+                tc_fence_after();
+                const uint32_t d1 = tmem_base + lane_base + (uint32_t)(g.d1_col + (int)db * g.KC);
+                float v[5][8];  // up to 5 K-groups per thread and chunk (KC <= 80, two threads per reactor); static indices only
+#pragma unroll
+                for (int c5 = 0; c5 < 5; ++c5) {
+                    const int kg = half + 2 * c5;
+                    if (kg < kgroups) tmem_ld8(d1 + (uint32_t)(kg * 8), v[c5]);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bars + 8 * (BAR_D1_EMPTY + db));  // this chunk's layer-1 accumulator may be overwritten
                 mbar_wait(bars + 8 * (BAR_A_EMPTY + ab), (use & 1u) ^ 1u);
                 uint8_t *abuf = smem + g.off_a + ab * g.a_chunk_bytes;
-                for (int kg = half; kg < kgroups; kg += 2) {
-                    const int j0 = kc * g.KC + kg * 8;
-                    float v[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q += 4) {
-                        const float4 w0 = *reinterpret_cast<const float4 *>(sw1 + 0 * H1 + j0 + q);
-                        const float4 w1 = *reinterpret_cast<const float4 *>(sw1 + 1 * H1 + j0 + q);
-                        const float4 w2 = *reinterpret_cast<const float4 *>(sw1 + 2 * H1 + j0 + q);
-                        const float4 w3 = *reinterpret_cast<const float4 *>(sw1 + 3 * H1 + j0 + q);
-                        const float4 bb = *reinterpret_cast<const float4 *>(sw1 + 4 * H1 + j0 + q);
-                        v[q + 0] = fmaxf(fmaf(w3.x, s.w, fmaf(w2.x, s.z, fmaf(w1.x, s.y, fmaf(w0.x, s.x, bb.x)))), 0.0f);
-                        v[q + 1] = fmaxf(fmaf(w3.y, s.w, fmaf(w2.y, s.z, fmaf(w1.y, s.y, fmaf(w0.y, s.x, bb.y)))), 0.0f);
-                        v[q + 2] = fmaxf(fmaf(w3.z, s.w, fmaf(w2.z, s.z, fmaf(w1.z, s.y, fmaf(w0.z, s.x, bb.z)))), 0.0f);
-                        v[q + 3] = fmaxf(fmaf(w3.w, s.w, fmaf(w2.w, s.z, fmaf(w1.w, s.y, fmaf(w0.w, s.x, bb.w)))), 0.0f);
+                for (int c5 = 0; c5 < 5; ++c5) {
+                    const int kg = half + 2 * c5;
+                    if (kg < kgroups) {
+                        __nv_bfloat162 h01 = __floats2bfloat162_rn(fmaxf(v[c5][0], 0.f), fmaxf(v[c5][1], 0.f));
+                        __nv_bfloat162 h23 = __floats2bfloat162_rn(fmaxf(v[c5][2], 0.f), fmaxf(v[c5][3], 0.f));
+                        __nv_bfloat162 h45 = __floats2bfloat162_rn(fmaxf(v[c5][4], 0.f), fmaxf(v[c5][5], 0.f));
+                        __nv_bfloat162 h67 = __floats2bfloat162_rn(fmaxf(v[c5][6], 0.f), fmaxf(v[c5][7], 0.f));
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t *>(&h01); pk.y = *reinterpret_cast<uint32_t *>(&h23);
+                        pk.z = *reinterpret_cast<uint32_t *>(&h45); pk.w = *reinterpret_cast<uint32_t *>(&h67);
+                        *reinterpret_cast<uint4 *>(abuf + (size_t)kg * (TC_M * 16) + m * 16) = pk;  // [kg][m][8 x bf16]
                     }
-                    __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
-                    __nv_bfloat162 h45 = __floats2bfloat162_rn(v[4], v[5]), h67 = __floats2bfloat162_rn(v[6], v[7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<uint32_t *>(&h01); pk.y = *reinterpret_cast<uint32_t *>(&h23);
-                    pk.z = *reinterpret_cast<uint32_t *>(&h45); pk.w = *reinterpret_cast<uint32_t *>(&h67);
-                    *reinterpret_cast<uint4 *>(abuf + (size_t)kg * (TC_M * 16) + m * 16) = pk;  // [kg][m][8 x bf16]
                 }
                 fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 mbar_arrive(bars + 8 * (BAR_A_FULL + ab));
@@ -250,16 +308,22 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             tc_fence_after();
             float o0 = 0.0f, o1 = 0.0f;
             const int c_begin = half * cols_per_half;
-            for (int c = 0; c < cols_per_half; c += 8) {
-                float v[8];
-                tmem_ld8(tmem_base + lane_base + (uint32_t)(c_begin + c), v);
+            const uint32_t d2 = tmem_base + lane_base + (uint32_t)c_begin;
+            float va[8], vb[8];
+            tmem_ld8(d2, va);
+            for (int c = 0; c < cols_per_half; c += 16) {  // two 8-column groups per trip, loads one group ahead of the math
                 tmem_ld_wait();
-                const float *b2p = sep + c_begin + c;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float h = fmaxf(v[q] + b2p[q], 0.0f);
-                    o0 = fmaf(b2p[NP + q], h, o0);
-                    o1 = fmaf(b2p[2 * NP + q], h, o1);
+                if (c + 8 < cols_per_half) tmem_ld8(d2 + (uint32_t)(c + 8), vb);
+                // constants as 16-byte broadcast loads (c_begin and c are multiples of 8 floats: 32-byte aligned); scalar
+                // LDS here made the epilogue shared-memory-issue bound (24 wavefronts per 8 columns and warp)
+                const float4 *b2v = reinterpret_cast<const float4 *>(sep + c_begin + c);
+                const float4 *w0v = reinterpret_cast<const float4 *>(sep + NP + c_begin + c);
+                const float4 *w1v = reinterpret_cast<const float4 *>(sep + 2 * NP + c_begin + c);
+                epi8(va, b2v[0], b2v[1], w0v[0], w0v[1], w1v[0], w1v[1], o0, o1);
+                if (c + 8 < cols_per_half) {
+                    tmem_ld_wait();
+                    if (c + 16 < cols_per_half) tmem_ld8(d2 + (uint32_t)(c + 16), va);
+                    epi8(vb, b2v[2], b2v[3], w0v[2], w0v[3], w1v[2], w1v[3], o0, o1);
                 }
             }
             tc_fence_before();  // TMEM reads are complete before anybody re-arms the accumulator
@@ -269,11 +333,6 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             const float2 p0 = sp[m], p1 = sp[TC_M + m];
             const float mu0 = tanhf((p0.x + p1.x) + b3x), mu1 = tanhf((p0.y + p1.y) + b3y);  // same order in both threads
             // ---- (c) noise, action maps, env step, record (both threads of a pair compute, half 0 stores) ---
-            const uint32_t gstep = t_base + (uint32_t)k;
-            float2 nz;
-            if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
-            else if (sigma != 0.0f) { nz = philox_normal2(p.seed, env, gstep); nz.x *= sigma; nz.y *= sigma; }
-            else nz = make_float2(0.f, 0.f);
             float2 env_a, buf_a;
             action_maps(mu0, nz.x, env_a.x, buf_a.x);
             action_maps(mu1, nz.y, env_a.y, buf_a.y);
@@ -322,30 +381,59 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
     } else {
         // =========================== MMA issuer ==========================================================
         if (lane == 0) {
+            // The issuing thread is a single dependent instruction stream: everything loop-invariant is hoisted so
+            // that one MMA costs a 64-bit add per operand plus the instruction itself (measured before hoisting:
+            // ~130 cycles of descriptor arithmetic per MMA against ~76 cycles of tensor time — the issuer was the bottleneck).
             const uint32_t idesc0 = umma_idesc_bf16(TC_M, g.N0), idesc1 = g.N1 ? umma_idesc_bf16(TC_M, g.N1) : 0;
             const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)NP * 16, sbo = 128;
+            const uint64_t a_step = (uint64_t)((2u * lbo_a) >> 4), b_step = (uint64_t)((2u * lbo_b) >> 4);  // one K=16 step, in 16-byte units
+            const uint64_t n1_off = (uint64_t)(((uint32_t)g.N0 * 16u) >> 4);
+            uint64_t a_desc0[TC_ASTAGES], b_desc0[TC_WSTAGES];
+#pragma unroll
+            for (int b = 0; b < TC_ASTAGES; ++b) a_desc0[b] = umma_desc(smem_base + g.off_a + b * g.a_chunk_bytes, lbo_a, sbo);
+#pragma unroll
+            for (int b = 0; b < TC_WSTAGES; ++b) b_desc0[b] = umma_desc(smem_base + g.off_w + b * g.w_chunk_bytes, lbo_b, sbo);
+            const int ksteps = g.KC / 16;
+            // layer 1: one K=16 MMA per chunk, A1 = split-bf16 observation rows, B1 = this chunk's rows of the W1 image
+            const uint32_t idesc_l1 = umma_idesc_bf16(TC_M, g.KC);
+            const uint64_t da1 = umma_desc(smem_base + g.off_a1, TC_M * 16, sbo);
+            const uint64_t dw1_0 = umma_desc(smem_base + g.off_w1, (uint32_t)H1 * 16, sbo);
+            const uint64_t w1_step = (uint64_t)(((uint32_t)g.KC * 16u) >> 4);
+            uint32_t d1_uses[2] = {0, 0};  // completed uses of each layer-1 accumulator buffer
+            auto issue_l1 = [&](int kc) {
+                const uint32_t db = (uint32_t)kc & 1u;
+                const uint32_t uses = db ? d1_uses[1] : d1_uses[0];
+                mbar_wait(bars + 8 * (BAR_D1_EMPTY + db), (uses & 1u) ^ 1u);  // env threads drained the previous use
+                tc_fence_after();
+                tc_mma_bf16(tmem_base + (uint32_t)(g.d1_col + (int)db * g.KC), da1, dw1_0 + (uint64_t)kc * w1_step, idesc_l1, 0u);
+                tc_commit(bars + 8 * (BAR_D1_FULL + db));
+                if (db) d1_uses[1] += 1; else d1_uses[0] += 1;
+            };
             uint32_t gc = 0;
             for (int64_t k = 0; k < K; ++k) {
+                mbar_wait(bars + 8 * BAR_A1_FULL, (uint32_t)(k & 1));  // this step's observation rows are in shared memory
+                tc_fence_after();
+                issue_l1(0);
+                if (g.NKC > 1) issue_l1(1);
                 for (int kc = 0; kc < g.NKC; ++kc, ++gc) {
                     const uint32_t wb = gc % TC_WSTAGES, wuse = gc / TC_WSTAGES, ab = gc & 1u, ause = gc >> 1;
                     mbar_wait(bars + 8 * (BAR_W_FULL + wb), wuse & 1u);
                     mbar_wait(bars + 8 * (BAR_A_FULL + ab), ause & 1u);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + g.off_a + ab * g.a_chunk_bytes;
-                    const uint32_t b_addr = smem_base + g.off_w + wb * g.w_chunk_bytes;
-                    for (int j = 0; j < g.KC / 16; ++j) {
-                        const uint32_t acc = (kc > 0 || j > 0) ? 1u : 0u;
-                        const uint64_t da = umma_desc(a_addr + (uint32_t)(2 * j) * lbo_a, lbo_a, sbo);
-                        const uint64_t db0 = umma_desc(b_addr + (uint32_t)(2 * j) * lbo_b, lbo_b, sbo);
-                        tc_mma_bf16(tmem_base, da, db0, idesc0, acc);
-                        if (g.N1) {
-                            const uint64_t db1 = umma_desc(b_addr + (uint32_t)(2 * j) * lbo_b + (uint32_t)g.N0 * 16, lbo_b, sbo);
-                            tc_mma_bf16(tmem_base + (uint32_t)g.N0, da, db1, idesc1, acc);
-                        }
+                    uint64_t da = ab == 0 ? a_desc0[0] : a_desc0[1];
+                    uint64_t dbw = wb == 0 ? b_desc0[0] : (wb == 1 ? b_desc0[1] : b_desc0[2]);
+                    uint32_t acc = kc > 0 ? 1u : 0u;
+                    for (int j = 0; j < ksteps; ++j) {
+                        tc_mma_bf16(tmem_base, da, dbw, idesc0, acc);
+                        if (g.N1) tc_mma_bf16(tmem_base + (uint32_t)g.N0, da, dbw + n1_off, idesc1, acc);
+                        da += a_step;
+                        dbw += b_step;
+                        acc = 1u;
                     }
                     tc_commit(bars + 8 * (BAR_W_EMPTY + wb));  // operand buffers are free once these MMAs retire
                     tc_commit(bars + 8 * (BAR_A_EMPTY + ab));
                     if (kc == g.NKC - 1) tc_commit(bars + 8 * BAR_D_FULL);
+                    if (kc + 2 < g.NKC) issue_l1(kc + 2);  // its accumulator buffer was drained before A chunk kc was published
                 }
             }
         }
