@@ -28,4 +28,4 @@ for _ in range(launches):
 e1.record()
 e1.synchronize()
 ms = e0.elapsed_time(e1) / launches
-print(f"n={n} K={K}: {ms:.3f} ms/launch, {n * K / ms / 1e6:.1f} M transitions/s, {n * K * 244400 / ms / 1e9:.1f} TFLOP/s (actor)")
+print(f"n={n} K={K}: {ms:.3f} ms/launch, {n * K / ms / 1e6:.1f} G transitions/s, {n * K * 244400 / ms / 1e9:.1f} TFLOP/s (actor)")

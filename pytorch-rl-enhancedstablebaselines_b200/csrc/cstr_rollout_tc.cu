@@ -270,7 +270,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             else nz = make_float2(0.f, 0.f);
             // ---- ... then turn each layer-1 accumulator chunk (TMEM) into the bf16 A operand of layer 2 (relu + pack) ---
             for (int kc = 0; kc < g.NKC; ++kc, ++gchunk) {
-                const uint32_t ab = gchunk & 1u, use = gchunk >> 1;
+                const uint32_t ab = gchunk & 1u;
                 const uint32_t db = (uint32_t)kc & 1u, duse = (uint32_t)(k * ((g.NKC + 1 - (int)db) / 2) + (kc >> 1));
                 mbar_wait(bars + 8 * (BAR_D1_FULL + db), duse & 1u);
                 tc_fence_after();
@@ -284,7 +284,9 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(bars + 8 * (BAR_D1_EMPTY + db));  // this chunk's layer-1 accumulator may be overwritten
-                mbar_wait(bars + 8 * (BAR_A_EMPTY + ab), (use & 1u) ^ 1u);
+                // No "A buffer empty" barrier: the layer-1 MMA of THIS chunk was issued after the layer-2 MMAs that last read
+                // this A buffer (chunk g-2) on the same in-order tensor pipe, and its commit (D1_FULL, waited above) tracks
+                // completion of everything issued before it — so the buffer is already free.
                 uint8_t *abuf = smem + g.off_a + ab * g.a_chunk_bytes;
 #pragma unroll
                 for (int c5 = 0; c5 < 5; ++c5) {
@@ -416,7 +418,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                 issue_l1(0);
                 if (g.NKC > 1) issue_l1(1);
                 for (int kc = 0; kc < g.NKC; ++kc, ++gc) {
-                    const uint32_t wb = gc % TC_WSTAGES, wuse = gc / TC_WSTAGES, ab = gc & 1u, ause = gc >> 1;
+                    const uint32_t wb = gc % TC_WSTAGES, wuse = gc / TC_WSTAGES, ab = gc & 1u, ause = gc >> 1;  // A_FULL phase = use count of the A buffer
                     mbar_wait(bars + 8 * (BAR_W_FULL + wb), wuse & 1u);
                     mbar_wait(bars + 8 * (BAR_A_FULL + ab), ause & 1u);
                     tc_fence_after();
@@ -431,7 +433,6 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                         acc = 1u;
                     }
                     tc_commit(bars + 8 * (BAR_W_EMPTY + wb));  // operand buffers are free once these MMAs retire
-                    tc_commit(bars + 8 * (BAR_A_EMPTY + ab));
                     if (kc == g.NKC - 1) tc_commit(bars + 8 * BAR_D_FULL);
                     if (kc + 2 < g.NKC) issue_l1(kc + 2);  // its accumulator buffer was drained before A chunk kc was published
                 }

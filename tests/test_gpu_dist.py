@@ -1,0 +1,63 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): the N>1 path on real devices — NCCL flat-bucket gradient
+all-reduce and shard invariance of the fused rollout across ranks (torchrun, one process per GPU)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import importlib, json, os, sys
+sys.path.insert(0, os.environ["CSTR_ROOT"])
+import torch, torch.distributed as dist
+pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+# (1) env shards: rank r steps ids [r*n, (r+1)*n); the union must equal a single-device run of 2n reactors
+n, T = 4096, 50
+env = pkg.dist.make_sharded_env(world * n, rank, world, device=dev, seed=11, monitor=False)
+env.reset()
+rew = env.tape(T, None)["rewards"]
+gathered = [torch.empty_like(rew) for _ in range(world)]
+dist.all_gather(gathered, rew)
+ok_shard = None
+if rank == 0:
+    full = pkg.GpuCSTRVecEnv(world * n, device=dev, seed=11, monitor=False)
+    full.reset()
+    ok_shard = bool(torch.equal(torch.cat([g.to(dev) for g in gathered], dim=1), full.tape(T, None)["rewards"]))
+# (2) data-parallel gradient: averaged shard gradients == full-batch gradients (one flat NCCL all-reduce)
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(4, 400), torch.nn.ReLU(), torch.nn.Linear(400, 300), torch.nn.ReLU(), torch.nn.Linear(300, 2)).to(dev)
+pkg.dist.broadcast_parameters(net.parameters())
+g = torch.Generator().manual_seed(5)
+x, y = torch.randn(64 * world, 4, generator=g).to(dev), torch.randn(64 * world, 2, generator=g).to(dev)
+torch.nn.functional.mse_loss(net(x[rank * 64:(rank + 1) * 64]), y[rank * 64:(rank + 1) * 64]).backward()
+bucket = pkg.dist.allreduce_gradients(list(net.parameters()))
+shard_grads = [p.grad.clone() for p in net.parameters()]
+net.zero_grad()
+torch.nn.functional.mse_loss(net(x), y).backward()
+err = max(float((a - p.grad).abs().max()) for a, p in zip(shard_grads, net.parameters()))
+if rank == 0:
+    print(json.dumps({"ok_shard": ok_shard, "grad_err": err, "bucket": bucket.numel(), "world": world}))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_nccl_allreduce_and_shard_invariance(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, CSTR_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["ok_shard"] is True
+    assert res["grad_err"] < 1e-6 and res["bucket"] == 122_902 and res["world"] == 2
