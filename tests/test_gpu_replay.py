@@ -133,3 +133,36 @@ def test_buffer_ctor_contract(pkg):
     b = pkg.GpuReplayBuffer(100, device="auto", n_envs=3)
     assert b.buffer_size == 33 and b.obs_shape == (4,) and b.action_dim == 2 and b.device.type == "cuda"
     b.device = "cuda"  # load_replay_buffer assigns it (off_policy_algorithm.py:254)
+
+
+def test_bcq_dataset_10m_transitions(pkg):
+    """BASELINE config #4 shape: a 10,000,000-transition CSTR dataset (25,000 reactors x 400 steps of the tape kernel
+    with random actions) resident on the GPU in the n_envs=1 layout OfflineAlgorithm expects (640 MB of records);
+    size-independent properties + spot parity of sampled rows against the oracle step."""
+    import build_oracle as B
+
+    n, T = 25_000, 400
+    env = pkg.GpuCSTRVecEnv(n, seed=21, monitor=False)
+    env.reset()
+    obs0 = env.state.clone()
+    acts = torch.rand((T, n, 2), device="cuda") * 2 - 1
+    res = env.tape(T, acts, want_obs=True)
+    buf = pkg.GpuReplayBuffer(n * T, device="cuda", n_envs=1, index_mode="philox", seed=5)
+    assert buf.buffer_size == 10_000_000 and buf.records.numel() * 4 == 640_000_000
+    obs = torch.cat([obs0[None], res["obs"][:-1]], 0)  # observation before each step
+    rec = buf.records.view(T, n, 16)
+    rec[..., 0:4], rec[..., 4:8], rec[..., 8:10] = obs, res["obs"], acts
+    rec[..., 10], rec[..., 11], rec[..., 12] = res["rewards"], res["dones"].float(), res["dones"].float()
+    buf.pos, buf.full = 0, True
+    s = buf.sample(65_536)
+    assert s.observations.shape == (65_536, 4) and s.dones.shape == (65_536, 1)
+    assert float(s.dones.sum().item()) == 0.0  # every done in this dataset is a time-limit truncation: dones*(1-timeouts) == 0
+    assert float(s.observations.abs().max().item()) <= 1.0 and float(s.rewards.max().item()) <= 0.0
+    # sampled (obs, action) -> (next_obs, reward) must be the strict step, bit for bit (rows that are not the truncation row)
+    o, a = s.observations.cpu().numpy(), s.actions.cpu().numpy()
+    nx, r, _, _, _ = B.step_f32(o, a, np.zeros(len(o), np.int32), exp_mode=B.EXP_SHARED, sq_mode=B.SQ_MUL)
+    same = (nx == s.next_observations.cpu().numpy()).all(axis=1)
+    assert same.mean() > 0.995  # the ~1/400 truncation rows store the post-reset observation in this construction
+    assert np.array_equal(r[same], s.rewards.cpu().numpy()[same, 0])
+    small = buf.sample(256)  # the reference's batch size
+    assert small.actions.shape == (256, 2)
