@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 5
+#define CSTR_B200_ABI_VERSION 6
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -159,15 +159,22 @@ int cstr_replay_sample_philox(uint64_t seed, uint64_t draw, int64_t n_envs, int6
  *   actor_mode 0: fp32 CUDA-core actor (parity path)
  *   actor_mode 1: bf16 tcgen05 tensor-core hidden layer, fp32 accumulate (throughput path);
  *                 needs the packed weights from cstr_actor_pack_bf16.
- * noise: sigma * N(0,1) from Philox (stream "noise") when noise == NULL, else the (K,n,2) tensor.
+ * noise: TANH actors add sigma * N(0,1) exploration noise (NormalActionNoise) — from Philox (stream "noise") when
+ * noise == NULL, else the (K,n,2) tensor is added as is.  GAUSSIAN actors use the same source as their eps ~ N(0,1)
+ * (noise tensor = eps itself; sigma is ignored).
  * warmup != 0: uniform random actions instead of the actor (learning_starts phase, :386-388).
  * Each step writes ring row (pos0 + k) % rows of the replay records and leaves `state` at the
  * observation to act on next.  rows = ring capacity in rows.                                       */
+#define CSTR_ACTOR_TANH 0     /* TD3/DDPG actor: a = tanh(head)            core/td3/policies.py:75-78          */
+#define CSTR_ACTOR_GAUSSIAN 1 /* SAC actor: a = tanh(mu + exp(clamp(log_std,-20,2)) * eps), eps ~ N(0,1)
+                                 core/sac/policies.py:151-168, core/common/distributions.py:207-260           */
 typedef struct cstr_actor_f32 {
     const float *W1, *b1; /* (H1,4), (H1) */
     const float *W2, *b2; /* (H2,H1), (H2) */
-    const float *W3, *b3; /* (2,H2), (2)  */
+    const float *W3, *b3; /* TANH: (2,H2), (2).  GAUSSIAN: (4,H2), (4) = rows [mu_0, mu_1, log_std_0, log_std_1] */
     int32_t H1, H2;
+    int32_t kind;         /* CSTR_ACTOR_TANH | CSTR_ACTOR_GAUSSIAN */
+    int32_t reserved;
 } cstr_actor_f32;
 
 int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, int actor_mode,

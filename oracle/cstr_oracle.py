@@ -426,6 +426,19 @@ def actor_forward(obs: np.ndarray, weights) -> np.ndarray:
     return np.tanh(h)
 
 
+def sac_actor_forward(obs: np.ndarray, weights, eps: np.ndarray) -> np.ndarray:
+    """SAC squashed-Gaussian actor (core/sac/policies.py:151-168, distributions.py:207-260):
+    trunk = relu(W2 relu(W1 x + b1) + b2); mu, log_std heads; a = tanh(mu + exp(clamp(log_std,-20,2)) * eps).
+    ``weights`` = [(W1,b1),(W2,b2),(W3,b3)] with W3 (4,H2) = rows [mu_0, mu_1, log_std_0, log_std_1]."""
+    h = np.asarray(obs, np.float64)
+    for W, b in weights[:2]:
+        h = np.maximum(h @ np.asarray(W, np.float64).T + np.asarray(b, np.float64), 0.0)
+    W3, b3 = weights[2]
+    head = h @ np.asarray(W3, np.float64).T + np.asarray(b3, np.float64)
+    mu, log_std = head[:, :2], np.clip(head[:, 2:], -20.0, 2.0)
+    return np.tanh(mu + np.exp(log_std) * np.asarray(eps, np.float64))
+
+
 def sample_action_maps(mu: np.ndarray, noise: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """float32 chain for a Box(-1,1) action space: predict's unscale, _sample_action's scale,
     + noise, clip, unscale.  Returns (env_action, buffer_action)."""

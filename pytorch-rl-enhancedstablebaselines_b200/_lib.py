@@ -9,10 +9,11 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
+ACTOR_TANH, ACTOR_GAUSSIAN = 0, 1
 
 
 class CstrLibraryError(RuntimeError):
@@ -39,6 +40,7 @@ class ActorF32(Structure):
         ("W2", c_void_p), ("b2", c_void_p),
         ("W3", c_void_p), ("b3", c_void_p),
         ("H1", c_int32), ("H2", c_int32),
+        ("kind", c_int32), ("reserved", c_int32),
     ]
 
 

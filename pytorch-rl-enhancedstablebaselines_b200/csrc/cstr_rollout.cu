@@ -23,7 +23,7 @@ namespace cstr {
 constexpr int ROLL_M = 128;  // reactors per CTA
 constexpr int ROLL_NB = 12;  // layer-2 outputs per register pass
 
-template <int MODE>
+template <int MODE, int KIND>
 __global__ void __launch_bounds__(ROLL_M)
 rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, float sigma, const float2 *__restrict__ noise, int warmup,
                    uint32_t t_base, float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode,
@@ -63,7 +63,10 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
             }
             // each thread only reads back its own column m: no barrier needed between layers
             // ---- layer 2 + 3: out = W3 relu(W2 h1 + b2) + b3, 12 hidden units per pass
-            float o0 = __ldg(actor.b3), o1 = __ldg(actor.b3 + 1);
+            constexpr int NOUT = KIND == CSTR_ACTOR_GAUSSIAN ? 4 : 2;
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < NOUT; ++r) o[r] = __ldg(actor.b3 + r);
             for (int nb = 0; nb < H2; nb += ROLL_NB) {
                 float acc[ROLL_NB];
 #pragma unroll
@@ -91,18 +94,21 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
                 for (int q = 0; q < ROLL_NB; ++q) {
                     if (nb + q < H2) {
                         const float h = fmaxf(acc[q] + __ldg(actor.b2 + nb + q), 0.0f);
-                        o0 = fmaf(__ldg(actor.W3 + nb + q), h, o0);
-                        o1 = fmaf(__ldg(actor.W3 + H2 + nb + q), h, o1);
+#pragma unroll
+                        for (int r = 0; r < NOUT; ++r) o[r] = fmaf(__ldg(actor.W3 + (size_t)r * H2 + nb + q), h, o[r]);
                     }
                 }
             }
-            const float mu0 = tanhf(o0), mu1 = tanhf(o1);
             float2 nz;
             if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
+            else if (KIND == CSTR_ACTOR_GAUSSIAN) nz = philox_normal2(p.seed, env, g);
             else if (sigma != 0.0f) { nz = philox_normal2(p.seed, env, g); nz.x *= sigma; nz.y *= sigma; }
             else nz = make_float2(0.f, 0.f);
-            action_maps(mu0, nz.x, env_a.x, buf_a.x);
-            action_maps(mu1, nz.y, env_a.y, buf_a.y);
+            float mu0, mu1;
+            float2 add;
+            actor_head<KIND>(o, nz, mu0, mu1, add);
+            action_maps(mu0, add.x, env_a.x, buf_a.x);
+            action_maps(mu1, add.y, env_a.y, buf_a.y);
         }
         // ---- env step + transition record
         const float4 obs = s;
@@ -153,6 +159,7 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
         if (!actor || !actor->W1 || !actor->b1 || !actor->W2 || !actor->b2 || !actor->W3 || !actor->b3)
             return fail_arg(CSTR_EINVAL, "rollout: actor weights missing");
         if (actor->H1 <= 0 || actor->H2 <= 0 || (actor->H1 & 3)) return fail_arg(CSTR_EINVAL, "rollout: H1 must be a positive multiple of 4");
+        if (actor->kind != CSTR_ACTOR_TANH && actor->kind != CSTR_ACTOR_GAUSSIAN) return fail_arg(CSTR_EINVAL, "rollout: unknown actor kind");
         if (!aligned(actor->W1, 16) || !aligned(actor->W2, 16)) return fail_arg(CSTR_EALIGN, "rollout: W1/W2 16 B alignment");
     }
     if (n == 0 || K == 0) return 0;
@@ -166,15 +173,18 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
     if (smem > 227 * 1024) return fail_arg(CSTR_EINVAL, "rollout: H1 too large for the fp32 path (max 452)");
     const int grid = (int)((n + ROLL_M - 1) / ROLL_M);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (math_mode == CSTR_MATH_STRICT) {
-        if ((rc = check_cuda(cudaFuncSetAttribute(rollout_f32_kernel<CSTR_MATH_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))) return rc;
-        rollout_f32_kernel<CSTR_MATH_STRICT><<<grid, ROLL_M, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state,
-                                                                         step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum);
-    } else {
-        if ((rc = check_cuda(cudaFuncSetAttribute(rollout_f32_kernel<CSTR_MATH_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"))) return rc;
-        rollout_f32_kernel<CSTR_MATH_FAST><<<grid, ROLL_M, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state,
-                                                                       step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum);
-    }
+    int rc = 0;
+#define CSTR_LAUNCH_ROLL(MODE, KIND)                                                                                                       \
+    do {                                                                                                                                   \
+        rc = check_cuda(cudaFuncSetAttribute(rollout_f32_kernel<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
+        if (!rc)                                                                                                                           \
+            rollout_f32_kernel<MODE, KIND><<<grid, ROLL_M, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state, \
+                                                                       step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum); \
+    } while (0)
+    const bool gauss = a.kind == CSTR_ACTOR_GAUSSIAN;
+    if (math_mode == CSTR_MATH_STRICT) { if (gauss) CSTR_LAUNCH_ROLL(CSTR_MATH_STRICT, CSTR_ACTOR_GAUSSIAN); else CSTR_LAUNCH_ROLL(CSTR_MATH_STRICT, CSTR_ACTOR_TANH); }
+    else { if (gauss) CSTR_LAUNCH_ROLL(CSTR_MATH_FAST, CSTR_ACTOR_GAUSSIAN); else CSTR_LAUNCH_ROLL(CSTR_MATH_FAST, CSTR_ACTOR_TANH); }
+#undef CSTR_LAUNCH_ROLL
+    if (rc) return rc;
     return check_launch("rollout_f32_kernel");
 }

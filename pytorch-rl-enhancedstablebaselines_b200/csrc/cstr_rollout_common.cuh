@@ -29,6 +29,23 @@ __device__ __forceinline__ float2 philox_normal2(uint64_t seed, uint64_t env, ui
     return make_float2(rad * cs, rad * sn);
 }
 
+// Actor head -> squashed action in [-1,1] and the additive exploration noise that follows it.
+//   TANH (TD3):      a = tanh(o[0..1]);  noise = sigma*N(0,1) (or the caller's tensor)        td3/policies.py:75-78, noise.py:29-48
+//   GAUSSIAN (SAC):  a = tanh(mu + exp(clamp(log_std,-20,2))*eps), no additive noise          sac/policies.py:151-168
+template <int KIND>
+__device__ __forceinline__ void actor_head(const float o[4], float2 nz, float &a0, float &a1, float2 &add_noise) {
+    if (KIND == CSTR_ACTOR_TANH) {
+        a0 = tanhf(o[0]);
+        a1 = tanhf(o[1]);
+        add_noise = nz;
+    } else {
+        const float s0 = expf(clampf(o[2], -20.0f, 2.0f)), s1 = expf(clampf(o[3], -20.0f, 2.0f));
+        a0 = tanhf(fmaf(s0, nz.x, o[0]));
+        a1 = tanhf(fmaf(s1, nz.y, o[1]));
+        add_noise = make_float2(0.0f, 0.0f);
+    }
+}
+
 __device__ __forceinline__ void store_record(float4 *__restrict__ rec, float4 obs, float4 next_obs, float2 act, float reward, bool done) {
     rec[0] = obs;
     rec[1] = next_obs;

@@ -70,8 +70,8 @@ static bool make_geometry(int H1, int H2, TcGeometry &g) {
     g.off_w1 = 256;                                             // [0,256): mbarriers + tmem base
     g.off_a1 = up(g.off_w1 + 2u * H1 * 16);                     // W1 split-bf16 UMMA image [2][H1][8 x bf16]
     g.off_ep = up(g.off_a1 + 2u * TC_M * 16);                   // layer-1 A operand [2][128][8 x bf16]
-    g.off_part = up(g.off_ep + 3u * g.NP * 4);                  // b2, W3[0], W3[1] (zero padded)
-    g.off_a = up(g.off_part + 2 * 2 * TC_M * 2 * 4);            // layer-3 partial sums [step parity][half][m]
+    g.off_part = up(g.off_ep + 5u * g.NP * 4);                  // b2 and up to four W3 rows (zero padded)
+    g.off_a = up(g.off_part + 2 * 2 * TC_M * 4 * 4);            // layer-3 partial sums [step parity][half][m] x float4
     g.off_w = up(g.off_a + TC_ASTAGES * g.a_chunk_bytes);
     g.smem_bytes = up(g.off_w + TC_WSTAGES * g.w_chunk_bytes);
     return g.smem_bytes <= 227u * 1024u;
@@ -133,16 +133,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 8 hidden units of the layer-2/3 epilogue: h = relu(acc + b2); o += W3 * h
-__device__ __forceinline__ void epi8(const float v[8], float4 ba, float4 bb, float4 w0a, float4 w0b, float4 w1a, float4 w1b, float &o0, float &o1) {
+// 8 hidden units of the layer-2/3 epilogue: h = relu(acc + b2); o[r] += W3[r] * h for the NOUT head rows.
+// sep = [1 + NOUT][NP] floats (b2, then the W3 rows), col = first of the 8 columns (multiple of 8: 32-byte aligned).
+template <int NOUT>
+__device__ __forceinline__ void epi8(const float v[8], const float *sep, int NP, int col, float o[4]) {
+    const float4 *bv = reinterpret_cast<const float4 *>(sep + col);
+    const float4 ba = bv[0], bb = bv[1];
     const float b[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-    const float w0[8] = {w0a.x, w0a.y, w0a.z, w0a.w, w0b.x, w0b.y, w0b.z, w0b.w};
-    const float w1[8] = {w1a.x, w1a.y, w1a.z, w1a.w, w1b.x, w1b.y, w1b.z, w1b.w};
+    float h[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float h = fmaxf(v[q] + b[q], 0.0f);
-        o0 = fmaf(w0[q], h, o0);
-        o1 = fmaf(w1[q], h, o1);
+    for (int q = 0; q < 8; ++q) h[q] = fmaxf(v[q] + b[q], 0.0f);
+#pragma unroll
+    for (int r = 0; r < NOUT; ++r) {
+        const float4 *wv = reinterpret_cast<const float4 *>(sep + (size_t)(1 + r) * NP + col);
+        const float4 wa = wv[0], wb = wv[1];
+        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[r] = fmaf(w[q], h[q], o[r]);
     }
 }
 
@@ -165,7 +172,7 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
 // barrier slots inside the first 256 bytes of shared memory
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_FULL = 6, BAR_A_EMPTY = 8, BAR_D_FULL = 10, BAR_A1_FULL = 11, BAR_D1_FULL = 12, BAR_D1_EMPTY = 14, BAR_COUNT = 16 };
 
-template <int MODE>
+template <int MODE, int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, const uint8_t *__restrict__ packed_w2, TcGeometry g,
                   float sigma, const float2 *__restrict__ noise, uint32_t t_base, float4 *__restrict__ state,
@@ -175,8 +182,9 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bars = smem_base;  // BAR_COUNT x 8 bytes
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 128);
-    float *sep = reinterpret_cast<float *>(smem + g.off_ep);     // [3][NP]: b2, W3 row 0, W3 row 1
-    float2 *spart = reinterpret_cast<float2 *>(smem + g.off_part);
+    constexpr int NOUT = KIND == CSTR_ACTOR_GAUSSIAN ? 4 : 2;
+    float *sep = reinterpret_cast<float *>(smem + g.off_ep);     // [1 + NOUT][NP]: b2, then the W3 rows
+    float4 *spart = reinterpret_cast<float4 *>(smem + g.off_part);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H1 = g.H1, NP = g.NP;
 
@@ -215,8 +223,8 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
     for (int j = tid; j < NP; j += TC_THREADS) {
         const bool in = j < g.H2;
         sep[0 * NP + j] = in ? __ldg(actor.b2 + j) : 0.0f;
-        sep[1 * NP + j] = in ? __ldg(actor.W3 + j) : 0.0f;
-        sep[2 * NP + j] = in ? __ldg(actor.W3 + g.H2 + j) : 0.0f;
+#pragma unroll
+        for (int r = 0; r < NOUT; ++r) sep[(1 + r) * NP + j] = in ? __ldg(actor.W3 + (size_t)r * g.H2 + j) : 0.0f;
     }
     fence_proxy_async();  // the W1 image above is read by the tensor core (async proxy)
     tc_fence_before();
@@ -234,7 +242,9 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         float4 s = live ? state[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         int sc = live ? step_count[i] : 0, ep = live ? episode[i] : 0;
         const uint64_t env = (uint64_t)(p.env_offset + i);
-        const float b3x = __ldg(actor.b3), b3y = __ldg(actor.b3 + 1);
+        float b3[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < NOUT; ++r) b3[r] = __ldg(actor.b3 + r);
         double acc_r = 0.0;
         double sb[4] = {0.0, 0.0, 0.0, 0.0};
         if (static_base && live) {
@@ -266,6 +276,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             }
             float2 nz;  // exploration noise does not depend on the actor: drawn here, while the first MMAs are in flight
             if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
+            else if (KIND == CSTR_ACTOR_GAUSSIAN) nz = philox_normal2(p.seed, env, gstep);  // eps ~ N(0,1) of the squashed Gaussian
             else if (sigma != 0.0f) { nz = philox_normal2(p.seed, env, gstep); nz.x *= sigma; nz.y *= sigma; }
             else nz = make_float2(0.f, 0.f);
             // ---- ... then turn each layer-1 accumulator chunk (TMEM) into the bf16 A operand of layer 2 (relu + pack) ---
@@ -308,7 +319,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             // ---- (b) epilogue: TMEM row -> b2, relu, W3 --------------------------------------------------
             mbar_wait(bars + 8 * BAR_D_FULL, (uint32_t)(k & 1));
             tc_fence_after();
-            float o0 = 0.0f, o1 = 0.0f;
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
             const int c_begin = half * cols_per_half;
             const uint32_t d2 = tmem_base + lane_base + (uint32_t)c_begin;
             float va[8], vb[8];
@@ -316,28 +327,27 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             for (int c = 0; c < cols_per_half; c += 16) {  // two 8-column groups per trip, loads one group ahead of the math
                 tmem_ld_wait();
                 if (c + 8 < cols_per_half) tmem_ld8(d2 + (uint32_t)(c + 8), vb);
-                // constants as 16-byte broadcast loads (c_begin and c are multiples of 8 floats: 32-byte aligned); scalar
-                // LDS here made the epilogue shared-memory-issue bound (24 wavefronts per 8 columns and warp)
-                const float4 *b2v = reinterpret_cast<const float4 *>(sep + c_begin + c);
-                const float4 *w0v = reinterpret_cast<const float4 *>(sep + NP + c_begin + c);
-                const float4 *w1v = reinterpret_cast<const float4 *>(sep + 2 * NP + c_begin + c);
-                epi8(va, b2v[0], b2v[1], w0v[0], w0v[1], w1v[0], w1v[1], o0, o1);
+                // constants come as 16-byte broadcast loads (scalar LDS made the epilogue shared-memory-issue bound)
+                epi8<NOUT>(va, sep, NP, c_begin + c, o);
                 if (c + 8 < cols_per_half) {
                     tmem_ld_wait();
                     if (c + 16 < cols_per_half) tmem_ld8(d2 + (uint32_t)(c + 16), va);
-                    epi8(vb, b2v[2], b2v[3], w0v[2], w0v[3], w1v[2], w1v[3], o0, o1);
+                    epi8<NOUT>(vb, sep, NP, c_begin + c + 8, o);
                 }
             }
             tc_fence_before();  // TMEM reads are complete before anybody re-arms the accumulator
-            float2 *sp = spart + (size_t)(k & 1) * (2 * TC_M);  // double-buffered by step parity: one barrier per step
-            sp[half * TC_M + m] = make_float2(o0, o1);
+            float4 *sp = spart + (size_t)(k & 1) * (2 * TC_M);  // double-buffered by step parity: one barrier per step
+            sp[half * TC_M + m] = make_float4(o[0], o[1], o[2], o[3]);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float2 p0 = sp[m], p1 = sp[TC_M + m];
-            const float mu0 = tanhf((p0.x + p1.x) + b3x), mu1 = tanhf((p0.y + p1.y) + b3y);  // same order in both threads
+            const float4 p0 = sp[m], p1 = sp[TC_M + m];
+            const float head[4] = {(p0.x + p1.x) + b3[0], (p0.y + p1.y) + b3[1], (p0.z + p1.z) + b3[2], (p0.w + p1.w) + b3[3]};  // same order in both threads
+            float mu0, mu1;
+            float2 add;
+            actor_head<KIND>(head, nz, mu0, mu1, add);
             // ---- (c) noise, action maps, env step, record (both threads of a pair compute, half 0 stores) ---
             float2 env_a, buf_a;
-            action_maps(mu0, nz.x, env_a.x, buf_a.x);
-            action_maps(mu1, nz.y, env_a.y, buf_a.y);
+            action_maps(mu0, add.x, env_a.x, buf_a.x);
+            action_maps(mu1, add.y, env_a.y, buf_a.y);
             const float4 obs = s;
             const StepResult r = (MODE == CSTR_MATH_STRICT) ? step_strict_f32(s, env_a, sc, (float)p.target_c2, p.max_steps)
                                                             : step_fast_f32(s, env_a, sc, (float)p.target_c2, p.max_steps);
@@ -478,18 +488,20 @@ int cstr_rollout_tc_launch(const cstr_env_params *p, int64_t n, int64_t K, int m
     if ((int64_t)K * g.NKC >= (int64_t)1 << 31) return fail_arg(CSTR_EINVAL, "rollout(tc): K too large");
     const int grid = (int)((n + TC_M - 1) / TC_M);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (math_mode == CSTR_MATH_STRICT) {
-        if ((rc = check_cuda(cudaFuncSetAttribute(rollout_tc_kernel<CSTR_MATH_STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes), "smem attr"))) return rc;
-        rollout_tc_kernel<CSTR_MATH_STRICT><<<grid, TC_THREADS, g.smem_bytes, st>>>(*p, n, K, *actor, (const uint8_t *)packed_bf16, g, sigma, (const float2 *)noise,
-                                                                                    t_base, (float4 *)state, step_count, episode, static_base, rows, pos0,
-                                                                                    (float4 *)records, reward_sum);
-    } else {
-        if ((rc = check_cuda(cudaFuncSetAttribute(rollout_tc_kernel<CSTR_MATH_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes), "smem attr"))) return rc;
-        rollout_tc_kernel<CSTR_MATH_FAST><<<grid, TC_THREADS, g.smem_bytes, st>>>(*p, n, K, *actor, (const uint8_t *)packed_bf16, g, sigma, (const float2 *)noise,
-                                                                                  t_base, (float4 *)state, step_count, episode, static_base, rows, pos0,
-                                                                                  (float4 *)records, reward_sum);
-    }
+    int rc = 0;
+#define CSTR_LAUNCH_TC(MODE, KIND)                                                                                                          \
+    do {                                                                                                                                    \
+        rc = check_cuda(cudaFuncSetAttribute(rollout_tc_kernel<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes), "smem attr"); \
+        if (!rc)                                                                                                                            \
+            rollout_tc_kernel<MODE, KIND><<<grid, TC_THREADS, g.smem_bytes, st>>>(*p, n, K, *actor, (const uint8_t *)packed_bf16, g, sigma, (const float2 *)noise, \
+                                                                                  t_base, (float4 *)state, step_count, episode, static_base, rows, pos0,   \
+                                                                                  (float4 *)records, reward_sum);                          \
+    } while (0)
+    const bool gauss = actor->kind == CSTR_ACTOR_GAUSSIAN;
+    if (math_mode == CSTR_MATH_STRICT) { if (gauss) CSTR_LAUNCH_TC(CSTR_MATH_STRICT, CSTR_ACTOR_GAUSSIAN); else CSTR_LAUNCH_TC(CSTR_MATH_STRICT, CSTR_ACTOR_TANH); }
+    else { if (gauss) CSTR_LAUNCH_TC(CSTR_MATH_FAST, CSTR_ACTOR_GAUSSIAN); else CSTR_LAUNCH_TC(CSTR_MATH_FAST, CSTR_ACTOR_TANH); }
+#undef CSTR_LAUNCH_TC
+    if (rc) return rc;
     return check_launch("rollout_tc_kernel");
 }
 

@@ -17,40 +17,75 @@ from .env import _MATH, GpuCSTRVecEnv
 
 
 class ActorWeights:
-    """fp32 weights of ``tanh(W3 relu(W2 relu(W1 x + b1) + b2) + b3)`` on the device, torch Linear layout
-    (out,in) — the ``mu`` Sequential of the TD3 ``Actor`` (core/td3/policies.py:20-83)."""
+    """fp32 weights of a 4 -> H1 -> H2 -> head actor on the device, torch Linear layout (out,in).
 
-    def __init__(self, W1, b1, W2, b2, W3, b3, device="cuda"):
+    ``kind="tanh"``     TD3/DDPG: ``tanh(W3 relu(W2 relu(W1 x + b1) + b2) + b3)`` — the ``mu`` Sequential of the TD3
+                        ``Actor`` (core/td3/policies.py:20-83); W3 is (2,H2).
+    ``kind="gaussian"`` SAC: ``tanh(mu + exp(clamp(log_std,-20,2)) * eps)`` on the trunk ``latent_pi`` with heads ``mu`` and
+                        ``log_std`` (core/sac/policies.py:25-178); W3 is (4,H2) = rows [mu_0, mu_1, log_std_0, log_std_1].
+    """
+
+    def __init__(self, W1, b1, W2, b2, W3, b3, device="cuda", kind: str = "tanh"):
         torch = _lib.require_cuda()
         dev = torch.device(device)
+        if kind not in ("tanh", "gaussian"):
+            raise ValueError("kind must be 'tanh' or 'gaussian'")
 
         def put(x):
             return torch.as_tensor(x).detach().to(device=dev, dtype=torch.float32).contiguous()
 
         self.W1, self.b1, self.W2, self.b2, self.W3, self.b3 = (put(x) for x in (W1, b1, W2, b2, W3, b3))
         self.H1, self.H2 = int(self.W1.shape[0]), int(self.W2.shape[0])
-        if tuple(self.W1.shape) != (self.H1, 4) or tuple(self.W2.shape) != (self.H2, self.H1) or tuple(self.W3.shape) != (2, self.H2):
-            raise ValueError("actor must be 4 -> H1 -> H2 -> 2")
+        self.kind = kind
+        n_out = 2 if kind == "tanh" else 4
+        if (tuple(self.W1.shape) != (self.H1, 4) or tuple(self.W2.shape) != (self.H2, self.H1) or tuple(self.W3.shape) != (n_out, self.H2)
+                or tuple(self.b3.shape) != (n_out,)):
+            raise ValueError(f"actor must be 4 -> H1 -> H2 -> {n_out}")
         if self.H1 % 4:
             raise ValueError("H1 must be a multiple of 4")
         self.device = dev
         self.packed_bf16 = None
         self._struct = _lib.ActorF32(W1=self.W1.data_ptr(), b1=self.b1.data_ptr(), W2=self.W2.data_ptr(), b2=self.b2.data_ptr(),
-                                     W3=self.W3.data_ptr(), b3=self.b3.data_ptr(), H1=self.H1, H2=self.H2)
+                                     W3=self.W3.data_ptr(), b3=self.b3.data_ptr(), H1=self.H1, H2=self.H2,
+                                     kind=_lib.ACTOR_TANH if kind == "tanh" else _lib.ACTOR_GAUSSIAN, reserved=0)
+
+    @staticmethod
+    def _linears(module):
+        return [m for m in module.modules() if hasattr(m, "weight") and getattr(m, "weight").dim() == 2]
 
     @classmethod
     def from_module(cls, mu_sequential, device="cuda") -> "ActorWeights":
-        """From the reference actor's ``mu`` ``nn.Sequential`` (Linear, ReLU, Linear, ReLU, Linear, Tanh)."""
-        lin = [m for m in mu_sequential if hasattr(m, "weight")]
+        """From the reference TD3 actor's ``mu`` ``nn.Sequential`` (Linear, ReLU, Linear, ReLU, Linear, Tanh)."""
+        lin = cls._linears(mu_sequential)
         if len(lin) != 3:
             raise ValueError("expected three Linear layers")
         return cls(lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias, device=device)
 
-    def refresh_from_module(self, mu_sequential) -> None:
-        """Copy updated parameters in place (device-to-device) after an optimiser step."""
-        lin = [m for m in mu_sequential if hasattr(m, "weight")]
-        for dst, src in zip((self.W1, self.b1, self.W2, self.b2, self.W3, self.b3),
-                            (lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)):
+    @classmethod
+    def from_sac_actor(cls, latent_pi, mu, log_std, device="cuda") -> "ActorWeights":
+        """From the reference SAC ``Actor``: ``actor.latent_pi`` (Linear, ReLU, Linear, ReLU), ``actor.mu``, ``actor.log_std``."""
+        torch = _lib.require_cuda()
+        lin = cls._linears(latent_pi)
+        if len(lin) != 2:
+            raise ValueError("expected a two-layer trunk")
+        W3 = torch.cat([mu.weight.detach(), log_std.weight.detach()], 0)
+        b3 = torch.cat([mu.bias.detach(), log_std.bias.detach()], 0)
+        return cls(lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, W3, b3, device=device, kind="gaussian")
+
+    def _sources(self, *modules):
+        torch = _lib.require_cuda()
+        if self.kind == "tanh":
+            lin = self._linears(modules[0])
+            return [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias]
+        latent_pi, mu, log_std = modules
+        lin = self._linears(latent_pi)
+        return [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, torch.cat([mu.weight.detach(), log_std.weight.detach()], 0),
+                torch.cat([mu.bias.detach(), log_std.bias.detach()], 0)]
+
+    def refresh_from_module(self, *modules) -> None:
+        """Copy updated parameters in place (device-to-device) after an optimiser step: ``refresh_from_module(actor.mu)``
+        for TD3, ``refresh_from_module(actor.latent_pi, actor.mu, actor.log_std)`` for SAC."""
+        for dst, src in zip((self.W1, self.b1, self.W2, self.b2, self.W3, self.b3), self._sources(*modules)):
             dst.copy_(src.detach(), non_blocking=True)
         if self.packed_bf16 is not None:
             self.pack_bf16()
@@ -75,7 +110,8 @@ class FusedRollout:
     """Collects transitions from ``env`` straight into ``buffer`` with the fused kernel.
 
     :param actor_mode: ``"fp32"`` (CUDA-core parity path) or ``"tc"`` (bf16 tcgen05 hidden layer).
-    :param sigma: std of the Gaussian exploration noise (``NormalActionNoise``, noise.py:29-48).
+    :param sigma: std of the Gaussian exploration noise (``NormalActionNoise``, noise.py:29-48); ignored for
+        ``kind="gaussian"`` actors, whose only randomness is their own eps ~ N(0,1).
     """
 
     def __init__(self, env: GpuCSTRVecEnv, buffer: GpuReplayBuffer, actor: Optional[ActorWeights] = None, sigma: float = 0.1,

@@ -148,3 +148,46 @@ def test_td3_example_learns_end_to_end():
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["updates"] == 240 and res["transitions"] == 30 * 8 * 32768
     assert res["mean_reward_last"] > res["mean_reward_first"] + 0.05, res
+
+
+@pytest.mark.parametrize("actor_mode,atol", [("fp32", 3e-6), ("tc", 5e-3)])
+def test_sac_gaussian_actor_rollout(pkg, actor_mode, atol):
+    """SAC-shaped actor (4-256-256, mu/log_std heads, tanh-squashed Gaussian) in the fused rollout, eps injected."""
+    torch.manual_seed(3)
+    trunk = torch.nn.Sequential(torch.nn.Linear(4, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU())
+    mu, log_std = torch.nn.Linear(256, 2), torch.nn.Linear(256, 2)
+    with torch.no_grad():
+        log_std.bias.add_(-1.0)
+    actor = pkg.ActorWeights.from_sac_actor(trunk, mu, log_std)
+    assert actor.kind == "gaussian" and tuple(actor.W3.shape) == (4, 256)
+    n, K = 128 * 3 + 5, 2
+    env = pkg.GpuCSTRVecEnv(n, seed=2, monitor=False)
+    env.reset()
+    buf = pkg.GpuReplayBuffer(8 * n, device="cuda", n_envs=n)
+    eps = np.random.default_rng(0).standard_normal((K, n, 2)).astype(np.float32)
+    state = env.state.cpu().numpy().copy()
+    pkg.FusedRollout(env, buf, actor, sigma=0.3, actor_mode=actor_mode).collect(K, noise=torch.as_tensor(eps, device="cuda"))
+    rec = buf.records.cpu().numpy()
+    lin = [m for m in trunk if isinstance(m, torch.nn.Linear)]
+    w = [(lin[0].weight.detach().numpy(), lin[0].bias.detach().numpy()), (lin[1].weight.detach().numpy(), lin[1].bias.detach().numpy()),
+         (np.concatenate([mu.weight.detach().numpy(), log_std.weight.detach().numpy()]), np.concatenate([mu.bias.detach().numpy(), log_std.bias.detach().numpy()]))]
+    sc = np.zeros(n, np.int32)
+    for k in range(K):
+        assert np.array_equal(rec[k, :, 0:4], state)
+        a = O.sac_actor_forward(state, w, eps[k]).astype(np.float32)
+        _, a_buf = O.sample_action_maps(a, np.zeros_like(a))  # SAC adds no action noise (sigma is ignored)
+        np.testing.assert_allclose(rec[k, :, 8:10], a_buf, rtol=0, atol=atol)
+        # reference torch actor on the same eps (distributions.py): tanh(mean + std * eps)
+        with torch.no_grad():
+            lat = trunk(torch.as_tensor(state))
+            ref = torch.tanh(mu(lat) + torch.exp(torch.clamp(log_std(lat), -20, 2)) * torch.as_tensor(eps[k])).numpy()
+        np.testing.assert_allclose(rec[k, :, 8:10], ref, rtol=0, atol=max(atol, 5e-6))
+        state, r, tr, sc, _ = B.step_f32(state, _env_action_from_buffer_action(rec[k, :, 8:10]), sc, exp_mode=B.EXP_SHARED, sq_mode=B.SQ_MUL)
+        assert np.array_equal(rec[k, :, 4:8], state) and np.array_equal(rec[k, :, 10], r)
+    # Philox eps: the spread of the stored action around the deterministic one matches std = exp(log_std)
+    env2 = pkg.GpuCSTRVecEnv(128 * 64, seed=9, monitor=False)
+    env2.reset()
+    buf2 = pkg.GpuReplayBuffer(2 * env2.num_envs, device="cuda", n_envs=env2.num_envs)
+    pkg.FusedRollout(env2, buf2, actor, actor_mode=actor_mode).collect(1)
+    a2 = buf2.records[0, :, 8:10].cpu().numpy()
+    assert np.abs(a2).max() <= 1.0 and 0.05 < a2.std() < 1.0
