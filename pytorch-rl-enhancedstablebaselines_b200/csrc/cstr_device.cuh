@@ -332,9 +332,13 @@ __device__ __forceinline__ StepResult step_fast_raw(float4 &x, float2 a, bool ba
     const float nT2 = clampf(fmaf(dT2, DT, T2), CSTR_SLO_T, CSTR_SHI_T);
     const float nerr = fabsf(nC2 - target) * 2.5f;
     const float conc = nerr * fmaf(-5.0f, nerr, -2.0f);
-    float tp = 0.0f;
-    tp -= nT1 < 280.0f ? (280.0f - nT1) * (0.2f / 280.0f) : (nT1 > 350.0f ? (nT1 - 350.0f) * (0.5f / 350.0f) : 0.0f);
-    tp -= nT2 < 280.0f ? (280.0f - nT2) * (0.2f / 280.0f) : (nT2 > 350.0f ? (nT2 - 350.0f) * (0.5f / 350.0f) : 0.0f);
+    // soft temperature constraints (:331-341) without branches: 0.2*(280-T)/280 below 280 K, 0.5*(T-350)/350 above 350 K
+    const float CLO = 0.2f / 280.0f, CHI = 0.5f / 350.0f;
+    float pen = CLO * fmaxf(280.0f - nT1, 0.0f);
+    pen = fmaf(CHI, fmaxf(nT1 - 350.0f, 0.0f), pen);
+    pen = fmaf(CLO, fmaxf(280.0f - nT2, 0.0f), pen);
+    pen = fmaf(CHI, fmaxf(nT2 - 350.0f, 0.0f), pen);
+    const float tp = -pen;
     out.reward = bad ? -10.0f : fmaf(0.5f, tp, conc);
     out.truncated = bad | (step_count >= max_steps);
     out.bad = bad;

@@ -151,94 +151,131 @@ __device__ __forceinline__ void block_sum_to(double v, double *dst) {
 // After the first step the register state is always "in the box" (it is either this kernel's own
 // output or a fresh reset: a bad/NaN row truncates and is reset at once), so the loop runs the
 // clamp-free cores; strict keeps the normalised state, fast keeps the RAW state across steps.
-constexpr int TAPE_PF = 8;  // actions in flight per thread (cp.async depth)
+constexpr int TAPE_PF = 8;  // action loads in flight per thread
 
-__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// Per-thread cursor of the tape kernel: everything one control interval touches, passed by reference so the
+// unrolled loops below share one definition of "a step".
+struct TapeCursor {
+    float4 s;        // strict: normalised state; fast: RAW state
+    int sc, ep;
+    bool bad_state, unboxed;
+    double acc;
+    const float2 *pa;  // next action to prefetch for this thread
+    float *pr;         // this step's reward slot
+    uint8_t *pd;       // this step's done slot
+    float4 *po;        // this step's obs slot
+};
+
+template <int MODE, bool CHECK, bool SUM, bool OBS>
+__device__ __forceinline__ void tape_step(const cstr_env_params &p, int64_t i, int64_t n, float target, double *static_base, float2 a,
+                                          TapeCursor &c, bool has_r, bool has_d) {
+    StepResult r;
+    if (MODE == MODE_STRICT) {
+        // a state that did not come out of step_strict_core may lie outside the box (caller-injected, or a static-mode
+        // reset, which the reference does not clip: twoseriescstr.py:245-253) -> clamp it on first use
+        float4 sx = c.s;
+        if (c.unboxed) sx = clamp_unit4(c.s);
+        r = step_strict_core<CHECK>(c.s, sx, a, c.bad_state, c.sc, target, p.max_steps);
+        c.unboxed = r.bad;  // a bad row keeps its (possibly unboxed) state
+    } else {
+        r = step_fast_raw<CHECK>(c.s, a, c.bad_state, c.sc, target, p.max_steps);
+    }
+    c.bad_state = false;
+    if (has_r) *c.pr = r.reward;
+    if (has_d) *c.pd = (uint8_t)r.truncated;
+    if (SUM) c.acc += (double)r.reward;
+    bool wrote_obs = false;
+    if (r.truncated) {
+        c.s = reset_f32_env(p, i, c.ep, static_base);
+        if (OBS && MODE != MODE_STRICT) { *c.po = c.s; wrote_obs = true; }
+        if (MODE != MODE_STRICT) c.s = fast_denorm(c.s);
+        c.unboxed = p.init_mode != CSTR_INIT_RANDOM;
+        c.sc = 0;
+    }
+    if (OBS && !wrote_obs) *c.po = (MODE == MODE_STRICT) ? c.s : fast_norm(c.s);
+    c.pr += n;
+    c.pd += n;
+    if (OBS) c.po += n;
 }
 
+// SUM / OBS are compile-time so the common launch (rewards + dones only) carries no dead work.
+// After the first step the register state is always "in the box" (it is either this kernel's own
+// output or a fresh reset: a bad/NaN row truncates and is reset at once), so the loop runs the
+// clamp-free cores; strict keeps the normalised state, fast keeps the RAW state across steps.
+//
+// Action prefetch: a step is only ~100-240 instructions and a scheduler holds 3-4 warps at 65,536 reactors, so
+// every thread keeps TAPE_PF action loads in flight in a REGISTER ring.  The main loop is unrolled by TAPE_PF with
+// unconditional refills, which makes every ring slot a fixed register (a rolled loop with predicated refills made
+// ptxas copy each freshly loaded value at once and exposed the full HBM latency: 70 % long-scoreboard stalls);
+// the last <= 2*TAPE_PF-1 steps run through a guarded copy of the same body.
 template <int MODE, bool PHILOX, bool SUM, bool OBS>
 __global__ void __launch_bounds__(256)
-tape_f32_kernel(cstr_env_params p, int64_t n, int64_t T, const float2 *__restrict__ actions, uint32_t t_base,
+tape_f32_kernel(cstr_env_params p, int64_t n, int64_t T64, const float2 *__restrict__ actions, uint32_t t_base,
                 float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode, double *static_base,
-                float *__restrict__ rewards, uint8_t *__restrict__ dones, float4 *__restrict__ obs_tape, double *reward_sum) {
+                float *__restrict__ rewards, uint8_t *__restrict__ dones, float4 *__restrict__ obs_tape, double *reward_sum, float target) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
-    double acc = 0.0;
+    const int T = (int)T64;
+    TapeCursor c;
+    c.acc = 0.0;
     if (live) {
-        float4 s = state[i];
-        bool bad_state = any_nan4(s);
-        if (MODE != MODE_STRICT) s = fast_denorm(s);  // fast: RAW state in registers (clipped); strict: normalised
-        // strict: a state that did not come out of step_strict_core may lie outside the box (caller-injected, or a
-        // static-mode reset, which the reference does not clip: twoseriescstr.py:245-253) -> clamp it on first use
-        bool unboxed = true;
-        int sc = step_count[i], ep = episode[i];
-        const uint64_t env = (uint64_t)(p.env_offset + i);
-        const float target = (float)p.target_c2;
-        uint4 cache = make_uint4(0, 0, 0, 0);
-        // Action staging: each thread cp.async's its own 8-byte action of step t+TAPE_PF into a private
-        // shared-memory slot (LDGSTS: no registers tied up, no dependent MOV), so TAPE_PF loads per thread
-        // are always in flight.  A step is only ~110-230 instructions and a scheduler holds 3-4 warps at
-        // 65,536 reactors, so without this every step would expose the ~800-cycle HBM latency
-        // (measured: 70 % of stall samples were long-scoreboard on the register-ring variant).
-        // The slot being refilled (t+TAPE_PF) is never the one being read (ring of TAPE_PF+1): no WAR hazard,
-        // and every slot is private to its thread: no barrier.
-        extern __shared__ float2 stage[];
-        const int tid = threadIdx.x, bdim = blockDim.x;
-        if (!PHILOX) {
-#pragma unroll
-            for (int d = 0; d < TAPE_PF; ++d) {
-                if (d < T) cp_async_8(&stage[d * bdim + tid], &actions[(int64_t)d * n + i]);
-                cp_async_commit();
-            }
-        }
-        int slot_rd = 0, slot_wr = TAPE_PF;
-        for (int64_t t = 0; t < T; ++t) {
-            float2 a;
-            if (PHILOX) {
+        c.s = state[i];
+        c.bad_state = any_nan4(c.s);
+        if (MODE != MODE_STRICT) c.s = fast_denorm(c.s);  // fast: RAW state in registers (clipped); strict: normalised
+        c.unboxed = true;
+        c.sc = step_count[i];
+        c.ep = episode[i];
+        const bool has_r = rewards != nullptr, has_d = dones != nullptr;
+        c.pr = rewards + i;
+        c.pd = dones + i;
+        c.po = obs_tape + i;
+        if (PHILOX) {
+            const uint64_t env = (uint64_t)(p.env_offset + i);
+            uint4 cache = make_uint4(0, 0, 0, 0);
+            for (int t = 0; t < T; ++t) {
                 const uint32_t g = t_base + (uint32_t)t;
-                a = philox_action(p.seed, env, g, cache, t == 0 || (g & 1u) == 0);
-            } else {
-                cp_async_wait<TAPE_PF - 1>();
-                a = stage[slot_rd * bdim + tid];
-                if (t + TAPE_PF < T) cp_async_8(&stage[slot_wr * bdim + tid], &actions[(t + TAPE_PF) * n + i]);
-                cp_async_commit();
-                slot_rd = (slot_rd == TAPE_PF) ? 0 : slot_rd + 1;
-                slot_wr = (slot_wr == TAPE_PF) ? 0 : slot_wr + 1;
+                const float2 a = philox_action(p.seed, env, g, cache, t == 0 || (g & 1u) == 0);
+                tape_step<MODE, false, SUM, OBS>(p, i, n, target, static_base, a, c, has_r, has_d);
             }
-            StepResult r;
-            if (MODE == MODE_STRICT) {
-                float4 sx = s;
-                if (unboxed) sx = clamp_unit4(s);
-                r = step_strict_core<!PHILOX>(s, sx, a, bad_state, sc, target, p.max_steps);
-                unboxed = r.bad;  // a bad row keeps its (possibly unboxed) state
-            } else {
-                r = step_fast_raw<!PHILOX>(s, a, bad_state, sc, target, p.max_steps);
+        } else {
+            float2 ring[TAPE_PF];
+            c.pa = actions + i;
+#pragma unroll
+            for (int j = 0; j < TAPE_PF; ++j) {
+                ring[j] = (j < T) ? *c.pa : make_float2(0.f, 0.f);
+                if (j + 1 < T) c.pa += n;  // ends up pointing at step min(TAPE_PF, T-1)... only dereferenced when in range
             }
-            bad_state = false;
-            if (rewards) rewards[t * n + i] = r.reward;
-            if (dones) dones[t * n + i] = (uint8_t)r.truncated;
-            if (SUM) acc += (double)r.reward;
-            if (r.truncated) {
-                s = reset_f32_env(p, i, ep, static_base);
-                if (OBS && MODE != MODE_STRICT) obs_tape[t * n + i] = s;
-                if (MODE != MODE_STRICT) s = fast_denorm(s);
-                unboxed = p.init_mode != CSTR_INIT_RANDOM;
-                sc = 0;
-                if (OBS && MODE != MODE_STRICT) continue;
+            int t = 0;
+            // full groups: every refill t+TAPE_PF+j (j < TAPE_PF) is in range  <=>  t + 2*TAPE_PF <= T
+            for (; t + 2 * TAPE_PF <= T; t += TAPE_PF) {
+#pragma unroll
+                for (int j = 0; j < TAPE_PF; ++j) {
+                    const float2 a = ring[j];
+                    ring[j] = *c.pa;  // action of step t + TAPE_PF + j
+                    c.pa += n;
+                    tape_step<MODE, true, SUM, OBS>(p, i, n, target, static_base, a, c, has_r, has_d);
+                }
             }
-            if (OBS) obs_tape[t * n + i] = (MODE == MODE_STRICT) ? s : fast_norm(s);
+            // tail: fewer than 2*TAPE_PF steps left; refills are guarded
+            for (; t < T; t += TAPE_PF) {
+#pragma unroll
+                for (int j = 0; j < TAPE_PF; ++j) {
+                    if (t + j < T) {
+                        const float2 a = ring[j];
+                        if (t + TAPE_PF + j < T) {
+                            ring[j] = *c.pa;
+                            if (t + TAPE_PF + j + 1 < T) c.pa += n;
+                        }
+                        tape_step<MODE, true, SUM, OBS>(p, i, n, target, static_base, a, c, has_r, has_d);
+                    }
+                }
+            }
         }
-        state[i] = (MODE == MODE_STRICT) ? s : fast_norm(s);
-        step_count[i] = sc;
-        episode[i] = ep;
+        state[i] = (MODE == MODE_STRICT) ? c.s : fast_norm(c.s);
+        step_count[i] = c.sc;
+        episode[i] = c.ep;
     }
-    if (SUM) block_sum_to(acc, reward_sum);
+    if (SUM) block_sum_to(c.acc, reward_sum);
 }
 
 template <bool PHILOX>
@@ -407,8 +444,8 @@ int cstr_tape_f32(const cstr_env_params *p, int64_t n, int64_t T, int math_mode,
     env_launch_geometry(n, grid, block);
     cudaStream_t st = (cudaStream_t)stream;
 #define CSTR_LAUNCH_TAPE(MODE, PH, SUM, OBS)                                                                                     \
-    tape_f32_kernel<MODE, PH, SUM, OBS><<<grid, block, PH ? 0 : (TAPE_PF + 1) * block * sizeof(float2), st>>>(*p, n, T, (const float2 *)actions, t_base, (float4 *)state, step_count, \
-                                                                episode, static_base, rewards, dones, (float4 *)obs_tape, reward_sum)
+    tape_f32_kernel<MODE, PH, SUM, OBS><<<grid, block, 0, st>>>(*p, n, T, (const float2 *)actions, t_base, (float4 *)state, step_count, \
+                                                                episode, static_base, rewards, dones, (float4 *)obs_tape, reward_sum, (float)p->target_c2)
 #define CSTR_TAPE_FLAGS(MODE, PH)                                         \
     do {                                                                  \
         if (reward_sum) {                                                 \
