@@ -209,7 +209,7 @@ __device__ __forceinline__ void tape_step(const cstr_env_params &p, int64_t i, i
 // ptxas copy each freshly loaded value at once and exposed the full HBM latency: 70 % long-scoreboard stalls);
 // the last <= 2*TAPE_PF-1 steps run through a guarded copy of the same body.
 template <int MODE, bool PHILOX, bool SUM, bool OBS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 tape_f32_kernel(cstr_env_params p, int64_t n, int64_t T64, const float2 *__restrict__ actions, uint32_t t_base,
                 float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode, double *static_base,
                 float *__restrict__ rewards, uint8_t *__restrict__ dones, float4 *__restrict__ obs_tape, double *reward_sum, float target) {
@@ -246,15 +246,21 @@ tape_f32_kernel(cstr_env_params p, int64_t n, int64_t T64, const float2 *__restr
                 if (j + 1 < T) c.pa += n;  // ends up pointing at step min(TAPE_PF, T-1)... only dereferenced when in range
             }
             int t = 0;
-            // full groups: every refill t+TAPE_PF+j (j < TAPE_PF) is in range  <=>  t + 2*TAPE_PF <= T
+            // full groups: every refill t+TAPE_PF+j (j < TAPE_PF) is in range  <=>  t + 2*TAPE_PF <= T.
+            // All TAPE_PF refills of a group are issued up front, before its first step: each load then has a whole group
+            // (~TAPE_PF x 100+ instructions x the resident warps) to land.  (Refilling slot j inside step j left one slot whose
+            // loop-carried register copy sat right behind its load: 20 % of the stall samples on that single MOV.)
             for (; t + 2 * TAPE_PF <= T; t += TAPE_PF) {
+                float2 cur[TAPE_PF];
+#pragma unroll
+                for (int j = 0; j < TAPE_PF; ++j) cur[j] = ring[j];
 #pragma unroll
                 for (int j = 0; j < TAPE_PF; ++j) {
-                    const float2 a = ring[j];
                     ring[j] = *c.pa;  // action of step t + TAPE_PF + j
                     c.pa += n;
-                    tape_step<MODE, true, SUM, OBS>(p, i, n, target, static_base, a, c, has_r, has_d);
                 }
+#pragma unroll
+                for (int j = 0; j < TAPE_PF; ++j) tape_step<MODE, true, SUM, OBS>(p, i, n, target, static_base, cur[j], c, has_r, has_d);
             }
             // tail: fewer than 2*TAPE_PF steps left; refills are guarded
             for (; t < T; t += TAPE_PF) {
