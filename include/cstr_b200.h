@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 6
+#define CSTR_B200_ABI_VERSION 7
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -177,11 +177,24 @@ typedef struct cstr_actor_f32 {
     int32_t reserved;
 } cstr_actor_f32;
 
+/* Monitor-style episode accounting for the fused rollout (core/common/monitor.py:85-111, the feed of
+ * ep_info_buffer, core/common/base_class.py:462-481), all on the device: ep_return (n,) double is the running return of
+ * every reactor (in/out); when an episode ends its (return, length) is appended to `finished` (capacity pairs of floats)
+ * at index atomicAdd(count); entries beyond the capacity are counted but dropped.                                      */
+typedef struct cstr_episode_stats {
+    double *ep_return;   /* (n,) in/out */
+    float *finished;     /* (capacity, 2): return, length */
+    uint32_t *count;     /* device counter, caller-zeroed */
+    uint32_t capacity;
+    uint32_t reserved;
+} cstr_episode_stats;
+
 int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, int actor_mode,
                        const cstr_actor_f32 *actor, const void *packed_bf16, float sigma,
                        const float *noise, int warmup, uint32_t t_base, float *state,
                        int32_t *step_count, int32_t *episode, double *static_base, int64_t rows,
-                       int64_t pos0, float *records, double *reward_sum, void *stream);
+                       int64_t pos0, float *records, double *reward_sum, const cstr_episode_stats *stats /* nullable */,
+                       void *stream);
 
 /* Packs W2 (H2,H1) fp32 into the bf16 UMMA shared-memory image the tensor-core path streams with
  * TMA-style bulk copies; returns the required size in bytes when dst == NULL.                      */

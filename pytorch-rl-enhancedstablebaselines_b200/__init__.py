@@ -10,11 +10,12 @@ from . import _build, _lib, dist
 from ._lib import CstrLibraryError
 from .buffer import GpuReplayBuffer, ReplayBufferSamples, bind_replay_buffer_class
 from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
-from .rollout import ActorWeights, FusedRollout
+from .rollout import ActorWeights, EpisodeStats, FusedRollout
 
 __all__ = [
     "ActorWeights",
     "CstrLibraryError",
+    "EpisodeStats",
     "FusedRollout",
     "GpuCSTRVecEnv",
     "GpuReplayBuffer",

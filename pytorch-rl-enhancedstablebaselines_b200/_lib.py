@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -44,6 +44,12 @@ class ActorF32(Structure):
     ]
 
 
+class EpisodeStatsStruct(Structure):
+    """struct cstr_episode_stats"""
+
+    _fields_ = [("ep_return", c_void_p), ("finished", c_void_p), ("count", c_void_p), ("capacity", c_uint32), ("reserved", c_uint32)]
+
+
 P = c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)  — mirrors include/cstr_b200.h one to one
@@ -60,7 +66,7 @@ _SIGNATURES = {
     "cstr_replay_sample": (c_int, [c_int64, c_int64, P, P, P, P, P, P, P, P, P]),
     "cstr_replay_sample_philox": (c_int, [c_uint64, c_uint64, c_int64, c_int64, c_int64, P, P, P, P, P, P, P, P, P]),
     "cstr_rollout_fused": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, c_int, POINTER(ActorF32), P, c_float, P, c_int,
-                                   c_uint32, P, P, P, P, c_int64, c_int64, P, P, P]),
+                                   c_uint32, P, P, P, P, c_int64, c_int64, P, P, POINTER(EpisodeStatsStruct), P]),
     "cstr_actor_pack_bf16": (c_int64, [POINTER(ActorF32), P, P]),
     "cstr_probe_pipe": (c_int, [c_int, c_int64, c_int, c_int, P, P]),
     "cstr_selftest": (c_int, [c_int, P, P]),

@@ -27,7 +27,8 @@ template <int MODE, int KIND>
 __global__ void __launch_bounds__(ROLL_M)
 rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, float sigma, const float2 *__restrict__ noise, int warmup,
                    uint32_t t_base, float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode,
-                   double *static_base, int64_t rows, int64_t pos0, float4 *__restrict__ records, double *reward_sum) {
+                   double *static_base, int64_t rows, int64_t pos0, float4 *__restrict__ records, double *reward_sum, cstr_episode_stats stats,
+                   int has_stats) {
     extern __shared__ float h1[];  // [H1][ROLL_M]
     const int m = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * ROLL_M + m;
@@ -37,6 +38,7 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
     int sc = live ? step_count[i] : 0, ep = live ? episode[i] : 0;
     const uint64_t env = (uint64_t)(p.env_offset + i);
     double acc_r = 0.0;
+    double ep_ret = (has_stats && live) ? stats.ep_return[i] : 0.0;
     uint4 cache = make_uint4(0, 0, 0, 0);
 
     for (int64_t k = 0; k < K; ++k) {
@@ -118,6 +120,7 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
             const int64_t row = (pos0 + k) % rows;
             store_record(records + ((size_t)row * n + i) * 4, obs, s, buf_a, r.reward, r.truncated);
             acc_r += (double)r.reward;
+            episode_account(stats, has_stats != 0, ep_ret, r.reward, r.truncated, sc);
         }
         if (r.truncated) {
             if (live) s = reset_f32_env(p, i, ep, static_base);
@@ -128,6 +131,7 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
         state[i] = s;
         step_count[i] = sc;
         episode[i] = ep;
+        if (has_stats) stats.ep_return[i] = ep_ret;
     }
     if (reward_sum) {
 #pragma unroll
@@ -144,12 +148,12 @@ using namespace cstr;
 int cstr_rollout_tc_launch(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, const cstr_actor_f32 *actor,
                            const void *packed_bf16, float sigma, const float *noise, int warmup, uint32_t t_base, float *state,
                            int32_t *step_count, int32_t *episode, double *static_base, int64_t rows, int64_t pos0, float *records,
-                           double *reward_sum, void *stream);
+                           double *reward_sum, const cstr_episode_stats *stats, void *stream);
 
 extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, int actor_mode,
                                   const cstr_actor_f32 *actor, const void *packed_bf16, float sigma, const float *noise, int warmup,
                                   uint32_t t_base, float *state, int32_t *step_count, int32_t *episode, double *static_base,
-                                  int64_t rows, int64_t pos0, float *records, double *reward_sum, void *stream) {
+                                  int64_t rows, int64_t pos0, float *records, double *reward_sum, const cstr_episode_stats *stats, void *stream) {
     if (!p || n < 0 || K < 0 || !state || !step_count || !episode || !records || rows <= 0 || pos0 < 0)
         return fail_arg(CSTR_EINVAL, "rollout: null pointer or bad size");
     if (p->init_mode == CSTR_INIT_STATIC && !static_base) return fail_arg(CSTR_EINVAL, "static init_mode needs static_base");
@@ -162,10 +166,11 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
         if (actor->kind != CSTR_ACTOR_TANH && actor->kind != CSTR_ACTOR_GAUSSIAN) return fail_arg(CSTR_EINVAL, "rollout: unknown actor kind");
         if (!aligned(actor->W1, 16) || !aligned(actor->W2, 16)) return fail_arg(CSTR_EALIGN, "rollout: W1/W2 16 B alignment");
     }
+    if (stats && (!stats->ep_return || !stats->finished || !stats->count)) return fail_arg(CSTR_EINVAL, "rollout: episode stats pointers missing");
     if (n == 0 || K == 0) return 0;
     if (actor_mode == 1 && !warmup)
         return cstr_rollout_tc_launch(p, n, K, math_mode, actor, packed_bf16, sigma, noise, warmup, t_base, state, step_count, episode,
-                                      static_base, rows, pos0, records, reward_sum, stream);
+                                      static_base, rows, pos0, records, reward_sum, stats, stream);
     if (actor_mode != 0 && actor_mode != 1) return fail_arg(CSTR_EINVAL, "rollout: unknown actor_mode");
     cstr_actor_f32 a = {};
     if (actor) a = *actor;
@@ -179,8 +184,13 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
         rc = check_cuda(cudaFuncSetAttribute(rollout_f32_kernel<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
         if (!rc)                                                                                                                           \
             rollout_f32_kernel<MODE, KIND><<<grid, ROLL_M, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state, \
-                                                                       step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum); \
+                                                                       step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum, st_copy, has_stats); \
     } while (0)
+    cstr_episode_stats st_copy = {};
+    const int has_stats = stats != nullptr;
+    if (stats) {
+        st_copy = *stats;
+    }
     const bool gauss = a.kind == CSTR_ACTOR_GAUSSIAN;
     if (math_mode == CSTR_MATH_STRICT) { if (gauss) CSTR_LAUNCH_ROLL(CSTR_MATH_STRICT, CSTR_ACTOR_GAUSSIAN); else CSTR_LAUNCH_ROLL(CSTR_MATH_STRICT, CSTR_ACTOR_TANH); }
     else { if (gauss) CSTR_LAUNCH_ROLL(CSTR_MATH_FAST, CSTR_ACTOR_GAUSSIAN); else CSTR_LAUNCH_ROLL(CSTR_MATH_FAST, CSTR_ACTOR_TANH); }

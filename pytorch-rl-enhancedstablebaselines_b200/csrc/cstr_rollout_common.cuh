@@ -46,6 +46,20 @@ __device__ __forceinline__ void actor_head(const float o[4], float2 nz, float &a
     }
 }
 
+// Monitor semantics on device: running return per reactor; finished episodes appended to a compact list.
+__device__ __forceinline__ void episode_account(const cstr_episode_stats &st, bool enabled, double &ep_ret, float reward, bool done, int length) {
+    if (!enabled) return;
+    ep_ret += (double)reward;
+    if (done) {
+        const uint32_t idx = atomicAdd(st.count, 1u);
+        if (idx < st.capacity) {
+            st.finished[2 * idx] = (float)ep_ret;
+            st.finished[2 * idx + 1] = (float)length;
+        }
+        ep_ret = 0.0;
+    }
+}
+
 __device__ __forceinline__ void store_record(float4 *__restrict__ rec, float4 obs, float4 next_obs, float2 act, float reward, bool done) {
     rec[0] = obs;
     rec[1] = next_obs;

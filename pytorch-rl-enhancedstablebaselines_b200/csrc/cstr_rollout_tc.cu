@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, const uint8_t *__restrict__ packed_w2, TcGeometry g,
                   float sigma, const float2 *__restrict__ noise, uint32_t t_base, float4 *__restrict__ state,
                   int32_t *__restrict__ step_count, int32_t *__restrict__ episode, double *static_base, int64_t rows, int64_t pos0,
-                  float4 *__restrict__ records, double *reward_sum) {
+                  float4 *__restrict__ records, double *reward_sum, cstr_episode_stats stats, int has_stats) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bars = smem_base;  // BAR_COUNT x 8 bytes
@@ -246,6 +246,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
 #pragma unroll
         for (int r = 0; r < NOUT; ++r) b3[r] = __ldg(actor.b3 + r);
         double acc_r = 0.0;
+        double ep_ret = (has_stats && live && half == 0) ? stats.ep_return[i] : 0.0;
         double sb[4] = {0.0, 0.0, 0.0, 0.0};
         if (static_base && live) {
 #pragma unroll
@@ -355,6 +356,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                 const int64_t row = (pos0 + k) % rows;
                 store_record(records + ((size_t)row * n + i) * 4, obs, s, buf_a, r.reward, r.truncated);
                 acc_r += (double)r.reward;
+                episode_account(stats, has_stats != 0, ep_ret, r.reward, r.truncated, sc);
             }
             if (r.truncated) {
                 // both threads of a pair draw the same reset from the same Philox counter; in static mode each keeps its own
@@ -368,6 +370,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             state[i] = s;
             step_count[i] = sc;
             episode[i] = ep;
+            if (has_stats) stats.ep_return[i] = ep_ret;
             if (static_base) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) static_base[4 * i + q] = sb[q];
@@ -479,7 +482,7 @@ using namespace cstr;
 int cstr_rollout_tc_launch(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, const cstr_actor_f32 *actor,
                            const void *packed_bf16, float sigma, const float *noise, int warmup, uint32_t t_base, float *state,
                            int32_t *step_count, int32_t *episode, double *static_base, int64_t rows, int64_t pos0, float *records,
-                           double *reward_sum, void *stream) {
+                           double *reward_sum, const cstr_episode_stats *stats, void *stream) {
     (void)warmup;
     TcGeometry g;
     if (!make_geometry(actor->H1, actor->H2, g)) return fail_arg(CSTR_EINVAL, "rollout(tc): H1 must be a multiple of 16 (<=1024), H2 <= 512, and fit in shared memory");
@@ -495,8 +498,11 @@ int cstr_rollout_tc_launch(const cstr_env_params *p, int64_t n, int64_t K, int m
         if (!rc)                                                                                                                            \
             rollout_tc_kernel<MODE, KIND><<<grid, TC_THREADS, g.smem_bytes, st>>>(*p, n, K, *actor, (const uint8_t *)packed_bf16, g, sigma, (const float2 *)noise, \
                                                                                   t_base, (float4 *)state, step_count, episode, static_base, rows, pos0,   \
-                                                                                  (float4 *)records, reward_sum);                          \
+                                                                                  (float4 *)records, reward_sum, st_copy, has_stats);     \
     } while (0)
+    cstr_episode_stats st_copy = {};
+    const int has_stats = stats != nullptr;
+    if (stats) st_copy = *stats;
     const bool gauss = actor->kind == CSTR_ACTOR_GAUSSIAN;
     if (math_mode == CSTR_MATH_STRICT) { if (gauss) CSTR_LAUNCH_TC(CSTR_MATH_STRICT, CSTR_ACTOR_GAUSSIAN); else CSTR_LAUNCH_TC(CSTR_MATH_STRICT, CSTR_ACTOR_TANH); }
     else { if (gauss) CSTR_LAUNCH_TC(CSTR_MATH_FAST, CSTR_ACTOR_GAUSSIAN); else CSTR_LAUNCH_TC(CSTR_MATH_FAST, CSTR_ACTOR_TANH); }

@@ -106,6 +106,32 @@ class ActorWeights:
         return self.packed_bf16
 
 
+class EpisodeStats:
+    """Device-side ``Monitor`` for the fused rollout (monitor.py:85-111): running return per reactor and a compact list of
+    finished episodes ``(return, length)`` that ``pop()`` hands to the host — the feed of ``ep_info_buffer`` /
+    ``rollout/ep_rew_mean`` (base_class.py:462-481, off_policy_algorithm.py:413-435) without any per-env Python."""
+
+    def __init__(self, num_envs: int, device="cuda", capacity: int = 1 << 20):
+        torch = _lib.require_cuda()
+        self.device = torch.device(device)
+        self.capacity = int(capacity)
+        self.ep_return = torch.zeros(num_envs, dtype=torch.float64, device=self.device)
+        self.finished = torch.zeros((self.capacity, 2), dtype=torch.float32, device=self.device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.dropped = 0
+        self._struct = _lib.EpisodeStatsStruct(ep_return=self.ep_return.data_ptr(), finished=self.finished.data_ptr(),
+                                               count=self.count.data_ptr(), capacity=self.capacity, reserved=0)
+
+    def pop(self):
+        """(k,2) float32 NumPy array of the episodes finished since the last call: columns return, length."""
+        k = int(self.count.item())
+        kept = min(k, self.capacity)
+        self.dropped += k - kept
+        out = self.finished[:kept].cpu().numpy().copy()
+        self.count.zero_()
+        return out
+
+
 class FusedRollout:
     """Collects transitions from ``env`` straight into ``buffer`` with the fused kernel.
 
@@ -134,12 +160,13 @@ class FusedRollout:
         if actor_mode == "tc" and actor is not None and actor.packed_bf16 is None:
             actor.pack_bf16()
 
-    def collect(self, K: int, warmup: bool = False, noise=None, reward_sum=None) -> None:
+    def collect(self, K: int, warmup: bool = False, noise=None, reward_sum=None, stats: Optional[EpisodeStats] = None) -> None:
         """K env steps for every reactor; K ring rows are appended to the buffer.
 
         :param warmup: uniform random actions instead of the actor (``learning_starts`` phase).
         :param noise: optional device tensor (K,N,2) float32 added instead of Philox noise (parity tests).
         :param reward_sum: optional device float64[1] accumulating the sum of rewards.
+        :param stats: optional :class:`EpisodeStats` (device-side Monitor).
         """
         env, buf = self.env, self.buffer
         torch = env._torch
@@ -157,7 +184,8 @@ class FusedRollout:
                 byref(env._params), env.num_envs, K, _MATH[env.math], int(self.actor_mode == "tc"),
                 byref(self.actor._struct) if self.actor is not None else None, _lib.ptr(packed), self.sigma, _lib.ptr(noise), int(warmup),
                 self.t & 0xFFFFFFFF, _lib.ptr(env.state), _lib.ptr(env.step_count), _lib.ptr(env.episode), env._sb_ptr(),
-                buf.buffer_size, buf.pos, _lib.ptr(buf.records), _lib.ptr(reward_sum), env._stream())
+                buf.buffer_size, buf.pos, _lib.ptr(buf.records), _lib.ptr(reward_sum), byref(stats._struct) if stats is not None else None,
+                env._stream())
         _lib.check(rc, "cstr_rollout_fused")
         self.launches += 1
         self.t += K

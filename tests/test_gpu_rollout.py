@@ -191,3 +191,34 @@ def test_sac_gaussian_actor_rollout(pkg, actor_mode, atol):
     pkg.FusedRollout(env2, buf2, actor, actor_mode=actor_mode).collect(1)
     a2 = buf2.records[0, :, 8:10].cpu().numpy()
     assert np.abs(a2).max() <= 1.0 and 0.05 < a2.std() < 1.0
+
+
+@pytest.mark.parametrize("actor_mode", ["fp32", "tc"])
+def test_device_episode_stats(pkg, golden, actor_mode):
+    """Monitor semantics on the device: every finished episode's (return, length) comes back exactly once and the
+    return equals the sum of that reactor's recorded rewards since its last reset."""
+    g, _ = _actor(golden)
+    n, K = 128 * 2 + 9, 12
+    env = pkg.GpuCSTRVecEnv(n, seed=6, monitor=False)
+    env.reset()
+    start = torch.arange(n, device="cuda", dtype=torch.int32) % 7 + 392  # reactors truncate at different steps of the launch
+    env.step_count.copy_(start)
+    buf = pkg.GpuReplayBuffer(16 * n, device="cuda", n_envs=n)
+    actor = pkg.ActorWeights(g["W1"], g["b1"], g["W2"], g["b2"], g["W3"], g["b3"])
+    stats = pkg.EpisodeStats(n)
+    roll = pkg.FusedRollout(env, buf, actor, sigma=0.1, actor_mode=actor_mode)
+    roll.collect(K, stats=stats)
+    fin = stats.pop()
+    rec = buf.records.cpu().numpy()[:K]
+    rewards, dones = rec[:, :, 10], rec[:, :, 11] > 0
+    assert len(fin) == n == int(dones.sum())  # each reactor finishes exactly one episode in this window
+    first_done = dones.argmax(axis=0)
+    expect_ret = np.array([rewards[: first_done[i] + 1, i].astype(np.float64).sum() for i in range(n)])
+    assert sorted(np.round(fin[:, 0], 3)) == pytest.approx(sorted(np.round(expect_ret, 3)), abs=2e-3)
+    assert (fin[:, 1] == 400).all()
+    # the running returns now hold the partial sums of the new episodes
+    tail = np.array([rewards[first_done[i] + 1:, i].astype(np.float64).sum() for i in range(n)])
+    np.testing.assert_allclose(stats.ep_return.cpu().numpy(), tail, rtol=1e-6, atol=1e-6)
+    assert len(stats.pop()) == 0
+    roll.collect(3, stats=stats)
+    assert len(stats.pop()) == 0  # nobody finishes in the next 3 steps
