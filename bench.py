@@ -260,19 +260,18 @@ def run_ours(args) -> None:
         step_other()
     _, per_other = time_launches(torch, step_other, 10)
     other_ms = statistics.mean(per_other)
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # clocks are sampled (100 ms period) from just before the warm-up until the end of the e2e loop: the timed region
+    # itself lasts only milliseconds, so the window is the whole GPU-busy phase around it
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     t_wall0 = time.time()
+    for _ in range(args.warmup):
+        step()
     barrier()
     total_ms, per = time_launches(torch, step, args.steps)
     barrier()
-    t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -310,6 +309,7 @@ def run_ours(args) -> None:
     h2d = T * n * 8 + n * (16 + 4 + 4)
     d2h = T * n * (4 + 1) + n * (16 + 4 + 4)
     assert int(h_done.sum().item()) == n
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
 
     if rank != 0:
         if dist is not None:
