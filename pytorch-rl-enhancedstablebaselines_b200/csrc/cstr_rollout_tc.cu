@@ -31,7 +31,7 @@ namespace cstr {
 
 constexpr int TC_M = 128;             // reactors per CTA = UMMA M
 constexpr int TC_ENV_THREADS = 256;   // two threads per reactor
-constexpr int TC_THREADS = 320;       // + loader warp + MMA warp
+constexpr int TC_THREADS = 352;       // + loader warp + two MMA-issuer warps
 constexpr int TC_WSTAGES = 3;
 constexpr int TC_ASTAGES = 2;
 
@@ -170,7 +170,7 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 // barrier slots inside the first 256 bytes of shared memory
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_FULL = 6, BAR_A_EMPTY = 8, BAR_D_FULL = 10, BAR_A1_FULL = 11, BAR_D1_FULL = 12, BAR_D1_EMPTY = 14, BAR_COUNT = 16 };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = 3, BAR_A_FULL = 6, BAR_A_EMPTY = 8, BAR_D_FULL = 10, BAR_A1_FULL = 11, BAR_D1_FULL = 12, BAR_D1_EMPTY = 14, BAR_ORDER = 16, BAR_COUNT = 18 };
 
 template <int MODE, int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -194,6 +194,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         for (int b = 0; b < TC_ASTAGES; ++b) { mbar_init(bars + 8 * (BAR_A_FULL + b), TC_ENV_THREADS); mbar_init(bars + 8 * (BAR_A_EMPTY + b), 1); }
         mbar_init(bars + 8 * BAR_D_FULL, 1);
         mbar_init(bars + 8 * BAR_A1_FULL, TC_ENV_THREADS);
+        for (int b = 0; b < 2; ++b) mbar_init(bars + 8 * (BAR_ORDER + b), 1);
         for (int b = 0; b < 2; ++b) { mbar_init(bars + 8 * (BAR_D1_FULL + b), 1); mbar_init(bars + 8 * (BAR_D1_EMPTY + b), TC_ENV_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -394,46 +395,58 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             }
         }
     } else {
-        // =========================== MMA issuer ==========================================================
+        // =========================== MMA issuers (warps 9 and 10) ==========================================
+        // Two issuing threads take alternate chunks.  tcgen05.mma issue is effectively synchronous (the thread blocks
+        // ~76 cycles per MMA while the pipe is busy) and every tcgen05.commit / mbarrier wait costs the issuing thread
+        // another 75-130 cycles: with one issuer a chunk cost ~1,450 cycles for 760 cycles of tensor time.  With two, one
+        // thread's commits, waits and layer-1 MMA overlap the other thread's layer-2 MMAs.  Pipe order between the two
+        // threads is the ORDER token (tcgen05.fence::before_thread_sync + mbarrier arrive / wait + fence::after).
         if (lane == 0) {
-            // The issuing thread is a single dependent instruction stream: everything loop-invariant is hoisted so
-            // that one MMA costs a 64-bit add per operand plus the instruction itself (measured before hoisting:
-            // ~130 cycles of descriptor arithmetic per MMA against ~76 cycles of tensor time — the issuer was the bottleneck).
+            const uint32_t me = (uint32_t)(warp - 9);  // chunk gc is issued by thread (gc & 1)
             const uint32_t idesc0 = umma_idesc_bf16(TC_M, g.N0), idesc1 = g.N1 ? umma_idesc_bf16(TC_M, g.N1) : 0;
             const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)NP * 16, sbo = 128;
             const uint64_t a_step = (uint64_t)((2u * lbo_a) >> 4), b_step = (uint64_t)((2u * lbo_b) >> 4);  // one K=16 step, in 16-byte units
             const uint64_t n1_off = (uint64_t)(((uint32_t)g.N0 * 16u) >> 4);
             uint64_t a_desc0[TC_ASTAGES], b_desc0[TC_WSTAGES];
 #pragma unroll
-            for (int b = 0; b < TC_ASTAGES; ++b) a_desc0[b] = umma_desc(smem_base + g.off_a + b * g.a_chunk_bytes, lbo_a, sbo);
+            for (int b2 = 0; b2 < TC_ASTAGES; ++b2) a_desc0[b2] = umma_desc(smem_base + g.off_a + b2 * g.a_chunk_bytes, lbo_a, sbo);
 #pragma unroll
-            for (int b = 0; b < TC_WSTAGES; ++b) b_desc0[b] = umma_desc(smem_base + g.off_w + b * g.w_chunk_bytes, lbo_b, sbo);
+            for (int b2 = 0; b2 < TC_WSTAGES; ++b2) b_desc0[b2] = umma_desc(smem_base + g.off_w + b2 * g.w_chunk_bytes, lbo_b, sbo);
             const int ksteps = g.KC / 16;
             // layer 1: one K=16 MMA per chunk, A1 = split-bf16 observation rows, B1 = this chunk's rows of the W1 image
             const uint32_t idesc_l1 = umma_idesc_bf16(TC_M, g.KC);
             const uint64_t da1 = umma_desc(smem_base + g.off_a1, TC_M * 16, sbo);
             const uint64_t dw1_0 = umma_desc(smem_base + g.off_w1, (uint32_t)H1 * 16, sbo);
             const uint64_t w1_step = (uint64_t)(((uint32_t)g.KC * 16u) >> 4);
-            uint32_t d1_uses[2] = {0, 0};  // completed uses of each layer-1 accumulator buffer
-            auto issue_l1 = [&](int kc) {
+            const uint32_t d1_per_step[2] = {(uint32_t)((g.NKC + 1) / 2), (uint32_t)(g.NKC / 2)};  // uses of each layer-1 buffer per step
+            auto issue_l1 = [&](int64_t k, int kc) {
                 const uint32_t db = (uint32_t)kc & 1u;
-                const uint32_t uses = db ? d1_uses[1] : d1_uses[0];
+                const uint32_t uses = (uint32_t)k * (db ? d1_per_step[1] : d1_per_step[0]) + (uint32_t)(kc >> 1);  // uses before this one
                 mbar_wait(bars + 8 * (BAR_D1_EMPTY + db), (uses & 1u) ^ 1u);  // env threads drained the previous use
                 tc_fence_after();
                 tc_mma_bf16(tmem_base + (uint32_t)(g.d1_col + (int)db * g.KC), da1, dw1_0 + (uint64_t)kc * w1_step, idesc_l1, 0u);
                 tc_commit(bars + 8 * (BAR_D1_FULL + db));
-                if (db) d1_uses[1] += 1; else d1_uses[0] += 1;
             };
+            uint32_t order_waits = 0;  // completed waits on my ORDER token
             uint32_t gc = 0;
             for (int64_t k = 0; k < K; ++k) {
-                mbar_wait(bars + 8 * BAR_A1_FULL, (uint32_t)(k & 1));  // this step's observation rows are in shared memory
-                tc_fence_after();
-                issue_l1(0);
-                if (g.NKC > 1) issue_l1(1);
+                // the first two layer-1 MMAs of the step go to the threads that own chunks 0 and 1
+                const uint32_t own0 = gc & 1u, own1 = own0 ^ 1u;
+                if (me == own0 || (g.NKC > 1 && me == own1)) {
+                    mbar_wait(bars + 8 * BAR_A1_FULL, (uint32_t)(k & 1));  // this step's observation rows are in shared memory
+                    tc_fence_after();
+                    if (me == own0) issue_l1(k, 0);
+                    if (g.NKC > 1 && me == own1) issue_l1(k, 1);
+                }
                 for (int kc = 0; kc < g.NKC; ++kc, ++gc) {
+                    if ((gc & 1u) != me) continue;
                     const uint32_t wb = gc % TC_WSTAGES, wuse = gc / TC_WSTAGES, ab = gc & 1u, ause = gc >> 1;  // A_FULL phase = use count of the A buffer
                     mbar_wait(bars + 8 * (BAR_W_FULL + wb), wuse & 1u);
                     mbar_wait(bars + 8 * (BAR_A_FULL + ab), ause & 1u);
+                    if (gc > 0) {  // the other thread has issued chunk gc-1: keeps the accumulation order (chunk 0 overwrites)
+                        mbar_wait(bars + 8 * (BAR_ORDER + me), order_waits & 1u);
+                        order_waits += 1;
+                    }
                     tc_fence_after();
                     uint64_t da = ab == 0 ? a_desc0[0] : a_desc0[1];
                     uint64_t dbw = wb == 0 ? b_desc0[0] : (wb == 1 ? b_desc0[1] : b_desc0[2]);
@@ -445,9 +458,11 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                         dbw += b_step;
                         acc = 1u;
                     }
+                    tc_fence_before();
+                    mbar_arrive(bars + 8 * (BAR_ORDER + (me ^ 1u)));  // hand the pipe to the other issuer
                     tc_commit(bars + 8 * (BAR_W_EMPTY + wb));  // operand buffers are free once these MMAs retire
-                    if (kc == g.NKC - 1) tc_commit(bars + 8 * BAR_D_FULL);
-                    if (kc + 2 < g.NKC) issue_l1(kc + 2);  // its accumulator buffer was drained before A chunk kc was published
+                    if (kc == g.NKC - 1) tc_commit(bars + 8 * BAR_D_FULL);  // in-order pipe: the last chunk retires after all others
+                    if (kc + 2 < g.NKC) issue_l1(k, kc + 2);  // its accumulator buffer was drained before A chunk kc was published
                 }
             }
         }
