@@ -257,7 +257,14 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const int cols_per_half = NP / 2;
 
+#ifdef CSTR_TC_TIMING
+        long long T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
+#define CSTR_TICK(x) x = clock64()
+#else
+#define CSTR_TICK(x)
+#endif
         for (int64_t k = 0; k < K; ++k) {
+            CSTR_TICK(T0);
             // ---- (a) layer 1 on the tensor core: publish this step's split-bf16 observation row (A1) ... -------------
             const uint32_t gstep = t_base + (uint32_t)k;
             {
@@ -318,8 +325,10 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                 fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 mbar_arrive(bars + 8 * (BAR_A_FULL + ab));
             }
+            CSTR_TICK(T1);
             // ---- (b) epilogue: TMEM row -> b2, relu, W3 --------------------------------------------------
             mbar_wait(bars + 8 * BAR_D_FULL, (uint32_t)(k & 1));
+            CSTR_TICK(T2);
             tc_fence_after();
             float o[4] = {0.f, 0.f, 0.f, 0.f};
             const int c_begin = half * cols_per_half;
@@ -337,6 +346,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                     epi8<NOUT>(vb, sep, NP, c_begin + c + 8, o);
                 }
             }
+            CSTR_TICK(T3);
             tc_fence_before();  // TMEM reads are complete before anybody re-arms the accumulator
             float4 *sp = spart + (size_t)(k & 1) * (2 * TC_M);  // double-buffered by step parity: one barrier per step
             sp[half * TC_M + m] = make_float4(o[0], o[1], o[2], o[3]);
@@ -359,6 +369,11 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                 acc_r += (double)r.reward;
                 episode_account(stats, has_stats != 0, ep_ret, r.reward, r.truncated, sc);
             }
+#ifdef CSTR_TC_TIMING
+            CSTR_TICK(T4);
+            if (blockIdx.x == 0 && tid == 0 && (k == 6 || k == 7))
+                printf("tc-timing k=%d chunks=%lld drain=%lld epilogue=%lld tail=%lld total=%lld cycles\n", (int)k, T1 - T0, T2 - T1, T3 - T2, T4 - T3, T4 - T0);
+#endif
             if (r.truncated) {
                 // both threads of a pair draw the same reset from the same Philox counter; in static mode each keeps its own
                 // copy of the drifting base state (Q2) and only half 0 writes it back at the end of the launch

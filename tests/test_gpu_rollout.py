@@ -160,7 +160,7 @@ def test_sac_gaussian_actor_rollout(pkg, actor_mode, atol):
         log_std.bias.add_(-1.0)
     actor = pkg.ActorWeights.from_sac_actor(trunk, mu, log_std)
     assert actor.kind == "gaussian" and tuple(actor.W3.shape) == (4, 256)
-    n, K = 128 * 3 + 5, 2
+    n, K = 128 * 3 + 5, 9  # 9 steps x 4 K-chunks: every mbarrier phase wraps several times with an even chunk count
     env = pkg.GpuCSTRVecEnv(n, seed=2, monitor=False)
     env.reset()
     buf = pkg.GpuReplayBuffer(8 * n, device="cuda", n_envs=n)
