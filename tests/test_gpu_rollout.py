@@ -163,7 +163,7 @@ def test_sac_gaussian_actor_rollout(pkg, actor_mode, atol):
     n, K = 128 * 3 + 5, 9  # 9 steps x 4 K-chunks: every mbarrier phase wraps several times with an even chunk count
     env = pkg.GpuCSTRVecEnv(n, seed=2, monitor=False)
     env.reset()
-    buf = pkg.GpuReplayBuffer(8 * n, device="cuda", n_envs=n)
+    buf = pkg.GpuReplayBuffer(16 * n, device="cuda", n_envs=n)
     eps = np.random.default_rng(0).standard_normal((K, n, 2)).astype(np.float32)
     state = env.state.cpu().numpy().copy()
     pkg.FusedRollout(env, buf, actor, sigma=0.3, actor_mode=actor_mode).collect(K, noise=torch.as_tensor(eps, device="cuda"))
