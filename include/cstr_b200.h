@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 7
+#define CSTR_B200_ABI_VERSION 8
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -132,6 +132,14 @@ int cstr_replay_add(int64_t n_envs, int64_t pos, const float *obs, const float *
                     const float *action, const float *reward, const uint8_t *done,
                     const uint8_t *timeout, float *records, void *stream);
 
+/* Optional VecNormalize statistics applied inside the gather (ReplayBuffer._normalize_obs/_normalize_reward,
+ * buffers.py:143-155,314-323): stats = the 16-double device block of cstr_norm_update.  NULL = no normalisation.      */
+typedef struct cstr_norm_params {
+    const double *stats;
+    double epsilon, clip_obs, clip_reward; /* VecNormalize.epsilon / clip_obs / clip_reward */
+    int32_t norm_obs, norm_reward;         /* VecNormalize.norm_obs / norm_reward           */
+} cstr_norm_params;
+
 /* cstr_replay_sample replaces ReplayBuffer._get_samples + to_torch (buffers.py:307-325,128-140):
  * gathers `batch` transitions at (batch_inds[i], env_inds[i]) into contiguous outputs
  * obs (B,4), act (B,2), next_obs (B,4), dones (B,1) = dones*(1-timeouts), rewards (B,1).
@@ -140,7 +148,7 @@ int cstr_replay_add(int64_t n_envs, int64_t pos, const float *obs, const float *
 int cstr_replay_sample(int64_t n_envs, int64_t batch, const int64_t *batch_inds,
                        const int64_t *env_inds, const float *records, float *out_obs,
                        float *out_act, float *out_next_obs, float *out_dones, float *out_rewards,
-                       void *stream);
+                       const cstr_norm_params *norm /* nullable */, void *stream);
 
 /* Fast mode: indices drawn in-kernel from Philox (stream "sample", counter = (i, draw)): row uniform
  * in [0, upper), env uniform in [0, n_envs) by 32x32->64 multiply-shift.  Optionally returns the
@@ -148,7 +156,20 @@ int cstr_replay_sample(int64_t n_envs, int64_t batch, const int64_t *batch_inds,
 int cstr_replay_sample_philox(uint64_t seed, uint64_t draw, int64_t n_envs, int64_t upper,
                               int64_t batch, const float *records, float *out_obs, float *out_act,
                               float *out_next_obs, float *out_dones, float *out_rewards,
-                              int64_t *out_batch_inds, int64_t *out_env_inds, void *stream);
+                              int64_t *out_batch_inds, int64_t *out_env_inds,
+                              const cstr_norm_params *norm /* nullable */, void *stream);
+
+/* ---- VecNormalize on the device ------------------------------------------------------------------------
+ * cstr_norm_update replaces the statistics part of VecNormalize.step_wait (core/common/vec_env/vec_normalize.py:
+ * 174-223) and RunningMeanStd.update (core/common/running_mean_std.py:36-56): obs (n,4) updates the observation
+ * mean/var (NULL: skip); reward (n,) advances returns = returns*gamma + reward, updates the return mean/var and zeroes
+ * returns on done rows (NULL: skip).  stats: 16 doubles on the device = obs mean[4], obs var[4], obs count, ret mean,
+ * ret var, ret count (initialise mean 0, var 1, count 1e-4); scratch: 16 doubles, zero before the first call.
+ * cstr_norm_apply replaces normalize_obs / normalize_reward (:225-259) for whole vectors (either side nullable).   */
+int cstr_norm_update(int64_t n, const float *obs, const float *reward, const uint8_t *done, double *returns,
+                     double gamma, double *stats, double *scratch, void *stream);
+int cstr_norm_apply(int64_t n, const float *obs_in, const float *reward_in, const double *stats, double epsilon,
+                    double clip_obs, double clip_reward, float *obs_out, float *reward_out, void *stream);
 
 /* ---- fused rollout --------------------------------------------------------------------------------
  * Replaces, for K consecutive env steps of N reactors, OffPolicyAlgorithm._sample_action +

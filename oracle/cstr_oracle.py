@@ -411,6 +411,66 @@ class ReplayOracle:
 
 
 # ----------------------------------------------------------------------------------------------
+# VecNormalize (core/common/vec_env/vec_normalize.py:174-298, core/common/running_mean_std.py:4-56)
+# ----------------------------------------------------------------------------------------------
+class RunningMeanStdOracle:
+    """running_mean_std.py:4-56 — ``exact=False`` keeps the reference's float32 batch moments (np.mean/np.var of the
+    float32 array), ``exact=True`` takes them in float64 as the CUDA reduction does."""
+
+    def __init__(self, shape=(), epsilon: float = 1e-4, exact: bool = False):
+        self.mean, self.var, self.count, self.exact = np.zeros(shape, np.float64), np.ones(shape, np.float64), epsilon, exact
+
+    def update(self, arr: np.ndarray) -> None:  # :35-39
+        a = np.asarray(arr, np.float64) if self.exact else np.asarray(arr)
+        self.update_from_moments(np.mean(a, axis=0), np.var(a, axis=0), a.shape[0])
+
+    def update_from_moments(self, bmean, bvar, bcount) -> None:  # :41-56
+        delta = bmean - self.mean
+        tot = self.count + bcount
+        new_mean = self.mean + delta * bcount / tot
+        m2 = self.var * self.count + bvar * bcount + np.square(delta) * self.count * bcount / (self.count + bcount)
+        self.mean, self.var, self.count = new_mean, m2 / (self.count + bcount), bcount + self.count
+
+
+class VecNormalizeOracle:
+    """The statistics/normalisation half of VecNormalize, fed with the raw (obs, reward, done) of each step."""
+
+    def __init__(self, n_envs: int, gamma=0.99, epsilon=1e-8, clip_obs=10.0, clip_reward=10.0, training=True, norm_obs=True,
+                 norm_reward=True, exact: bool = False):
+        self.obs_rms, self.ret_rms = RunningMeanStdOracle((4,), exact=exact), RunningMeanStdOracle((), exact=exact)
+        self.returns = np.zeros(n_envs)
+        self.gamma, self.epsilon, self.clip_obs, self.clip_reward = gamma, epsilon, clip_obs, clip_reward
+        self.training, self.norm_obs, self.norm_reward = training, norm_obs, norm_reward
+
+    def normalize_obs(self, obs):  # :225-246
+        if not self.norm_obs:
+            return np.array(obs, copy=True)
+        return np.clip((obs - self.obs_rms.mean) / np.sqrt(self.obs_rms.var + self.epsilon), -self.clip_obs, self.clip_obs).astype(np.float32)
+
+    def normalize_reward(self, reward):  # :248-259
+        if self.norm_reward:
+            reward = np.clip(reward / np.sqrt(self.ret_rms.var + self.epsilon), -self.clip_reward, self.clip_reward)
+        return np.asarray(reward).astype(np.float32)
+
+    def reset(self, obs):  # :287-298
+        self.returns = np.zeros_like(self.returns)
+        if self.training and self.norm_obs:
+            self.obs_rms.update(obs)
+        return self.normalize_obs(obs)
+
+    def step(self, obs, rewards, dones):  # :174-209
+        if self.training and self.norm_obs:
+            self.obs_rms.update(obs)
+        nobs = self.normalize_obs(obs)
+        if self.training:
+            self.returns = self.returns * self.gamma + rewards  # :221
+            self.ret_rms.update(self.returns)
+        nrew = self.normalize_reward(rewards)
+        self.returns[np.asarray(dones, bool)] = 0
+        return nobs, nrew
+
+
+# ----------------------------------------------------------------------------------------------
 # action plumbing and the TD3 actor (off_policy_algorithm.py:398-406, policies.py:388-413,
 # td3/policies.py:75-78 + torch_layers.py:110-183)
 # ----------------------------------------------------------------------------------------------

@@ -11,6 +11,8 @@ the output of the reference's own code on seeded inputs:
   replay.npz     ReplayBuffer.add/sample under np.random.seed             core/common/buffers.py:247-325
   td3_actor.npz  TD3Policy actor forward / predict / _sample_action maps  core/td3/policies.py:75-78,
                                                                            core/common/off_policy_algorithm.py:364-411
+  vecnorm.npz    VecNormalize over DummyVecEnv (statistics, normalised obs/reward, normalised replay sample)
+                                                                           core/common/vec_env/vec_normalize.py:174-298
 Host note: NumPy's float32 exp is a SIMD kernel whose code path depends on the CPU, so the fp32
 fixtures are bit-stable only on hosts taking the same path; tests re-check them with the ulp-level
 tolerance stated in tests/test_golden.py and bit-exactly in tests/test_oracle_vs_reference.py (live).
@@ -203,6 +205,53 @@ def gen_actor(m, core) -> None:
                         env_action=action, buffer_action=buffer_action, **W, **Bz)
 
 
+def gen_vecnorm(m, core) -> None:
+    from core.common.buffers import ReplayBuffer
+    from core.common.vec_env import DummyVecEnv, VecNormalize
+
+    N, T, seed = 16, 120, 5
+    def make():
+        e = m.TwoSeriesCSTREnv(init_mode="random")
+        e.max_steps = 50  # plain attribute in the reference (twoseriescstr.py:99): short episodes -> several auto-resets in T steps
+        return e
+
+    venv = DummyVecEnv([make for _ in range(N)])
+    venv.seed(seed)
+    vn = VecNormalize(venv, gamma=0.99)
+    buf = ReplayBuffer(128 * N, venv.observation_space, venv.action_space, device="cpu", n_envs=N)
+    nobs0 = vn.reset()
+    raw0 = vn.get_original_obs()
+    rng = np.random.default_rng(23)
+    actions = rng.uniform(-1, 1, (T, N, 2)).astype(np.float32)
+    keys = ("raw_obs", "raw_rew", "done", "norm_obs", "norm_rew", "obs_mean", "obs_var", "obs_count", "ret_mean", "ret_var", "ret_count", "returns")
+    rec = {k: [] for k in keys}
+    last_raw = raw0
+    for t in range(T):
+        o, r, d, infos = vn.step(actions[t])
+        raw_o, raw_r = vn.get_original_obs(), vn.get_original_reward()
+        nxt = raw_o.copy()
+        for i, info in enumerate(infos):
+            if d[i]:
+                nxt[i] = vn.unnormalize_obs(info["terminal_observation"])  # off_policy_algorithm.py:468-481 stores the ORIGINAL obs
+        buf.add(last_raw, nxt, actions[t], raw_r, d, infos)
+        last_raw = raw_o
+        for k, v in zip(keys, (raw_o, raw_r, d, o, r, vn.obs_rms.mean, vn.obs_rms.var, vn.obs_rms.count, vn.ret_rms.mean, vn.ret_rms.var,
+                               vn.ret_rms.count, vn.returns)):
+            rec[k].append(np.array(v, copy=True))
+    np.random.seed(3)
+    s = buf.sample(256, env=vn)
+    np.random.seed(3)
+    bi = np.random.randint(0, buf.size(), size=256)
+    ei = np.random.randint(0, high=N, size=(256,))
+    out = {k: np.stack(v) for k, v in rec.items()}
+    out.update(seed=seed, raw_obs0=raw0, norm_obs0=nobs0, actions=actions, batch_inds=bi, env_inds=ei,
+               store_observations=buf.observations[:T], store_next_observations=buf.next_observations[:T], store_actions=buf.actions[:T],
+               store_rewards=buf.rewards[:T], store_dones=buf.dones[:T], store_timeouts=buf.timeouts[:T],
+               s_obs=s.observations.numpy(), s_act=s.actions.numpy(), s_next_obs=s.next_observations.numpy(), s_dones=s.dones.numpy(),
+               s_rewards=s.rewards.numpy())
+    np.savez_compressed(os.path.join(OUT, "vecnorm.npz"), **out)
+
+
 def main() -> None:
     if not refload.available():
         raise SystemExit("reference tree not found; fixtures can only be generated in the build container")
@@ -215,6 +264,7 @@ def main() -> None:
     gen_reset(m)
     gen_replay(core)
     gen_actor(m, core)
+    gen_vecnorm(m, core)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -66,10 +66,10 @@ def main() -> None:
         ep = [e["r"] for e in model.ep_info_buffer]
         eval_env = GpuVecEnv(num_envs=1, init_mode="static", reset_rng="pcg64", seed=7)
         mean_r, std_r = evaluate_policy(model, eval_env, n_eval_episodes=2, warn=False)
-        launches[name] = env.launches + buf.launches
+        launches[name] = getattr(env, "launches", 0) + buf.launches
         print(f"[{name}] {steps} timesteps in {dt:.1f} s | buffer size {buf.size()} rows x {buf.n_envs} envs, pos {buf.pos} | "
               f"episodes logged {len(ep)} (mean return {np.mean(ep) if ep else float('nan'):.1f}) | eval return {mean_r:.1f} +- {std_r:.1f} | "
-              f"CUDA launches: env {env.launches}, buffer {buf.launches}", flush=True)
+              f"CUDA launches: env {env.unwrapped.launches if hasattr(env, 'unwrapped') else env.launches}, buffer {buf.launches}", flush=True)
         return model
 
     common = dict(replay_buffer_class=GpuBuffer, buffer_size=64_000, learning_starts=800, batch_size=256, device="cuda", seed=42)
@@ -78,6 +78,34 @@ def main() -> None:
     ma = dict(n_agents=2, observation_splits=[[0, 1], [2, 3]], action_splits=[[0], [1]], learning_rate_list=[1e-3, 1e-3])
     run("MADDPG", lambda env: core.MADDPG(policy="MlpPolicy", env=env, train_freq=(1, "step"), gradient_steps=2, **ma, **common), 4800)
     run("IDDPG", lambda env: core.IDDPG(policy="MlpPolicy", env=env, train_freq=(1, "step"), gradient_steps=2, **ma, **common), 4800)
+
+    # ---- TD3 under VecNormalize: statistics, normalisation and the normalised sample all on the device ---------------
+    from core.common.vec_env import VecNormalize, unwrap_vec_normalize
+
+    GpuNorm = pkg.bind_vec_normalize_class(VecNormalize)
+
+    def make_norm(env):
+        wrapped = GpuNorm(env, gamma=0.99)
+        assert isinstance(wrapped, VecNormalize) and unwrap_vec_normalize(wrapped) is wrapped
+        model = core.TD3("MlpPolicy", wrapped, action_noise=noise(), train_freq=(1, "step"), gradient_steps=4, **common)
+        assert model.get_vec_normalize_env() is wrapped
+        return model
+
+    m = run("TD3+VecNormalize", make_norm, 8000)
+    vn = m.get_vec_normalize_env()
+    print(f"[TD3+VecNormalize] obs_rms.count {vn.obs_rms.count:.1f} mean {np.round(vn.obs_rms.mean, 3)} var {np.round(vn.obs_rms.var, 4)} | "
+          f"ret_rms.var {float(vn.ret_rms.var):.3f} | normaliser launches {vn.launches}", flush=True)
+    with tempfile.TemporaryDirectory() as tmp:  # VecNormalize.save/load interchange with the reference class
+        vn.save(os.path.join(tmp, "vn.pkl"))
+        back = pkg.GpuVecNormalize.load(os.path.join(tmp, "vn.pkl"), GpuVecEnv(num_envs=16, init_mode="static", reset_rng="pcg64", seed=1))
+        assert np.array_equal(back.obs_rms.var, vn.obs_rms.var)
+        ref_vn = vn.to_reference(VecNormalize, DummyVecEnv([lambda: ref_env_mod.TwoSeriesCSTREnv(init_mode="static")]))
+        probe = np.random.default_rng(0).uniform(-1, 1, (5, 4)).astype(np.float32)
+        assert np.array_equal(ref_vn.normalize_obs(probe), vn.normalize_obs(probe))
+        ref_vn.save(os.path.join(tmp, "ref.pkl"))
+        adopted = pkg.GpuVecNormalize.load(os.path.join(tmp, "ref.pkl"), GpuVecEnv(num_envs=16, init_mode="static", reset_rng="pcg64", seed=1))
+        assert np.array_equal(adopted.normalize_obs(probe), vn.normalize_obs(probe))
+        print("[TD3+VecNormalize] save/load + to_reference/from_reference: normalised values identical on both sides", flush=True)
 
     # ---- BCQ offline: dataset generated by the GPU tape kernel, handed over in the reference's pickle format -------
     n, T = 2500, 400

@@ -10,6 +10,7 @@ from . import _build, _lib, dist
 from ._lib import CstrLibraryError
 from .buffer import GpuReplayBuffer, ReplayBufferSamples, bind_replay_buffer_class
 from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
+from .normalize import GpuVecNormalize, bind_vec_normalize_class
 from .rollout import ActorWeights, EpisodeStats, FusedRollout
 
 __all__ = [
@@ -19,6 +20,8 @@ __all__ = [
     "FusedRollout",
     "GpuCSTRVecEnv",
     "GpuReplayBuffer",
+    "GpuVecNormalize",
+    "bind_vec_normalize_class",
     "LazyInfos",
     "ReplayBufferSamples",
     "TwoSeriesCSTREnv",

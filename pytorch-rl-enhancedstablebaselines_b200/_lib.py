@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -50,6 +50,13 @@ class EpisodeStatsStruct(Structure):
     _fields_ = [("ep_return", c_void_p), ("finished", c_void_p), ("count", c_void_p), ("capacity", c_uint32), ("reserved", c_uint32)]
 
 
+class NormParams(Structure):
+    """struct cstr_norm_params"""
+
+    _fields_ = [("stats", c_void_p), ("epsilon", c_double), ("clip_obs", c_double), ("clip_reward", c_double),
+                ("norm_obs", c_int32), ("norm_reward", c_int32)]
+
+
 P = c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)  — mirrors include/cstr_b200.h one to one
@@ -63,8 +70,10 @@ _SIGNATURES = {
     "cstr_tape_f64": (c_int, [POINTER(EnvParams), c_int64, c_int64, P, c_uint32, P, P, P, P, P, P, P, P, P]),
     "cstr_tape_f32_host": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, P, P, P, P, P, P, P]),
     "cstr_replay_add": (c_int, [c_int64, c_int64, P, P, P, P, P, P, P, P]),
-    "cstr_replay_sample": (c_int, [c_int64, c_int64, P, P, P, P, P, P, P, P, P]),
-    "cstr_replay_sample_philox": (c_int, [c_uint64, c_uint64, c_int64, c_int64, c_int64, P, P, P, P, P, P, P, P, P]),
+    "cstr_replay_sample": (c_int, [c_int64, c_int64, P, P, P, P, P, P, P, P, POINTER(NormParams), P]),
+    "cstr_replay_sample_philox": (c_int, [c_uint64, c_uint64, c_int64, c_int64, c_int64, P, P, P, P, P, P, P, P, POINTER(NormParams), P]),
+    "cstr_norm_update": (c_int, [c_int64, P, P, P, P, c_double, P, P, P]),
+    "cstr_norm_apply": (c_int, [c_int64, P, P, P, c_double, c_double, c_double, P, P, P]),
     "cstr_rollout_fused": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, c_int, POINTER(ActorF32), P, c_float, P, c_int,
                                    c_uint32, P, P, P, P, c_int64, c_int64, P, P, POINTER(EpisodeStatsStruct), P]),
     "cstr_actor_pack_bf16": (c_int64, [POINTER(ActorF32), P, P]),

@@ -221,7 +221,7 @@ class GpuReplayBuffer:
         with torch.cuda.device(self._device):
             rc = self._libc.cstr_replay_sample_philox(self.seed & (2**64 - 1), self._draw, self.n_envs, upper_bound, batch_size,
                                                       _lib.ptr(self.records), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones),
-                                                      _lib.ptr(rew), None, None, self._stream())
+                                                      _lib.ptr(rew), None, None, self._norm_arg(env), self._stream())
         _lib.check(rc, "cstr_replay_sample_philox")
         self._draw += 1
         self.launches += 1
@@ -240,13 +240,23 @@ class GpuReplayBuffer:
         obs, act, nobs, dones, rew = self._alloc_out(B)
         with torch.cuda.device(self._device):
             rc = self._libc.cstr_replay_sample(self.n_envs, B, _lib.ptr(bi), _lib.ptr(ei), _lib.ptr(self.records), _lib.ptr(obs),
-                                               _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones), _lib.ptr(rew), self._stream())
+                                               _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones), _lib.ptr(rew), self._norm_arg(env), self._stream())
         _lib.check(rc, "cstr_replay_sample")
         self.launches += 1
         return self._finish(obs, act, nobs, dones, rew, env)
 
+    def _norm_arg(self, env):
+        """Device VecNormalize statistics are applied inside the gather kernel (None otherwise)."""
+        params = getattr(env, "norm_params", None)
+        if params is None:
+            return None
+        self._norm_keepalive = params()  # ctypes struct must outlive the call
+        from ctypes import byref
+
+        return byref(self._norm_keepalive)
+
     def _finish(self, obs, act, nobs, dones, rew, env) -> ReplayBufferSamples:
-        if env is not None:
+        if env is not None and getattr(env, "norm_params", None) is None:
             # VecNormalize statistics live on the host in the reference (vec_normalize.py:174-259):
             # normalise there and come back (compat path; the device version is the §8f-4 "next" row)
             torch = self._torch
@@ -307,7 +317,7 @@ class GpuReplayBuffer:
         return ref
 
     def __getstate__(self):
-        state = {k: v for k, v in self.__dict__.items() if k not in ("records", "_torch", "_libc", "_device")}
+        state = {k: v for k, v in self.__dict__.items() if k not in ("records", "_torch", "_libc", "_device", "_norm_keepalive")}
         state.update(self.to_numpy_arrays())
         state["device"] = str(self._device)
         return state

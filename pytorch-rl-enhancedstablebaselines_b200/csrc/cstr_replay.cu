@@ -6,6 +6,7 @@
 //   sample : 16 B of indices + one 64 B record read (two whole sectors) + 48 B written per sample
 #include "cstr_abi.cuh"
 #include "cstr_device.cuh"
+#include "cstr_norm.cuh"
 
 namespace cstr {
 
@@ -27,31 +28,49 @@ replay_add_kernel(int64_t n, const float4 *__restrict__ obs, const float4 *__res
     rec[3] = make_float4(to, 0.0f, 0.0f, 0.0f);
 }
 
+struct NormArgs {  // by-value copy of cstr_norm_params (stats == nullptr: off)
+    const double *stats;
+    double eps, clip_obs, clip_reward;
+    int norm_obs, norm_reward;
+};
+
+__device__ __forceinline__ float4 norm4(float4 o, const NormArgs &na) {
+    const double *s = na.stats;
+    return make_float4(normalize_obs_value(o.x, s[0], s[4], na.eps, na.clip_obs), normalize_obs_value(o.y, s[1], s[5], na.eps, na.clip_obs),
+                       normalize_obs_value(o.z, s[2], s[6], na.eps, na.clip_obs), normalize_obs_value(o.w, s[3], s[7], na.eps, na.clip_obs));
+}
+
 __device__ __forceinline__ void gather_one(const float4 *__restrict__ records, int64_t flat, int64_t i, float4 *out_obs, float2 *out_act,
-                                           float4 *out_next_obs, float *out_dones, float *out_rewards) {
+                                           float4 *out_next_obs, float *out_dones, float *out_rewards, const NormArgs &na) {
     const float4 *rec = records + 4 * flat;
-    const float4 o = __ldg(rec), no = __ldg(rec + 1), ar = __ldg(rec + 2);
+    float4 o = __ldg(rec), no = __ldg(rec + 1);
+    const float4 ar = __ldg(rec + 2);
     const float to = __ldg(reinterpret_cast<const float *>(rec + 3));
+    float rew = ar.z;
+    if (na.stats) {  // VecNormalize inside the gather (buffers.py:314-323)
+        if (na.norm_obs) { o = norm4(o, na); no = norm4(no, na); }
+        if (na.norm_reward) rew = normalize_reward_value(rew, na.stats[10], na.eps, na.clip_reward);
+    }
     out_obs[i] = o;
     out_next_obs[i] = no;
     out_act[i] = make_float2(ar.x, ar.y);
-    out_rewards[i] = ar.z;
+    out_rewards[i] = rew;
     out_dones[i] = __fmul_rn(ar.w, __fsub_rn(1.0f, to));  // dones * (1 - timeouts), buffers.py:322
 }
 
 __global__ void __launch_bounds__(256)
 replay_sample_kernel(int64_t n_envs, int64_t batch, const int64_t *__restrict__ batch_inds, const int64_t *__restrict__ env_inds,
                      const float4 *__restrict__ records, float4 *out_obs, float2 *out_act, float4 *out_next_obs, float *out_dones,
-                     float *out_rewards) {
+                     float *out_rewards, NormArgs na) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
-    gather_one(records, batch_inds[i] * n_envs + env_inds[i], i, out_obs, out_act, out_next_obs, out_dones, out_rewards);
+    gather_one(records, batch_inds[i] * n_envs + env_inds[i], i, out_obs, out_act, out_next_obs, out_dones, out_rewards, na);
 }
 
 __global__ void __launch_bounds__(256)
 replay_sample_philox_kernel(uint64_t seed, uint64_t draw, int64_t n_envs, int64_t upper, int64_t batch, const float4 *__restrict__ records,
                             float4 *out_obs, float2 *out_act, float4 *out_next_obs, float *out_dones, float *out_rewards,
-                            int64_t *out_batch_inds, int64_t *out_env_inds) {
+                            int64_t *out_batch_inds, int64_t *out_env_inds, NormArgs na) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
     const uint4 r = philox_env(seed, (uint64_t)i, (uint32_t)draw, STREAM_SAMPLE, (uint32_t)(draw >> 32) & 0xffu);
@@ -61,7 +80,7 @@ replay_sample_philox_kernel(uint64_t seed, uint64_t draw, int64_t n_envs, int64_
     const int64_t e = (int64_t)__umul64hi(w1, (uint64_t)n_envs);
     if (out_batch_inds) out_batch_inds[i] = b;
     if (out_env_inds) out_env_inds[i] = e;
-    gather_one(records, b * n_envs + e, i, out_obs, out_act, out_next_obs, out_dones, out_rewards);
+    gather_one(records, b * n_envs + e, i, out_obs, out_act, out_next_obs, out_dones, out_rewards, na);
 }
 
 }  // namespace cstr
@@ -83,6 +102,12 @@ int cstr_replay_add(int64_t n_envs, int64_t pos, const float *obs, const float *
     return check_launch("replay_add_kernel");
 }
 
+static NormArgs norm_args(const cstr_norm_params *norm) {
+    NormArgs na = {nullptr, 0.0, 0.0, 0.0, 0, 0};
+    if (norm && norm->stats) na = {norm->stats, norm->epsilon, norm->clip_obs, norm->clip_reward, norm->norm_obs, norm->norm_reward};
+    return na;
+}
+
 static int check_sample_out(const float *records, float *out_obs, float *out_act, float *out_next_obs, float *out_dones, float *out_rewards) {
     if (!records || !out_obs || !out_act || !out_next_obs || !out_dones || !out_rewards)
         return fail_arg(CSTR_EINVAL, "replay_sample: null pointer");
@@ -92,26 +117,27 @@ static int check_sample_out(const float *records, float *out_obs, float *out_act
 }
 
 int cstr_replay_sample(int64_t n_envs, int64_t batch, const int64_t *batch_inds, const int64_t *env_inds, const float *records,
-                       float *out_obs, float *out_act, float *out_next_obs, float *out_dones, float *out_rewards, void *stream) {
+                       float *out_obs, float *out_act, float *out_next_obs, float *out_dones, float *out_rewards,
+                       const cstr_norm_params *norm, void *stream) {
     if (n_envs <= 0 || batch < 0 || !batch_inds || !env_inds) return fail_arg(CSTR_EINVAL, "replay_sample: bad sizes or null indices");
     if (int rc = check_sample_out(records, out_obs, out_act, out_next_obs, out_dones, out_rewards)) return rc;
     if (batch == 0) return 0;
     const int block = 128, grid = (int)((batch + block - 1) / block);
     replay_sample_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(n_envs, batch, batch_inds, env_inds, (const float4 *)records, (float4 *)out_obs,
-                                                                    (float2 *)out_act, (float4 *)out_next_obs, out_dones, out_rewards);
+                                                                    (float2 *)out_act, (float4 *)out_next_obs, out_dones, out_rewards, norm_args(norm));
     return check_launch("replay_sample_kernel");
 }
 
 int cstr_replay_sample_philox(uint64_t seed, uint64_t draw, int64_t n_envs, int64_t upper, int64_t batch, const float *records,
                               float *out_obs, float *out_act, float *out_next_obs, float *out_dones, float *out_rewards,
-                              int64_t *out_batch_inds, int64_t *out_env_inds, void *stream) {
+                              int64_t *out_batch_inds, int64_t *out_env_inds, const cstr_norm_params *norm, void *stream) {
     if (n_envs <= 0 || upper <= 0 || batch < 0) return fail_arg(CSTR_EINVAL, "replay_sample_philox: bad sizes (empty buffer?)");
     if (int rc = check_sample_out(records, out_obs, out_act, out_next_obs, out_dones, out_rewards)) return rc;
     if (batch == 0) return 0;
     const int block = 128, grid = (int)((batch + block - 1) / block);
     replay_sample_philox_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(seed, draw, n_envs, upper, batch, (const float4 *)records,
                                                                            (float4 *)out_obs, (float2 *)out_act, (float4 *)out_next_obs,
-                                                                           out_dones, out_rewards, out_batch_inds, out_env_inds);
+                                                                           out_dones, out_rewards, out_batch_inds, out_env_inds, norm_args(norm));
     return check_launch("replay_sample_philox_kernel");
 }
 

@@ -528,6 +528,11 @@ class GpuCSTRVecEnv:
             self._params.target_c2 = float(value)
         elif attr_name == "render_mode":
             self.render_mode = value
+        elif attr_name == "max_steps":  # plain attribute in the reference (twoseriescstr.py:99,438)
+            if int(value) <= 0:
+                raise ValueError("max_steps must be positive")
+            self.max_steps = int(value)
+            self._params.max_steps = int(value)
         else:
             raise AttributeError(f"attribute {attr_name!r} cannot be set on the batched CSTR env")
 

@@ -119,3 +119,27 @@ def test_actor_and_action_maps(golden):
     assert np.array_equal(a, g["env_action"]) and np.array_equal(s, g["buffer_action"])
     a0, _ = O.sample_action_maps(g["mu"], np.zeros_like(g["noise"]))
     np.testing.assert_allclose(a0, g["predict"], rtol=0, atol=1.2e-7)
+
+
+def test_vecnormalize_oracle_vs_reference_fixture(golden):
+    """VecNormalizeOracle replays the reference's VecNormalize(DummyVecEnv) run (vec_normalize.py:174-298)."""
+    g = golden("vecnorm.npz")
+    T, N = g["raw_rew"].shape
+    same, exact = O.VecNormalizeOracle(N), O.VecNormalizeOracle(N, exact=True)
+    assert np.array_equal(same.reset(g["raw_obs0"]), g["norm_obs0"])
+    exact.reset(g["raw_obs0"])
+    for t in range(T):
+        nobs, nrew = same.step(g["raw_obs"][t], g["raw_rew"][t], g["done"][t])
+        exact.step(g["raw_obs"][t], g["raw_rew"][t], g["done"][t])
+        assert np.array_equal(nobs, g["norm_obs"][t]) and np.array_equal(nrew, g["norm_rew"][t])
+        np.testing.assert_allclose(same.obs_rms.mean, g["obs_mean"][t], rtol=1e-12)
+        np.testing.assert_allclose(same.obs_rms.var, g["obs_var"][t], rtol=1e-12)
+        np.testing.assert_allclose(same.ret_rms.var, g["ret_var"][t], rtol=1e-12)
+        np.testing.assert_allclose(same.returns, g["returns"][t], rtol=0, atol=0)
+        np.testing.assert_allclose(exact.obs_rms.var, g["obs_var"][t], rtol=2e-5)  # float64 vs float32 batch moments
+        np.testing.assert_allclose(exact.ret_rms.var, g["ret_var"][t], rtol=2e-5)
+    assert same.obs_rms.count == pytest.approx(float(g["obs_count"][-1]))
+    # the fused sample of the fixture is the normalised gather of the stored ORIGINAL transitions (buffers.py:314-323)
+    b, e = g["batch_inds"], g["env_inds"]
+    assert np.array_equal(same.normalize_obs(g["store_observations"][b, e]), g["s_obs"])
+    assert np.array_equal(same.normalize_reward(g["store_rewards"][b, e].reshape(-1, 1)), g["s_rewards"])

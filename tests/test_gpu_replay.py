@@ -79,7 +79,7 @@ def test_philox_sampling(pkg, G=None):
     B_ = 20000
     outs = buf._alloc_out(B_)
     bi = torch.empty(B_, dtype=torch.int64, device="cuda"); ei = torch.empty(B_, dtype=torch.int64, device="cuda")
-    rc = lib.cstr_replay_sample_philox(9, 0, n, 5, B_, buf.records.data_ptr(), *(t.data_ptr() for t in outs), bi.data_ptr(), ei.data_ptr(), None)
+    rc = lib.cstr_replay_sample_philox(9, 0, n, 5, B_, buf.records.data_ptr(), *(t.data_ptr() for t in outs), bi.data_ptr(), ei.data_ptr(), None, None)
     assert rc == 0
     torch.cuda.synchronize()
     b, e = bi.cpu().numpy(), ei.cpu().numpy()
