@@ -13,6 +13,7 @@ the output of the reference's own code on seeded inputs:
                                                                            core/common/off_policy_algorithm.py:364-411
   vecnorm.npz    VecNormalize over DummyVecEnv (statistics, normalised obs/reward, normalised replay sample)
                                                                            core/common/vec_env/vec_normalize.py:174-298
+  td3_update.npz TD3.train for 6 gradient steps (weights, Adam state, losses) on CPU torch   core/td3/td3.py:154-211
 Host note: NumPy's float32 exp is a SIMD kernel whose code path depends on the CPU, so the fp32
 fixtures are bit-stable only on hosts taking the same path; tests re-check them with the ulp-level
 tolerance stated in tests/test_golden.py and bit-exactly in tests/test_oracle_vs_reference.py (live).
@@ -252,6 +253,67 @@ def gen_vecnorm(m, core) -> None:
     np.savez_compressed(os.path.join(OUT, "vecnorm.npz"), **out)
 
 
+def td3_update_reference_run(m, core, net_arch, K=6, B=64) -> dict:
+    """Run the reference's TD3.train for K gradient steps on CPU torch and return everything needed to replay it."""
+    import torch
+    from types import SimpleNamespace
+    from core.common.vec_env import DummyVecEnv
+
+    torch.set_num_threads(1)
+    venv = DummyVecEnv([(lambda: m.TwoSeriesCSTREnv(init_mode="random")) for _ in range(4)])
+    model = core.TD3("MlpPolicy", venv, buffer_size=4000, batch_size=B, learning_starts=0, device="cpu", seed=5, policy_kwargs=dict(net_arch=list(net_arch)))
+    logged = {}
+    model._logger = SimpleNamespace(record=lambda k, v, **kw: logged.__setitem__(k, v))
+    rng = np.random.default_rng(31)
+    buf = model.replay_buffer
+    for _ in range(200):  # synthetic transitions: the update only sees what sample() returns
+        o = rng.uniform(-1, 1, (4, 4)).astype(np.float32)
+        no = rng.uniform(-1, 1, (4, 4)).astype(np.float32)
+        a = rng.uniform(-1, 1, (4, 2)).astype(np.float32)
+        r = rng.normal(-1, 1, 4).astype(np.float32)
+        d = rng.random(4) < 0.05
+        buf.add(o, no, a, r, d, [{"TimeLimit.truncated": bool(x and rng.random() < 0.5)} for x in d])
+
+    def nets():
+        pol = model.policy
+        get = lambda seq: [t.detach().numpy().copy() for t in seq.parameters()]  # noqa: E731
+        return {"actor": get(pol.actor.mu), "actor_target": get(pol.actor_target.mu), "critic0": get(pol.critic.q_networks[0]),
+                "critic1": get(pol.critic.q_networks[1]), "critic0_target": get(pol.critic_target.q_networks[0]),
+                "critic1_target": get(pol.critic_target.q_networks[1])}
+
+    out = {}
+    for name, ps in nets().items():
+        for i, t in enumerate(ps):
+            out[f"init_{name}_{i}"] = t
+    np.random.seed(17)
+    batches = [buf.sample(B) for _ in range(K)]
+    torch.manual_seed(23)
+    noise = [torch.empty(B, 2).normal_(0, model.target_policy_noise).numpy().copy() for _ in range(K)]
+    np.random.seed(17)
+    torch.manual_seed(23)
+    model.train(gradient_steps=K, batch_size=B)
+    for name, ps in nets().items():
+        for i, t in enumerate(ps):
+            out[f"final_{name}_{i}"] = t
+    for tag, opt in (("actor", model.actor.optimizer), ("critic", model.critic.optimizer)):
+        for i, prm in enumerate(opt.param_groups[0]["params"]):
+            st = opt.state[prm]
+            out[f"adam_{tag}_m_{i}"], out[f"adam_{tag}_v_{i}"] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+            out[f"adam_{tag}_step"] = np.array(float(st["step"]))
+    for k, f in zip(("obs", "act", "next_obs", "dones", "rewards"), ("observations", "actions", "next_observations", "dones", "rewards")):
+        out["batch_" + k] = np.stack([getattr(b, f).numpy() for b in batches])
+    out["noise"] = np.stack(noise)
+    out["critic_loss_mean"], out["actor_loss_mean"] = np.array(logged["train/critic_loss"]), np.array(logged["train/actor_loss"])
+    out["hyper"] = np.array([model.gamma, model.tau, model.policy_delay, model.target_policy_noise, model.target_noise_clip, model.lr_schedule(1)])
+    return out
+
+
+def gen_td3_update(m, core) -> None:
+    # net_arch [64, 48] keeps the fixture small; the restatement is architecture-agnostic (the default [400, 300] is compared live in
+    # tests/test_oracle_vs_reference.py when the reference tree is present)
+    np.savez_compressed(os.path.join(OUT, "td3_update.npz"), **td3_update_reference_run(m, core, [64, 48]))
+
+
 def main() -> None:
     if not refload.available():
         raise SystemExit("reference tree not found; fixtures can only be generated in the build container")
@@ -265,6 +327,7 @@ def main() -> None:
     gen_replay(core)
     gen_actor(m, core)
     gen_vecnorm(m, core)
+    gen_td3_update(m, core)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

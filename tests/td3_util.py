@@ -1,0 +1,35 @@
+"""Helpers shared by the TD3-update parity tests (CPU oracle and GPU)."""
+import numpy as np
+
+NETS = ("actor", "critic0", "critic1", "actor_target", "critic0_target", "critic1_target")
+
+
+def nets_from(g, prefix):
+    return {name: [np.asarray(g[f"{prefix}_{name}_{i}"]) for i in range(6)] for name in NETS}
+
+
+def make_oracle(T, g):
+    n = nets_from(g, "init")
+    gamma, tau, delay, _sigma, clip, lr = [float(x) for x in g["hyper"]]
+    return T.TD3UpdateOracle(n["actor"], [n["critic0"], n["critic1"]], n["actor_target"], [n["critic0_target"], n["critic1_target"]], lr=lr,
+                             gamma=gamma, tau=tau, policy_delay=int(delay), target_noise_clip=clip)
+
+
+def replay(o, g):
+    for k in range(g["noise"].shape[0]):
+        o.step(g["batch_obs"][k], g["batch_act"][k], g["batch_next_obs"][k], g["batch_dones"][k], g["batch_rewards"][k], g["noise"][k])
+    return {"actor": o.actor, "critic0": o.critics[0], "critic1": o.critics[1], "actor_target": o.actor_target,
+            "critic0_target": o.critic_targets[0], "critic1_target": o.critic_targets[1]}
+
+
+def random_nets(rng, h1, h2):
+    """torch nn.Linear default init (kaiming-uniform a=sqrt(5) -> U(+-1/sqrt(fan_in)) for weights and biases)."""
+    def mlp(i, o):
+        out = []
+        for fi, fo in ((i, h1), (h1, h2), (h2, o)):
+            b = 1.0 / np.sqrt(fi)
+            out += [rng.uniform(-b, b, (fo, fi)).astype(np.float32), rng.uniform(-b, b, fo).astype(np.float32)]
+        return out
+    a, c0, c1 = mlp(4, 2), mlp(6, 1), mlp(6, 1)
+    cp = lambda ps: [t.copy() for t in ps]  # noqa: E731
+    return {"actor": a, "critic0": c0, "critic1": c1, "actor_target": cp(a), "critic0_target": cp(c0), "critic1_target": cp(c1)}

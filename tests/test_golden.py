@@ -143,3 +143,23 @@ def test_vecnormalize_oracle_vs_reference_fixture(golden):
     b, e = g["batch_inds"], g["env_inds"]
     assert np.array_equal(same.normalize_obs(g["store_observations"][b, e]), g["s_obs"])
     assert np.array_equal(same.normalize_reward(g["store_rewards"][b, e].reshape(-1, 1)), g["s_rewards"])
+
+
+def test_td3_update_oracle_vs_reference_fixture(golden):
+    """TD3UpdateOracle replays 6 gradient steps of the reference's TD3.train (td3.py:154-211) on the recorded batches and noise."""
+    import td3_oracle as T
+    import td3_util as U
+
+    g = golden("td3_update.npz")
+    o = U.make_oracle(T, g)
+    final = U.replay(o, g)
+    ref = U.nets_from(g, "final")
+    for name in U.NETS:
+        for a, b in zip(final[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=5e-6)  # measured 9e-7 (float32 GEMM summation order)
+    assert np.mean(o.critic_losses) == pytest.approx(float(g["critic_loss_mean"]), rel=1e-5)
+    assert np.mean(o.actor_losses) == pytest.approx(float(g["actor_loss_mean"]), rel=1e-5)
+    assert o.critic_opt.step_count == int(g["adam_critic_step"]) == 6 and o.actor_opt.step_count == int(g["adam_actor_step"]) == 3
+    for i in range(12):
+        np.testing.assert_allclose(o.critic_opt.m[i], g[f"adam_critic_m_{i}"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(o.critic_opt.v[i], g[f"adam_critic_v_{i}"], rtol=1e-4, atol=1e-9)

@@ -96,3 +96,19 @@ def test_replay_buffer_live():
     assert np.array_equal(s.observations.numpy(), obs) and np.array_equal(s.actions.numpy(), act)
     assert np.array_equal(s.next_observations.numpy(), nobs) and np.array_equal(s.dones.numpy(), dones)
     assert np.array_equal(s.rewards.numpy(), rew)
+
+
+def test_td3_update_default_arch_live(ref_env_module):
+    """The TD3 gradient-step restatement against the reference's TD3.train at the default [400, 300] architecture."""
+    import make_golden
+    import td3_oracle as T
+    import td3_util as U
+
+    g = make_golden.td3_update_reference_run(ref_env_module, refload.load_core(), [400, 300], K=4, B=32)
+    o = U.make_oracle(T, g)
+    final = U.replay(o, g)
+    ref = U.nets_from(g, "final")
+    for name in U.NETS:
+        for a, b in zip(final[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)
+    assert np.mean(o.critic_losses) == pytest.approx(float(g["critic_loss_mean"]), rel=1e-5)
