@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 8
+#define CSTR_B200_ABI_VERSION 9
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -170,6 +170,50 @@ int cstr_norm_update(int64_t n, const float *obs, const float *reward, const uin
                      double gamma, double *stats, double *scratch, void *stream);
 int cstr_norm_apply(int64_t n, const float *obs_in, const float *reward_in, const double *stats, double epsilon,
                     double clip_obs, double clip_reward, float *obs_out, float *reward_out, void *stream);
+
+/* ---- TD3 gradient step ----------------------------------------------------------------
+ * Replaces one iteration of the loop body of TD3.train (core/td3/td3.py:162-206) after the batch has been sampled:
+ * target policy smoothing + twin-min target (:166-175), critic forward / MSE / backward (:178-186), Adam step of the
+ * critic optimiser, and on every policy_delay-th update the actor loss -Q1(s, pi(s)).mean(), its backward, the
+ * actor's Adam step and polyak_update of both target nets (:189-200, core/common/utils.py:457-481).
+ * Networks: create_mlp(4, 2, [h1, h2]) + tanh for the actor, create_mlp(6, 1, [h1, h2]) for each of the two critics
+ * (core/td3/policies.py:58, core/common/policies.py:966; torch nn.Linear layout), float32 arithmetic throughout.
+ *
+ * All five parameter-shaped blocks (params, targets, grads, adam_m, adam_v) use ONE flat layout of
+ * cstr_td3_param_count(h1, h2) floats = [actor | critic0 | critic1], each net W1 b1 W2 b2 W3 b3 with every tensor
+ * padded to a multiple of 4 floats; cstr_td3_layout writes the 18 tensor offsets (net-major) + the total.
+ * counters are the values AFTER this update (1-based): n_updates decides the policy step, critic_step / actor_step
+ * are the Adam step numbers used for the bias corrections.
+ * phases: run a subset so a data-parallel caller can all-reduce `grads` between GRAD and APPLY.
+ * noise: (batch,2) N(0, target_policy_noise) draws, or NULL = Philox (key seed, counter (row, n_updates), stream 5).
+ * losses (nullable, 4 floats, device): [0] += critic loss, [1] += 1, [2] += actor loss, [3] += 1.                   */
+typedef struct cstr_td3_config {
+    int32_t h1, h2;       /* hidden sizes, multiples of 4 */
+    int32_t batch;
+    int32_t policy_delay;
+    float gamma, tau, lr, beta1, beta2, eps, target_policy_noise, target_noise_clip;
+    uint64_t seed;
+} cstr_td3_config;
+
+typedef struct cstr_td3_state {
+    float *params, *targets, *grads, *adam_m, *adam_v; /* device, cstr_td3_param_count floats each, 16-byte aligned */
+    float *workspace;                                  /* device, >= cstr_td3_workspace_bytes(cfg)                  */
+    int64_t workspace_bytes;
+    float *losses;                                     /* device, 4 floats, or NULL                                 */
+} cstr_td3_state;
+
+#define CSTR_TD3_CRITIC_GRAD 1
+#define CSTR_TD3_CRITIC_APPLY 2
+#define CSTR_TD3_ACTOR_GRAD 4
+#define CSTR_TD3_ACTOR_APPLY 8
+#define CSTR_TD3_ALL 15
+
+int64_t cstr_td3_param_count(int32_t h1, int32_t h2);
+int cstr_td3_layout(int32_t h1, int32_t h2, int64_t *offsets /* 19 */);
+int64_t cstr_td3_workspace_bytes(const cstr_td3_config *cfg);
+int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *state, const float *obs, const float *actions,
+                    const float *next_obs, const float *dones, const float *rewards, const float *noise,
+                    int64_t n_updates, int64_t critic_step, int64_t actor_step, int32_t phases, void *stream);
 
 /* ---- fused rollout --------------------------------------------------------------------------------
  * Replaces, for K consecutive env steps of N reactors, OffPolicyAlgorithm._sample_action +

@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -57,6 +57,23 @@ class NormParams(Structure):
                 ("norm_obs", c_int32), ("norm_reward", c_int32)]
 
 
+class Td3Config(Structure):
+    """struct cstr_td3_config"""
+
+    _fields_ = [("h1", c_int32), ("h2", c_int32), ("batch", c_int32), ("policy_delay", c_int32), ("gamma", c_float), ("tau", c_float),
+                ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("target_policy_noise", c_float),
+                ("target_noise_clip", c_float), ("seed", c_uint64)]
+
+
+class Td3State(Structure):
+    """struct cstr_td3_state"""
+
+    _fields_ = [("params", c_void_p), ("targets", c_void_p), ("grads", c_void_p), ("adam_m", c_void_p), ("adam_v", c_void_p),
+                ("workspace", c_void_p), ("workspace_bytes", c_int64), ("losses", c_void_p)]
+
+
+TD3_CRITIC_GRAD, TD3_CRITIC_APPLY, TD3_ACTOR_GRAD, TD3_ACTOR_APPLY, TD3_ALL = 1, 2, 4, 8, 15
+
 P = c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)  — mirrors include/cstr_b200.h one to one
@@ -74,6 +91,10 @@ _SIGNATURES = {
     "cstr_replay_sample_philox": (c_int, [c_uint64, c_uint64, c_int64, c_int64, c_int64, P, P, P, P, P, P, P, P, POINTER(NormParams), P]),
     "cstr_norm_update": (c_int, [c_int64, P, P, P, P, c_double, P, P, P]),
     "cstr_norm_apply": (c_int, [c_int64, P, P, P, c_double, c_double, c_double, P, P, P]),
+    "cstr_td3_param_count": (c_int64, [c_int32, c_int32]),
+    "cstr_td3_layout": (c_int, [c_int32, c_int32, POINTER(c_int64)]),
+    "cstr_td3_workspace_bytes": (c_int64, [POINTER(Td3Config)]),
+    "cstr_td3_update": (c_int, [POINTER(Td3Config), POINTER(Td3State), P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int32, P]),
     "cstr_rollout_fused": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, c_int, POINTER(ActorF32), P, c_float, P, c_int,
                                    c_uint32, P, P, P, P, c_int64, c_int64, P, P, POINTER(EpisodeStatsStruct), P]),
     "cstr_actor_pack_bf16": (c_int64, [POINTER(ActorF32), P, P]),

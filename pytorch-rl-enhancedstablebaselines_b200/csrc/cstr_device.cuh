@@ -30,7 +30,7 @@ namespace cstr {
 
 // ---- Philox4x32-10 ---------------------------------------------------------------------------------
 // counter = (env_lo, env_hi, c2, (stream << 8) | call), key = (seed_lo, seed_hi)
-enum : uint32_t { STREAM_RESET = 1u, STREAM_ACTION = 2u, STREAM_NOISE = 3u, STREAM_SAMPLE = 4u };
+enum : uint32_t { STREAM_RESET = 1u, STREAM_ACTION = 2u, STREAM_NOISE = 3u, STREAM_SAMPLE = 4u, STREAM_TD3 = 5u };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll

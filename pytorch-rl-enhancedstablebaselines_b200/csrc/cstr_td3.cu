@@ -1,0 +1,723 @@
+// TD3 gradient step on the device: everything between `replay_buffer.sample()` and the end of one
+// iteration of the loop in TD3.train, as a fixed sequence of hand-written float32 kernels on one stream.
+//
+// Replaces (reference file:line):
+//   TD3.train loop body                     core/td3/td3.py:162-206
+//   Actor / ContinuousCritic forward        core/td3/policies.py:58,75-78, core/common/policies.py:966-987 (create_mlp, torch_layers.py:110-183)
+//   autograd backward of those MLPs         (torch autograd; restated in oracle/td3_oracle.py::mlp_backward)
+//   th.optim.Adam.step (defaults)           torch/optim/adam.py single-tensor path
+//   polyak_update                           core/common/utils.py:457-481
+//
+// Arithmetic: float32 FFMA (the reference's torch default: no TF32/BF16), so parity with the oracle is summation-order
+// tolerance (tests/test_gpu_td3.py).  Everything is deterministic: no atomics; batch reductions go through fixed-order
+// partial sums.
+//
+// Parameter block (floats): [actor | critic0 | critic1], each net = W1 (H1,in) b1 W2 (H2,H1) b2 W3 (out,H2) b3 in torch nn.Linear
+// layout, every tensor padded to a multiple of 4 floats (16-byte aligned rows for float4 access).  `params`, `targets`,
+// `grads`, `adam_m`, `adam_v` all share that layout, so Adam / polyak / the NCCL gradient bucket are single flat ranges.
+#include "cstr_abi.cuh"
+#include "cstr_device.cuh"
+
+namespace cstr {
+
+constexpr int OBS = 4, ACT = 2;
+
+struct NetLayout {  // offsets (floats) inside one net block
+    int in, out, h1, h2;
+    int64_t w1, b1, w2, b2, w3, b3, size;
+};
+
+__host__ __device__ inline int64_t pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
+
+inline NetLayout net_layout(int in, int out, int h1, int h2) {
+    NetLayout L;
+    L.in = in, L.out = out, L.h1 = h1, L.h2 = h2;
+    int64_t o = 0;
+    L.w1 = o, o += pad4((int64_t)h1 * in);
+    L.b1 = o, o += pad4(h1);
+    L.w2 = o, o += pad4((int64_t)h2 * h1);
+    L.b2 = o, o += pad4(h2);
+    L.w3 = o, o += pad4((int64_t)out * h2);
+    L.b3 = o, o += pad4(out);
+    L.size = o;
+    return L;
+}
+
+struct Td3Layout {
+    NetLayout actor, critic;
+    int64_t actor_off, critic_off[2], total;
+};
+
+inline Td3Layout td3_layout(int h1, int h2) {
+    Td3Layout T;
+    T.actor = net_layout(OBS, ACT, h1, h2);
+    T.critic = net_layout(OBS + ACT, 1, h1, h2);
+    T.actor_off = 0;
+    T.critic_off[0] = T.actor.size;
+    T.critic_off[1] = T.actor.size + T.critic.size;
+    T.total = T.actor.size + 2 * T.critic.size;
+    return T;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// layer 1: h1[z][b][j] = relu(b1[j] + sum_i x[b][i] W1[j][i]),  x = [obs | act]  (K = 4 or 6: no GEMM needed)
+// ------------------------------------------------------------------------------------------------------------------
+template <int IN>
+__global__ void __launch_bounds__(256)
+td3_layer1_kernel(int B, int H1, const float4 *__restrict__ obs, const float2 *__restrict__ act, const float *__restrict__ W1, const float *__restrict__ b1,
+                  int64_t w_stride_z, float *__restrict__ h1, int64_t h_stride_z) {
+    const int q = H1 >> 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * q) return;
+    const int b = (int)(i / q), j = (int)(i % q) * 4;
+    const int z = blockIdx.y;
+    const float *W = W1 + z * w_stride_z + (int64_t)j * IN;
+    const float4 o = obs[b];
+    float x[IN];
+    x[0] = o.x, x[1] = o.y, x[2] = o.z, x[3] = o.w;
+    if (IN == 6) {
+        const float2 a = act[b];
+        x[4] = a.x, x[5] = a.y;
+    }
+    const float4 bias = *reinterpret_cast<const float4 *>(b1 + z * w_stride_z + j);
+    float r[4] = {bias.x, bias.y, bias.z, bias.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < IN; ++k) r[c] = fmaf(x[k], __ldg(W + c * IN + k), r[c]);
+    *reinterpret_cast<float4 *>(h1 + z * h_stride_z + (int64_t)b * H1 + j) =
+        make_float4(fmaxf(r[0], 0.f), fmaxf(r[1], 0.f), fmaxf(r[2], 0.f), fmaxf(r[3], 0.f));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the hidden-layer GEMM (H1 x H2), three roles from one tiled FFMA kernel:
+//   FWD    h2  = relu(h1  @ W2^T + b2)        A = h1  (M=B, K=H1, k-contiguous)   Bm = W2 (N=H2 rows, k-contiguous)
+//   DGRAD  dz1 = (dz2 @ W2) * (h1 > 0)        A = dz2 (M=B, K=H2, k-contiguous)   Bm = W2 (K=H2 rows, n-contiguous)
+//   WGRAD  dW2 = dz2^T @ h1   (split over B)  A = dz2 (K=B rows, m-contiguous)    Bm = h1 (K=B rows, n-contiguous)
+// CTA tile 128 x 64 x 16, 256 threads, 8 x 4 accumulators per thread, double-buffered shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+enum { G_FWD = 0, G_DGRAD = 1, G_WGRAD = 2 };
+constexpr int BM = 128, BN = 64, BK = 16, LDA_S = BM + 4, LDB_S = BN + 4;
+
+struct GemmArgs {
+    const float *A, *Bm, *aux;
+    float *C;
+    int M, N, K, lda, ldb, ldc, ldaux;
+    int64_t a_z, b_z, c_z, aux_z;  // per-net strides (floats)
+    int splits, k_per_split;
+    int64_t c_split;               // WGRAD: slab stride
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) td3_gemm_kernel(GemmArgs g) {
+    __shared__ __align__(16) float As[2][BK][LDA_S];
+    __shared__ __align__(16) float Bs[2][BK][LDB_S];
+    const int tid = threadIdx.x, tn = tid & 15, tm = tid >> 4;
+    const int z = blockIdx.z / g.splits, split = blockIdx.z % g.splits;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const float *A = g.A + z * g.a_z, *Bm = g.Bm + z * g.b_z;
+    int k_begin = 0, k_end = g.K;
+    if (MODE == G_WGRAD) {
+        k_begin = split * g.k_per_split;
+        k_end = min(g.K, k_begin + g.k_per_split);
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    float4 ra[2], rb;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_global = [&](int k0) {
+        if (MODE == G_WGRAD) {  // A rows = k, m-contiguous: 16 x 128 floats = 512 float4
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + i * 256, kk = idx >> 5, mq = (idx & 31) * 4;
+                const int k = k0 + kk, m = m0 + mq;
+                ra[i] = (k < k_end && m < g.M) ? *reinterpret_cast<const float4 *>(A + (int64_t)k * g.lda + m) : zero4;
+            }
+        } else {  // A rows = m, k-contiguous: 128 x 16 floats
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + i * 256, row = idx >> 2, kq = (idx & 3) * 4;
+                const int m = m0 + row, k = k0 + kq;
+                ra[i] = (m < g.M && k < k_end) ? *reinterpret_cast<const float4 *>(A + (int64_t)m * g.lda + k) : zero4;
+            }
+        }
+        if (MODE == G_FWD) {  // Bm rows = n, k-contiguous: 64 x 16
+            const int row = tid >> 2, kq = (tid & 3) * 4;
+            const int n = n0 + row, k = k0 + kq;
+            rb = (n < g.N && k < k_end) ? *reinterpret_cast<const float4 *>(Bm + (int64_t)n * g.ldb + k) : zero4;
+        } else {  // Bm rows = k, n-contiguous: 16 x 64
+            const int kk = tid >> 4, nq = (tid & 15) * 4;
+            const int k = k0 + kk, n = n0 + nq;
+            rb = (k < k_end && n < g.N) ? *reinterpret_cast<const float4 *>(Bm + (int64_t)k * g.ldb + n) : zero4;
+        }
+    };
+    auto store_shared = [&](int buf) {
+        if (MODE == G_WGRAD) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + i * 256, kk = idx >> 5, mq = (idx & 31) * 4;
+                *reinterpret_cast<float4 *>(&As[buf][kk][mq]) = ra[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int idx = tid + i * 256, row = idx >> 2, kq = (idx & 3) * 4;
+                As[buf][kq + 0][row] = ra[i].x;
+                As[buf][kq + 1][row] = ra[i].y;
+                As[buf][kq + 2][row] = ra[i].z;
+                As[buf][kq + 3][row] = ra[i].w;
+            }
+        }
+        if (MODE == G_FWD) {
+            const int row = tid >> 2, kq = (tid & 3) * 4;
+            Bs[buf][kq + 0][row] = rb.x;
+            Bs[buf][kq + 1][row] = rb.y;
+            Bs[buf][kq + 2][row] = rb.z;
+            Bs[buf][kq + 3][row] = rb.w;
+        } else {
+            const int kk = tid >> 4, nq = (tid & 15) * 4;
+            *reinterpret_cast<float4 *>(&Bs[buf][kk][nq]) = rb;
+        }
+    };
+
+    const int n_iter = (k_end - k_begin + BK - 1) / BK;
+    if (n_iter > 0) {
+        load_global(k_begin);
+        store_shared(0);
+    }
+    __syncthreads();
+    for (int it = 0; it < n_iter; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < n_iter) load_global(k_begin + (it + 1) * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][tm * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][tm * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tn * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (it + 1 < n_iter) store_shared(buf ^ 1);
+        __syncthreads();
+    }
+
+    const int n = n0 + tn * 4;
+    if (n >= g.N) return;
+    float *C = g.C + z * g.c_z + (MODE == G_WGRAD ? split * g.c_split : 0);
+    float4 bias = zero4;
+    if (MODE == G_FWD) bias = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + tm * 8 + i;
+        if (m >= g.M) break;
+        float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (MODE == G_FWD) {
+            v = make_float4(fmaxf(v.x + bias.x, 0.f), fmaxf(v.y + bias.y, 0.f), fmaxf(v.z + bias.z, 0.f), fmaxf(v.w + bias.w, 0.f));
+        } else if (MODE == G_DGRAD) {
+            const float4 h = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + (int64_t)m * g.ldaux + n);
+            v = make_float4(h.x > 0.f ? v.x : 0.f, h.y > 0.f ? v.y : 0.f, h.z > 0.f ? v.z : 0.f, h.w > 0.f ? v.w : 0.f);
+        }
+        *reinterpret_cast<float4 *>(C + (int64_t)m * g.ldc + n) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// row heads: one warp per batch row
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float row_dot(const float *__restrict__ h, const float *__restrict__ w, int H, int lane) {
+    float s = 0.f;
+    for (int k = lane * 4; k < H; k += 128) {
+        const float4 a = *reinterpret_cast<const float4 *>(h + k), b = *reinterpret_cast<const float4 *>(w + k);
+        s = fmaf(a.x, b.x, s), s = fmaf(a.y, b.y, s), s = fmaf(a.z, b.z, s), s = fmaf(a.w, b.w, s);
+    }
+    return warp_sum(s);
+}
+
+// actor head: a = tanh(h2 @ W3^T + b3) [+ clip(noise) -> clamp(-1,1)]                              td3.py:168-170 / policies.py:75-78
+__global__ void __launch_bounds__(256)
+td3_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *__restrict__ W3, const float *__restrict__ b3, int smooth,
+                      const float2 *__restrict__ noise, float sigma, float clip, uint64_t seed, uint32_t update_index, float2 *__restrict__ out) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float *h = h2 + (int64_t)b * H2;
+    const float p0 = row_dot(h, W3, H2, lane) + b3[0], p1 = row_dot(h, W3 + H2, H2, lane) + b3[1];
+    if (lane) return;
+    float a0 = tanhf(p0), a1 = tanhf(p1);
+    if (smooth) {
+        float2 nz;
+        if (noise) nz = noise[b];
+        else {
+            const uint4 r = philox_env(seed, (uint64_t)b, update_index, STREAM_TD3, 0);
+            const float u1 = fmaf(u24(r.x), 1.0f, 5.9604644775390625e-08f), u2 = u24(r.y);
+            const float rad = sqrtf(-2.0f * logf(u1));
+            float sn, cs;
+            sincospif(2.0f * u2, &sn, &cs);
+            nz = make_float2(sigma * rad * cs, sigma * rad * sn);
+        }
+        a0 = fminf(fmaxf(a0 + fminf(fmaxf(nz.x, -clip), clip), -1.f), 1.f);
+        a1 = fminf(fmaxf(a1 + fminf(fmaxf(nz.y, -clip), clip), -1.f), 1.f);
+    }
+    out[b] = make_float2(a0, a1);
+}
+
+// target head: target = r + (1 - done) * gamma * min(q1_target, q2_target)                         td3.py:173-175
+__global__ void __launch_bounds__(256)
+td3_target_head_kernel(int B, int H2, const float *__restrict__ h2, int64_t h_z, const float *__restrict__ W3, const float *__restrict__ b3, int64_t w_z,
+                       const float *__restrict__ rewards, const float *__restrict__ dones, float gamma, float *__restrict__ target) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float q0 = row_dot(h2 + (int64_t)b * H2, W3, H2, lane) + b3[0];
+    const float q1 = row_dot(h2 + h_z + (int64_t)b * H2, W3 + w_z, H2, lane) + b3[w_z];
+    if (lane == 0) target[b] = rewards[b] + (1.f - dones[b]) * gamma * fminf(q0, q1);
+}
+
+// critic head (z = critic): q = h2 . w3 + b3; loss += (q-target)^2; dq = 2 (q-target)/B; dz2 = dq * w3 * (h2 > 0)   td3.py:178-186
+// policy head  (POLICY):    q1 = h2 . w3 + b3; loss += q1;          dq = -1/B                                        td3.py:191
+template <bool POLICY>
+__global__ void __launch_bounds__(256)
+td3_critic_head_kernel(int B, int H2, const float *__restrict__ h2, int64_t h_z, const float *__restrict__ W3, const float *__restrict__ b3, int64_t w_z,
+                       const float *__restrict__ target, float *__restrict__ dq_out, float *__restrict__ dz2, float *__restrict__ loss_partial) {
+    __shared__ float sl[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x * 8 + warp, z = blockIdx.y;
+    float contrib = 0.f;
+    if (b < B) {
+        const float *h = h2 + z * h_z + (int64_t)b * H2, *w = W3 + z * w_z;
+        const float q = row_dot(h, w, H2, lane) + b3[z * w_z];
+        float dq;
+        if (POLICY) {
+            contrib = q;
+            dq = -1.f / (float)B;
+        } else {
+            const float diff = q - target[b];
+            contrib = diff * diff;
+            dq = (2.f / (float)B) * diff;
+        }
+        if (lane == 0) dq_out[(int64_t)z * B + b] = dq;
+        float *d = dz2 + z * h_z + (int64_t)b * H2;
+        for (int k = lane * 4; k < H2; k += 128) {
+            const float4 a = *reinterpret_cast<const float4 *>(h + k), ww = *reinterpret_cast<const float4 *>(w + k);
+            *reinterpret_cast<float4 *>(d + k) =
+                make_float4(a.x > 0.f ? dq * ww.x : 0.f, a.y > 0.f ? dq * ww.y : 0.f, a.z > 0.f ? dq * ww.z : 0.f, a.w > 0.f ? dq * ww.w : 0.f);
+        }
+    }
+    if (lane == 0) sl[warp] = contrib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += sl[i];
+        loss_partial[(int64_t)z * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// policy gradient through the critic input and the tanh:  da = dz1c @ W1c[:, 4:6];  dpre = da * (1 - a^2);
+// dz2a = (dpre @ W3a) * (h2a > 0)                                                                   td3.py:191-196 (autograd)
+__global__ void __launch_bounds__(256)
+td3_actor_bwd_head_kernel(int B, int H1, int H2, const float *__restrict__ dz1c, const float *__restrict__ W1c, const float2 *__restrict__ a_pi,
+                          const float *__restrict__ W3a, const float *__restrict__ h2a, float2 *__restrict__ dpre_out, float *__restrict__ dz2a) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float *d = dz1c + (int64_t)b * H1;
+    float s0 = 0.f, s1 = 0.f;
+    for (int j = lane; j < H1; j += 32) {
+        const float v = d[j];
+        s0 = fmaf(v, __ldg(W1c + j * (OBS + ACT) + OBS), s0);
+        s1 = fmaf(v, __ldg(W1c + j * (OBS + ACT) + OBS + 1), s1);
+    }
+    s0 = warp_sum(s0), s1 = warp_sum(s1);
+    const float2 a = a_pi[b];
+    const float p0 = s0 * (1.f - a.x * a.x), p1 = s1 * (1.f - a.y * a.y);
+    if (lane == 0) dpre_out[b] = make_float2(p0, p1);
+    const float *h = h2a + (int64_t)b * H2;
+    float *o = dz2a + (int64_t)b * H2;
+    for (int k = lane * 4; k < H2; k += 128) {
+        const float4 hh = *reinterpret_cast<const float4 *>(h + k);
+        const float4 w0 = *reinterpret_cast<const float4 *>(W3a + k), w1 = *reinterpret_cast<const float4 *>(W3a + H2 + k);
+        *reinterpret_cast<float4 *>(o + k) = make_float4(hh.x > 0.f ? fmaf(p1, w1.x, p0 * w0.x) : 0.f, hh.y > 0.f ? fmaf(p1, w1.y, p0 * w0.y) : 0.f,
+                                                         hh.z > 0.f ? fmaf(p1, w1.z, p0 * w0.z) : 0.f, hh.w > 0.f ? fmaf(p1, w1.w, p0 * w0.w) : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// skinny weight gradients:  out_w[j][i] (or [i][j]) = sum_b X[b][j] * Y[b][i],  out_b = sum_b X[b][j]  (or sum_b Y[b][i])
+//   layer 1:  X = dz1 (B,H1), Y = [obs | act]        -> dW1 (H1,in), db1 (H1)
+//   layer 2 bias: X = dz2 (B,H2), no Y               -> db2 (H2)
+//   layer 3:  X = h2 (B,H2),  Y = dq / dpre (B,out)  -> dW3 (out,H2) [transposed store], db3 = sum_b Y
+// One CTA owns 32 columns j and walks the whole batch (fixed order: deterministic), 8 warps interleaved over rows.
+// ------------------------------------------------------------------------------------------------------------------
+struct SkinnyArgs {
+    const float *X;
+    int64_t x_z;
+    int ldx, H, B;
+    const float *Y0;  // (B, n0) shared over z unless y_z != 0
+    const float *Y1;  // (B, n1)
+    int n0, ld0, n1, ld1;
+    int64_t y_z;
+    float *out_w, *out_b;  // out_b: sum_b X (x_bias) or sum_b Y (y_bias)
+    int64_t out_z;
+    int transposed;
+};
+
+template <int NY, bool YBIAS>
+__global__ void __launch_bounds__(256) td3_skinny_wgrad_kernel(SkinnyArgs s) {
+    __shared__ float red[8][NY + 1][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
+    const int j = blockIdx.x * 32 + lane;
+    const bool live = j < s.H;
+    const float *X = s.X + z * s.x_z;
+    const float *Y0 = s.Y0 ? s.Y0 + z * s.y_z : nullptr;
+    float acc[NY + 1];
+#pragma unroll
+    for (int i = 0; i <= NY; ++i) acc[i] = 0.f;
+    for (int b = warp; b < s.B; b += 8) {
+        const float x = live ? X[(int64_t)b * s.ldx + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) {
+            const float y = i < s.n0 ? Y0[(int64_t)b * s.ld0 + i] : s.Y1[(int64_t)b * s.ld1 + (i - s.n0)];
+            acc[i] = fmaf(x, y, acc[i]);
+        }
+        if (!YBIAS) acc[NY] += x;  // bias gradient = column sum of X
+    }
+    if (YBIAS && blockIdx.x == 0 && lane < NY)  // bias gradient = column sum of Y (layer 3): lane i of CTA 0 walks column i
+        for (int b = warp; b < s.B; b += 8) acc[NY] += Y0[(int64_t)b * s.ld0 + lane];
+#pragma unroll
+    for (int i = 0; i <= NY; ++i) red[warp][i][lane] = acc[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < (NY + 1) * 32; e += 256) {
+        const int i = e >> 5, l = e & 31, jj = blockIdx.x * 32 + l;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][i][l];
+        if (i < NY) {
+            if (jj < s.H) {
+                if (s.transposed) s.out_w[z * s.out_z + (int64_t)i * s.H + jj] = v;
+                else s.out_w[z * s.out_z + (int64_t)jj * NY + i] = v;
+            }
+        } else if (s.out_b) {
+            if (YBIAS) {
+                if (blockIdx.x == 0 && l < NY) s.out_b[z * s.out_z + l] = v;
+            } else if (jj < s.H) {
+                s.out_b[z * s.out_z + jj] = v;
+            }
+        }
+    }
+}
+
+// dW2 = sum of the split-K slabs (fixed order)
+__global__ void __launch_bounds__(256)
+td3_sum_slabs_kernel(int64_t n4, int splits, const float4 *__restrict__ slabs, int64_t slab_stride4, int64_t z_stride4, float4 *__restrict__ out,
+                     int64_t out_z4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int z = blockIdx.y;
+    float4 s = slabs[z * z_stride4 + i];
+    for (int k = 1; k < splits; ++k) {
+        const float4 v = slabs[k * slab_stride4 + z * z_stride4 + i];
+        s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+    }
+    out[z * out_z4 + i] = s;
+}
+
+// Adam (torch single-tensor formulas) over a flat range, optionally followed by the polyak update of another flat range;
+// block 0 / thread 0 also folds the per-CTA loss partials into the running loss sums.
+struct ApplyArgs {
+    float *p, *t;
+    const float *g;
+    float *m, *v;
+    int64_t adam_lo, adam_hi;      // Adam on [adam_lo, adam_hi)
+    int64_t polyak_lo, polyak_hi;  // polyak on [polyak_lo, polyak_hi) (after Adam where the ranges overlap)
+    float beta1, beta2, eps, step_size, bc2_sqrt, tau;
+    const float *loss_partial;
+    int n_loss_partial;
+    float loss_scale;
+    float *loss_acc;  // [0] += scale * sum(partials), [1] += 1
+};
+
+__global__ void __launch_bounds__(256) td3_apply_kernel(ApplyArgs a) {
+    const int64_t lo = min(a.adam_lo, a.polyak_lo < a.polyak_hi ? a.polyak_lo : a.adam_lo);
+    const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss_acc) {
+        float s = 0.f;
+        for (int k = 0; k < a.n_loss_partial; ++k) s += a.loss_partial[k];
+        a.loss_acc[0] += s * a.loss_scale;
+        a.loss_acc[1] += 1.f;
+    }
+    float p;
+    bool have = false;
+    if (i >= a.adam_lo && i < a.adam_hi) {
+        const float g = a.g[i];
+        float m = a.m[i], v = a.v[i];
+        m = m + (g - m) * (1.f - a.beta1);           // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * a.beta2 + (1.f - a.beta2) * g * g;   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+        p = a.p[i] - a.step_size * (m / denom);      // param.addcdiv_(exp_avg, denom, value=-step_size)
+        a.p[i] = p, a.m[i] = m, a.v[i] = v;
+        have = true;
+    }
+    if (i >= a.polyak_lo && i < a.polyak_hi) {
+        if (!have) p = a.p[i];
+        a.t[i] = a.t[i] * (1.f - a.tau) + a.tau * p;  // utils.py:480-481
+    }
+}
+
+}  // namespace cstr
+
+using namespace cstr;
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Workspace {  // carved out of the caller's workspace buffer (floats)
+    float *h1[2], *h2[2];    // forward activations, [z] slabs contiguous: h1[0] + B*H1 == h1[1]
+    float *dz1, *dz2;        // 2 slabs each
+    float *t_h1, *t_h2;      // target-critic activations (2 slabs)
+    float *a_h1, *a_h2;      // actor / actor-target activations
+    float *next_act, *a_pi, *target, *dq, *dpre, *loss_partial, *slabs;
+    int splits, n_row_blocks;
+    int64_t floats;
+};
+
+int choose_splits(int B) {
+    int s = (B + 511) / 512;
+    if (s < 1) s = 1;
+    if (s > 16) s = 16;
+    return s;
+}
+
+Workspace carve(float *base, int B, int H1, int H2) {
+    Workspace w;
+    int64_t o = 0;
+    auto take = [&](int64_t n) {
+        float *p = base ? base + o : nullptr;
+        o += pad4(n);
+        return p;
+    };
+    const int64_t bh1 = (int64_t)B * H1, bh2 = (int64_t)B * H2;
+    w.h1[0] = take(2 * bh1), w.h1[1] = w.h1[0] ? w.h1[0] + bh1 : nullptr;
+    w.h2[0] = take(2 * bh2), w.h2[1] = w.h2[0] ? w.h2[0] + bh2 : nullptr;
+    w.dz1 = take(2 * bh1), w.dz2 = take(2 * bh2);
+    w.t_h1 = take(2 * bh1), w.t_h2 = take(2 * bh2);
+    w.a_h1 = take(bh1), w.a_h2 = take(bh2);
+    w.next_act = take(2 * (int64_t)B), w.a_pi = take(2 * (int64_t)B), w.target = take(B), w.dq = take(2 * (int64_t)B), w.dpre = take(2 * (int64_t)B);
+    w.n_row_blocks = (B + 7) / 8;
+    w.loss_partial = take(2 * (int64_t)w.n_row_blocks);
+    w.splits = choose_splits(B);
+    w.slabs = take((int64_t)w.splits * 2 * pad4((int64_t)H1 * H2));
+    w.floats = o;
+    return w;
+}
+
+int check_cfg(const cstr_td3_config *c) {
+    if (!c) return fail_arg(CSTR_EINVAL, "td3: null config");
+    if (c->h1 < 4 || c->h2 < 4 || (c->h1 & 3) || (c->h2 & 3) || c->h1 > 4096 || c->h2 > 4096)
+        return fail_arg(CSTR_EINVAL, "td3: hidden sizes must be multiples of 4 in [4, 4096]");
+    if (c->batch < 1 || c->batch > (1 << 22)) return fail_arg(CSTR_EINVAL, "td3: batch must be in [1, 4194304]");
+    if (c->policy_delay < 1) return fail_arg(CSTR_EINVAL, "td3: policy_delay must be >= 1");
+    return 0;
+}
+
+template <int MODE>
+int launch_gemm(const GemmArgs &g, int Z, cudaStream_t st, const char *what) {
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, Z * g.splits);
+    td3_gemm_kernel<MODE><<<grid, 256, 0, st>>>(g);
+    return check_launch(what);
+}
+
+struct Net {  // pointers of one net (or the first of a z-batched pair) inside a flat block
+    float *w1, *b1, *w2, *b2, *w3, *b3;
+};
+Net net_at(float *base, int64_t off, const NetLayout &L) { return Net{base + off + L.w1, base + off + L.b1, base + off + L.w2, base + off + L.b2, base + off + L.w3, base + off + L.b3}; }
+
+// h1 = relu(L1(x)), h2 = relu(L2(h1)) for Z nets that are `z_stride` floats apart
+int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float *act, const Net &n, int64_t z_stride, int Z, float *h1, float *h2,
+                   cudaStream_t st) {
+    const int64_t threads = (int64_t)B * (H1 / 4);
+    dim3 grid((unsigned)((threads + 255) / 256), Z);
+    if (in == OBS)
+        td3_layer1_kernel<OBS><<<grid, 256, 0, st>>>(B, H1, (const float4 *)obs, nullptr, n.w1, n.b1, z_stride, h1, (int64_t)B * H1);
+    else
+        td3_layer1_kernel<OBS + ACT><<<grid, 256, 0, st>>>(B, H1, (const float4 *)obs, (const float2 *)act, n.w1, n.b1, z_stride, h1, (int64_t)B * H1);
+    if (int rc = check_launch("td3_layer1_kernel")) return rc;
+    GemmArgs g{};
+    g.A = h1, g.Bm = n.w2, g.aux = n.b2, g.C = h2;
+    g.M = B, g.N = H2, g.K = H1, g.lda = H1, g.ldb = H1, g.ldc = H2, g.ldaux = 0;
+    g.a_z = (int64_t)B * H1, g.b_z = z_stride, g.c_z = (int64_t)B * H2, g.aux_z = z_stride;
+    g.splits = 1, g.k_per_split = H1, g.c_split = 0;
+    return launch_gemm<G_FWD>(g, Z, st, "td3_gemm_kernel<fwd>");
+}
+
+// given dz2 (and h1, x): dz1 (optional), then every weight gradient of the hidden and input layers into the flat grads
+int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float *act, const Net &n, const Net &gn, int64_t z_stride, int Z,
+                    const float *h1, const float *dz2, float *dz1, const Workspace &w, bool want_weight_grads, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = dz2, g.Bm = n.w2, g.aux = h1, g.C = dz1;
+    g.M = B, g.N = H1, g.K = H2, g.lda = H2, g.ldb = H1, g.ldc = H1, g.ldaux = H1;
+    g.a_z = (int64_t)B * H2, g.b_z = z_stride, g.c_z = (int64_t)B * H1, g.aux_z = (int64_t)B * H1;
+    g.splits = 1, g.k_per_split = H2, g.c_split = 0;
+    if (int rc = launch_gemm<G_DGRAD>(g, Z, st, "td3_gemm_kernel<dgrad>")) return rc;
+    if (!want_weight_grads) return 0;
+    // dW2 = dz2^T @ h1, split over the batch into slabs, then summed in order
+    const int64_t w2n = pad4((int64_t)H1 * H2);
+    GemmArgs q{};
+    q.A = dz2, q.Bm = h1, q.aux = nullptr, q.C = w.slabs;
+    q.M = H2, q.N = H1, q.K = B, q.lda = H2, q.ldb = H1, q.ldc = H1, q.ldaux = 0;
+    q.a_z = (int64_t)B * H2, q.b_z = (int64_t)B * H1, q.c_z = w2n, q.aux_z = 0;
+    q.splits = w.splits, q.k_per_split = (B + w.splits - 1) / w.splits, q.c_split = 2 * w2n;
+    if (int rc = launch_gemm<G_WGRAD>(q, Z, st, "td3_gemm_kernel<wgrad>")) return rc;
+    const int64_t n4 = (int64_t)H1 * H2 / 4;
+    td3_sum_slabs_kernel<<<dim3((unsigned)((n4 + 255) / 256), Z), 256, 0, st>>>(n4, w.splits, (const float4 *)w.slabs, 2 * w2n / 4, w2n / 4, (float4 *)gn.w2,
+                                                                              z_stride / 4);
+    if (int rc = check_launch("td3_sum_slabs_kernel")) return rc;
+    // db2 = colsum(dz2)
+    SkinnyArgs s{};
+    s.X = dz2, s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
+    s.out_w = nullptr, s.out_b = gn.b2, s.out_z = z_stride;
+    td3_skinny_wgrad_kernel<0, false><<<dim3((H2 + 31) / 32, Z), 256, 0, st>>>(s);
+    if (int rc = check_launch("td3_skinny_wgrad_kernel<b2>")) return rc;
+    // dW1 = dz1^T @ [obs | act], db1 = colsum(dz1)
+    SkinnyArgs t{};
+    t.X = dz1, t.x_z = (int64_t)B * H1, t.ldx = H1, t.H = H1, t.B = B;
+    t.Y0 = obs, t.n0 = OBS, t.ld0 = OBS, t.Y1 = act, t.n1 = in - OBS, t.ld1 = ACT, t.y_z = 0;
+    t.out_w = gn.w1, t.out_b = gn.b1, t.out_z = z_stride;
+    if (in == OBS) td3_skinny_wgrad_kernel<OBS, false><<<dim3((H1 + 31) / 32, Z), 256, 0, st>>>(t);
+    else td3_skinny_wgrad_kernel<OBS + ACT, false><<<dim3((H1 + 31) / 32, Z), 256, 0, st>>>(t);
+    return check_launch("td3_skinny_wgrad_kernel<w1>");
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t cstr_td3_param_count(int32_t h1, int32_t h2) {
+    if (h1 < 4 || h2 < 4 || (h1 & 3) || (h2 & 3)) return -1;
+    return td3_layout(h1, h2).total;
+}
+
+int cstr_td3_layout(int32_t h1, int32_t h2, int64_t *offsets) {
+    if (!offsets || h1 < 4 || h2 < 4 || (h1 & 3) || (h2 & 3)) return fail_arg(CSTR_EINVAL, "td3_layout: bad sizes or null output");
+    const Td3Layout T = td3_layout(h1, h2);
+    const int64_t base[3] = {T.actor_off, T.critic_off[0], T.critic_off[1]};
+    for (int n = 0; n < 3; ++n) {
+        const NetLayout &L = n == 0 ? T.actor : T.critic;
+        const int64_t o[6] = {L.w1, L.b1, L.w2, L.b2, L.w3, L.b3};
+        for (int k = 0; k < 6; ++k) offsets[n * 6 + k] = base[n] + o[k];
+    }
+    offsets[18] = T.total;
+    return 0;
+}
+
+int64_t cstr_td3_workspace_bytes(const cstr_td3_config *cfg) {
+    if (check_cfg(cfg)) return -1;
+    return carve(nullptr, cfg->batch, cfg->h1, cfg->h2).floats * (int64_t)sizeof(float);
+}
+
+int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const float *obs, const float *actions, const float *next_obs,
+                    const float *dones, const float *rewards, const float *noise, int64_t n_updates, int64_t critic_step, int64_t actor_step,
+                    int32_t phases, void *stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    if (!stt || !stt->params || !stt->targets || !stt->grads || !stt->adam_m || !stt->adam_v || !stt->workspace)
+        return fail_arg(CSTR_EINVAL, "td3_update: null state pointer");
+    if (!obs || !actions || !next_obs || !dones || !rewards) return fail_arg(CSTR_EINVAL, "td3_update: null batch pointer");
+    if (!aligned(obs, 16) || !aligned(next_obs, 16) || !aligned(actions, 8) || (noise && !aligned(noise, 8)) || !aligned(stt->params, 16) ||
+        !aligned(stt->targets, 16) || !aligned(stt->grads, 16) || !aligned(stt->adam_m, 16) || !aligned(stt->adam_v, 16) || !aligned(stt->workspace, 16))
+        return fail_arg(CSTR_EALIGN, "td3_update: 16 B (obs/params/workspace) / 8 B (actions, noise) alignment");
+    const int B = cfg->batch, H1 = cfg->h1, H2 = cfg->h2;
+    const Workspace w = carve(stt->workspace, B, H1, H2);
+    if (stt->workspace_bytes < w.floats * (int64_t)sizeof(float)) return fail_arg(CSTR_EINVAL, "td3_update: workspace too small (cstr_td3_workspace_bytes)");
+    if (n_updates < 1 || critic_step < 1 || actor_step < 0) return fail_arg(CSTR_EINVAL, "td3_update: counters are 1-based (value after this update)");
+    const Td3Layout T = td3_layout(H1, H2);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cz = T.critic.size;
+    const Net actor = net_at(stt->params, T.actor_off, T.actor), actor_t = net_at(stt->targets, T.actor_off, T.actor);
+    const Net critic = net_at(stt->params, T.critic_off[0], T.critic), critic_t = net_at(stt->targets, T.critic_off[0], T.critic);
+    const Net g_actor = net_at(stt->grads, T.actor_off, T.actor), g_critic = net_at(stt->grads, T.critic_off[0], T.critic);
+    const int rb = w.n_row_blocks;
+    const bool policy_step = (n_updates % cfg->policy_delay) == 0;
+
+    if (phases & CSTR_TD3_CRITIC_GRAD) {
+        // ---- target (td3.py:166-175) ----
+        if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor_t, 0, 1, w.a_h1, w.a_h2, st)) return rc;
+        td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor_t.w3, actor_t.b3, 1, (const float2 *)noise, cfg->target_policy_noise,
+                                                 cfg->target_noise_clip, cfg->seed, (uint32_t)n_updates, (float2 *)w.next_act);
+        if (int rc = check_launch("td3_actor_head_kernel")) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, st)) return rc;
+        td3_target_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.t_h2, (int64_t)B * H2, critic_t.w3, critic_t.b3, cz, rewards, dones, cfg->gamma, w.target);
+        if (int rc = check_launch("td3_target_head_kernel")) return rc;
+        // ---- current Q, loss, backward (td3.py:178-186) ----
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], st)) return rc;
+        td3_critic_head_kernel<false><<<dim3(rb, 2), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, w.dq, w.dz2,
+                                                                  w.loss_partial);
+        if (int rc = check_launch("td3_critic_head_kernel")) return rc;
+        SkinnyArgs s{};  // dW3 = dq^T @ h2, db3 = sum dq
+        s.X = w.h2[0], s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
+        s.Y0 = w.dq, s.n0 = 1, s.ld0 = 1, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = B;
+        s.out_w = g_critic.w3, s.out_b = g_critic.b3, s.out_z = cz, s.transposed = 1;
+        td3_skinny_wgrad_kernel<1, true><<<dim3((H2 + 31) / 32, 2), 256, 0, st>>>(s);
+        if (int rc = check_launch("td3_skinny_wgrad_kernel<w3>")) return rc;
+        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st)) return rc;
+    }
+    if (phases & CSTR_TD3_CRITIC_APPLY) {
+        ApplyArgs a{};
+        a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
+        a.adam_lo = T.critic_off[0], a.adam_hi = T.total, a.polyak_lo = a.polyak_hi = 0;
+        const double bc1 = 1.0 - pow((double)cfg->beta1, (double)critic_step), bc2 = 1.0 - pow((double)cfg->beta2, (double)critic_step);
+        a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = (float)((double)cfg->lr / bc1), a.bc2_sqrt = (float)sqrt(bc2);
+        a.tau = cfg->tau;
+        a.loss_partial = w.loss_partial, a.n_loss_partial = 2 * rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses;
+        const int64_t n = a.adam_hi - a.adam_lo;
+        td3_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+        if (int rc = check_launch("td3_apply_kernel<critic>")) return rc;
+    }
+    if (policy_step && (phases & CSTR_TD3_ACTOR_GRAD)) {
+        // ---- actor loss = -Q1(s, pi(s)).mean() and its backward (td3.py:189-196) ----
+        if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, st)) return rc;
+        td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, 0, nullptr, 0.f, 0.f, 0, 0, (float2 *)w.a_pi);
+        if (int rc = check_launch("td3_actor_head_kernel<pi>")) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 1, w.h1[0], w.h2[0], st)) return rc;
+        td3_critic_head_kernel<true><<<dim3(rb, 1), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, nullptr, w.dq, w.dz2,
+                                                                 w.loss_partial);
+        if (int rc = check_launch("td3_critic_head_kernel<policy>")) return rc;
+        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, g_critic, cz, 1, w.h1[0], w.dz2, w.dz1, w, false, st)) return rc;
+        // through the critic's input layer and the tanh into the actor; dz2 of the actor reuses slab 1 of the dz2 buffer
+        float *dz2a = w.dz2 + (int64_t)B * H2, *dz1a = w.dz1 + (int64_t)B * H1;
+        td3_actor_bwd_head_kernel<<<rb, 256, 0, st>>>(B, H1, H2, w.dz1, critic.w1, (const float2 *)w.a_pi, actor.w3, w.a_h2, (float2 *)w.dpre, dz2a);
+        if (int rc = check_launch("td3_actor_bwd_head_kernel")) return rc;
+        SkinnyArgs s{};  // dW3a = dpre^T @ h2a, db3a = sum dpre
+        s.X = w.a_h2, s.x_z = 0, s.ldx = H2, s.H = H2, s.B = B;
+        s.Y0 = w.dpre, s.n0 = ACT, s.ld0 = ACT, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = 0;
+        s.out_w = g_actor.w3, s.out_b = g_actor.b3, s.out_z = 0, s.transposed = 1;
+        td3_skinny_wgrad_kernel<ACT, true><<<dim3((H2 + 31) / 32, 1), 256, 0, st>>>(s);
+        if (int rc = check_launch("td3_skinny_wgrad_kernel<actor w3>")) return rc;
+        if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, dz2a, dz1a, w, true, st)) return rc;
+    }
+    if (policy_step && (phases & CSTR_TD3_ACTOR_APPLY)) {
+        if (actor_step < 1) return fail_arg(CSTR_EINVAL, "td3_update: actor_step must be >= 1 on a policy step");
+        ApplyArgs a{};
+        a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
+        a.adam_lo = T.actor_off, a.adam_hi = T.actor_off + T.actor.size, a.polyak_lo = 0, a.polyak_hi = T.total;
+        const double bc1 = 1.0 - pow((double)cfg->beta1, (double)actor_step), bc2 = 1.0 - pow((double)cfg->beta2, (double)actor_step);
+        a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = (float)((double)cfg->lr / bc1), a.bc2_sqrt = (float)sqrt(bc2);
+        a.tau = cfg->tau;
+        a.loss_partial = w.loss_partial, a.n_loss_partial = rb, a.loss_scale = -1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 2 : nullptr;
+        td3_apply_kernel<<<(unsigned)((T.total + 255) / 256), 256, 0, st>>>(a);
+        if (int rc = check_launch("td3_apply_kernel<actor+polyak>")) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,273 @@
+"""TD3 gradient steps on the device behind the reference's ``TD3.train`` surface.
+
+``FusedTD3Update`` owns five flat float32 device blocks (``params, targets, grads, adam_m, adam_v``, layout from
+``cstr_td3_layout``) and runs one iteration of the loop body of ``TD3.train`` (``core/td3/td3.py:162-206``) per
+``update()`` call through ``cstr_td3_update`` — target smoothing, twin-min target, critic forward/MSE/backward, Adam,
+delayed actor update, polyak — as hand-written float32 CUDA kernels.  No torch autograd, no cuBLAS.
+
+``adopt_policy`` re-points the parameters of the reference's ``TD3Policy`` modules at views of the flat blocks, so
+``policy.predict``, ``model.save`` and the fused rollout keep seeing the live weights without copies.
+``bind_td3_class(TD3)`` returns a subclass of the reference algorithm whose ``train()`` runs here.
+"""
+from __future__ import annotations
+
+from ctypes import byref, c_int64
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+NET_NAMES = ("actor", "critic0", "critic1")
+_TENSORS = ("W1", "b1", "W2", "b2", "W3", "b3")
+
+
+class FusedTD3Update:
+    def __init__(self, net_arch: Sequence[int] = (400, 300), batch_size: int = 256, device: Any = "cuda", gamma: float = 0.99, tau: float = 0.005,
+                 learning_rate: float = 1e-3, policy_delay: int = 2, target_policy_noise: float = 0.2, target_noise_clip: float = 0.5,
+                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self._libc = _lib.load()
+        if len(net_arch) != 2:
+            raise ValueError("FusedTD3Update supports the two-hidden-layer MLPs of TD3's MlpPolicy (net_arch=[h1, h2])")
+        self.h1, self.h2 = int(net_arch[0]), int(net_arch[1])
+        if self.h1 % 4 or self.h2 % 4:
+            raise ValueError("hidden sizes must be multiples of 4")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CstrLibraryError("FusedTD3Update needs a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.gamma, self.tau, self.learning_rate = float(gamma), float(tau), float(learning_rate)
+        self.policy_delay, self.target_policy_noise, self.target_noise_clip = int(policy_delay), float(target_policy_noise), float(target_noise_clip)
+        self.betas, self.eps, self.seed = (float(betas[0]), float(betas[1])), float(eps), int(seed)
+        offs = (c_int64 * 19)()
+        _lib.check(self._libc.cstr_td3_layout(self.h1, self.h2, offs), "cstr_td3_layout")
+        self.param_count = int(offs[18])
+        self._offsets = {(NET_NAMES[n], _TENSORS[k]): int(offs[n * 6 + k]) for n in range(3) for k in range(6)}
+        self.actor_range = (0, self._offsets[("critic0", "W1")])
+        self.critic_range = (self._offsets[("critic0", "W1")], self.param_count)
+        with torch.cuda.device(self.device):
+            z = lambda: torch.zeros(self.param_count, dtype=torch.float32, device=self.device)  # noqa: E731
+            self.params, self.targets, self.grads, self.adam_m, self.adam_v = z(), z(), z(), z(), z()
+            self.loss_sums = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._workspace = None
+        self._batch = 0
+        self._set_batch(int(batch_size))
+        self.n_updates = 0
+        self.critic_step = 0
+        self.actor_step = 0
+        self.launches = 0
+
+    # ---- layout ---------------------------------------------------------------------------------------------------
+    def _shape(self, net: str, tensor: str):
+        i, o = (4, 2) if net == "actor" else (6, 1)
+        return {"W1": (self.h1, i), "b1": (self.h1,), "W2": (self.h2, self.h1), "b2": (self.h2,), "W3": (o, self.h2), "b3": (o,)}[tensor]
+
+    def views(self, block: str = "params") -> Dict[str, List[Any]]:
+        """``{net: [W1, b1, W2, b2, W3, b3]}`` as views of one flat block (``params|targets|grads|adam_m|adam_v``)."""
+        flat = getattr(self, block)
+        out = {}
+        for net in NET_NAMES:
+            out[net] = []
+            for t in _TENSORS:
+                shape = self._shape(net, t)
+                off = self._offsets[(net, t)]
+                out[net].append(flat[off:off + int(np.prod(shape))].view(shape))
+        return out
+
+    def _set_batch(self, batch: int) -> None:
+        if batch == self._batch:
+            return
+        cfg = self._config(batch)
+        need = int(self._libc.cstr_td3_workspace_bytes(byref(cfg)))
+        if need < 0:
+            msg = self._libc.cstr_last_error()
+            raise ValueError(msg.decode() if msg else "bad TD3 configuration")
+        with self._torch.cuda.device(self.device):
+            self._workspace = self._torch.empty(need // 4, dtype=self._torch.float32, device=self.device)
+        self._batch = batch
+
+    def _config(self, batch: int) -> "_lib.Td3Config":
+        return _lib.Td3Config(h1=self.h1, h2=self.h2, batch=batch, policy_delay=self.policy_delay, gamma=self.gamma, tau=self.tau, lr=self.learning_rate,
+                              beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_policy_noise=self.target_policy_noise,
+                              target_noise_clip=self.target_noise_clip, seed=self.seed & (2**64 - 1))
+
+    # ---- weights in / out -------------------------------------------------------------------------------------------
+    def load_nets(self, nets: Dict[str, Sequence[Any]]) -> None:
+        """``nets`` maps ``actor, critic0, critic1`` (and optionally ``*_target``) to six arrays/tensors in nn.Linear layout."""
+        torch = self._torch
+        for block, suffix in (("params", ""), ("targets", "_target")):
+            v = self.views(block)
+            for net in NET_NAMES:
+                src = nets.get(net + suffix, nets[net] if suffix else None)
+                for dst, s in zip(v[net], src):
+                    dst.copy_(torch.as_tensor(np.asarray(s) if not isinstance(s, torch.Tensor) else s).to(self.device, torch.float32).reshape(dst.shape))
+
+    def nets(self) -> Dict[str, List[np.ndarray]]:
+        out = {}
+        for block, suffix in (("params", ""), ("targets", "_target")):
+            for net, ts in self.views(block).items():
+                out[net + suffix] = [t.cpu().numpy() for t in ts]
+        return out
+
+    def adopt_modules(self, actor, critics: Sequence[Any], actor_target, critic_targets: Sequence[Any]) -> None:
+        """Copy the weights of ``nn.Sequential(Linear, ReLU, Linear, ReLU, Linear[, Tanh])`` modules in and re-point their
+        parameters at the flat blocks (zero-copy sharing from then on)."""
+        pairs = [("params", "actor", actor), ("params", "critic0", critics[0]), ("params", "critic1", critics[1]),
+                 ("targets", "actor", actor_target), ("targets", "critic0", critic_targets[0]), ("targets", "critic1", critic_targets[1])]
+        for block, net, module in pairs:
+            ps = list(module.parameters())
+            if len(ps) != 6:
+                raise ValueError("expected a 3-layer MLP (6 parameter tensors)")
+            for view, p in zip(self.views(block)[net], ps):
+                if tuple(p.shape) != tuple(view.shape):
+                    raise ValueError(f"shape mismatch for {net}: module {tuple(p.shape)} vs layout {tuple(view.shape)}")
+                view.copy_(p.data.to(self.device, self._torch.float32))
+                p.data = view
+
+    def adopt_policy(self, policy) -> None:
+        """The reference's ``TD3Policy`` (core/td3/policies.py:172-210): ``actor.mu``, ``critic.q_networks`` and the targets."""
+        if len(policy.critic.q_networks) != 2:
+            raise ValueError("FusedTD3Update implements the twin-critic TD3 (n_critics=2)")
+        self.adopt_modules(policy.actor.mu, list(policy.critic.q_networks), policy.actor_target.mu, list(policy.critic_target.q_networks))
+        self._opt_params = {"actor": list(policy.actor.mu.parameters()), "critic": [p for q in policy.critic.q_networks for p in q.parameters()]}
+
+    def import_optimizer_state(self, actor_optimizer, critic_optimizer) -> None:
+        """Take over Adam moments / step counts of ``torch.optim.Adam`` optimisers created over the adopted modules."""
+        for tag, opt, nets in (("actor", actor_optimizer, ("actor",)), ("critic", critic_optimizer, ("critic0", "critic1"))):
+            group = opt.param_groups[0]
+            self.betas, self.eps = (float(group["betas"][0]), float(group["betas"][1])), float(group["eps"])
+            m = [t for n in nets for t in self.views("adam_m")[n]]
+            v = [t for n in nets for t in self.views("adam_v")[n]]
+            step = 0
+            for p, mv, vv in zip(group["params"], m, v):
+                st = opt.state.get(p)
+                if st:
+                    mv.copy_(st["exp_avg"])
+                    vv.copy_(st["exp_avg_sq"])
+                    step = int(float(st["step"]))
+            if tag == "actor":
+                self.actor_step = step
+            else:
+                self.critic_step = step
+
+    def export_optimizer_state(self, actor_optimizer, critic_optimizer) -> None:
+        """Write moments / step counts back so ``model.save`` and a later torch ``optimizer.step()`` continue from here."""
+        torch = self._torch
+        for opt, nets, step in ((actor_optimizer, ("actor",), self.actor_step), (critic_optimizer, ("critic0", "critic1"), self.critic_step)):
+            if step == 0:
+                continue
+            m = [t for n in nets for t in self.views("adam_m")[n]]
+            v = [t for n in nets for t in self.views("adam_v")[n]]
+            for p, mv, vv in zip(opt.param_groups[0]["params"], m, v):
+                opt.state[p] = {"step": torch.tensor(float(step)), "exp_avg": mv, "exp_avg_sq": vv}
+
+    # ---- the gradient step ----------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def _f32(self, t, cols):
+        torch = self._torch
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.ascontiguousarray(t), device=self.device)
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        if t.numel() != self._batch * cols:
+            raise ValueError(f"batch tensor has {t.numel()} elements, expected {self._batch}x{cols}")
+        return t
+
+    def update(self, batch, noise=None, allreduce: Optional[Callable[[Any], None]] = None) -> None:
+        """One iteration of the loop body (td3.py:162-206) on ``batch`` (``ReplayBufferSamples`` or a 5-tuple in that order).
+        ``noise``: explicit N(0, target_policy_noise) draws (B,2) for parity tests; default = Philox in the kernel.
+        ``allreduce``: called on the flat gradient range between backward and Adam (data-parallel training)."""
+        obs, act, nobs, dones, rew = batch
+        self._set_batch(int(obs.shape[0]))
+        obs, act, nobs = self._f32(obs, 4), self._f32(act, 2), self._f32(nobs, 4)
+        dones, rew = self._f32(dones, 1), self._f32(rew, 1)
+        nz = None if noise is None else self._f32(noise, 2)
+        self.n_updates += 1
+        self.critic_step += 1
+        policy_step = self.n_updates % self.policy_delay == 0
+        if policy_step:
+            self.actor_step += 1
+        cfg = self._config(self._batch)
+        st = _lib.Td3State(params=self.params.data_ptr(), targets=self.targets.data_ptr(), grads=self.grads.data_ptr(), adam_m=self.adam_m.data_ptr(),
+                           adam_v=self.adam_v.data_ptr(), workspace=self._workspace.data_ptr(), workspace_bytes=self._workspace.numel() * 4,
+                           losses=self.loss_sums.data_ptr())
+
+        def run(phases):
+            rc = self._libc.cstr_td3_update(byref(cfg), byref(st), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones), _lib.ptr(rew),
+                                            _lib.ptr(nz), self.n_updates, self.critic_step, max(self.actor_step, 0), phases, self._stream())
+            _lib.check(rc, "cstr_td3_update")
+
+        with self._torch.cuda.device(self.device):
+            if allreduce is None:
+                run(_lib.TD3_ALL)
+            else:
+                run(_lib.TD3_CRITIC_GRAD)
+                allreduce(self.grads[self.critic_range[0]:self.critic_range[1]])
+                run(_lib.TD3_CRITIC_APPLY | _lib.TD3_ACTOR_GRAD)
+                if policy_step:
+                    allreduce(self.grads[self.actor_range[0]:self.actor_range[1]])
+                run(_lib.TD3_ACTOR_APPLY)
+        self.launches += 26 if not policy_step else 50
+
+    def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, allreduce=None) -> None:
+        """``TD3.train(gradient_steps, batch_size)`` (td3.py:154-206): sample + update, ``gradient_steps`` times."""
+        bs = int(batch_size or self._batch)
+        for _ in range(gradient_steps):
+            self.update(buffer.sample(bs, env=env), allreduce=allreduce)
+
+    def pop_losses(self):
+        """(mean critic loss, mean actor loss or None) since the last call — what TD3.train logs (td3.py:207-210)."""
+        s = self.loss_sums.cpu().numpy().astype(np.float64)
+        self.loss_sums.zero_()
+        critic = s[0] / s[1] if s[1] else None
+        actor = s[2] / s[3] if s[3] else None
+        return critic, actor
+
+
+def bind_td3_class(td3_base: type) -> type:
+    """Return a subclass of the reference's ``TD3`` whose ``train()`` (core/td3/td3.py:154-211) runs on ``cstr_td3_update``.
+    Rollout collection, logging, saving and ``predict`` stay the reference's code; the policy modules share memory with the
+    flat parameter blocks."""
+
+    class FusedTD3(td3_base):  # type: ignore[misc, valid-type]
+        _fused: Optional[FusedTD3Update] = None
+
+        def _fused_engine(self, batch_size: int) -> FusedTD3Update:
+            if self._fused is None:
+                arch = self.policy.net_arch if isinstance(self.policy.net_arch, (list, tuple)) else self.policy.net_arch["pi"]
+                eng = FusedTD3Update(arch, batch_size, self.device, self.gamma, self.tau, float(self.lr_schedule(self._current_progress_remaining)),
+                                     self.policy_delay, self.target_policy_noise, self.target_noise_clip, seed=int(self.seed or 0))
+                eng.adopt_policy(self.policy)
+                eng.import_optimizer_state(self.actor.optimizer, self.critic.optimizer)
+                eng.n_updates = int(self._n_updates)
+                self._fused = eng
+            return self._fused
+
+        def train(self, gradient_steps: int, batch_size: int = 100) -> None:
+            self.policy.set_training_mode(True)
+            self._update_learning_rate([self.actor.optimizer, self.critic.optimizer])
+            eng = self._fused_engine(batch_size)
+            eng.learning_rate = float(self.lr_schedule(self._current_progress_remaining))
+            eng.train(gradient_steps, self.replay_buffer, batch_size, env=self._vec_normalize_env)
+            self._n_updates = eng.n_updates
+            critic_loss, actor_loss = eng.pop_losses()
+            self.logger.record("train/n_updates", self._n_updates, exclude="tensorboard")
+            if actor_loss is not None:
+                self.logger.record("train/actor_loss", actor_loss)
+            self.logger.record("train/critic_loss", critic_loss)
+
+        def _excluded_save_params(self):
+            return super()._excluded_save_params() + ["_fused"]
+
+        def save(self, *args, **kwargs):
+            if self._fused is not None:
+                self._fused.export_optimizer_state(self.actor.optimizer, self.critic.optimizer)
+            return super().save(*args, **kwargs)
+
+    FusedTD3.__name__ = "TD3"
+    FusedTD3.__qualname__ = "TD3"
+    return FusedTD3
