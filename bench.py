@@ -320,6 +320,7 @@ def run_ours(args) -> None:
     # ---- extras (rank 0, N=1 only: variants that explain the headline) ---------------------------------------------
     extras = {}
     if world == 1 and not args.no_extras:
+        args._ffma_peak = peaks.get("fp32_ffma_tflops") if peaks else None
         extras = run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args)
     # ---- CPU baseline on a bounded sample ----------------------------------------------------------------------------
     cpu = None
@@ -455,10 +456,61 @@ def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict
                 ex[f"fused_rollout_{mode_name}_transitions_per_s"] = rate_of(lambda: roll.collect(Kr), ne * Kr, reps=3)
             except Exception as exc:
                 ex[f"fused_rollout_{mode_name}_transitions_per_s"] = f"unavailable: {exc}"
+        del roll, er, buf
+        ex["td3_update"] = td3_update_extras(pkg, torch, device, peaks_tflops=args._ffma_peak)
     except Exception as exc:  # extras must never take the headline down
         ex["error"] = repr(exc)
     torch.cuda.synchronize(device)
     return ex
+
+
+def td3_update_extras(pkg, torch, device, peaks_tflops) -> dict:
+    """one TD3 gradient step (sample + cstr_td3_update), float32, [400,300] nets, at the reference's default
+    batch (256) and at 4096; beside it the same update in eager torch on this GPU (what the unmodified reference's TD3.train
+    executes on a CUDA device: autograd + cuBLAS sgemm + torch.optim.Adam) and the NumPy restatement on the host (cpu_baseline)."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import run_td3 as R
+    import td3_oracle as TO
+    import td3_util as TU
+
+    out = {"flop_per_sample": R.flops_per_sample(400, 300), "dtype": "f32", "net_arch": [400, 300]}
+    n_envs = 65536
+    buf = pkg.GpuReplayBuffer(16 * n_envs, device=device, n_envs=n_envs, index_mode="philox")
+    buf.records.uniform_(-1, 1)
+    buf.records[..., 11:13] = 0
+    buf.pos, buf.full = 0, True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for B in (256, 4096):
+        torch.manual_seed(0)
+        eng = pkg.FusedTD3Update([400, 300], B, device=device)
+        eng.adopt_modules(R.mlp(4, 2, True, device), [R.mlp(6, 1, False, device), R.mlp(6, 1, False, device)], R.mlp(4, 2, True, device),
+                          [R.mlp(6, 1, False, device), R.mlp(6, 1, False, device)])
+        ms = R.timed(lambda: eng.update(buf.sample(B)), 200)
+        ref = R.TorchTD3(device)
+        ms_t = R.timed(lambda: ref.update(buf.sample(B)), 100)
+        tf = out["flop_per_sample"] * B / (ms * 1e-3) / 1e12
+        row = {"updates_per_s": 1e3 / ms, "samples_per_s": B * 1e3 / ms, "ms_per_update": ms, "algorithmic_tflops": tf,
+               "frac_of_ffma_peak": tf / peaks_tflops if peaks_tflops else None, "torch_eager_same_gpu_ms_per_update": ms_t}
+        if B == 256:  # cpu_baseline: NumPy restatement of TD3.train on the host (multi-threaded BLAS), a few gradient steps
+            rng = np.random.default_rng(0)
+            nets = TU.random_nets(rng, 400, 300)
+            o = TO.TD3UpdateOracle(nets["actor"], [nets["critic0"], nets["critic1"]])
+            mk = lambda: (rng.uniform(-1, 1, (B, 4)).astype(np.float32), rng.uniform(-1, 1, (B, 2)).astype(np.float32),  # noqa: E731
+                          rng.uniform(-1, 1, (B, 4)).astype(np.float32), np.zeros((B, 1), np.float32), rng.normal(size=(B, 1)).astype(np.float32),
+                          rng.normal(0, 0.2, (B, 2)).astype(np.float32))
+            o.step(*mk())
+            t0 = time.perf_counter()
+            k = 0
+            while time.perf_counter() - t0 < 2.0:
+                o.step(*mk())
+                k += 1
+            row["cpu_oracle_updates_per_s"] = k / (time.perf_counter() - t0)
+        out[f"batch_{B}"] = row
+        del eng, ref
+    return out
 
 
 def main() -> None:

@@ -107,6 +107,19 @@ def main() -> None:
         assert np.array_equal(adopted.normalize_obs(probe), vn.normalize_obs(probe))
         print("[TD3+VecNormalize] save/load + to_reference/from_reference: normalised values identical on both sides", flush=True)
 
+    # ---- TD3 with the gradient steps on the device too (bind_td3_class): learn() is the reference's, train() is cstr_td3_update ----
+    FusedTD3 = pkg.bind_td3_class(core.TD3)
+    m = run("TD3 fused update", lambda env: FusedTD3("MlpPolicy", env, action_noise=noise(), train_freq=(1, "step"), gradient_steps=4, **common), 8000)
+    assert isinstance(m, core.TD3) and m._fused is not None and m._n_updates == m._fused.n_updates
+    assert m.policy.actor.mu[0].weight.data_ptr() == m._fused.views("params")["actor"][0].data_ptr()
+    with tempfile.TemporaryDirectory() as tmp:  # save/load through the reference's zip format, Adam state included
+        m.save(os.path.join(tmp, "td3"))
+        back = core.TD3.load(os.path.join(tmp, "td3"), device="cuda")
+        assert torch.equal(back.policy.actor.mu[2].weight, m.policy.actor.mu[2].weight)
+        st = back.critic.optimizer.state_dict()["state"]
+        assert len(st) == 12 and float(st[0]["step"]) == m._fused.critic_step
+    print(f"[TD3 fused update] n_updates {m._n_updates}, kernel launches {m._fused.launches}; model.save -> TD3.load round trip ok", flush=True)
+
     # ---- BCQ offline: dataset generated by the GPU tape kernel, handed over in the reference's pickle format -------
     n, T = 2500, 400
     env = pkg.GpuCSTRVecEnv(n, seed=3, monitor=False)

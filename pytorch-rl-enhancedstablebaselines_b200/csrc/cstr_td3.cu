@@ -366,24 +366,28 @@ struct SkinnyArgs {
     const float *Y1;  // (B, n1)
     int n0, ld0, n1, ld1;
     int64_t y_z;
-    float *out_w, *out_b;  // out_b: sum_b X (x_bias) or sum_b Y (y_bias)
+    float *part;      // [chunk][z][NY + 1][Hp] partial sums (Hp = H rounded up to 32)
+    float *out_w, *out_b;  // out_b: sum_b X (layers 1, 2) or sum_b Y (layer 3)
     int64_t out_z;
-    int transposed;
+    int transposed, chunks, rows_per_chunk;
 };
+constexpr int SKINNY_ROWS = 64;  // batch rows per CTA
 
 template <int NY, bool YBIAS>
 __global__ void __launch_bounds__(256) td3_skinny_wgrad_kernel(SkinnyArgs s) {
     __shared__ float red[8][NY + 1][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, z = blockIdx.z, chunk = blockIdx.y;
     const int j = blockIdx.x * 32 + lane;
     const bool live = j < s.H;
-    const float *X = s.X + z * s.x_z;
+    const float *X = s.X + z * s.x_z + (live ? j : 0);
     const float *Y0 = s.Y0 ? s.Y0 + z * s.y_z : nullptr;
+    const int b_lo = chunk * s.rows_per_chunk, b_hi = min(s.B, b_lo + s.rows_per_chunk);
     float acc[NY + 1];
 #pragma unroll
     for (int i = 0; i <= NY; ++i) acc[i] = 0.f;
-    for (int b = warp; b < s.B; b += 8) {
-        const float x = live ? X[(int64_t)b * s.ldx + j] : 0.f;
+#pragma unroll 4
+    for (int b = b_lo + warp; b < b_hi; b += 8) {
+        const float x = live ? X[(int64_t)b * s.ldx] : 0.f;
 #pragma unroll
         for (int i = 0; i < NY; ++i) {
             const float y = i < s.n0 ? Y0[(int64_t)b * s.ld0 + i] : s.Y1[(int64_t)b * s.ld1 + (i - s.n0)];
@@ -391,28 +395,38 @@ __global__ void __launch_bounds__(256) td3_skinny_wgrad_kernel(SkinnyArgs s) {
         }
         if (!YBIAS) acc[NY] += x;  // bias gradient = column sum of X
     }
-    if (YBIAS && blockIdx.x == 0 && lane < NY)  // bias gradient = column sum of Y (layer 3): lane i of CTA 0 walks column i
-        for (int b = warp; b < s.B; b += 8) acc[NY] += Y0[(int64_t)b * s.ld0 + lane];
+    if (YBIAS && blockIdx.x == 0 && lane < NY)  // bias gradient = column sum of Y (layer 3): lane i of the first column block
+        for (int b = b_lo + warp; b < b_hi; b += 8) acc[NY] += Y0[(int64_t)b * s.ld0 + lane];
 #pragma unroll
     for (int i = 0; i <= NY; ++i) red[warp][i][lane] = acc[i];
     __syncthreads();
+    const int Hp = gridDim.x * 32;
+    float *part = s.part + ((int64_t)chunk * gridDim.z + z) * (NY + 1) * Hp;
     for (int e = threadIdx.x; e < (NY + 1) * 32; e += 256) {
-        const int i = e >> 5, l = e & 31, jj = blockIdx.x * 32 + l;
+        const int i = e >> 5, l = e & 31;
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += red[w][i][l];
-        if (i < NY) {
-            if (jj < s.H) {
-                if (s.transposed) s.out_w[z * s.out_z + (int64_t)i * s.H + jj] = v;
-                else s.out_w[z * s.out_z + (int64_t)jj * NY + i] = v;
-            }
-        } else if (s.out_b) {
-            if (YBIAS) {
-                if (blockIdx.x == 0 && l < NY) s.out_b[z * s.out_z + l] = v;
-            } else if (jj < s.H) {
-                s.out_b[z * s.out_z + jj] = v;
-            }
-        }
+        part[(int64_t)i * Hp + blockIdx.x * 32 + l] = v;
+    }
+}
+
+// second stage: sum the chunks in order and scatter into the gradient tensors
+template <int NY, bool YBIAS>
+__global__ void __launch_bounds__(256) td3_skinny_reduce_kernel(SkinnyArgs s, int Hp, int Z) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+    if (e >= (NY + 1) * Hp) return;
+    const int i = e / Hp, jj = e % Hp;
+    if (i == NY) {
+        if (!s.out_b || (YBIAS ? jj >= NY : jj >= s.H)) return;
+    } else if (jj >= s.H || !s.out_w) return;
+    float v = 0.f;
+    for (int c = 0; c < s.chunks; ++c) v += s.part[((int64_t)c * Z + z) * (NY + 1) * Hp + e];
+    if (i < NY) {
+        if (s.transposed) s.out_w[z * s.out_z + (int64_t)i * s.H + jj] = v;
+        else s.out_w[z * s.out_z + (int64_t)jj * NY + i] = v;
+    } else {
+        s.out_b[z * s.out_z + jj] = v;
     }
 }
 
@@ -487,16 +501,25 @@ struct Workspace {  // carved out of the caller's workspace buffer (floats)
     float *dz1, *dz2;        // 2 slabs each
     float *t_h1, *t_h2;      // target-critic activations (2 slabs)
     float *a_h1, *a_h2;      // actor / actor-target activations
-    float *next_act, *a_pi, *target, *dq, *dpre, *loss_partial, *slabs;
+    float *next_act, *a_pi, *target, *dq, *dpre, *loss_partial, *slabs, *skinny;
     int splits, n_row_blocks;
     int64_t floats;
 };
 
-int choose_splits(int B) {
-    int s = (B + 511) / 512;
-    if (s < 1) s = 1;
-    if (s > 16) s = 16;
-    return s;
+constexpr int MAX_SPLITS = 16;
+
+// split-K factor of the dW2 GEMM: minimise (CTA rounds per SM) x (k-iterations per CTA) over the 148 SMs
+int choose_splits(int B, int H1, int H2, int Z) {
+    const int64_t tiles = (int64_t)((H2 + BM - 1) / BM) * ((H1 + BN - 1) / BN) * Z;
+    const int sms = sm_count();
+    int best = 1;
+    int64_t best_cost = INT64_MAX;
+    for (int s = 1; s <= MAX_SPLITS && s * 32 <= B + 31; ++s) {
+        const int64_t rounds = (tiles * s + sms - 1) / sms, iters = ((B + s - 1) / s + BK - 1) / BK;
+        const int64_t cost = rounds * iters + 2 * s;  // + the slab-sum traffic
+        if (cost < best_cost) best_cost = cost, best = s;
+    }
+    return best;
 }
 
 Workspace carve(float *base, int B, int H1, int H2) {
@@ -516,8 +539,10 @@ Workspace carve(float *base, int B, int H1, int H2) {
     w.next_act = take(2 * (int64_t)B), w.a_pi = take(2 * (int64_t)B), w.target = take(B), w.dq = take(2 * (int64_t)B), w.dpre = take(2 * (int64_t)B);
     w.n_row_blocks = (B + 7) / 8;
     w.loss_partial = take(2 * (int64_t)w.n_row_blocks);
-    w.splits = choose_splits(B);
-    w.slabs = take((int64_t)w.splits * 2 * pad4((int64_t)H1 * H2));
+    w.splits = 0;  // chosen per launch (choose_splits)
+    w.slabs = take((int64_t)MAX_SPLITS * 2 * pad4((int64_t)H1 * H2));
+    const int64_t hp = ((int64_t)(H1 > H2 ? H1 : H2) + 31) / 32 * 32;
+    w.skinny = take((int64_t)((B + SKINNY_ROWS - 1) / SKINNY_ROWS) * 2 * (OBS + ACT + 1) * hp);
     w.floats = o;
     return w;
 }
@@ -529,6 +554,18 @@ int check_cfg(const cstr_td3_config *c) {
     if (c->batch < 1 || c->batch > (1 << 22)) return fail_arg(CSTR_EINVAL, "td3: batch must be in [1, 4194304]");
     if (c->policy_delay < 1) return fail_arg(CSTR_EINVAL, "td3: policy_delay must be >= 1");
     return 0;
+}
+
+template <int NY, bool YBIAS>
+int launch_skinny(SkinnyArgs s, int Z, float *part, cudaStream_t st, const char *what) {
+    s.part = part;
+    s.rows_per_chunk = SKINNY_ROWS;
+    s.chunks = (s.B + SKINNY_ROWS - 1) / SKINNY_ROWS;
+    const int cols = (s.H + 31) / 32, Hp = cols * 32;
+    td3_skinny_wgrad_kernel<NY, YBIAS><<<dim3(cols, s.chunks, Z), 256, 0, st>>>(s);
+    if (int rc = check_launch(what)) return rc;
+    td3_skinny_reduce_kernel<NY, YBIAS><<<dim3(((NY + 1) * Hp + 255) / 256, Z), 256, 0, st>>>(s, Hp, Z);
+    return check_launch(what);
 }
 
 template <int MODE>
@@ -577,26 +614,25 @@ int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float
     q.A = dz2, q.Bm = h1, q.aux = nullptr, q.C = w.slabs;
     q.M = H2, q.N = H1, q.K = B, q.lda = H2, q.ldb = H1, q.ldc = H1, q.ldaux = 0;
     q.a_z = (int64_t)B * H2, q.b_z = (int64_t)B * H1, q.c_z = w2n, q.aux_z = 0;
-    q.splits = w.splits, q.k_per_split = (B + w.splits - 1) / w.splits, q.c_split = 2 * w2n;
+    const int splits = choose_splits(B, H1, H2, Z);
+    q.splits = splits, q.k_per_split = (B + splits - 1) / splits, q.c_split = 2 * w2n;
     if (int rc = launch_gemm<G_WGRAD>(q, Z, st, "td3_gemm_kernel<wgrad>")) return rc;
     const int64_t n4 = (int64_t)H1 * H2 / 4;
-    td3_sum_slabs_kernel<<<dim3((unsigned)((n4 + 255) / 256), Z), 256, 0, st>>>(n4, w.splits, (const float4 *)w.slabs, 2 * w2n / 4, w2n / 4, (float4 *)gn.w2,
+    td3_sum_slabs_kernel<<<dim3((unsigned)((n4 + 255) / 256), Z), 256, 0, st>>>(n4, splits, (const float4 *)w.slabs, 2 * w2n / 4, w2n / 4, (float4 *)gn.w2,
                                                                               z_stride / 4);
     if (int rc = check_launch("td3_sum_slabs_kernel")) return rc;
     // db2 = colsum(dz2)
     SkinnyArgs s{};
     s.X = dz2, s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
     s.out_w = nullptr, s.out_b = gn.b2, s.out_z = z_stride;
-    td3_skinny_wgrad_kernel<0, false><<<dim3((H2 + 31) / 32, Z), 256, 0, st>>>(s);
-    if (int rc = check_launch("td3_skinny_wgrad_kernel<b2>")) return rc;
+    if (int rc = launch_skinny<0, false>(s, Z, w.skinny, st, "td3_skinny_wgrad_kernel<b2>")) return rc;
     // dW1 = dz1^T @ [obs | act], db1 = colsum(dz1)
     SkinnyArgs t{};
     t.X = dz1, t.x_z = (int64_t)B * H1, t.ldx = H1, t.H = H1, t.B = B;
     t.Y0 = obs, t.n0 = OBS, t.ld0 = OBS, t.Y1 = act, t.n1 = in - OBS, t.ld1 = ACT, t.y_z = 0;
     t.out_w = gn.w1, t.out_b = gn.b1, t.out_z = z_stride;
-    if (in == OBS) td3_skinny_wgrad_kernel<OBS, false><<<dim3((H1 + 31) / 32, Z), 256, 0, st>>>(t);
-    else td3_skinny_wgrad_kernel<OBS + ACT, false><<<dim3((H1 + 31) / 32, Z), 256, 0, st>>>(t);
-    return check_launch("td3_skinny_wgrad_kernel<w1>");
+    if (in == OBS) return launch_skinny<OBS, false>(t, Z, w.skinny, st, "td3_skinny_wgrad_kernel<w1>");
+    return launch_skinny<OBS + ACT, false>(t, Z, w.skinny, st, "td3_skinny_wgrad_kernel<w1>");
 }
 
 }  // namespace
@@ -667,8 +703,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         s.X = w.h2[0], s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
         s.Y0 = w.dq, s.n0 = 1, s.ld0 = 1, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = B;
         s.out_w = g_critic.w3, s.out_b = g_critic.b3, s.out_z = cz, s.transposed = 1;
-        td3_skinny_wgrad_kernel<1, true><<<dim3((H2 + 31) / 32, 2), 256, 0, st>>>(s);
-        if (int rc = check_launch("td3_skinny_wgrad_kernel<w3>")) return rc;
+        if (int rc = launch_skinny<1, true>(s, 2, w.skinny, st, "td3_skinny_wgrad_kernel<w3>")) return rc;
         if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st)) return rc;
     }
     if (phases & CSTR_TD3_CRITIC_APPLY) {
@@ -701,8 +736,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         s.X = w.a_h2, s.x_z = 0, s.ldx = H2, s.H = H2, s.B = B;
         s.Y0 = w.dpre, s.n0 = ACT, s.ld0 = ACT, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = 0;
         s.out_w = g_actor.w3, s.out_b = g_actor.b3, s.out_z = 0, s.transposed = 1;
-        td3_skinny_wgrad_kernel<ACT, true><<<dim3((H2 + 31) / 32, 1), 256, 0, st>>>(s);
-        if (int rc = check_launch("td3_skinny_wgrad_kernel<actor w3>")) return rc;
+        if (int rc = launch_skinny<ACT, true>(s, 1, w.skinny, st, "td3_skinny_wgrad_kernel<actor w3>")) return rc;
         if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, dz2a, dz1a, w, true, st)) return rc;
     }
     if (policy_step && (phases & CSTR_TD3_ACTOR_APPLY)) {
