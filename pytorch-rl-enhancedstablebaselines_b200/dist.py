@@ -64,6 +64,18 @@ def allreduce_gradients(params: Iterable, group=None, average: bool = True, buck
     return bucket
 
 
+def allreduce_flat(flat, group=None, average: bool = True):
+    """In-place all-reduce (mean by default) of an already flat gradient range — the ``allreduce=`` hook of
+    ``FusedTD3Update.update``: the flat ``grads`` block IS the NCCL bucket, no packing copies."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(dist.get_world_size(group))
+    return flat
+
+
 def broadcast_parameters(params: Iterable, src: int = 0, group=None) -> None:
     """Make every rank start from rank ``src``'s parameters (one flat broadcast)."""
     import torch

@@ -44,8 +44,36 @@ shard_grads = [p.grad.clone() for p in net.parameters()]
 net.zero_grad()
 torch.nn.functional.mse_loss(net(x), y).backward()
 err = max(float((a - p.grad).abs().max()) for a, p in zip(shard_grads, net.parameters()))
+# (3) data-parallel TD3 gradient steps: each rank updates on its half of the batch with the flat gradient block all-reduced
+#     between backward and Adam -> every rank ends with the weights of a single-device run on the whole batch
+import numpy as np
+rng = np.random.default_rng(9)
+B = 128 * world
+def mlp(i, o):
+    out = []
+    for fi, fo in ((i, 400), (400, 300), (300, o)):
+        out += [rng.uniform(-1, 1, (fo, fi)).astype(np.float32) / np.sqrt(fi), rng.uniform(-0.05, 0.05, fo).astype(np.float32)]
+    return out
+nets = {"actor": mlp(4, 2), "critic0": mlp(6, 1), "critic1": mlp(6, 1)}
+batches = [(rng.uniform(-1, 1, (B, 4)).astype(np.float32), rng.uniform(-1, 1, (B, 2)).astype(np.float32), rng.uniform(-1, 1, (B, 4)).astype(np.float32),
+            np.zeros((B, 1), np.float32), rng.normal(size=(B, 1)).astype(np.float32), rng.normal(0, 0.2, (B, 2)).astype(np.float32)) for _ in range(4)]
+dp = pkg.FusedTD3Update([400, 300], B // world, device=dev)
+dp.load_nets(nets)
+sl = slice(rank * (B // world), (rank + 1) * (B // world))
+for b in batches:
+    dp.update(tuple(t[sl] for t in b[:5]), noise=b[5][sl], allreduce=pkg.dist.allreduce_flat)
+td3_err = None
+peers = [torch.empty_like(dp.params) for _ in range(world)]
+dist.all_gather(peers, dp.params)
 if rank == 0:
-    print(json.dumps({"ok_shard": ok_shard, "grad_err": err, "bucket": bucket.numel(), "world": world}))
+    full = pkg.FusedTD3Update([400, 300], B, device=dev)
+    full.load_nets(nets)
+    for b in batches:
+        full.update(b[:5], noise=b[5])
+    td3_err = max(float((full.params - dp.params).abs().max()), float((full.targets - dp.targets).abs().max()))
+    td3_same = all(bool(torch.equal(p.to(dev), dp.params)) for p in peers)
+if rank == 0:
+    print(json.dumps({"ok_shard": ok_shard, "grad_err": err, "bucket": bucket.numel(), "world": world, "td3_err": td3_err, "td3_ranks_equal": td3_same}))
 dist.destroy_process_group()
 '''
 
@@ -61,3 +89,4 @@ def test_nccl_allreduce_and_shard_invariance(tmp_path):
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["ok_shard"] is True
     assert res["grad_err"] < 1e-6 and res["bucket"] == 122_902 and res["world"] == 2
+    assert res["td3_ranks_equal"] is True and res["td3_err"] < 2e-5  # DP TD3 update == single-device update on the whole batch
