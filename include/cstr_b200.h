@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 9
+#define CSTR_B200_ABI_VERSION 10
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -193,7 +193,11 @@ typedef struct cstr_td3_config {
     int32_t policy_delay;
     float gamma, tau, lr, beta1, beta2, eps, target_policy_noise, target_noise_clip;
     uint64_t seed;
+    int32_t gemm_mode;    /* CSTR_TD3_GEMM_FP32: FFMA tiles (the reference's float32 arithmetic);                      */
+    int32_t reserved;     /* CSTR_TD3_GEMM_TENSOR: tcgen05 bf16x3 split (3 bf16 planes per operand, 6 MMAs, fp32-grade)  */
 } cstr_td3_config;
+#define CSTR_TD3_GEMM_FP32 0
+#define CSTR_TD3_GEMM_TENSOR 1
 
 typedef struct cstr_td3_state {
     float *params, *targets, *grads, *adam_m, *adam_v; /* device, cstr_td3_param_count floats each, 16-byte aligned */

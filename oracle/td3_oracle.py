@@ -101,16 +101,17 @@ class TD3UpdateOracle:
         q_next = np.minimum(*[mlp_forward(c, xin, False)[0] for c in self.critic_targets])  # :173-174
         target = (rewards + (F32(1) - dones) * F32(self.gamma) * q_next).astype(F32)  # :175
         x = np.concatenate([obs, actions], 1)
-        grads, loss = [], 0.0
+        grads, loss, hidden = [], 0.0, []
         for c in self.critics:
             q, cache = mlp_forward(c, x, False)
+            hidden.append((cache[1], cache[2]))
             diff = q - target
             loss += float(np.mean(diff * diff, dtype=F32))  # F.mse_loss, summed over critics (:181)
             g, _ = mlp_backward(c, cache, (F32(2) / F32(B)) * diff, False)
             grads += g
         self.critic_losses.append(loss)
         self.critic_opt.step(grads)
-        out = {"target_q": target, "critic_grads": grads}
+        out = {"target_q": target, "critic_grads": grads, "critic_hidden": hidden}
         if self.n_updates % self.policy_delay == 0:  # :189
             a, acache = mlp_forward(self.actor, obs, True)
             q1, ccache = mlp_forward(self.critics[0], np.concatenate([obs, a], 1), False)  # q1_forward (:191)
@@ -122,4 +123,5 @@ class TD3UpdateOracle:
                 polyak(c, t, self.tau)
             polyak(self.actor, self.actor_target, self.tau)
             out["actor_grads"] = ag
+            out["policy_hidden"] = [(acache[1], acache[2]), (ccache[1], ccache[2])]  # actor, critic0 at pi(s)
         return out

@@ -229,6 +229,10 @@ __global__ void __launch_bounds__(256, 2) td3_gemm_kernel(GemmArgs g) {
     }
 }
 
+}  // namespace cstr
+#include "cstr_td3_tc.cuh"
+namespace cstr {
+
 // ------------------------------------------------------------------------------------------------------------------
 // row heads: one warp per batch row
 // ------------------------------------------------------------------------------------------------------------------
@@ -509,8 +513,10 @@ struct Workspace {  // carved out of the caller's workspace buffer (floats)
 constexpr int MAX_SPLITS = 16;
 
 // split-K factor of the dW2 GEMM: minimise (CTA rounds per SM) x (k-iterations per CTA) over the 148 SMs
+int g_gemm_mode_for_splits();
 int choose_splits(int B, int H1, int H2, int Z) {
-    const int64_t tiles = (int64_t)((H2 + BM - 1) / BM) * ((H1 + BN - 1) / BN) * Z;
+    const bool tc = g_gemm_mode_for_splits() == CSTR_TD3_GEMM_TENSOR;
+    const int64_t tiles = tc ? (int64_t)((H2 + TC_BM - 1) / TC_BM) * tc_tile(H1).n_tiles * Z : (int64_t)((H2 + BM - 1) / BM) * ((H1 + BN - 1) / BN) * Z;
     const int sms = sm_count();
     int best = 1;
     int64_t best_cost = INT64_MAX;
@@ -553,6 +559,7 @@ int check_cfg(const cstr_td3_config *c) {
         return fail_arg(CSTR_EINVAL, "td3: hidden sizes must be multiples of 4 in [4, 4096]");
     if (c->batch < 1 || c->batch > (1 << 22)) return fail_arg(CSTR_EINVAL, "td3: batch must be in [1, 4194304]");
     if (c->policy_delay < 1) return fail_arg(CSTR_EINVAL, "td3: policy_delay must be >= 1");
+    if (c->gemm_mode != CSTR_TD3_GEMM_FP32 && c->gemm_mode != CSTR_TD3_GEMM_TENSOR) return fail_arg(CSTR_EINVAL, "td3: gemm_mode must be 0 (fp32 FFMA) or 1 (bf16x3 tensor)");
     return 0;
 }
 
@@ -568,12 +575,29 @@ int launch_skinny(SkinnyArgs s, int Z, float *part, cudaStream_t st, const char 
     return check_launch(what);
 }
 
+int g_gemm_mode_for_splits();
+int g_gemm_mode = 0;  // set per cstr_td3_update call from cfg->gemm_mode (0 = FFMA, 1 = bf16x3 tcgen05)
+
 template <int MODE>
 int launch_gemm(const GemmArgs &g, int Z, cudaStream_t st, const char *what) {
+    if (g_gemm_mode == CSTR_TD3_GEMM_TENSOR) {
+        const TcTile t = tc_tile(g.N);
+        static bool attr_set[3] = {false, false, false};
+        if (!attr_set[MODE]) {
+            if (int rc = check_cuda(cudaFuncSetAttribute(td3_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "td3_gemm_tc smem attr"))
+                return rc;
+            attr_set[MODE] = true;
+        }
+        dim3 grid(t.n_tiles, (g.M + TC_BM - 1) / TC_BM, Z * g.splits);
+        td3_gemm_tc_kernel<MODE><<<grid, TC_GEMM_THREADS, t.smem_bytes, st>>>(g, t.n_tile, t.tmem_cols);
+        return check_launch(what);
+    }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, Z * g.splits);
     td3_gemm_kernel<MODE><<<grid, 256, 0, st>>>(g);
     return check_launch(what);
 }
+
+int g_gemm_mode_for_splits() { return g_gemm_mode; }
 
 struct Net {  // pointers of one net (or the first of a z-batched pair) inside a flat block
     float *w1, *b1, *w2, *b2, *w3, *b3;
@@ -678,6 +702,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
     if (n_updates < 1 || critic_step < 1 || actor_step < 0) return fail_arg(CSTR_EINVAL, "td3_update: counters are 1-based (value after this update)");
     const Td3Layout T = td3_layout(H1, H2);
     cudaStream_t st = (cudaStream_t)stream;
+    g_gemm_mode = cfg->gemm_mode;
     const int64_t cz = T.critic.size;
     const Net actor = net_at(stt->params, T.actor_off, T.actor), actor_t = net_at(stt->targets, T.actor_off, T.actor);
     const Net critic = net_at(stt->params, T.critic_off[0], T.critic), critic_t = net_at(stt->targets, T.critic_off[0], T.critic);

@@ -25,7 +25,7 @@ _TENSORS = ("W1", "b1", "W2", "b2", "W3", "b3")
 class FusedTD3Update:
     def __init__(self, net_arch: Sequence[int] = (400, 300), batch_size: int = 256, device: Any = "cuda", gamma: float = 0.99, tau: float = 0.005,
                  learning_rate: float = 1e-3, policy_delay: int = 2, target_policy_noise: float = 0.2, target_noise_clip: float = 0.5,
-                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0):
+                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0, gemm: str = "fp32"):
         torch = _lib.require_cuda()
         self._torch = torch
         self._libc = _lib.load()
@@ -42,6 +42,9 @@ class FusedTD3Update:
         self.gamma, self.tau, self.learning_rate = float(gamma), float(tau), float(learning_rate)
         self.policy_delay, self.target_policy_noise, self.target_noise_clip = int(policy_delay), float(target_policy_noise), float(target_noise_clip)
         self.betas, self.eps, self.seed = (float(betas[0]), float(betas[1])), float(eps), int(seed)
+        if gemm not in ("fp32", "tensor"):
+            raise ValueError("gemm must be 'fp32' (FFMA tiles, the reference's arithmetic) or 'tensor' (tcgen05 bf16x3 split, fp32-grade)")
+        self.gemm = gemm
         offs = (c_int64 * 19)()
         _lib.check(self._libc.cstr_td3_layout(self.h1, self.h2, offs), "cstr_td3_layout")
         self.param_count = int(offs[18])
@@ -92,7 +95,7 @@ class FusedTD3Update:
     def _config(self, batch: int) -> "_lib.Td3Config":
         return _lib.Td3Config(h1=self.h1, h2=self.h2, batch=batch, policy_delay=self.policy_delay, gamma=self.gamma, tau=self.tau, lr=self.learning_rate,
                               beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_policy_noise=self.target_policy_noise,
-                              target_noise_clip=self.target_noise_clip, seed=self.seed & (2**64 - 1))
+                              target_noise_clip=self.target_noise_clip, seed=self.seed & (2**64 - 1), gemm_mode=int(self.gemm == "tensor"))
 
     # ---- weights in / out -------------------------------------------------------------------------------------------
     def load_nets(self, nets: Dict[str, Sequence[Any]]) -> None:

@@ -58,7 +58,7 @@ def _random_batches(rng, K, B):
             for _ in range(K)]
 
 
-@pytest.mark.parametrize("arch,B,K", [([400, 300], 256, 4), ([36, 20], 100, 4), ([400, 300], 1000, 2), ([128, 256], 7, 3)])
+@pytest.mark.parametrize("arch,B,K", [([400, 300], 256, 4), ([36, 20], 100, 4), ([400, 300], 1000, 2), ([128, 256], 7, 3), ([512, 512], 300, 2)])
 def test_vs_oracle(pkg, arch, B, K):
     rng = np.random.default_rng(B)
     nets = U.random_nets(rng, *arch)
@@ -67,15 +67,7 @@ def test_vs_oracle(pkg, arch, B, K):
     for batch in _random_batches(rng, K, B):
         out = o.step(*batch)
         eng.update(batch[:5], noise=batch[5])
-        gv = eng.views("grads")
-        for z, name in enumerate(("critic0", "critic1")):  # gradients of this step, tensor by tensor
-            for k in range(6):
-                want = out["critic_grads"][z * 6 + k]
-                np.testing.assert_allclose(gv[name][k].cpu().numpy(), want, rtol=0, atol=2e-5 * max(np.abs(want).max(), 1e-3), err_msg=f"{name} grad {k}")
-        if "actor_grads" in out:
-            for k in range(6):
-                want = out["actor_grads"][k]
-                np.testing.assert_allclose(gv["actor"][k].cpu().numpy(), want, rtol=0, atol=2e-5 * max(np.abs(want).max(), 1e-3), err_msg=f"actor grad {k}")
+        _assert_grads(eng, out, 2e-5)
     got = eng.nets()
     want = {"actor": o.actor, "critic0": o.critics[0], "critic1": o.critics[1], "actor_target": o.actor_target,
             "critic0_target": o.critic_targets[0], "critic1_target": o.critic_targets[1]}
@@ -83,6 +75,76 @@ def test_vs_oracle(pkg, arch, B, K):
     critic_loss, actor_loss = eng.pop_losses()
     assert critic_loss == pytest.approx(np.mean(o.critic_losses), rel=1e-5)
     assert actor_loss == pytest.approx(np.mean(o.actor_losses), rel=1e-4, abs=1e-6)
+
+
+def _assert_grads(eng, out, rel):
+    gv = eng.views("grads")
+    for z, name in enumerate(("critic0", "critic1")):  # gradients of this step, tensor by tensor
+        for k in range(6):
+            want = out["critic_grads"][z * 6 + k]
+            np.testing.assert_allclose(gv[name][k].cpu().numpy(), want, rtol=0, atol=rel * max(np.abs(want).max(), 1e-3), err_msg=f"{name} grad {k}")
+    if "actor_grads" in out:
+        for k in range(6):
+            want = out["actor_grads"][k]
+            np.testing.assert_allclose(gv["actor"][k].cpu().numpy(), want, rtol=0, atol=rel * max(np.abs(want).max(), 1e-3), err_msg=f"actor grad {k}")
+
+
+def _relu_flips(eng, B, H1, H2, slots, hidden):
+    """ReLU masks of the engine's activations (workspace slabs) vs the oracle's: a pre-activation within the GEMM rounding error of
+    zero may land on either side, which changes the backward pass discontinuously (one flipped unit moves a whole gradient row)."""
+    ws = eng._workspace
+    off = {"h1": 0, "h2": 2 * B * H1, "a_h1": 6 * B * H1 + 6 * B * H2, "a_h2": 7 * B * H1 + 6 * B * H2}
+    flips = 0
+    for (name, z), h in zip(slots, hidden):
+        H = H1 if name.endswith("h1") else H2
+        a = off[name] + z * B * H
+        got = ws[a:a + B * H].cpu().numpy().reshape(B, H)
+        diff = (got > 0) != (h > 0)
+        assert np.all(np.maximum(np.abs(got[diff]), np.abs(h[diff])) < 2e-5), "a mask differs where the activation is not ~0"
+        flips += int(diff.sum())
+    return flips
+
+
+def _assert_grads_flip_aware(eng, out, flips, keys):
+    gv = eng.views("grads")
+    for name, want_list in keys:
+        for k, want in enumerate(want_list):
+            got = gv[name][k].cpu().numpy()
+            if flips == 0:  # same ReLU masks: fp32-grade agreement (measured 3e-6 of the max; tensor-core accumulation truncates)
+                np.testing.assert_allclose(got, want, rtol=0, atol=1e-5 * max(np.abs(want).max(), 1e-3), err_msg=f"{name} grad {k}")
+            else:  # each flipped unit adds one dq*w3-sized term: far below a bf16-grade error (4e-3 of the max on every element)
+                assert np.linalg.norm(got - want) <= 1.5e-3 * flips * max(np.linalg.norm(want), 1e-6), f"{name} grad {k}"  # measured 5e-4 for one flip
+
+
+@pytest.mark.parametrize("arch,B", [([400, 300], 256), ([400, 300], 1000), ([36, 20], 100), ([128, 256], 7), ([512, 512], 300), ([64, 48], 4096)])
+def test_tensor_core_gemm_vs_oracle(pkg, arch, B):
+    """gemm="tensor": the hidden-layer GEMMs on tcgen05, every fp32 operand split into 3 bf16 planes (6 MMAs per K-step).
+    Measured 3e-6 of the tensor's max against the FFMA path; bar 1e-5 on every gradient when the ReLU masks agree with the
+    oracle's (checked), an L2 bar per flipped unit otherwise (flips are rare and only where |activation| < 2e-5)."""
+    H1, H2 = arch
+    for delay in (2, 1):  # a critic-only step, then (fresh engine) a policy step: the workspace holds the activations of the last phase
+        rng = np.random.default_rng(B + delay)
+        nets = U.random_nets(rng, *arch)
+        o = T.TD3UpdateOracle(nets["actor"], [nets["critic0"], nets["critic1"]], policy_delay=delay)
+        eng = _engine(pkg, nets, arch, B, gemm="tensor", policy_delay=delay)
+        batch = _random_batches(rng, 1, B)[0]
+        out = o.step(*batch)
+        snaps = []
+        eng.update(batch[:5], noise=batch[5], allreduce=lambda flat: snaps.append(1) if snaps else snaps.append(
+            _relu_flips(eng, B, H1, H2, [("h1", 0), ("h2", 0), ("h1", 1), ("h2", 1)], [h for pair in out["critic_hidden"] for h in pair])))
+        flips = snaps[0]
+        assert flips <= max(2, B * (H1 + H2) // 50_000)
+        _assert_grads_flip_aware(eng, out, flips, [("critic0", out["critic_grads"][:6]), ("critic1", out["critic_grads"][6:])])
+        if delay == 1:
+            pflips = flips + _relu_flips(eng, B, H1, H2, [("a_h1", 0), ("a_h2", 0), ("h1", 0), ("h2", 0)], [h for pair in out["policy_hidden"] for h in pair])
+            _assert_grads_flip_aware(eng, out, pflips, [("actor", out["actor_grads"])])
+        critic_loss, actor_loss = eng.pop_losses()
+        assert critic_loss == pytest.approx(o.critic_losses[0], rel=2e-5)
+        if delay == 1:
+            assert actor_loss == pytest.approx(o.actor_losses[0], rel=1e-4, abs=1e-6)
+            for name, want in (("actor", o.actor), ("critic0", o.critics[0]), ("critic1", o.critics[1])):
+                for a, b in zip(eng.nets()[name], want):  # Adam's first step is lr * g/|g|: bounded by lr whatever the gradient error
+                    assert np.abs(a - b).max() <= 2.1e-3 and (np.abs(a - b) > 2e-5).mean() < (5e-3 if pflips == 0 else 0.5), name
 
 
 def test_deterministic_phases_and_philox_noise(pkg):
@@ -154,7 +216,8 @@ def test_adopts_torch_modules_in_place(pkg):
         pkg.FusedTD3Update([401, 300], 8)
 
 
-def test_training_dynamics_track_eager_torch(pkg):
+@pytest.mark.parametrize("gemm", ["fp32", "tensor"])
+def test_training_dynamics_track_eager_torch(pkg, gemm):
     """300 gradient steps on real CSTR transitions, fused kernels vs the same update in eager torch (fp32 autograd, torch Adam):
     same batches, independent smoothing noise -> the learned critic and actor agree statistically (chaos amplifies ulps, so this
     is a dynamics check, not a bit check; measured |dq| 0.002 at q = -1.3)."""
@@ -177,7 +240,7 @@ def test_training_dynamics_track_eager_torch(pkg):
         buf.add(o, st, a, rew, done, None, timeouts=done)
     torch.manual_seed(0)
     ref = R.TorchTD3(dev)
-    eng = pkg.FusedTD3Update([400, 300], 256, device=dev, seed=0)
+    eng = pkg.FusedTD3Update([400, 300], 256, device=dev, seed=0, gemm=gemm)
     get = lambda m: [p.detach().clone() for p in m.parameters()]  # noqa: E731
     eng.load_nets({"actor": get(ref.actor), "critic0": get(ref.critics[0]), "critic1": get(ref.critics[1])})
     for _ in range(300):
