@@ -79,6 +79,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--once", action="store_true", help="few launches only (for ncu)")
     ap.add_argument("--no-torch", action="store_true")
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor"])
     args = ap.parse_args()
     pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
     dev = torch.device("cuda", 0)
@@ -91,7 +92,7 @@ def main():
     out = {}
     for B in args.batch:
         torch.manual_seed(0)
-        eng = pkg.FusedTD3Update([400, 300], B, device=dev)
+        eng = pkg.FusedTD3Update([400, 300], B, device=dev, gemm=args.gemm)
         ref = TorchTD3(dev)
         eng.adopt_modules(mlp(4, 2, True, dev), [mlp(6, 1, False, dev), mlp(6, 1, False, dev)], mlp(4, 2, True, dev),
                           [mlp(6, 1, False, dev), mlp(6, 1, False, dev)])

@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every csrc/*.cu into libcstr_b200.so (cross-compiles without a GPU)."""
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB_PATH + ".tmp", *sources()]
+    extra = os.environ.get("CSTR_NVCC_EXTRA", "").split()  # e.g. -DCSTR_TC_TIMING / -DCSTR_TD3_TIMING (clock64 phase instrumentation)
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB_PATH + ".tmp", *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     # the image's $CC wrapper is not a usable nvcc host compiler; let nvcc pick the system g++

@@ -20,6 +20,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -76,17 +79,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return d;
 }
 
-// split 8 consecutive-k floats into the three bf16 planes and store one 16-byte core-matrix row per plane
+// split 8 consecutive-k floats into the three bf16 planes and store one 16-byte core-matrix row per plane.
+// Planes by truncation (x1 = x & 0xffff0000, r = x - x1 exact, ...): three planes still carry 24 mantissa bits, and the split is
+// LOP/FADD/PRMT only (cvt.rn.bf16x2 runs on the quarter-rate conversion pipe and was the producer bottleneck).
 __device__ __forceinline__ void split_store(const float v[8], uint32_t addr, uint32_t plane_stride) {
     uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float a = v[2 * i], b = v[2 * i + 1];
-        p1[i] = pack_bf16x2(a, b);
-        const float ra = a - __uint_as_float(p1[i] << 16), rb = b - __uint_as_float(p1[i] & 0xffff0000u);
-        p2[i] = pack_bf16x2(ra, rb);
-        const float sa = ra - __uint_as_float(p2[i] << 16), sb = rb - __uint_as_float(p2[i] & 0xffff0000u);
-        p3[i] = pack_bf16x2(sa, sb);
+        const uint32_t a = __float_as_uint(v[2 * i]), b = __float_as_uint(v[2 * i + 1]);
+        p1[i] = __byte_perm(a, b, 0x7632);  // {hi16(a) -> bits 0..15, hi16(b) -> bits 16..31}
+        const float ra = v[2 * i] - __uint_as_float(a & 0xffff0000u), rb = v[2 * i + 1] - __uint_as_float(b & 0xffff0000u);
+        const uint32_t a2 = __float_as_uint(ra), b2 = __float_as_uint(rb);
+        p2[i] = __byte_perm(a2, b2, 0x7632);
+        const float sa = ra - __uint_as_float(a2 & 0xffff0000u), sb = rb - __uint_as_float(b2 & 0xffff0000u);
+        p3[i] = __byte_perm(__float_as_uint(sa), __float_as_uint(sb), 0x7632);
     }
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + plane_stride), "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]) : "memory");
@@ -95,24 +101,28 @@ __device__ __forceinline__ void split_store(const float v[8], uint32_t addr, uin
 
 }  // namespace tc5
 
-constexpr int TC_BM = 128, TC_KC = 16, TC_STAGES = 3, TC_GEMM_THREADS = 256, TC_MAX_BCHUNKS = 2;  // n_tile <= 256 -> <= 512 B chunks / 256 threads
+#ifndef TD3_TC_PRODUCERS
+#define TD3_TC_PRODUCERS 512
+#endif
+#ifndef TD3_TC_ACC
+#define TD3_TC_ACC 1
+#endif
+constexpr int TC_BM = 128, TC_KC = 16, TC_STAGES = 3, TC_PRODUCERS = TD3_TC_PRODUCERS, TC_NACC = TD3_TC_ACC, TC_GEMM_THREADS = TC_PRODUCERS + 32, TC_SLOTS = TC_PRODUCERS == 512 ? 2 : 3;  // 256 A chunks + <= 512 B chunks over 512 threads
 
-// 8 floats = one (row r, k-group) chunk of an operand tile.  KMAJ: memory rows are operand rows (k contiguous);
-// otherwise memory rows are k (operand rows contiguous).
+// 8 floats = one (row r, k-group) chunk of an operand tile, through a per-thread pointer that the caller advances by one stage.
+// KMAJ: memory rows are operand rows (k contiguous) -> two float4; otherwise memory rows are k -> 8 loads `ld` apart.
+// k_left = k_end - (k of the chunk's first element): only the last stage of a K range is partial.
 template <bool KMAJ>
-__device__ __forceinline__ void load_chunk(const float *__restrict__ src, int ld, int r, int r_end, int k, int k_end, float v[8]) {
+__device__ __forceinline__ void load_chunk(const float *__restrict__ p, int64_t ld, bool row_ok, int k_left, float v[8]) {
     if (KMAJ) {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 a = z, b = z;
-        if (r < r_end) {
-            const float *p = src + (int64_t)r * ld + k;
-            if (k < k_end) a = *reinterpret_cast<const float4 *>(p);
-            if (k + 4 < k_end) b = *reinterpret_cast<const float4 *>(p + 4);
-        }
+        if (row_ok && k_left > 0) a = *reinterpret_cast<const float4 *>(p);
+        if (row_ok && k_left > 4) b = *reinterpret_cast<const float4 *>(p + 4);
         v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (r < r_end && k + j < k_end) ? src[(int64_t)(k + j) * ld + r] : 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = (row_ok && j < k_left) ? p[j * ld] : 0.f;
     }
 }
 
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
     constexpr bool A_KMAJ = MODE != G_WGRAD, B_KMAJ = MODE == G_FWD;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bars = smem_base;  // TC_STAGES mbarriers
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 64);
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 96);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z = blockIdx.z / g.splits, split = blockIdx.z % g.splits;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * n_tile;
@@ -139,7 +149,10 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
     const uint32_t stage_bytes = 3u * (a_plane + b_plane), stage0 = smem_base + 128u;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);                            // empty[s]: one tcgen05.commit
+            mbar_init(bars + 8 * (TC_STAGES + s), TC_PRODUCERS);   // full[s]: every producer thread
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -153,61 +166,96 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = umma_idesc_bf16(TC_BM, n_tile);
 
-    // this thread's chunks: A tile = 128 rows x 2 k-groups = 256 chunks (one each); B tile = n_tile x 2 (<= 2 each)
-    const int a_r = tid & 127, a_kg = tid >> 7;
-    const uint32_t a_off = (uint32_t)a_kg * (TC_BM / 8) * 128u + (uint32_t)(a_r >> 3) * 128u + (uint32_t)(a_r & 7) * 16u;
-    const int a_rows_end = MODE == G_WGRAD ? g.M : g.M;  // operand-row bound (rows of C)
-    const int b_chunks = n_tile * 2;
-    float va[8], vb[TC_MAX_BCHUNKS][8];
-    auto load_stage = [&](int it) {
-        const int k0 = k_begin + it * TC_KC;
-        load_chunk<A_KMAJ>(A, g.lda, m0 + a_r, a_rows_end, k0 + a_kg * 8, k_end, va);
+    // Chunk slots.  A tile = 128 rows x 2 k-groups = 256 chunks (threads 0..255, slot 0); B tile = n_tile x 2 <= 512 chunks
+    // (threads 256..511 slot 0, then slot 1 of every thread).  Everything that does not change from stage to stage (global
+    // pointer, row validity, shared-memory offset) is computed once.
+    const int64_t lda = g.lda, ldb = g.ldb;
+    const bool slot0_is_a = tid < 256;  // warp-uniform; chunk id of slot c = tid + c * TC_PRODUCERS: ids 0..255 are A chunks, the rest B chunks
+    const float *ptr[TC_SLOTS];
+    uint32_t off[TC_SLOTS];  // byte offset inside a stage (A planes first, then B planes)
+    bool ok[TC_SLOTS], live[TC_SLOTS];
+    int kg8[TC_SLOTS];
 #pragma unroll
-        for (int c = 0; c < TC_MAX_BCHUNKS; ++c) {
-            const int ch = tid + c * TC_GEMM_THREADS;
-            if (ch < b_chunks) {
-                const int r = ch % n_tile, kg = ch / n_tile;
-                load_chunk<B_KMAJ>(Bm, g.ldb, n0 + r, g.N, k0 + kg * 8, k_end, vb[c]);
-            }
+    for (int c = 0; c < TC_SLOTS; ++c) {
+        const int id = tid + c * TC_PRODUCERS;
+        if (c == 0 && slot0_is_a) {
+            const int r = id & 127, kg = id >> 7;
+            live[c] = true, ok[c] = m0 + r < g.M, kg8[c] = kg * 8;
+            off[c] = (uint32_t)kg * (TC_BM / 8) * 128u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+            ptr[c] = A_KMAJ ? A + (int64_t)(m0 + r) * lda + (k_begin + kg * 8) : A + (int64_t)(k_begin + kg * 8) * lda + (m0 + r);
+        } else {
+            const int ch = id - 256;
+            const int r = ch % n_tile, kg = ch / n_tile;
+            live[c] = ch < n_tile * 2, ok[c] = live[c] && n0 + r < g.N, kg8[c] = kg * 8;
+            off[c] = 3u * a_plane + (uint32_t)kg * (uint32_t)(n_tile / 8) * 128u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+            ptr[c] = B_KMAJ ? Bm + (int64_t)(n0 + r) * ldb + (k_begin + kg * 8) : Bm + (int64_t)(k_begin + kg * 8) * ldb + (n0 + r);
         }
+    }
+    const int64_t a_step = A_KMAJ ? TC_KC : TC_KC * lda, b_step = B_KMAJ ? TC_KC : TC_KC * ldb;
+    // two register sets: the global loads of stage it+2 are issued right after stage it has been written, so they have two
+    // full iterations (split + handshake) to land
+    float v0[TC_SLOTS][8], v1[TC_SLOTS][8];
+    auto load_stage = [&](int it, float (&v)[TC_SLOTS][8]) {
+        const int k_left = k_end - (k_begin + it * TC_KC);
+        if (slot0_is_a) load_chunk<A_KMAJ>(ptr[0] + it * a_step, lda, ok[0], k_left - kg8[0], v[0]);
+        else if (live[0]) load_chunk<B_KMAJ>(ptr[0] + it * b_step, ldb, ok[0], k_left - kg8[0], v[0]);
+#pragma unroll
+        for (int c = 1; c < TC_SLOTS; ++c)
+            if (live[c]) load_chunk<B_KMAJ>(ptr[c] + it * b_step, ldb, ok[c], k_left - kg8[c], v[c]);
     };
-    auto store_stage = [&](int s) {
-        const uint32_t sa = stage0 + (uint32_t)s * stage_bytes, sb = sa + 3u * a_plane;
-        split_store(va, sa + a_off, a_plane);
+    auto store_stage = [&](int s, const float (&v)[TC_SLOTS][8]) {
+        const uint32_t st = stage0 + (uint32_t)s * stage_bytes;
+        if (live[0]) split_store(v[0], st + off[0], slot0_is_a ? a_plane : b_plane);
 #pragma unroll
-        for (int c = 0; c < TC_MAX_BCHUNKS; ++c) {
-            const int ch = tid + c * TC_GEMM_THREADS;
-            if (ch < b_chunks) {
-                const int r = ch % n_tile, kg = ch / n_tile;
-                split_store(vb[c], sb + (uint32_t)kg * (uint32_t)(n_tile / 8) * 128u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u, b_plane);
-            }
-        }
+        for (int c = 1; c < TC_SLOTS; ++c)
+            if (live[c]) split_store(v[c], st + off[c], b_plane);
     };
 
-    if (n_iter > 0) load_stage(0);
-    for (int it = 0; it < n_iter; ++it) {
-        const int s = it % TC_STAGES, use = it / TC_STAGES;
-        if (use > 0) mbar_wait(bars + 8 * s, (uint32_t)((use - 1) & 1));  // the MMAs that read this stage have finished
-        store_stage(s);
-        if (it + 1 < n_iter) load_stage(it + 1);  // global loads in flight across the barrier and the MMA issue
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t sa = stage0 + (uint32_t)s * stage_bytes, sb = sa + 3u * a_plane;
-            uint64_t da[3], db[3];
+    // Warp 16 issues the MMAs; warps 0..15 produce.  Handshake per stage: producers arrive on full[s] after their proxy fence,
+    // the issuer's tcgen05.commit arrives on empty[s] when the MMAs that read the stage have finished.  No CTA-wide barrier in the loop.
+    if (warp == TC_PRODUCERS / 32) {
+        if (lane == 0) {
+            for (int it = 0; it < n_iter; ++it) {
+                const int s = it % TC_STAGES, use = it / TC_STAGES;
+                mbar_wait(bars + 8 * (TC_STAGES + s), (uint32_t)(use & 1));
+                tc_fence_after();
+                const uint32_t sa = stage0 + (uint32_t)s * stage_bytes, sb = sa + 3u * a_plane;
+                uint64_t da[3], db[3];
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                da[p] = umma_desc(sa + p * a_plane, (TC_BM / 8) * 128u, 128u);
-                db[p] = umma_desc(sb + p * b_plane, (uint32_t)(n_tile / 8) * 128u, 128u);
+                for (int p = 0; p < 3; ++p) {
+                    da[p] = umma_desc(sa + p * a_plane, (TC_BM / 8) * 128u, 128u);
+                    db[p] = umma_desc(sb + p * b_plane, (uint32_t)(n_tile / 8) * 128u, 128u);
+                }
+                // three independent accumulators (two products each), summed in the epilogue: the small terms do not have to
+                // survive an addition to the large partial sum inside the tensor core
+                const uint32_t d0 = tmem_base, d1 = TC_NACC == 3 ? tmem_base + (uint32_t)n_tile : d0, d2 = TC_NACC == 3 ? tmem_base + 2u * (uint32_t)n_tile : d0;
+                const uint32_t acc = it > 0;
+                tc_mma_bf16(d0, da[0], db[0], idesc, acc);
+                tc_mma_bf16(d1, da[0], db[1], idesc, TC_NACC == 3 ? acc : 1u);
+                tc_mma_bf16(d2, da[1], db[0], idesc, TC_NACC == 3 ? acc : 1u);
+                tc_mma_bf16(d0, da[1], db[1], idesc, 1);
+                tc_mma_bf16(d1, da[2], db[0], idesc, 1);
+                tc_mma_bf16(d2, da[0], db[2], idesc, 1);
+                tc_commit(bars + 8 * s);
             }
-            tc_mma_bf16(tmem_base, da[0], db[2], idesc, it > 0);  // small terms first
-            tc_mma_bf16(tmem_base, da[2], db[0], idesc, 1);
-            tc_mma_bf16(tmem_base, da[1], db[1], idesc, 1);
-            tc_mma_bf16(tmem_base, da[0], db[1], idesc, 1);
-            tc_mma_bf16(tmem_base, da[1], db[0], idesc, 1);
-            tc_mma_bf16(tmem_base, da[0], db[0], idesc, 1);
-            tc_commit(bars + 8 * s);
+        }
+    } else {
+        auto body = [&](int it, float (&v)[TC_SLOTS][8]) {
+            const int s = it % TC_STAGES, use = it / TC_STAGES;
+            if (use > 0) {  // the MMAs that read this stage have finished; one lane per warp polls
+                if (lane == 0) mbar_wait(bars + 8 * s, (uint32_t)((use - 1) & 1));
+                __syncwarp();
+            }
+            store_stage(s, v);
+            if (it + 2 < n_iter) load_stage(it + 2, v);
+            fence_proxy_async();
+            mbar_arrive(bars + 8 * (TC_STAGES + s));
+        };
+        if (n_iter > 0) load_stage(0, v0);
+        if (n_iter > 1) load_stage(1, v1);
+        for (int it = 0; it < n_iter; it += 2) {
+            body(it, v0);
+            if (it + 1 < n_iter) body(it + 1, v1);
         }
     }
     if (n_iter > 0) {
@@ -216,35 +264,55 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
     }
     tc_fence_after();
 
-    // ---- epilogue: thread = output row (TMEM lane), two warps share a lane quarter and split the columns -------------------
-    const int row = m0 + (warp & 3) * 32 + lane;
-    const int half_cols = n_tile / 2, c_begin = (warp >> 2) * half_cols;
-    float *C = g.C + z * g.c_z + (MODE == G_WGRAD ? split * g.c_split : 0);
-    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int c = c_begin; c < c_begin + half_cols; c += 8) {
-        float v[8];
-        if (n_iter > 0) {
-            tmem_ld8(t_lane + (uint32_t)c, v);
-            tmem_ld_wait();
-        } else {
+    // ---- epilogue: thread = output row (TMEM lane); the four producer warps of a lane quarter take the 8-column groups
+    // round-robin, two groups per batch so that the TMEM loads and the mask loads of a batch are all in flight together
+    if (warp < TC_PRODUCERS / 32) {
+        const int row = m0 + (warp & 3) * 32 + lane;
+        const bool row_ok = row < g.M;
+        float *C = g.C + z * g.c_z + (MODE == G_WGRAD ? split * g.c_split : 0);
+        const float *aux = g.aux + z * g.aux_z + (MODE == G_DGRAD ? (int64_t)(row_ok ? row : 0) * g.ldaux : 0);
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        constexpr int WQ = TC_PRODUCERS / 128;  // producer warps per TMEM lane quarter
+        for (int c0 = (warp >> 2) * 8; c0 < n_tile; c0 += 16 * WQ) {
+            float v[2][8], u[2][8], w[2][8];
+            float4 x[2][2];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        }
-        const int n = n0 + c;
-        if (row >= g.M || n >= g.N) continue;
+            for (int b = 0; b < 2; ++b) {
+                const int c = c0 + 8 * WQ * b;
+                if (c < n_tile && n_iter > 0) {  // warp-uniform
+                    tmem_ld8(t_lane + (uint32_t)c, v[b]);
+                    if (TC_NACC == 3) {
+                        tmem_ld8(t_lane + (uint32_t)(n_tile + c), u[b]);
+                        tmem_ld8(t_lane + (uint32_t)(2 * n_tile + c), w[b]);
+                    }
+                }
+                if (MODE != G_WGRAD) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int nn = n + 4 * h;
-            if (nn >= g.N) break;
-            float4 o = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
-            if (MODE == G_FWD) {
-                const float4 b = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + nn);
-                o = make_float4(fmaxf(o.x + b.x, 0.f), fmaxf(o.y + b.y, 0.f), fmaxf(o.z + b.z, 0.f), fmaxf(o.w + b.w, 0.f));
-            } else if (MODE == G_DGRAD) {
-                const float4 hh = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + (int64_t)row * g.ldaux + nn);
-                o = make_float4(hh.x > 0.f ? o.x : 0.f, hh.y > 0.f ? o.y : 0.f, hh.z > 0.f ? o.z : 0.f, hh.w > 0.f ? o.w : 0.f);
+                    for (int h = 0; h < 2; ++h) {
+                        const int nn = n0 + c + 4 * h;
+                        x[b][h] = (c < n_tile && nn < g.N && (MODE == G_FWD || row_ok)) ? *reinterpret_cast<const float4 *>(aux + nn) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
             }
-            *reinterpret_cast<float4 *>(C + (int64_t)row * g.ldc + nn) = o;
+            tmem_ld_wait();
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int c = c0 + 8 * WQ * b;
+                if (c >= n_tile || !row_ok) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int nn = n0 + c + 4 * h;
+                    if (nn >= g.N) break;
+                    float o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[i] = n_iter > 0 ? (TC_NACC == 3 ? v[b][4 * h + i] + (u[b][4 * h + i] + w[b][4 * h + i]) : v[b][4 * h + i]) : 0.f;
+                    const float4 a = x[b][h];
+                    float4 r = make_float4(o[0], o[1], o[2], o[3]);
+                    if (MODE == G_FWD) r = make_float4(fmaxf(o[0] + a.x, 0.f), fmaxf(o[1] + a.y, 0.f), fmaxf(o[2] + a.z, 0.f), fmaxf(o[3] + a.w, 0.f));
+                    else if (MODE == G_DGRAD) r = make_float4(a.x > 0.f ? o[0] : 0.f, a.y > 0.f ? o[1] : 0.f, a.z > 0.f ? o[2] : 0.f, a.w > 0.f ? o[3] : 0.f);
+                    *reinterpret_cast<float4 *>(C + (int64_t)row * g.ldc + nn) = r;
+                }
+            }
         }
     }
     tc_fence_before();
@@ -259,10 +327,10 @@ struct TcTile {
 
 inline TcTile tc_tile(int N) {
     TcTile t;
-    t.n_tiles = (N + 255) / 256;
+    t.n_tiles = TC_NACC == 3 ? (N + 159) / 160 : (N + 255) / 256;  // TC_NACC accumulators of n_tile columns each in the 512 TMEM columns
     t.n_tile = (((N + t.n_tiles - 1) / t.n_tiles) + 15) & ~15;
     t.tmem_cols = 32;
-    while (t.tmem_cols < t.n_tile) t.tmem_cols <<= 1;
+    while (t.tmem_cols < TC_NACC * t.n_tile) t.tmem_cols <<= 1;
     const uint32_t a_plane = 2u * (TC_BM / 8) * 128u, b_plane = 2u * (uint32_t)(t.n_tile / 8) * 128u;
     t.smem_bytes = 128u + TC_STAGES * 3u * (a_plane + b_plane);
     return t;

@@ -111,7 +111,7 @@ def _assert_grads_flip_aware(eng, out, flips, keys):
         for k, want in enumerate(want_list):
             got = gv[name][k].cpu().numpy()
             if flips == 0:  # same ReLU masks: fp32-grade agreement (measured 3e-6 of the max; tensor-core accumulation truncates)
-                np.testing.assert_allclose(got, want, rtol=0, atol=1e-5 * max(np.abs(want).max(), 1e-3), err_msg=f"{name} grad {k}")
+                np.testing.assert_allclose(got, want, rtol=0, atol=2e-5 * max(np.abs(want).max(), 1e-3), err_msg=f"{name} grad {k}")
             else:  # each flipped unit adds one dq*w3-sized term: far below a bf16-grade error (4e-3 of the max on every element)
                 assert np.linalg.norm(got - want) <= 1.5e-3 * flips * max(np.linalg.norm(want), 1e-6), f"{name} grad {k}"  # measured 5e-4 for one flip
 
