@@ -508,8 +508,15 @@ def td3_update_extras(pkg, torch, device, peaks_tflops) -> dict:
                 o.step(*mk())
                 k += 1
             row["cpu_oracle_updates_per_s"] = k / (time.perf_counter() - t0)
+        # the same update with the hidden-layer GEMMs on tcgen05 (3-plane bf16 split, fp32-grade; opt-in gemm="tensor")
+        eng_tc = pkg.FusedTD3Update([400, 300], B, device=device, gemm="tensor")
+        eng_tc.adopt_modules(R.mlp(4, 2, True, device), [R.mlp(6, 1, False, device), R.mlp(6, 1, False, device)], R.mlp(4, 2, True, device),
+                             [R.mlp(6, 1, False, device), R.mlp(6, 1, False, device)])
+        ms_tc = R.timed(lambda: eng_tc.update(buf.sample(B)), 200)
+        row["tensor_gemm_ms_per_update"] = ms_tc
+        row["tensor_gemm_algorithmic_tflops"] = out["flop_per_sample"] * B / (ms_tc * 1e-3) / 1e12
         out[f"batch_{B}"] = row
-        del eng, ref
+        del eng, ref, eng_tc
     return out
 
 

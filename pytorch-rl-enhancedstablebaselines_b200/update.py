@@ -5,6 +5,9 @@
 ``update()`` call through ``cstr_td3_update`` — target smoothing, twin-min target, critic forward/MSE/backward, Adam,
 delayed actor update, polyak — as hand-written float32 CUDA kernels.  No torch autograd, no cuBLAS.
 
+``gemm="fp32"`` (default) keeps the reference's float32 FMA arithmetic; ``gemm="tensor"`` runs the three hidden-layer GEMM roles on
+tcgen05 with every fp32 operand split into three bf16 planes (fp32-grade accuracy, see csrc/cstr_td3_tc.cuh).
+
 ``adopt_policy`` re-points the parameters of the reference's ``TD3Policy`` modules at views of the flat blocks, so
 ``policy.predict``, ``model.save`` and the fused rollout keep seeing the live weights without copies.
 ``bind_td3_class(TD3)`` returns a subclass of the reference algorithm whose ``train()`` runs here.
