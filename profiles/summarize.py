@@ -86,6 +86,23 @@ if os.path.exists(lpath):
         lines.append(f"| `{k}` | {len(v)} | {sum(v)/1e3:.1f} | {sum(v)/len(v)/1e3:.1f} | {sum(v)/tot:.3f} |")
     with open(os.path.join(PROF, f"{tag}_launches.csv"), "w") as fh:
         fh.write(open(lpath).read())
+# launch list of the TD3 gradient step (profiles/run_td3.py --batch 4096 --once, steady-state launches)
+tpath = os.path.join(OUT, f"{tag}_td3_launches.csv")
+if os.path.exists(tpath):
+    rows = [r for r in csv.reader(open(tpath)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        agg.setdefault(r[ki].split("(")[0].replace("void ", "")[:90], []).append(float(r[vi].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    lines.append(f"\n## {tag}_td3_launches.csv — launches 60..180 of `python profiles/run_td3.py --batch 4096 --once` (TD3 gradient steps, fp32 GEMM; "
+                 "cold-cache, serialised: compare shares)\n")
+    lines.append("| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|")
+    for k, v in agg.items():
+        lines.append(f"| `{k}` | {len(v)} | {sum(v)/1e3:.1f} | {sum(v)/len(v)/1e3:.1f} | {sum(v)/tot:.3f} |")
+    with open(os.path.join(PROF, f"{tag}_td3_launches.csv"), "w") as fh:
+        fh.write(open(tpath).read())
 open(os.path.join(PROF, f"{tag}_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
 json.dump(traffic, open(os.path.join(PROF, f"{tag}_traffic.json"), "w"), indent=1)
 print("\n".join(lines)[:6000])

@@ -62,31 +62,44 @@ inline Td3Layout td3_layout(int h1, int h2) {
 // ------------------------------------------------------------------------------------------------------------------
 // layer 1: h1[z][b][j] = relu(b1[j] + sum_i x[b][i] W1[j][i]),  x = [obs | act]  (K = 4 or 6: no GEMM needed)
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int L1_ROWS = 8;  // batch rows per thread: the 4 x IN weights of the thread's four units stay in registers
+
 template <int IN>
 __global__ void __launch_bounds__(256)
 td3_layer1_kernel(int B, int H1, const float4 *__restrict__ obs, const float2 *__restrict__ act, const float *__restrict__ W1, const float *__restrict__ b1,
                   int64_t w_stride_z, float *__restrict__ h1, int64_t h_stride_z) {
     const int q = H1 >> 2;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * q) return;
-    const int b = (int)(i / q), j = (int)(i % q) * 4;
+    const int row_groups = (B + L1_ROWS - 1) / L1_ROWS;
+    if (i >= (int64_t)row_groups * q) return;
+    const int b0 = (int)(i / q) * L1_ROWS, j = (int)(i % q) * 4;  // a warp covers 32 consecutive unit-quads of one row group
     const int z = blockIdx.y;
     const float *W = W1 + z * w_stride_z + (int64_t)j * IN;
-    const float4 o = obs[b];
-    float x[IN];
-    x[0] = o.x, x[1] = o.y, x[2] = o.z, x[3] = o.w;
-    if (IN == 6) {
-        const float2 a = act[b];
-        x[4] = a.x, x[5] = a.y;
-    }
-    const float4 bias = *reinterpret_cast<const float4 *>(b1 + z * w_stride_z + j);
-    float r[4] = {bias.x, bias.y, bias.z, bias.w};
+    float w[4][IN];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int k = 0; k < IN; ++k) r[c] = fmaf(x[k], __ldg(W + c * IN + k), r[c]);
-    *reinterpret_cast<float4 *>(h1 + z * h_stride_z + (int64_t)b * H1 + j) =
-        make_float4(fmaxf(r[0], 0.f), fmaxf(r[1], 0.f), fmaxf(r[2], 0.f), fmaxf(r[3], 0.f));
+        for (int k = 0; k < IN; ++k) w[c][k] = __ldg(W + c * IN + k);
+    const float4 bias = *reinterpret_cast<const float4 *>(b1 + z * w_stride_z + j);
+    float *out = h1 + z * h_stride_z + j;
+#pragma unroll
+    for (int r = 0; r < L1_ROWS; ++r) {
+        const int b = b0 + r;
+        if (b >= B) break;
+        const float4 o = obs[b];
+        float x[IN];
+        x[0] = o.x, x[1] = o.y, x[2] = o.z, x[3] = o.w;
+        if (IN == 6) {
+            const float2 a = act[b];
+            x[4] = a.x, x[5] = a.y;
+        }
+        float v[4] = {bias.x, bias.y, bias.z, bias.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int k = 0; k < IN; ++k) v[c] = fmaf(x[k], w[c][k], v[c]);
+        *reinterpret_cast<float4 *>(out + (int64_t)b * H1) = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -424,8 +437,18 @@ __global__ void __launch_bounds__(256) td3_skinny_reduce_kernel(SkinnyArgs s, in
     if (i == NY) {
         if (!s.out_b || (YBIAS ? jj >= NY : jj >= s.H)) return;
     } else if (jj >= s.H || !s.out_w) return;
-    float v = 0.f;
-    for (int c = 0; c < s.chunks; ++c) v += s.part[((int64_t)c * Z + z) * (NY + 1) * Hp + e];
+    const int64_t stride = (int64_t)Z * (NY + 1) * Hp;
+    const float *pp = s.part + (int64_t)z * (NY + 1) * Hp + e;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four loads in flight; the combination order is fixed
+    int c = 0;
+    for (; c + 4 <= s.chunks; c += 4) {
+        a0 += pp[(c + 0) * stride];
+        a1 += pp[(c + 1) * stride];
+        a2 += pp[(c + 2) * stride];
+        a3 += pp[(c + 3) * stride];
+    }
+    for (; c < s.chunks; ++c) a0 += pp[c * stride];
+    const float v = (a0 + a1) + (a2 + a3);
     if (i < NY) {
         if (s.transposed) s.out_w[z * s.out_z + (int64_t)i * s.H + jj] = v;
         else s.out_w[z * s.out_z + (int64_t)jj * NY + i] = v;
@@ -467,11 +490,20 @@ struct ApplyArgs {
 __global__ void __launch_bounds__(256) td3_apply_kernel(ApplyArgs a) {
     const int64_t lo = min(a.adam_lo, a.polyak_lo < a.polyak_hi ? a.polyak_lo : a.adam_lo);
     const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.loss_acc) {
+    if (blockIdx.x == 0 && a.loss_acc) {  // per-CTA loss partials -> running sums (block-wide, fixed order)
+        __shared__ float sl[256];
         float s = 0.f;
-        for (int k = 0; k < a.n_loss_partial; ++k) s += a.loss_partial[k];
-        a.loss_acc[0] += s * a.loss_scale;
-        a.loss_acc[1] += 1.f;
+        for (int k = threadIdx.x; k < a.n_loss_partial; k += 256) s += a.loss_partial[k];
+        sl[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sl[threadIdx.x] += sl[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            a.loss_acc[0] += sl[0] * a.loss_scale;
+            a.loss_acc[1] += 1.f;
+        }
     }
     float p;
     bool have = false;
@@ -607,7 +639,7 @@ Net net_at(float *base, int64_t off, const NetLayout &L) { return Net{base + off
 // h1 = relu(L1(x)), h2 = relu(L2(h1)) for Z nets that are `z_stride` floats apart
 int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float *act, const Net &n, int64_t z_stride, int Z, float *h1, float *h2,
                    cudaStream_t st) {
-    const int64_t threads = (int64_t)B * (H1 / 4);
+    const int64_t threads = (int64_t)((B + L1_ROWS - 1) / L1_ROWS) * (H1 / 4);
     dim3 grid((unsigned)((threads + 255) / 256), Z);
     if (in == OBS)
         td3_layer1_kernel<OBS><<<grid, 256, 0, st>>>(B, H1, (const float4 *)obs, nullptr, n.w1, n.b1, z_stride, h1, (int64_t)B * H1);
