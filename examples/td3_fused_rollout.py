@@ -9,9 +9,11 @@ Per iteration, on every rank:
                                      records for this rank's reactor shard, ONE kernel launch, nothing leaves the GPU;
   2. ``GpuReplayBuffer.sample(B)`` — Philox-index gather straight into the update's float32 tensors;
   3. TD3 update with the reference's semantics (``core/td3/td3.py:154-211``: target policy smoothing, twin-min
-     target, delayed actor, polyak) in plain torch — the update kernels are the "next" row, the
-     hot path here is 1–2; gradients are all-reduced with ONE flat NCCL bucket (``dist.allreduce_gradients``);
-  4. the fresh actor weights are handed back to the rollout kernel device-to-device.
+     target, delayed actor, polyak): ``--update fused`` (default) = ``FusedTD3Update`` (cstr_td3_update: hand-written
+     forward/backward/Adam/polyak kernels, the flat gradient block all-reduced in place with ONE NCCL call per phase);
+     ``--update torch`` = the same update in eager torch (autograd + cuBLAS) for comparison;
+  4. the fresh actor weights are handed back to the rollout kernel device-to-device (the nn.Module parameters are
+     views of the fused engine's flat parameter block, so no copy is involved on the update side).
 """
 from __future__ import annotations
 
@@ -58,6 +60,8 @@ def main():
     ap.add_argument("--rows", type=int, default=64, help="ring rows per rank")
     ap.add_argument("--actor-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--update", default="fused", choices=["fused", "torch"])
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor"], help="hidden-layer GEMMs of the fused update")
     args = ap.parse_args()
 
     pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
@@ -83,6 +87,12 @@ def main():
     weights = pkg.ActorWeights.from_module(actor, device=dev)
     roll = pkg.FusedRollout(env, buf, weights, sigma=0.1, actor_mode=args.actor_mode)
     gamma, tau, tnoise, tclip, delay = 0.99, 0.005, 0.2, 0.5, 2
+    fused = None
+    if args.update == "fused":
+        fused = pkg.FusedTD3Update([400, 300], args.batch, device=dev, gamma=gamma, tau=tau, learning_rate=3e-4, policy_delay=delay,
+                                   target_policy_noise=tnoise, target_noise_clip=tclip, seed=args.seed * 7919 + rank, gemm=args.gemm)
+        fused.adopt_modules(actor, list(critics), actor_t, list(critics_t))  # module parameters become views of the flat blocks
+        hook = pkg.dist.allreduce_flat if world > 1 else None
 
     env.reset()
     roll.collect(args.steps_per_iter, warmup=True)  # learning_starts phase: uniform random actions
@@ -96,6 +106,10 @@ def main():
         roll.collect(args.steps_per_iter, reward_sum=rsum)
         for _ in range(args.updates_per_iter):
             b = buf.sample(args.batch)
+            if fused is not None:
+                fused.update(b, allreduce=hook)
+                n_updates += 1
+                continue
             with torch.no_grad():
                 noise = (torch.randn_like(b.actions) * tnoise).clamp(-tclip, tclip)
                 na = (actor_t(b.next_observations) + noise).clamp(-1, 1)
@@ -120,14 +134,16 @@ def main():
         mean_r = pkg.dist.global_sum(float(rsum.item()), device=dev) / (args.n_envs * args.steps_per_iter)
         log.append(mean_r)
         if rank == 0 and (it % 5 == 0 or it == args.iters - 1):
-            print(f"iter {it:3d}  mean reward/step {mean_r:8.4f}  critic loss {float(loss_c.detach()):.4f}", flush=True)
+            closs = fused.pop_losses()[0] if fused is not None else float(loss_c.detach())
+            print(f"iter {it:3d}  mean reward/step {mean_r:8.4f}  critic loss {closs:.4f}", flush=True)
     torch.cuda.synchronize()
     dt = time.time() - t0
     if rank == 0:
         transitions = args.iters * args.steps_per_iter * args.n_envs
         print(json.dumps({"world_size": world, "n_envs": args.n_envs, "transitions": transitions, "seconds": dt,
                           "transitions_per_s_incl_updates": transitions / dt, "updates": n_updates,
-                          "mean_reward_first": log[0], "mean_reward_last": log[-1], "actor_mode": args.actor_mode}))
+                          "mean_reward_first": log[0], "mean_reward_last": log[-1], "actor_mode": args.actor_mode, "update": args.update,
+                          "gemm": args.gemm}))
     if world > 1:
         torch.distributed.destroy_process_group()
     return log

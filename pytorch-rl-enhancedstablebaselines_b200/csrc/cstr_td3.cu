@@ -538,16 +538,15 @@ struct Workspace {  // carved out of the caller's workspace buffer (floats)
     float *t_h1, *t_h2;      // target-critic activations (2 slabs)
     float *a_h1, *a_h2;      // actor / actor-target activations
     float *next_act, *a_pi, *target, *dq, *dpre, *loss_partial, *slabs, *skinny;
-    int splits, n_row_blocks;
+    int n_row_blocks;
+    bool tensor;  // hidden-layer GEMMs on tcgen05 (cfg->gemm_mode)
     int64_t floats;
 };
 
 constexpr int MAX_SPLITS = 16;
 
 // split-K factor of the dW2 GEMM: minimise (CTA rounds per SM) x (k-iterations per CTA) over the 148 SMs
-int g_gemm_mode_for_splits();
-int choose_splits(int B, int H1, int H2, int Z) {
-    const bool tc = g_gemm_mode_for_splits() == CSTR_TD3_GEMM_TENSOR;
+int choose_splits(int B, int H1, int H2, int Z, bool tc) {
     const int64_t tiles = tc ? (int64_t)((H2 + TC_BM - 1) / TC_BM) * tc_tile(H1).n_tiles * Z : (int64_t)((H2 + BM - 1) / BM) * ((H1 + BN - 1) / BN) * Z;
     const int sms = sm_count();
     int best = 1;
@@ -577,10 +576,10 @@ Workspace carve(float *base, int B, int H1, int H2) {
     w.next_act = take(2 * (int64_t)B), w.a_pi = take(2 * (int64_t)B), w.target = take(B), w.dq = take(2 * (int64_t)B), w.dpre = take(2 * (int64_t)B);
     w.n_row_blocks = (B + 7) / 8;
     w.loss_partial = take(2 * (int64_t)w.n_row_blocks);
-    w.splits = 0;  // chosen per launch (choose_splits)
     w.slabs = take((int64_t)MAX_SPLITS * 2 * pad4((int64_t)H1 * H2));
     const int64_t hp = ((int64_t)(H1 > H2 ? H1 : H2) + 31) / 32 * 32;
     w.skinny = take((int64_t)((B + SKINNY_ROWS - 1) / SKINNY_ROWS) * 2 * (OBS + ACT + 1) * hp);
+    w.tensor = false;
     w.floats = o;
     return w;
 }
@@ -607,12 +606,9 @@ int launch_skinny(SkinnyArgs s, int Z, float *part, cudaStream_t st, const char 
     return check_launch(what);
 }
 
-int g_gemm_mode_for_splits();
-int g_gemm_mode = 0;  // set per cstr_td3_update call from cfg->gemm_mode (0 = FFMA, 1 = bf16x3 tcgen05)
-
 template <int MODE>
-int launch_gemm(const GemmArgs &g, int Z, cudaStream_t st, const char *what) {
-    if (g_gemm_mode == CSTR_TD3_GEMM_TENSOR) {
+int launch_gemm(const GemmArgs &g, int Z, bool tensor, cudaStream_t st, const char *what) {
+    if (tensor) {
         const TcTile t = tc_tile(g.N);
         static bool attr_set[3] = {false, false, false};
         if (!attr_set[MODE]) {
@@ -629,8 +625,6 @@ int launch_gemm(const GemmArgs &g, int Z, cudaStream_t st, const char *what) {
     return check_launch(what);
 }
 
-int g_gemm_mode_for_splits() { return g_gemm_mode; }
-
 struct Net {  // pointers of one net (or the first of a z-batched pair) inside a flat block
     float *w1, *b1, *w2, *b2, *w3, *b3;
 };
@@ -638,7 +632,7 @@ Net net_at(float *base, int64_t off, const NetLayout &L) { return Net{base + off
 
 // h1 = relu(L1(x)), h2 = relu(L2(h1)) for Z nets that are `z_stride` floats apart
 int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float *act, const Net &n, int64_t z_stride, int Z, float *h1, float *h2,
-                   cudaStream_t st) {
+                   bool tensor, cudaStream_t st) {
     const int64_t threads = (int64_t)((B + L1_ROWS - 1) / L1_ROWS) * (H1 / 4);
     dim3 grid((unsigned)((threads + 255) / 256), Z);
     if (in == OBS)
@@ -651,7 +645,7 @@ int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float 
     g.M = B, g.N = H2, g.K = H1, g.lda = H1, g.ldb = H1, g.ldc = H2, g.ldaux = 0;
     g.a_z = (int64_t)B * H1, g.b_z = z_stride, g.c_z = (int64_t)B * H2, g.aux_z = z_stride;
     g.splits = 1, g.k_per_split = H1, g.c_split = 0;
-    return launch_gemm<G_FWD>(g, Z, st, "td3_gemm_kernel<fwd>");
+    return launch_gemm<G_FWD>(g, Z, tensor, st, "td3_gemm_kernel<fwd>");
 }
 
 // given dz2 (and h1, x): dz1 (optional), then every weight gradient of the hidden and input layers into the flat grads
@@ -662,7 +656,7 @@ int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float
     g.M = B, g.N = H1, g.K = H2, g.lda = H2, g.ldb = H1, g.ldc = H1, g.ldaux = H1;
     g.a_z = (int64_t)B * H2, g.b_z = z_stride, g.c_z = (int64_t)B * H1, g.aux_z = (int64_t)B * H1;
     g.splits = 1, g.k_per_split = H2, g.c_split = 0;
-    if (int rc = launch_gemm<G_DGRAD>(g, Z, st, "td3_gemm_kernel<dgrad>")) return rc;
+    if (int rc = launch_gemm<G_DGRAD>(g, Z, w.tensor, st, "td3_gemm_kernel<dgrad>")) return rc;
     if (!want_weight_grads) return 0;
     // dW2 = dz2^T @ h1, split over the batch into slabs, then summed in order
     const int64_t w2n = pad4((int64_t)H1 * H2);
@@ -670,9 +664,9 @@ int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float
     q.A = dz2, q.Bm = h1, q.aux = nullptr, q.C = w.slabs;
     q.M = H2, q.N = H1, q.K = B, q.lda = H2, q.ldb = H1, q.ldc = H1, q.ldaux = 0;
     q.a_z = (int64_t)B * H2, q.b_z = (int64_t)B * H1, q.c_z = w2n, q.aux_z = 0;
-    const int splits = choose_splits(B, H1, H2, Z);
+    const int splits = choose_splits(B, H1, H2, Z, w.tensor);
     q.splits = splits, q.k_per_split = (B + splits - 1) / splits, q.c_split = 2 * w2n;
-    if (int rc = launch_gemm<G_WGRAD>(q, Z, st, "td3_gemm_kernel<wgrad>")) return rc;
+    if (int rc = launch_gemm<G_WGRAD>(q, Z, w.tensor, st, "td3_gemm_kernel<wgrad>")) return rc;
     const int64_t n4 = (int64_t)H1 * H2 / 4;
     td3_sum_slabs_kernel<<<dim3((unsigned)((n4 + 255) / 256), Z), 256, 0, st>>>(n4, splits, (const float4 *)w.slabs, 2 * w2n / 4, w2n / 4, (float4 *)gn.w2,
                                                                               z_stride / 4);
@@ -729,12 +723,12 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         !aligned(stt->targets, 16) || !aligned(stt->grads, 16) || !aligned(stt->adam_m, 16) || !aligned(stt->adam_v, 16) || !aligned(stt->workspace, 16))
         return fail_arg(CSTR_EALIGN, "td3_update: 16 B (obs/params/workspace) / 8 B (actions, noise) alignment");
     const int B = cfg->batch, H1 = cfg->h1, H2 = cfg->h2;
-    const Workspace w = carve(stt->workspace, B, H1, H2);
+    Workspace w = carve(stt->workspace, B, H1, H2);
+    w.tensor = cfg->gemm_mode == CSTR_TD3_GEMM_TENSOR;
     if (stt->workspace_bytes < w.floats * (int64_t)sizeof(float)) return fail_arg(CSTR_EINVAL, "td3_update: workspace too small (cstr_td3_workspace_bytes)");
     if (n_updates < 1 || critic_step < 1 || actor_step < 0) return fail_arg(CSTR_EINVAL, "td3_update: counters are 1-based (value after this update)");
     const Td3Layout T = td3_layout(H1, H2);
     cudaStream_t st = (cudaStream_t)stream;
-    g_gemm_mode = cfg->gemm_mode;
     const int64_t cz = T.critic.size;
     const Net actor = net_at(stt->params, T.actor_off, T.actor), actor_t = net_at(stt->targets, T.actor_off, T.actor);
     const Net critic = net_at(stt->params, T.critic_off[0], T.critic), critic_t = net_at(stt->targets, T.critic_off[0], T.critic);
@@ -744,15 +738,15 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
 
     if (phases & CSTR_TD3_CRITIC_GRAD) {
         // ---- target (td3.py:166-175) ----
-        if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor_t, 0, 1, w.a_h1, w.a_h2, st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor_t, 0, 1, w.a_h1, w.a_h2, w.tensor, st)) return rc;
         td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor_t.w3, actor_t.b3, 1, (const float2 *)noise, cfg->target_policy_noise,
                                                  cfg->target_noise_clip, cfg->seed, (uint32_t)n_updates, (float2 *)w.next_act);
         if (int rc = check_launch("td3_actor_head_kernel")) return rc;
-        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st)) return rc;
         td3_target_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.t_h2, (int64_t)B * H2, critic_t.w3, critic_t.b3, cz, rewards, dones, cfg->gamma, w.target);
         if (int rc = check_launch("td3_target_head_kernel")) return rc;
         // ---- current Q, loss, backward (td3.py:178-186) ----
-        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st)) return rc;
         td3_critic_head_kernel<false><<<dim3(rb, 2), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, w.dq, w.dz2,
                                                                   w.loss_partial);
         if (int rc = check_launch("td3_critic_head_kernel")) return rc;
@@ -777,10 +771,10 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
     }
     if (policy_step && (phases & CSTR_TD3_ACTOR_GRAD)) {
         // ---- actor loss = -Q1(s, pi(s)).mean() and its backward (td3.py:189-196) ----
-        if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st)) return rc;
         td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, 0, nullptr, 0.f, 0.f, 0, 0, (float2 *)w.a_pi);
         if (int rc = check_launch("td3_actor_head_kernel<pi>")) return rc;
-        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 1, w.h1[0], w.h2[0], st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 1, w.h1[0], w.h2[0], w.tensor, st)) return rc;
         td3_critic_head_kernel<true><<<dim3(rb, 1), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, nullptr, w.dq, w.dz2,
                                                                  w.loss_partial);
         if (int rc = check_launch("td3_critic_head_kernel<policy>")) return rc;

@@ -85,3 +85,47 @@ def test_replay_and_rollout_ragged_sizes(pkg, golden, n):
     fo, vo, go = _padded((B_, 4), torch.float32)
     s = buf.sample(B_)
     assert s.observations.shape == (B_, 4) and bool(torch.isfinite(s.rewards).all().item())
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "tensor"])
+@pytest.mark.parametrize("B,arch", [(1, [36, 20]), (130, [400, 300]), (641, [132, 260])])
+def test_td3_update_ragged_sizes_and_argument_errors(pkg, B, arch, gemm):
+    """cstr_td3_update on ragged batches with every state block and the workspace inside canary-guarded allocations."""
+    import gpu_util as G
+
+    lib = G.L.load()
+    eng = pkg.FusedTD3Update(arch, B, gemm=gemm, policy_delay=1)
+    P = eng.param_count
+    blocks = {name: _padded((P,), torch.float32) for name in ("params", "targets", "grads", "adam_m", "adam_v")}
+    ws = _padded((eng._workspace.numel(),), torch.float32)
+    data = {name: _padded(shape, torch.float32) for name, shape in (("obs", (B, 4)), ("act", (B, 2)), ("nobs", (B, 4)), ("done", (B, 1)), ("rew", (B, 1)))}
+    torch.manual_seed(B)
+    for name in ("params", "targets"):
+        blocks[name][1].copy_(torch.randn(P, device="cuda") * 0.1)
+    for name in ("grads", "adam_m", "adam_v"):
+        blocks[name][1].zero_()
+    for name, (_, view, _) in data.items():
+        view.copy_(torch.rand(view.shape, device="cuda") * 2 - 1)
+    data["done"][1].zero_()
+    eng.params, eng.targets, eng.grads, eng.adam_m, eng.adam_v = (blocks[k][1] for k in ("params", "targets", "grads", "adam_m", "adam_v"))
+    eng._workspace = ws[1]
+    before = eng.params.clone()
+    for _ in range(2):
+        eng.update(tuple(data[k][1] for k in ("obs", "act", "nobs", "done", "rew")))
+    torch.cuda.synchronize()
+    for name, (full, _, guard) in {**blocks, **data, "workspace": ws}.items():
+        assert _guards_intact(full, guard, torch.float32), name
+    assert bool(torch.isfinite(eng.params).all().item()) and not torch.equal(before, eng.params)
+    # argument errors: negative code + message, nothing launched
+    cfg = eng._config(B)
+    st = G.L.Td3State(params=eng.params.data_ptr(), targets=eng.targets.data_ptr(), grads=eng.grads.data_ptr(), adam_m=eng.adam_m.data_ptr(),
+                      adam_v=eng.adam_v.data_ptr(), workspace=ws[1].data_ptr(), workspace_bytes=16, losses=None)
+    ptrs = [data[k][1].data_ptr() for k in ("obs", "act", "nobs", "done", "rew")]
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.cstr_td3_update(byref(cfg), byref(st), *ptrs, None, 1, 1, 1, 15, stream) < 0 and b"workspace" in lib.cstr_last_error()
+    st.workspace_bytes = ws[1].numel() * 4
+    assert lib.cstr_td3_update(byref(cfg), byref(st), ptrs[0] + 4, *ptrs[1:], None, 1, 1, 1, 15, stream) < 0 and b"alignment" in lib.cstr_last_error()
+    assert lib.cstr_td3_update(byref(cfg), byref(st), None, *ptrs[1:], None, 1, 1, 1, 15, stream) < 0
+    assert lib.cstr_td3_update(byref(cfg), byref(st), *ptrs, None, 0, 1, 1, 15, stream) < 0  # counters are 1-based
+    cfg.h1 = 37
+    assert lib.cstr_td3_update(byref(cfg), byref(st), *ptrs, None, 1, 1, 1, 15, stream) < 0 and lib.cstr_td3_param_count(37, 20) == -1
