@@ -516,6 +516,8 @@ def td3_update_extras(pkg, torch, device, peaks_tflops) -> dict:
         eng_tc.adopt_modules(R.mlp(4, 2, True, device), [R.mlp(6, 1, False, device), R.mlp(6, 1, False, device)], R.mlp(4, 2, True, device),
                              [R.mlp(6, 1, False, device), R.mlp(6, 1, False, device)])
         ms_tc = R.timed(lambda: eng_tc.update(buf.sample(B)), 200)
+        row["cuda_graph_ms_per_update"] = R.timed(lambda: eng.train(2, buf, B, graph=True), 100) / 2
+        row["tensor_gemm_cuda_graph_ms_per_update"] = R.timed(lambda: eng_tc.train(2, buf, B, graph=True), 100) / 2
         row["tensor_gemm_ms_per_update"] = ms_tc
         row["tensor_gemm_algorithmic_tflops"] = out["flop_per_sample"] * B / (ms_tc * 1e-3) / 1e12
         out[f"batch_{B}"] = row

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 10
+#define CSTR_B200_ABI_VERSION 11
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -158,6 +158,13 @@ int cstr_replay_sample_philox(uint64_t seed, uint64_t draw, int64_t n_envs, int6
                               float *out_next_obs, float *out_dones, float *out_rewards,
                               int64_t *out_batch_inds, int64_t *out_env_inds,
                               const cstr_norm_params *norm /* nullable */, void *stream);
+/* Same, with the draw counter read from device memory at execution time (no host scalar baked into the launch), so the call can
+ * be captured in a CUDA graph and replayed; whoever owns the counter advances it (cstr_td3_update in graph mode does). */
+int cstr_replay_sample_philox_dev(uint64_t seed, const int64_t *draw_dev, int64_t n_envs, int64_t upper,
+                              int64_t batch, const float *records, float *out_obs, float *out_act,
+                              float *out_next_obs, float *out_dones, float *out_rewards,
+                              int64_t *out_batch_inds, int64_t *out_env_inds,
+                              const cstr_norm_params *norm /* nullable */, void *stream);
 
 /* ---- VecNormalize on the device ------------------------------------------------------------------------
  * cstr_norm_update replaces the statistics part of VecNormalize.step_wait (core/common/vec_env/vec_normalize.py:
@@ -204,6 +211,13 @@ typedef struct cstr_td3_state {
     float *workspace;                                  /* device, >= cstr_td3_workspace_bytes(cfg)                  */
     int64_t workspace_bytes;
     float *losses;                                     /* device, 4 floats, or NULL                                 */
+    int64_t *counters;                                 /* device, 4 x int64 {n_updates, critic_step, actor_step, sample_draw} BEFORE this
+                                                          update, or NULL.  Non-NULL = graph mode: a one-thread kernel advances them at
+                                                          the start of the update and derives the Philox counter of the smoothing noise and
+                                                          the Adam bias corrections on the device, so nothing that changes from update to
+                                                          update is baked into a launch and a cycle of policy_delay updates can be captured
+                                                          in a CUDA graph and replayed (the by-value counters then only decide which
+                                                          kernels are launched, i.e. whether this is a policy step)                     */
 } cstr_td3_state;
 
 #define CSTR_TD3_CRITIC_GRAD 1

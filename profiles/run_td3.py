@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--once", action="store_true", help="few launches only (for ncu)")
     ap.add_argument("--no-torch", action="store_true")
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor"])
+    ap.add_argument("--graph", action="store_true", help="time train(graph=True): one CUDA-graph launch per policy_delay updates")
     args = ap.parse_args()
     pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
     dev = torch.device("cuda", 0)
@@ -97,7 +98,10 @@ def main():
         eng.adopt_modules(mlp(4, 2, True, dev), [mlp(6, 1, False, dev), mlp(6, 1, False, dev)], mlp(4, 2, True, dev),
                           [mlp(6, 1, False, dev), mlp(6, 1, False, dev)])
         steps = 4 if args.once else args.steps
-        ms = timed(lambda: eng.update(buf.sample(B)), steps)
+        if args.graph:
+            ms = timed(lambda: eng.train(2, buf, B, graph=True), steps // 2) / 2
+        else:
+            ms = timed(lambda: eng.update(buf.sample(B)), steps)
         row = {"fused_ms_per_update": ms, "fused_updates_per_s": 1e3 / ms, "fused_samples_per_s": B * 1e3 / ms,
                "algorithmic_tflops": flops_per_sample(400, 300) * B / (ms * 1e-3) / 1e12}
         if not args.no_torch and not args.once:

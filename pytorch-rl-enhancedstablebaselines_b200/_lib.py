@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -69,7 +69,7 @@ class Td3State(Structure):
     """struct cstr_td3_state"""
 
     _fields_ = [("params", c_void_p), ("targets", c_void_p), ("grads", c_void_p), ("adam_m", c_void_p), ("adam_v", c_void_p),
-                ("workspace", c_void_p), ("workspace_bytes", c_int64), ("losses", c_void_p)]
+                ("workspace", c_void_p), ("workspace_bytes", c_int64), ("losses", c_void_p), ("counters", c_void_p)]
 
 
 TD3_CRITIC_GRAD, TD3_CRITIC_APPLY, TD3_ACTOR_GRAD, TD3_ACTOR_APPLY, TD3_ALL = 1, 2, 4, 8, 15
@@ -89,6 +89,7 @@ _SIGNATURES = {
     "cstr_replay_add": (c_int, [c_int64, c_int64, P, P, P, P, P, P, P, P]),
     "cstr_replay_sample": (c_int, [c_int64, c_int64, P, P, P, P, P, P, P, P, POINTER(NormParams), P]),
     "cstr_replay_sample_philox": (c_int, [c_uint64, c_uint64, c_int64, c_int64, c_int64, P, P, P, P, P, P, P, P, POINTER(NormParams), P]),
+    "cstr_replay_sample_philox_dev": (c_int, [c_uint64, P, c_int64, c_int64, c_int64, P, P, P, P, P, P, P, P, POINTER(NormParams), P]),
     "cstr_norm_update": (c_int, [c_int64, P, P, P, P, c_double, P, P, P]),
     "cstr_norm_apply": (c_int, [c_int64, P, P, P, c_double, c_double, c_double, P, P, P]),
     "cstr_td3_param_count": (c_int64, [c_int32, c_int32]),

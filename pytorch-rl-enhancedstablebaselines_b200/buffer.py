@@ -227,6 +227,23 @@ class GpuReplayBuffer:
         self.launches += 1
         return self._finish(obs, act, nobs, dones, rew, env)
 
+    def sample_into(self, out, draw_counter, env=None) -> None:
+        """Philox sample into caller-owned tensors ``out = (obs, act, next_obs, dones, rewards)`` with the draw counter read from the
+        device tensor ``draw_counter`` (int64, 1 element) at execution time: nothing per-call is baked into the launch, so the call can
+        sit inside a CUDA graph (``FusedTD3Update.train(..., graph=True)``).  The caller advances the counter."""
+        if self.index_mode != "philox":
+            raise ValueError("sample_into needs index_mode='philox' (indices drawn inside the kernel)")
+        upper_bound = self.buffer_size if self.full else self.pos
+        if upper_bound <= 0:
+            raise ValueError("cannot sample from an empty replay buffer")
+        obs, act, nobs, dones, rew = out
+        with self._torch.cuda.device(self._device):
+            rc = self._libc.cstr_replay_sample_philox_dev(self.seed & (2**64 - 1), _lib.ptr(draw_counter), self.n_envs, upper_bound, obs.shape[0],
+                                                          _lib.ptr(self.records), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones),
+                                                          _lib.ptr(rew), None, None, self._norm_arg(env), self._stream())
+        _lib.check(rc, "cstr_replay_sample_philox_dev")
+        self.launches += 1
+
     def _get_samples(self, batch_inds: np.ndarray, env=None) -> ReplayBufferSamples:
         env_indices = np.random.randint(0, high=self.n_envs, size=(len(batch_inds),))  # buffers.py:309
         return self.gather(batch_inds, env_indices, env=env)

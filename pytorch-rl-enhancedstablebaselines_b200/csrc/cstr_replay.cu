@@ -68,11 +68,12 @@ replay_sample_kernel(int64_t n_envs, int64_t batch, const int64_t *__restrict__ 
 }
 
 __global__ void __launch_bounds__(256)
-replay_sample_philox_kernel(uint64_t seed, uint64_t draw, int64_t n_envs, int64_t upper, int64_t batch, const float4 *__restrict__ records,
+replay_sample_philox_kernel(uint64_t seed, uint64_t draw_arg, const int64_t *__restrict__ draw_dev, int64_t n_envs, int64_t upper, int64_t batch, const float4 *__restrict__ records,
                             float4 *out_obs, float2 *out_act, float4 *out_next_obs, float *out_dones, float *out_rewards,
                             int64_t *out_batch_inds, int64_t *out_env_inds, NormArgs na) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= batch) return;
+    const uint64_t draw = draw_dev ? (uint64_t)*draw_dev : draw_arg;  // device-resident draw counter: capturable in a CUDA graph
     const uint4 r = philox_env(seed, (uint64_t)i, (uint32_t)draw, STREAM_SAMPLE, (uint32_t)(draw >> 32) & 0xffu);
     // multiply-shift range reduction on 64-bit words: floor(u64 * range / 2^64)
     const uint64_t w0 = ((uint64_t)r.x << 32) | r.y, w1 = ((uint64_t)r.z << 32) | r.w;
@@ -128,17 +129,32 @@ int cstr_replay_sample(int64_t n_envs, int64_t batch, const int64_t *batch_inds,
     return check_launch("replay_sample_kernel");
 }
 
-int cstr_replay_sample_philox(uint64_t seed, uint64_t draw, int64_t n_envs, int64_t upper, int64_t batch, const float *records,
-                              float *out_obs, float *out_act, float *out_next_obs, float *out_dones, float *out_rewards,
-                              int64_t *out_batch_inds, int64_t *out_env_inds, const cstr_norm_params *norm, void *stream) {
+static int sample_philox(uint64_t seed, uint64_t draw, const int64_t *draw_dev, int64_t n_envs, int64_t upper, int64_t batch, const float *records,
+                         float *out_obs, float *out_act, float *out_next_obs, float *out_dones, float *out_rewards, int64_t *out_batch_inds,
+                         int64_t *out_env_inds, const cstr_norm_params *norm, void *stream) {
     if (n_envs <= 0 || upper <= 0 || batch < 0) return fail_arg(CSTR_EINVAL, "replay_sample_philox: bad sizes (empty buffer?)");
     if (int rc = check_sample_out(records, out_obs, out_act, out_next_obs, out_dones, out_rewards)) return rc;
     if (batch == 0) return 0;
     const int block = 128, grid = (int)((batch + block - 1) / block);
-    replay_sample_philox_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(seed, draw, n_envs, upper, batch, (const float4 *)records,
+    replay_sample_philox_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(seed, draw, draw_dev, n_envs, upper, batch, (const float4 *)records,
                                                                            (float4 *)out_obs, (float2 *)out_act, (float4 *)out_next_obs,
                                                                            out_dones, out_rewards, out_batch_inds, out_env_inds, norm_args(norm));
     return check_launch("replay_sample_philox_kernel");
+}
+
+int cstr_replay_sample_philox(uint64_t seed, uint64_t draw, int64_t n_envs, int64_t upper, int64_t batch, const float *records,
+                              float *out_obs, float *out_act, float *out_next_obs, float *out_dones, float *out_rewards,
+                              int64_t *out_batch_inds, int64_t *out_env_inds, const cstr_norm_params *norm, void *stream) {
+    return sample_philox(seed, draw, nullptr, n_envs, upper, batch, records, out_obs, out_act, out_next_obs, out_dones, out_rewards, out_batch_inds,
+                         out_env_inds, norm, stream);
+}
+
+int cstr_replay_sample_philox_dev(uint64_t seed, const int64_t *draw_dev, int64_t n_envs, int64_t upper, int64_t batch, const float *records,
+                                  float *out_obs, float *out_act, float *out_next_obs, float *out_dones, float *out_rewards,
+                                  int64_t *out_batch_inds, int64_t *out_env_inds, const cstr_norm_params *norm, void *stream) {
+    if (!draw_dev) return fail_arg(CSTR_EINVAL, "replay_sample_philox_dev: null draw counter");
+    return sample_philox(seed, 0, draw_dev, n_envs, upper, batch, records, out_obs, out_act, out_next_obs, out_dones, out_rewards, out_batch_inds,
+                         out_env_inds, norm, stream);
 }
 
 }  // extern "C"

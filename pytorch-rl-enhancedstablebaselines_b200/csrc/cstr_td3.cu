@@ -267,7 +267,8 @@ __device__ __forceinline__ float row_dot(const float *__restrict__ h, const floa
 // actor head: a = tanh(h2 @ W3^T + b3) [+ clip(noise) -> clamp(-1,1)]                              td3.py:168-170 / policies.py:75-78
 __global__ void __launch_bounds__(256)
 td3_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *__restrict__ W3, const float *__restrict__ b3, int smooth,
-                      const float2 *__restrict__ noise, float sigma, float clip, uint64_t seed, uint32_t update_index, float2 *__restrict__ out) {
+                      const float2 *__restrict__ noise, float sigma, float clip, uint64_t seed, uint32_t update_index, const float *__restrict__ dev_scalars,
+                      float2 *__restrict__ out) {
     const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
     const float *h = h2 + (int64_t)b * H2;
@@ -278,7 +279,8 @@ td3_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *
         float2 nz;
         if (noise) nz = noise[b];
         else {
-            const uint4 r = philox_env(seed, (uint64_t)b, update_index, STREAM_TD3, 0);
+            const uint32_t ui = dev_scalars ? __float_as_uint(dev_scalars[4]) : update_index;  // graph mode: counter lives on the device
+            const uint4 r = philox_env(seed, (uint64_t)b, ui, STREAM_TD3, 0);
             const float u1 = fmaf(u24(r.x), 1.0f, 5.9604644775390625e-08f), u2 = u24(r.y);
             const float rad = sqrtf(-2.0f * logf(u1));
             float sn, cs;
@@ -472,6 +474,23 @@ td3_sum_slabs_kernel(int64_t n4, int splits, const float4 *__restrict__ slabs, i
     out[z * out_z4 + i] = s;
 }
 
+// graph mode: the per-update scalars (Philox counter of the smoothing noise, Adam bias corrections) cannot be baked into a captured
+// launch, so they live on the device.  counters = {n_updates, critic_step, actor_step, sample_draw}; one thread advances them at the
+// start of an update and derives scalars = {step_size_c, bc2_sqrt_c, step_size_a, bc2_sqrt_a, bits(n_updates)} (double math as torch).
+__global__ void td3_tick_kernel(int64_t *counters, float *scalars, int policy_step, double lr, double beta1, double beta2) {
+    if (threadIdx.x || blockIdx.x) return;
+    const int64_t n = ++counters[0], cs = ++counters[1];
+    const int64_t as = policy_step ? ++counters[2] : counters[2];
+    counters[3] += 1;
+    scalars[0] = (float)(lr / (1.0 - pow(beta1, (double)cs)));
+    scalars[1] = (float)sqrt(1.0 - pow(beta2, (double)cs));
+    if (as > 0) {
+        scalars[2] = (float)(lr / (1.0 - pow(beta1, (double)as)));
+        scalars[3] = (float)sqrt(1.0 - pow(beta2, (double)as));
+    }
+    scalars[4] = __uint_as_float((uint32_t)n);
+}
+
 // Adam (torch single-tensor formulas) over a flat range, optionally followed by the polyak update of another flat range;
 // block 0 / thread 0 also folds the per-CTA loss partials into the running loss sums.
 struct ApplyArgs {
@@ -481,6 +500,7 @@ struct ApplyArgs {
     int64_t adam_lo, adam_hi;      // Adam on [adam_lo, adam_hi)
     int64_t polyak_lo, polyak_hi;  // polyak on [polyak_lo, polyak_hi) (after Adam where the ranges overlap)
     float beta1, beta2, eps, step_size, bc2_sqrt, tau;
+    const float *dev_scalars;  // graph mode: {step_size, bc2_sqrt} written by td3_tick_kernel (NULL: the by-value fields)
     const float *loss_partial;
     int n_loss_partial;
     float loss_scale;
@@ -507,13 +527,14 @@ __global__ void __launch_bounds__(256) td3_apply_kernel(ApplyArgs a) {
     }
     float p;
     bool have = false;
+    const float step_size = a.dev_scalars ? a.dev_scalars[0] : a.step_size, bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
     if (i >= a.adam_lo && i < a.adam_hi) {
         const float g = a.g[i];
         float m = a.m[i], v = a.v[i];
         m = m + (g - m) * (1.f - a.beta1);           // exp_avg.lerp_(grad, 1 - beta1)
         v = v * a.beta2 + (1.f - a.beta2) * g * g;   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-        const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-        p = a.p[i] - a.step_size * (m / denom);      // param.addcdiv_(exp_avg, denom, value=-step_size)
+        const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+        p = a.p[i] - step_size * (m / denom);      // param.addcdiv_(exp_avg, denom, value=-step_size)
         a.p[i] = p, a.m[i] = m, a.v[i] = v;
         have = true;
     }
@@ -537,7 +558,7 @@ struct Workspace {  // carved out of the caller's workspace buffer (floats)
     float *dz1, *dz2;        // 2 slabs each
     float *t_h1, *t_h2;      // target-critic activations (2 slabs)
     float *a_h1, *a_h2;      // actor / actor-target activations
-    float *next_act, *a_pi, *target, *dq, *dpre, *loss_partial, *slabs, *skinny;
+    float *next_act, *a_pi, *target, *dq, *dpre, *loss_partial, *slabs, *skinny, *scalars;
     int n_row_blocks;
     bool tensor;  // hidden-layer GEMMs on tcgen05 (cfg->gemm_mode)
     int64_t floats;
@@ -579,6 +600,7 @@ Workspace carve(float *base, int B, int H1, int H2) {
     w.slabs = take((int64_t)MAX_SPLITS * 2 * pad4((int64_t)H1 * H2));
     const int64_t hp = ((int64_t)(H1 > H2 ? H1 : H2) + 31) / 32 * 32;
     w.skinny = take((int64_t)((B + SKINNY_ROWS - 1) / SKINNY_ROWS) * 2 * (OBS + ACT + 1) * hp);
+    w.scalars = take(8);
     w.tensor = false;
     w.floats = o;
     return w;
@@ -735,12 +757,17 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
     const Net g_actor = net_at(stt->grads, T.actor_off, T.actor), g_critic = net_at(stt->grads, T.critic_off[0], T.critic);
     const int rb = w.n_row_blocks;
     const bool policy_step = (n_updates % cfg->policy_delay) == 0;
+    const float *dev_sc = stt->counters ? w.scalars : nullptr;  // graph mode (see td3_tick_kernel)
+    if (stt->counters && (phases & CSTR_TD3_CRITIC_GRAD)) {
+        td3_tick_kernel<<<1, 32, 0, st>>>(stt->counters, w.scalars, policy_step ? 1 : 0, (double)cfg->lr, (double)cfg->beta1, (double)cfg->beta2);
+        if (int rc = check_launch("td3_tick_kernel")) return rc;
+    }
 
     if (phases & CSTR_TD3_CRITIC_GRAD) {
         // ---- target (td3.py:166-175) ----
         if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor_t, 0, 1, w.a_h1, w.a_h2, w.tensor, st)) return rc;
         td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor_t.w3, actor_t.b3, 1, (const float2 *)noise, cfg->target_policy_noise,
-                                                 cfg->target_noise_clip, cfg->seed, (uint32_t)n_updates, (float2 *)w.next_act);
+                                                 cfg->target_noise_clip, cfg->seed, (uint32_t)n_updates, dev_sc, (float2 *)w.next_act);
         if (int rc = check_launch("td3_actor_head_kernel")) return rc;
         if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st)) return rc;
         td3_target_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.t_h2, (int64_t)B * H2, critic_t.w3, critic_t.b3, cz, rewards, dones, cfg->gamma, w.target);
@@ -764,6 +791,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         const double bc1 = 1.0 - pow((double)cfg->beta1, (double)critic_step), bc2 = 1.0 - pow((double)cfg->beta2, (double)critic_step);
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = (float)((double)cfg->lr / bc1), a.bc2_sqrt = (float)sqrt(bc2);
         a.tau = cfg->tau;
+        a.dev_scalars = dev_sc;
         a.loss_partial = w.loss_partial, a.n_loss_partial = 2 * rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses;
         const int64_t n = a.adam_hi - a.adam_lo;
         td3_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
@@ -772,7 +800,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
     if (policy_step && (phases & CSTR_TD3_ACTOR_GRAD)) {
         // ---- actor loss = -Q1(s, pi(s)).mean() and its backward (td3.py:189-196) ----
         if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st)) return rc;
-        td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, 0, nullptr, 0.f, 0.f, 0, 0, (float2 *)w.a_pi);
+        td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, 0, nullptr, 0.f, 0.f, 0, 0, nullptr, (float2 *)w.a_pi);
         if (int rc = check_launch("td3_actor_head_kernel<pi>")) return rc;
         if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 1, w.h1[0], w.h2[0], w.tensor, st)) return rc;
         td3_critic_head_kernel<true><<<dim3(rb, 1), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, nullptr, w.dq, w.dz2,
@@ -798,6 +826,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         const double bc1 = 1.0 - pow((double)cfg->beta1, (double)actor_step), bc2 = 1.0 - pow((double)cfg->beta2, (double)actor_step);
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = (float)((double)cfg->lr / bc1), a.bc2_sqrt = (float)sqrt(bc2);
         a.tau = cfg->tau;
+        a.dev_scalars = dev_sc ? dev_sc + 2 : nullptr;
         a.loss_partial = w.loss_partial, a.n_loss_partial = rb, a.loss_scale = -1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 2 : nullptr;
         td3_apply_kernel<<<(unsigned)((T.total + 255) / 256), 256, 0, st>>>(a);
         if (int rc = check_launch("td3_apply_kernel<actor+polyak>")) return rc;

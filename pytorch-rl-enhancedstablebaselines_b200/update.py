@@ -58,6 +58,10 @@ class FusedTD3Update:
             z = lambda: torch.zeros(self.param_count, dtype=torch.float32, device=self.device)  # noqa: E731
             self.params, self.targets, self.grads, self.adam_m, self.adam_v = z(), z(), z(), z(), z()
             self.loss_sums = torch.zeros(4, dtype=torch.float32, device=self.device)
+            self._counters = torch.zeros(4, dtype=torch.int64, device=self.device)  # graph mode: n_updates, critic_step, actor_step, sample_draw
+        self._graph = None
+        self._graph_key = None
+        self._graph_out = None
         self._workspace = None
         self._batch = 0
         self._set_batch(int(batch_size))
@@ -183,6 +187,65 @@ class FusedTD3Update:
             raise ValueError(f"batch tensor has {t.numel()} elements, expected {self._batch}x{cols}")
         return t
 
+    def _state(self, counters: bool) -> "_lib.Td3State":
+        return _lib.Td3State(params=self.params.data_ptr(), targets=self.targets.data_ptr(), grads=self.grads.data_ptr(), adam_m=self.adam_m.data_ptr(),
+                             adam_v=self.adam_v.data_ptr(), workspace=self._workspace.data_ptr(), workspace_bytes=self._workspace.numel() * 4,
+                             losses=self.loss_sums.data_ptr(), counters=self._counters.data_ptr() if counters else None)
+
+    # ---- CUDA-graph path: one captured cycle of policy_delay x (sample + update), replayed ------------------------------------
+    def _capture(self, buffer, batch_size: int, env) -> None:
+        torch = self._torch
+        self._set_batch(batch_size)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        out = (torch.empty((batch_size, 4), **f32), torch.empty((batch_size, 2), **f32), torch.empty((batch_size, 4), **f32),
+               torch.empty((batch_size, 1), **f32), torch.empty((batch_size, 1), **f32))
+        cfg, st = self._config(batch_size), self._state(counters=True)
+        draw = self._counters[3:4]
+
+        def cycle():
+            for k in range(1, self.policy_delay + 1):  # by-value counters only choose the launch structure: update k of the cycle
+                buffer.sample_into(out, draw, env=env)
+                rc = self._libc.cstr_td3_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+                                                _lib.ptr(out[4]), None, k, 1, 1, _lib.TD3_ALL, self._stream())
+                _lib.check(rc, "cstr_td3_update (graph capture)")
+
+        snapshot = [t.clone() for t in (self.params, self.targets, self.adam_m, self.adam_v, self.loss_sums, self._counters)]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):  # warm-up outside capture (first-launch attribute calls, lazy module loading)
+            cycle()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            cycle()
+        for dst, src in zip((self.params, self.targets, self.adam_m, self.adam_v, self.loss_sums, self._counters), snapshot):
+            dst.copy_(src)  # the warm-up cycle was a real update: undo it
+        self._graph, self._graph_out = graph, out
+        self._graph_key = (id(buffer), batch_size, buffer.size(), buffer.n_envs, id(env), self.policy_delay, self.learning_rate, self.params.data_ptr(),
+                           self._workspace.data_ptr())
+
+    def _train_graph(self, gradient_steps: int, buffer, batch_size: int, env) -> int:
+        """Replays whole cycles while the update count is cycle-aligned; returns the number of gradient steps done."""
+        if self.n_updates % self.policy_delay or gradient_steps < self.policy_delay:
+            return 0
+        key = (id(buffer), batch_size, buffer.size(), buffer.n_envs, id(env), self.policy_delay, self.learning_rate, self.params.data_ptr(),
+               self._workspace.data_ptr() if self._workspace is not None else 0)
+        if self._graph is None or key != self._graph_key:
+            self._capture(buffer, batch_size, env)
+        cycles = gradient_steps // self.policy_delay
+        self._counters.copy_(self._torch.tensor([self.n_updates, self.critic_step, self.actor_step, buffer._draw], dtype=self._torch.int64),
+                             non_blocking=True)
+        with self._torch.cuda.device(self.device):
+            for _ in range(cycles):
+                self._graph.replay()
+        done = cycles * self.policy_delay
+        self.n_updates += done
+        self.critic_step += done
+        self.actor_step += cycles
+        buffer._draw += done
+        self.launches += cycles * (26 * (self.policy_delay - 1) + 50 + self.policy_delay)
+        return done
+
     def update(self, batch, noise=None, allreduce: Optional[Callable[[Any], None]] = None) -> None:
         """One iteration of the loop body (td3.py:162-206) on ``batch`` (``ReplayBufferSamples`` or a 5-tuple in that order).
         ``noise``: explicit N(0, target_policy_noise) draws (B,2) for parity tests; default = Philox in the kernel.
@@ -198,9 +261,7 @@ class FusedTD3Update:
         if policy_step:
             self.actor_step += 1
         cfg = self._config(self._batch)
-        st = _lib.Td3State(params=self.params.data_ptr(), targets=self.targets.data_ptr(), grads=self.grads.data_ptr(), adam_m=self.adam_m.data_ptr(),
-                           adam_v=self.adam_v.data_ptr(), workspace=self._workspace.data_ptr(), workspace_bytes=self._workspace.numel() * 4,
-                           losses=self.loss_sums.data_ptr())
+        st = self._state(counters=False)
 
         def run(phases):
             rc = self._libc.cstr_td3_update(byref(cfg), byref(st), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones), _lib.ptr(rew),
@@ -219,10 +280,15 @@ class FusedTD3Update:
                 run(_lib.TD3_ACTOR_APPLY)
         self.launches += 26 if not policy_step else 50
 
-    def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, allreduce=None) -> None:
-        """``TD3.train(gradient_steps, batch_size)`` (td3.py:154-206): sample + update, ``gradient_steps`` times."""
+    def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, allreduce=None, graph: bool = False) -> None:
+        """``TD3.train(gradient_steps, batch_size)`` (td3.py:154-206): sample + update, ``gradient_steps`` times.
+        ``graph=True`` (single-GPU, Philox-index buffer): whole cycles of ``policy_delay`` updates are replayed from ONE captured CUDA
+        graph (27-51 launches per update become one graph launch per cycle); the remainder runs launch by launch."""
         bs = int(batch_size or self._batch)
-        for _ in range(gradient_steps):
+        done = 0
+        if graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox":
+            done = self._train_graph(gradient_steps, buffer, bs, env)
+        for _ in range(gradient_steps - done):
             self.update(buffer.sample(bs, env=env), allreduce=allreduce)
 
     def pop_losses(self):
@@ -258,7 +324,8 @@ def bind_td3_class(td3_base: type) -> type:
             self._update_learning_rate([self.actor.optimizer, self.critic.optimizer])
             eng = self._fused_engine(batch_size)
             eng.learning_rate = float(self.lr_schedule(self._current_progress_remaining))
-            eng.train(gradient_steps, self.replay_buffer, batch_size, env=self._vec_normalize_env)
+            # a full ring has a constant sampling range: cycles of policy_delay updates replay from one captured CUDA graph
+            eng.train(gradient_steps, self.replay_buffer, batch_size, env=self._vec_normalize_env, graph=bool(getattr(self.replay_buffer, "full", False)))
             self._n_updates = eng.n_updates
             critic_loss, actor_loss = eng.pop_losses()
             self.logger.record("train/n_updates", self._n_updates, exclude="tensorboard")

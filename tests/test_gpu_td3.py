@@ -257,3 +257,33 @@ def test_training_dynamics_track_eager_torch(pkg, gemm):
     assert float((q_fused - q_ref).abs().mean()) < 0.1 * float(q_ref.abs().mean())
     critic_loss, actor_loss = eng.pop_losses()
     assert 0 < critic_loss < 1.0 and actor_loss is not None
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "tensor"])
+def test_cuda_graph_replay_equals_launch_by_launch(pkg, gemm):
+    """train(graph=True) replays one captured cycle of policy_delay x (Philox sample + update) with every per-update scalar
+    (sample draw counter, smoothing-noise counter, Adam bias corrections) read from device memory: the weights must equal the
+    launch-by-launch path (bias corrections from CUDA's double pow instead of the host's: allow 1 ulp of the step size)."""
+    rng = np.random.default_rng(4)
+    nets = U.random_nets(rng, 400, 300)
+    n_envs = 512
+    buf = pkg.GpuReplayBuffer(32 * n_envs, n_envs=n_envs, index_mode="philox", seed=5)
+    buf.records.uniform_(-1, 1)
+    buf.records[..., 11:13] = 0
+    buf.pos, buf.full = 0, True
+
+    def run(graph, steps_list):
+        buf._draw = 0
+        eng = _engine(pkg, nets, [400, 300], 256, seed=9, gemm=gemm)
+        for s in steps_list:
+            eng.train(s, buf, 256, graph=graph)
+        return eng
+
+    a = run(False, [6, 5])
+    b = run(True, [6, 5])  # 3 cycles, then 2 cycles + 1 launch-by-launch step (odd remainder)
+    assert a.n_updates == b.n_updates == 11 and a.critic_step == b.critic_step == 11 and a.actor_step == b.actor_step == 5
+    assert b._graph is not None and buf._draw == 11
+    np.testing.assert_allclose(b.params.cpu().numpy(), a.params.cpu().numpy(), rtol=0, atol=3e-7)
+    np.testing.assert_allclose(b.targets.cpu().numpy(), a.targets.cpu().numpy(), rtol=0, atol=3e-7)
+    la, lb = a.pop_losses(), b.pop_losses()
+    assert lb[0] == pytest.approx(la[0], rel=1e-5) and lb[1] == pytest.approx(la[1], rel=1e-4)
