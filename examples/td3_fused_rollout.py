@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """TD3 end to end on the GPU-resident rollout path (config #3 shape, any number of GPUs).
 
-    python examples/td3_fused_rollout.py --n-envs 131072 --iters 40
-    torchrun --nproc-per-node 8 examples/td3_fused_rollout.py --n-envs 1048576 --iters 40   # env shards, DP update
+    python examples/td3_fused_rollout.py --n-envs 131072 --iters 200
+    torchrun --nproc-per-node 8 examples/td3_fused_rollout.py --n-envs 1048576 --iters 200   # env shards, DP update
 
 Per iteration, on every rank:
   1. ``FusedRollout.collect(K)``   — actor inference (tcgen05) + noise + bounds + CSTR step + reward/done + replay
@@ -53,7 +53,7 @@ def polyak(src, dst, tau):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-envs", type=int, default=131072, help="total reactors over all ranks")
-    ap.add_argument("--iters", type=int, default=40)
+    ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--steps-per-iter", type=int, default=8, help="env steps per fused launch")
     ap.add_argument("--updates-per-iter", type=int, default=8)
     ap.add_argument("--batch", type=int, default=4096, help="per-rank batch")
@@ -104,12 +104,11 @@ def main():
     for it in range(args.iters):
         rsum.zero_()
         roll.collect(args.steps_per_iter, reward_sum=rsum)
-        for _ in range(args.updates_per_iter):
+        if fused is not None:  # sample + update on the device; single GPU: whole policy_delay cycles replay from one CUDA graph
+            fused.train(args.updates_per_iter, buf, args.batch, allreduce=hook, graph=(world == 1))
+            n_updates += args.updates_per_iter
+        for _ in range(args.updates_per_iter if fused is None else 0):
             b = buf.sample(args.batch)
-            if fused is not None:
-                fused.update(b, allreduce=hook)
-                n_updates += 1
-                continue
             with torch.no_grad():
                 noise = (torch.randn_like(b.actions) * tnoise).clamp(-tclip, tclip)
                 na = (actor_t(b.next_observations) + noise).clamp(-1, 1)

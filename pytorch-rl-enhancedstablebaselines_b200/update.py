@@ -286,7 +286,8 @@ class FusedTD3Update:
         graph (27-51 launches per update become one graph launch per cycle); the remainder runs launch by launch."""
         bs = int(batch_size or self._batch)
         done = 0
-        if graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox":
+        # a captured cycle bakes the sampling range in: only worth capturing once the ring is full (its range is constant from then on)
+        if graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox" and buffer.full:
             done = self._train_graph(gradient_steps, buffer, bs, env)
         for _ in range(gradient_steps - done):
             self.update(buffer.sample(bs, env=env), allreduce=allreduce)
