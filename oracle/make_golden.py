@@ -14,6 +14,7 @@ the output of the reference's own code on seeded inputs:
   vecnorm.npz    VecNormalize over DummyVecEnv (statistics, normalised obs/reward, normalised replay sample)
                                                                            core/common/vec_env/vec_normalize.py:174-298
   td3_update.npz TD3.train for 6 gradient steps (weights, Adam state, losses) on CPU torch   core/td3/td3.py:154-211
+  sac_update.npz SAC.train for 5 gradient steps (actor, critics, entropy coefficient) on CPU torch  core/sac/sac.py:199-296
 Host note: NumPy's float32 exp is a SIMD kernel whose code path depends on the CPU, so the fp32
 fixtures are bit-stable only on hosts taking the same path; tests re-check them with the ulp-level
 tolerance stated in tests/test_golden.py and bit-exactly in tests/test_oracle_vs_reference.py (live).
@@ -314,6 +315,65 @@ def gen_td3_update(m, core) -> None:
     np.savez_compressed(os.path.join(OUT, "td3_update.npz"), **td3_update_reference_run(m, core, [64, 48]))
 
 
+def sac_update_reference_run(m, core, net_arch, K=5, B=64) -> dict:
+    """Run the reference's SAC.train for K gradient steps on CPU torch and return everything needed to replay it."""
+    import torch
+    from types import SimpleNamespace
+    from core.common.vec_env import DummyVecEnv
+
+    torch.set_num_threads(1)
+    venv = DummyVecEnv([(lambda: m.TwoSeriesCSTREnv(init_mode="random")) for _ in range(4)])
+    model = core.SAC("MlpPolicy", venv, buffer_size=4000, batch_size=B, learning_starts=0, device="cpu", seed=7, policy_kwargs=dict(net_arch=list(net_arch)))
+    logged = {}
+    model._logger = SimpleNamespace(record=lambda k, v, **kw: logged.__setitem__(k, v))
+    rng = np.random.default_rng(41)
+    buf = model.replay_buffer
+    for _ in range(200):
+        o = rng.uniform(-1, 1, (4, 4)).astype(np.float32)
+        no = rng.uniform(-1, 1, (4, 4)).astype(np.float32)
+        a = rng.uniform(-1, 1, (4, 2)).astype(np.float32)
+        r = rng.normal(-1, 1, 4).astype(np.float32)
+        d = rng.random(4) < 0.05
+        buf.add(o, no, a, r, d, [{"TimeLimit.truncated": False} for _ in d])
+
+    def nets():
+        pol = model.policy
+        lat = [t.detach().numpy().copy() for t in pol.actor.latent_pi.parameters()]
+        head_w = np.concatenate([pol.actor.mu.weight.detach().numpy(), pol.actor.log_std.weight.detach().numpy()], 0)
+        head_b = np.concatenate([pol.actor.mu.bias.detach().numpy(), pol.actor.log_std.bias.detach().numpy()], 0)
+        get = lambda seq: [t.detach().numpy().copy() for t in seq.parameters()]  # noqa: E731
+        return {"actor": lat + [head_w, head_b], "critic0": get(pol.critic.q_networks[0]), "critic1": get(pol.critic.q_networks[1]),
+                "critic0_target": get(pol.critic_target.q_networks[0]), "critic1_target": get(pol.critic_target.q_networks[1])}
+
+    out = {}
+    for name, ps in nets().items():
+        for i, t in enumerate(ps):
+            out[f"init_{name}_{i}"] = t
+    out["init_log_ent_coef"] = model.log_ent_coef.detach().numpy().copy()
+    np.random.seed(19)
+    batches = [buf.sample(B) for _ in range(K)]
+    torch.manual_seed(29)
+    eps = [[torch.empty(B, 2).normal_().numpy().copy() for _ in range(2)] for _ in range(K)]  # Normal.rsample: one standard-normal draw each
+    np.random.seed(19)
+    torch.manual_seed(29)
+    model.train(gradient_steps=K, batch_size=B)
+    for name, ps in nets().items():
+        for i, t in enumerate(ps):
+            out[f"final_{name}_{i}"] = t
+    out["final_log_ent_coef"] = model.log_ent_coef.detach().numpy().copy()
+    for k, f in zip(("obs", "act", "next_obs", "dones", "rewards"), ("observations", "actions", "next_observations", "dones", "rewards")):
+        out["batch_" + k] = np.stack([getattr(b, f).numpy() for b in batches])
+    out["eps_pi"], out["eps_next"] = np.stack([e[0] for e in eps]), np.stack([e[1] for e in eps])
+    for k in ("critic_loss", "actor_loss", "ent_coef", "ent_coef_loss"):
+        out[k + "_mean"] = np.array(logged["train/" + k])
+    out["hyper"] = np.array([model.gamma, model.tau, model.target_entropy, model.lr_schedule(1), model.target_update_interval])
+    return out
+
+
+def gen_sac_update(m, core) -> None:
+    np.savez_compressed(os.path.join(OUT, "sac_update.npz"), **sac_update_reference_run(m, core, [64, 48]))
+
+
 def main() -> None:
     if not refload.available():
         raise SystemExit("reference tree not found; fixtures can only be generated in the build container")
@@ -328,6 +388,7 @@ def main() -> None:
     gen_actor(m, core)
     gen_vecnorm(m, core)
     gen_td3_update(m, core)
+    gen_sac_update(m, core)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

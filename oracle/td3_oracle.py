@@ -125,3 +125,88 @@ class TD3UpdateOracle:
             out["actor_grads"] = ag
             out["policy_hidden"] = [(acache[1], acache[2]), (ccache[1], ccache[2])]  # actor, critic0 at pi(s)
         return out
+
+
+# ----------------------------------------------------------------------------------------------
+# SAC gradient step (core/sac/sac.py:199-296, core/sac/policies.py:147-175, core/common/distributions.py:207-260)
+# ----------------------------------------------------------------------------------------------
+LOG_STD_MIN, LOG_STD_MAX = -20.0, 2.0
+HALF_LOG_2PI = F32(0.5 * math.log(2.0 * math.pi))
+
+
+def sac_actor_forward(p: Params, obs: np.ndarray, eps: np.ndarray, squash_eps: float = 1e-6):
+    """Actor = latent MLP (2 ReLU layers) + [mu; log_std] head stacked as one (2A, H2) matrix (rows 0..A-1 = mu, A.. = log_std).
+    Returns (action, log_prob, cache) for the reparameterised sample u = mean + std * eps, a = tanh(u)."""
+    y, cache = mlp_forward(p, obs, False)
+    A = y.shape[1] // 2
+    mean, raw = y[:, :A], y[:, A:]
+    log_std = np.clip(raw, F32(LOG_STD_MIN), F32(LOG_STD_MAX))
+    std = np.exp(log_std)
+    u = mean + std * eps
+    a = np.tanh(u)
+    # Normal(mean, std).log_prob(u) summed over dims (with (u - mean)/std computed as torch does), minus the tanh correction
+    logp = (-((u - mean) ** 2) / (F32(2) * std * std) - log_std - HALF_LOG_2PI).sum(1) - np.log(F32(1) - a * a + F32(squash_eps)).sum(1)
+    return a.astype(F32), logp.astype(F32), (cache, raw, std.astype(F32), a.astype(F32))
+
+
+class SACUpdateOracle:
+    def __init__(self, actor: Params, critics: Sequence[Params], critic_targets=None, lr: float = 3e-4, gamma: float = 0.99, tau: float = 0.005,
+                 target_entropy: float = -2.0, log_ent_coef: float = 0.0, target_update_interval: int = 1):
+        cp = lambda ps: [np.array(a, F32, copy=True) for a in ps]  # noqa: E731
+        self.actor, self.critics = cp(actor), [cp(c) for c in critics]
+        self.critic_targets = [cp(c) for c in (critic_targets if critic_targets is not None else critics)]
+        self.gamma, self.tau, self.target_entropy, self.interval = gamma, tau, target_entropy, target_update_interval
+        self.log_ent_coef = [np.array([log_ent_coef], F32)]
+        self.actor_opt = Adam(self.actor, lr)
+        self.critic_opt = Adam([t for c in self.critics for t in c], lr)
+        self.ent_opt = Adam(self.log_ent_coef, lr)
+        self.gradient_step = 0
+        self.critic_losses, self.actor_losses, self.ent_coef_losses, self.ent_coefs = [], [], [], []
+
+    def step(self, obs, actions, next_obs, dones, rewards, eps_pi, eps_next) -> Dict[str, np.ndarray]:
+        """One iteration of sac.py:213-288.  eps_pi / eps_next are the standard-normal draws of the two rsample() calls."""
+        B, A = obs.shape[0], actions.shape[1]
+        a_pi, logp, (acache, raw, std, _) = sac_actor_forward(self.actor, obs, eps_pi)
+        logp = logp.reshape(-1, 1)
+        ent_coef = np.exp(self.log_ent_coef[0]).astype(F32)  # :230 (before the optimiser step)
+        self.ent_coefs.append(float(ent_coef[0]))
+        self.ent_coef_losses.append(float(-np.mean(self.log_ent_coef[0] * (logp + F32(self.target_entropy)), dtype=F32)))
+        self.ent_opt.step([np.array([-np.mean(logp + F32(self.target_entropy), dtype=F32)], F32)])  # :231-243
+        na, nlogp, _ = sac_actor_forward(self.actor, next_obs, eps_next)
+        xin = np.concatenate([next_obs, na], 1)
+        q_next = np.minimum(*[mlp_forward(c, xin, False)[0] for c in self.critic_targets]) - ent_coef * nlogp.reshape(-1, 1)  # :249-252
+        target = (rewards + (F32(1) - dones) * F32(self.gamma) * q_next).astype(F32)
+        x = np.concatenate([obs, actions], 1)
+        grads, loss = [], 0.0
+        for c in self.critics:
+            q, cache = mlp_forward(c, x, False)
+            diff = q - target
+            loss += 0.5 * float(np.mean(diff * diff, dtype=F32))  # :261
+            g, _ = mlp_backward(c, cache, (F32(1) / F32(B)) * diff, False)
+            grads += g
+        self.critic_losses.append(loss)
+        self.critic_opt.step(grads)
+        # actor loss (ent_coef * log_prob - min_i Q_i(s, a_pi)).mean() with the UPDATED critics (:271-281)
+        xp = np.concatenate([obs, a_pi], 1)
+        qs, caches = zip(*[mlp_forward(c, xp, False) for c in self.critics])
+        q_min = np.minimum(*qs)
+        self.actor_losses.append(float(np.mean(ent_coef * logp - q_min, dtype=F32)))
+        pick0 = qs[0] <= qs[1]  # torch.min returns the first index on ties
+        da = np.zeros_like(a_pi)
+        for i, c in enumerate(self.critics):
+            dq = np.where(pick0 if i == 0 else ~pick0, F32(-1) / F32(B), F32(0)).astype(F32)
+            _, dx = mlp_backward(c, caches[i], dq, False, need_dx=True)
+            da += dx[:, obs.shape[1]:]
+        a = a_pi
+        one_m = F32(1) - a * a
+        dlogp = ent_coef / F32(B)  # d loss / d log_prob, per row
+        du = da * one_m + dlogp * (F32(2) * a * one_m / (one_m + F32(1e-6)))  # through tanh: Q path + squash correction
+        dmean = du  # the Gaussian log-density is constant in mean under reparameterisation
+        dlog_std = (du * std * eps_pi - dlogp) * ((raw >= F32(LOG_STD_MIN)) & (raw <= F32(LOG_STD_MAX)))  # d(-log_std) = -1; clamp gate
+        ag, _ = mlp_backward(self.actor, acache, np.concatenate([dmean, dlog_std], 1).astype(F32), False)
+        self.actor_opt.step(ag)
+        if self.gradient_step % self.interval == 0:
+            for c, t in zip(self.critics, self.critic_targets):
+                polyak(c, t, self.tau)
+        self.gradient_step += 1
+        return {"target_q": target, "critic_grads": grads, "actor_grads": ag, "log_prob": logp, "a_pi": a_pi}

@@ -33,3 +33,31 @@ def random_nets(rng, h1, h2):
     a, c0, c1 = mlp(4, 2), mlp(6, 1), mlp(6, 1)
     cp = lambda ps: [t.copy() for t in ps]  # noqa: E731
     return {"actor": a, "critic0": c0, "critic1": c1, "actor_target": cp(a), "critic0_target": cp(c0), "critic1_target": cp(c1)}
+
+
+SAC_NETS = ("actor", "critic0", "critic1", "critic0_target", "critic1_target")
+
+
+def sac_nets_from(g, prefix):
+    return {name: [np.asarray(g[f"{prefix}_{name}_{i}"]) for i in range(6)] for name in SAC_NETS}
+
+
+def make_sac_oracle(T, g):
+    n = sac_nets_from(g, "init")
+    gamma, tau, target_entropy, lr, interval = [float(x) for x in g["hyper"]]
+    return T.SACUpdateOracle(n["actor"], [n["critic0"], n["critic1"]], [n["critic0_target"], n["critic1_target"]], lr=lr, gamma=gamma, tau=tau,
+                             target_entropy=target_entropy, log_ent_coef=float(g["init_log_ent_coef"][0]), target_update_interval=int(interval))
+
+
+def replay_sac(o, g):
+    for k in range(g["eps_pi"].shape[0]):
+        o.step(g["batch_obs"][k], g["batch_act"][k], g["batch_next_obs"][k], g["batch_dones"][k], g["batch_rewards"][k], g["eps_pi"][k], g["eps_next"][k])
+    return {"actor": o.actor, "critic0": o.critics[0], "critic1": o.critics[1], "critic0_target": o.critic_targets[0], "critic1_target": o.critic_targets[1]}
+
+
+def random_sac_nets(rng, h1, h2):
+    n = random_nets(rng, h1, h2)
+    b = 1.0 / np.sqrt(h2)
+    n["actor"][4] = rng.uniform(-b, b, (4, h2)).astype(np.float32)  # [mu; log_std] head
+    n["actor"][5] = rng.uniform(-b, b, 4).astype(np.float32)
+    return {k: n[k] for k in SAC_NETS}

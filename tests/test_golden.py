@@ -163,3 +163,22 @@ def test_td3_update_oracle_vs_reference_fixture(golden):
     for i in range(12):
         np.testing.assert_allclose(o.critic_opt.m[i], g[f"adam_critic_m_{i}"], rtol=0, atol=1e-6)
         np.testing.assert_allclose(o.critic_opt.v[i], g[f"adam_critic_v_{i}"], rtol=1e-4, atol=1e-9)
+
+
+def test_sac_update_oracle_vs_reference_fixture(golden):
+    """SACUpdateOracle replays 5 gradient steps of the reference's SAC.train (sac.py:199-296): actor, twin critics, targets,
+    automatic entropy coefficient, on the recorded batches and the two rsample() noise draws of every step."""
+    import td3_oracle as T
+    import td3_util as U
+
+    g = golden("sac_update.npz")
+    o = U.make_sac_oracle(T, g)
+    final = U.replay_sac(o, g)
+    ref = U.sac_nets_from(g, "final")
+    for name in U.SAC_NETS:
+        for a, b in zip(final[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)  # measured 2.7e-6
+    np.testing.assert_allclose(o.log_ent_coef[0], g["final_log_ent_coef"], rtol=0, atol=1e-7)
+    for got, key in ((o.critic_losses, "critic_loss_mean"), (o.actor_losses, "actor_loss_mean"), (o.ent_coefs, "ent_coef_mean"),
+                     (o.ent_coef_losses, "ent_coef_loss_mean")):
+        assert np.mean(got) == pytest.approx(float(g[key]), rel=1e-5)

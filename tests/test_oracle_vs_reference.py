@@ -112,3 +112,19 @@ def test_td3_update_default_arch_live(ref_env_module):
         for a, b in zip(final[name], ref[name]):
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)
     assert np.mean(o.critic_losses) == pytest.approx(float(g["critic_loss_mean"]), rel=1e-5)
+
+
+def test_sac_update_default_arch_live(ref_env_module):
+    """The SAC gradient-step restatement against the reference's SAC.train at its default [256, 256] architecture."""
+    import make_golden
+    import td3_oracle as T
+    import td3_util as U
+
+    g = make_golden.sac_update_reference_run(ref_env_module, refload.load_core(), [256, 256], K=3, B=32)
+    o = U.make_sac_oracle(T, g)
+    final = U.replay_sac(o, g)
+    ref = U.sac_nets_from(g, "final")
+    for name in U.SAC_NETS:
+        for a, b in zip(final[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)
+    assert np.mean(o.actor_losses) == pytest.approx(float(g["actor_loss_mean"]), rel=1e-5)
