@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 11
+#define CSTR_B200_ABI_VERSION 12
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -232,6 +232,33 @@ int64_t cstr_td3_workspace_bytes(const cstr_td3_config *cfg);
 int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *state, const float *obs, const float *actions,
                     const float *next_obs, const float *dones, const float *rewards, const float *noise,
                     int64_t n_updates, int64_t critic_step, int64_t actor_step, int32_t phases, void *stream);
+
+/* ---- SAC gradient step (second algorithm) -------------------------------------------------------
+ * Replaces one iteration of the loop body of SAC.train (core/sac/sac.py:213-288) after the batch has been sampled:
+ * squashed-Gaussian actor sample + log-prob (core/sac/policies.py:147-175, core/common/distributions.py:207-260), the
+ * automatic entropy-coefficient Adam step (:226-243), the soft twin-min target from the CURRENT actor (:245-254), critic
+ * forward / 0.5*sum MSE / backward / Adam (:256-268), actor loss (ent_coef*log_prob - min_i Q_i(s, a_pi)).mean() with its
+ * backward through both critics and the tanh-Gaussian, actor Adam, polyak of the critic targets (:270-286).
+ * Networks: actor = create_mlp(4, -, [h1, h2]) latent + [mu; log_std] head stored as ONE (4, h2) matrix (rows 0-1 mu,
+ * rows 2-3 log_std); critics as for TD3.  Flat block = cstr_sac_param_count(h1, h2) floats = [actor | critic0 | critic1 |
+ * log_ent_coef(+3 pad)]; cstr_sac_layout writes the 18 tensor offsets, the log_ent_coef offset and the block size.
+ * The state struct is cstr_td3_state (targets: only the critic ranges are used; losses: 8 floats = critic, actor,
+ * ent_coef_loss, ent_coef as {sum, count} pairs; counters must be NULL).  eps_pi / eps_next: (batch,2) standard-normal draws
+ * of the two rsample() calls, or NULL = Philox (key seed, counter (row, n_updates), stream 5, call 0 / 1).
+ * n_updates and adam_step are the values AFTER this update (1-based; all three optimisers share the step count).       */
+typedef struct cstr_sac_config {
+    int32_t h1, h2, batch, target_update_interval;
+    float gamma, tau, lr, beta1, beta2, eps, target_entropy, reserved0;
+    uint64_t seed;
+    int32_t gemm_mode, reserved1;
+} cstr_sac_config;
+
+int64_t cstr_sac_param_count(int32_t h1, int32_t h2);
+int cstr_sac_layout(int32_t h1, int32_t h2, int64_t *offsets /* 20 */);
+int64_t cstr_sac_workspace_bytes(const cstr_sac_config *cfg);
+int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *state, const float *obs, const float *actions,
+                    const float *next_obs, const float *dones, const float *rewards, const float *eps_pi,
+                    const float *eps_next, int64_t n_updates, int64_t adam_step, void *stream);
 
 /* ---- fused rollout --------------------------------------------------------------------------------
  * Replaces, for K consecutive env steps of N reactors, OffPolicyAlgorithm._sample_action +

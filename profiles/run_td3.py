@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--once", action="store_true", help="few launches only (for ncu)")
     ap.add_argument("--no-torch", action="store_true")
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor"])
+    ap.add_argument("--sac", action="store_true", help="time the SAC gradient step (cstr_sac_update, [256,256] nets) instead")
     ap.add_argument("--graph", action="store_true", help="time train(graph=True): one CUDA-graph launch per policy_delay updates")
     args = ap.parse_args()
     pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
@@ -91,7 +92,7 @@ def main():
     buf.records[..., 11:13] = 0
     buf.pos, buf.full = 0, True
     out = {}
-    for B in args.batch:
+    for B in args.batch if not args.sac else []:
         torch.manual_seed(0)
         eng = pkg.FusedTD3Update([400, 300], B, device=dev, gemm=args.gemm)
         ref = TorchTD3(dev)
@@ -108,6 +109,12 @@ def main():
             ms_t = timed(lambda: ref.update(buf.sample(B)), steps)
             row.update(torch_eager_ms_per_update=ms_t, speedup_vs_torch_eager=ms_t / ms)
         out[f"batch_{B}"] = row
+    for B in args.batch if args.sac else []:
+        eng = pkg.FusedSACUpdate([256, 256], B, device=dev, gemm=args.gemm)
+        eng.params[:eng._ent_offset].normal_(0, 0.05)
+        eng.targets.copy_(eng.params)
+        ms = timed(lambda: eng.update(buf.sample(B)), 4 if args.once else args.steps)
+        out[f"sac_batch_{B}"] = {"fused_ms_per_update": ms, "fused_updates_per_s": 1e3 / ms}
     print(json.dumps(out))
 
 

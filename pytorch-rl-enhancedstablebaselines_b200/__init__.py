@@ -11,7 +11,7 @@ from ._lib import CstrLibraryError
 from .buffer import GpuReplayBuffer, ReplayBufferSamples, bind_replay_buffer_class
 from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
 from .normalize import GpuVecNormalize, bind_vec_normalize_class
-from .update import FusedTD3Update, bind_td3_class
+from .update import FusedSACUpdate, FusedTD3Update, bind_sac_class, bind_td3_class
 from .rollout import ActorWeights, EpisodeStats, FusedRollout
 
 __all__ = [
@@ -23,6 +23,8 @@ __all__ = [
     "GpuReplayBuffer",
     "GpuVecNormalize",
     "FusedTD3Update",
+    "FusedSACUpdate",
+    "bind_sac_class",
     "bind_td3_class",
     "bind_vec_normalize_class",
     "LazyInfos",

@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -72,6 +72,14 @@ class Td3State(Structure):
                 ("workspace", c_void_p), ("workspace_bytes", c_int64), ("losses", c_void_p), ("counters", c_void_p)]
 
 
+class SacConfig(Structure):
+    """struct cstr_sac_config"""
+
+    _fields_ = [("h1", c_int32), ("h2", c_int32), ("batch", c_int32), ("target_update_interval", c_int32), ("gamma", c_float), ("tau", c_float),
+                ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("target_entropy", c_float), ("reserved0", c_float),
+                ("seed", c_uint64), ("gemm_mode", c_int32), ("reserved1", c_int32)]
+
+
 TD3_CRITIC_GRAD, TD3_CRITIC_APPLY, TD3_ACTOR_GRAD, TD3_ACTOR_APPLY, TD3_ALL = 1, 2, 4, 8, 15
 
 P = c_void_p
@@ -96,6 +104,10 @@ _SIGNATURES = {
     "cstr_td3_layout": (c_int, [c_int32, c_int32, POINTER(c_int64)]),
     "cstr_td3_workspace_bytes": (c_int64, [POINTER(Td3Config)]),
     "cstr_td3_update": (c_int, [POINTER(Td3Config), POINTER(Td3State), P, P, P, P, P, P, c_int64, c_int64, c_int64, c_int32, P]),
+    "cstr_sac_param_count": (c_int64, [c_int32, c_int32]),
+    "cstr_sac_layout": (c_int, [c_int32, c_int32, POINTER(c_int64)]),
+    "cstr_sac_workspace_bytes": (c_int64, [POINTER(SacConfig)]),
+    "cstr_sac_update": (c_int, [POINTER(SacConfig), POINTER(Td3State), P, P, P, P, P, P, P, c_int64, c_int64, P]),
     "cstr_rollout_fused": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, c_int, POINTER(ActorF32), P, c_float, P, c_int,
                                    c_uint32, P, P, P, P, c_int64, c_int64, P, P, POINTER(EpisodeStatsStruct), P]),
     "cstr_actor_pack_bf16": (c_int64, [POINTER(ActorF32), P, P]),

@@ -48,9 +48,9 @@ struct Td3Layout {
     int64_t actor_off, critic_off[2], total;
 };
 
-inline Td3Layout td3_layout(int h1, int h2) {
+inline Td3Layout td3_layout(int h1, int h2, int actor_out = ACT) {  // actor_out = 2 (TD3: tanh head) or 4 (SAC: [mu; log_std] head)
     Td3Layout T;
-    T.actor = net_layout(OBS, ACT, h1, h2);
+    T.actor = net_layout(OBS, actor_out, h1, h2);
     T.critic = net_layout(OBS + ACT, 1, h1, h2);
     T.actor_off = 0;
     T.critic_off[0] = T.actor.size;
@@ -309,7 +309,8 @@ td3_target_head_kernel(int B, int H2, const float *__restrict__ h2, int64_t h_z,
 template <bool POLICY>
 __global__ void __launch_bounds__(256)
 td3_critic_head_kernel(int B, int H2, const float *__restrict__ h2, int64_t h_z, const float *__restrict__ W3, const float *__restrict__ b3, int64_t w_z,
-                       const float *__restrict__ target, float *__restrict__ dq_out, float *__restrict__ dz2, float *__restrict__ loss_partial) {
+                       const float *__restrict__ target, float dq_scale, float *__restrict__ dq_out, float *__restrict__ dz2,
+                       float *__restrict__ loss_partial) {
     __shared__ float sl[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x * 8 + warp, z = blockIdx.y;
     float contrib = 0.f;
@@ -323,7 +324,7 @@ td3_critic_head_kernel(int B, int H2, const float *__restrict__ h2, int64_t h_z,
         } else {
             const float diff = q - target[b];
             contrib = diff * diff;
-            dq = (2.f / (float)B) * diff;
+            dq = dq_scale * diff;  // TD3: sum_i mse -> 2/B; SAC: 0.5 * sum_i mse -> 1/B
         }
         if (lane == 0) dq_out[(int64_t)z * B + b] = dq;
         float *d = dz2 + z * h_z + (int64_t)b * H2;
@@ -367,6 +368,181 @@ td3_actor_bwd_head_kernel(int B, int H1, int H2, const float *__restrict__ dz1c,
         const float4 w0 = *reinterpret_cast<const float4 *>(W3a + k), w1 = *reinterpret_cast<const float4 *>(W3a + H2 + k);
         *reinterpret_cast<float4 *>(o + k) = make_float4(hh.x > 0.f ? fmaf(p1, w1.x, p0 * w0.x) : 0.f, hh.y > 0.f ? fmaf(p1, w1.y, p0 * w0.y) : 0.f,
                                                          hh.z > 0.f ? fmaf(p1, w1.z, p0 * w0.z) : 0.f, hh.w > 0.f ? fmaf(p1, w1.w, p0 * w0.w) : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// SAC heads (core/sac/sac.py:213-281, core/sac/policies.py:147-175, core/common/distributions.py:207-260)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr float SAC_LOG_STD_MIN = -20.f, SAC_LOG_STD_MAX = 2.f, SAC_SQUASH_EPS = 1e-6f, SAC_HALF_LOG_2PI = 0.91893853320467274f;
+
+// squashed-Gaussian actor head: [mean; log_std] = h2 @ W3^T + b3 (W3 is (4,H2)), u = mean + std*eps, a = tanh(u),
+// log_prob = sum_i [-(u-mean)^2/(2 std^2) - log_std - 0.5 log 2pi] - sum_i log(1 - a^2 + 1e-6).
+// call 0 = actions_pi (keeps what the backward needs), call 1 = next_actions (no grad).
+__global__ void __launch_bounds__(256)
+sac_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *__restrict__ W3, const float *__restrict__ b3, const float2 *__restrict__ eps_in,
+                      uint64_t seed, uint32_t update_index, uint32_t call, float2 *__restrict__ act_out, float *__restrict__ logp_out,
+                      float2 *__restrict__ std_eps_out, float2 *__restrict__ raw_out, float *__restrict__ lp_partial) {
+    __shared__ float sl[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x * 8 + warp;
+    float lp = 0.f;
+    if (b < B) {
+        const float *h = h2 + (int64_t)b * H2;
+        float y[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) y[o] = row_dot(h, W3 + (int64_t)o * H2, H2, lane) + b3[o];
+        if (lane == 0) {
+            float2 e;
+            if (eps_in) e = eps_in[b];
+            else {
+                const uint4 r = philox_env(seed, (uint64_t)b, update_index, STREAM_TD3, call);
+                const float u1 = fmaf(u24(r.x), 1.0f, 5.9604644775390625e-08f), u2 = u24(r.y);
+                const float rad = sqrtf(-2.0f * logf(u1));
+                float sn, cs;
+                sincospif(2.0f * u2, &sn, &cs);
+                e = make_float2(rad * cs, rad * sn);
+            }
+            const float ev[2] = {e.x, e.y};
+            float a[2], se[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float ls = fminf(fmaxf(y[2 + i], SAC_LOG_STD_MIN), SAC_LOG_STD_MAX), sd = expf(ls);
+                se[i] = sd * ev[i];
+                const float u = y[i] + se[i], d = u - y[i];
+                a[i] = tanhf(u);
+                lp += -(d * d) / (2.f * sd * sd) - ls - SAC_HALF_LOG_2PI - logf(1.f - a[i] * a[i] + SAC_SQUASH_EPS);
+            }
+            act_out[b] = make_float2(a[0], a[1]);
+            logp_out[b] = lp;
+            if (std_eps_out) std_eps_out[b] = make_float2(se[0], se[1]);
+            if (raw_out) raw_out[b] = make_float2(y[2], y[3]);
+        }
+    }
+    if (lp_partial) {
+        if (lane == 0) sl[warp] = lp;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < 8; ++i) t += sl[i];
+            lp_partial[blockIdx.x] = t;
+        }
+    }
+}
+
+// entropy coefficient: ent_coef = exp(log_ent_coef) BEFORE the step (used by this update's target and actor loss),
+// loss = -(log_ent_coef * (log_prob + target_entropy)).mean(), one Adam step on the scalar            sac.py:226-243
+// scalars[5] = ent_coef of this update.  losses: [4] += ent_coef_loss, [5] += 1, [6] += ent_coef, [7] += 1.
+__global__ void sac_ent_coef_kernel(int B, int n_partial, const float *__restrict__ lp_partial, float target_entropy, float *__restrict__ log_ent_coef,
+                                    float *__restrict__ m, float *__restrict__ v, float beta1, float beta2, float eps, float step_size, float bc2_sqrt,
+                                    float *__restrict__ scalars, float *__restrict__ losses) {
+    __shared__ float sl[256];
+    float s = 0.f;
+    for (int k = threadIdx.x; k < n_partial; k += 256) s += lp_partial[k];
+    sl[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sl[threadIdx.x] += sl[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x) return;
+    const float mean_term = sl[0] / (float)B + target_entropy;  // mean(log_prob + target_entropy)
+    const float le = log_ent_coef[0], g = -mean_term;
+    scalars[5] = expf(le);
+    if (losses) {
+        losses[4] += -(le * mean_term), losses[5] += 1.f;
+        losses[6] += scalars[5], losses[7] += 1.f;
+    }
+    float mm = m[0], vv = v[0];
+    mm = mm + (g - mm) * (1.f - beta1);
+    vv = vv * beta2 + (1.f - beta2) * g * g;
+    log_ent_coef[0] = le - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+    m[0] = mm, v[0] = vv;
+}
+
+// target = r + (1 - done) * gamma * (min(q1_t, q2_t) - ent_coef * next_log_prob)                      sac.py:246-254
+__global__ void __launch_bounds__(256)
+sac_target_head_kernel(int B, int H2, const float *__restrict__ h2, int64_t h_z, const float *__restrict__ W3, const float *__restrict__ b3, int64_t w_z,
+                       const float *__restrict__ rewards, const float *__restrict__ dones, const float *__restrict__ next_logp,
+                       const float *__restrict__ scalars, float gamma, float *__restrict__ target) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float q0 = row_dot(h2 + (int64_t)b * H2, W3, H2, lane) + b3[0];
+    const float q1 = row_dot(h2 + h_z + (int64_t)b * H2, W3 + w_z, H2, lane) + b3[w_z];
+    if (lane == 0) target[b] = rewards[b] + (1.f - dones[b]) * gamma * (fminf(q0, q1) - scalars[5] * next_logp[b]);
+}
+
+// actor loss head: q_i(s, a_pi) for both critics, min -> the gradient -1/B goes to the smaller one (first on ties, as torch.min);
+// loss partial = ent_coef * log_prob - min q; dz2[z] = dq[z] * w3[z] * (h2[z] > 0)                                 sac.py:271-276
+__global__ void __launch_bounds__(256)
+sac_qmin_head_kernel(int B, int H2, const float *__restrict__ h2, int64_t h_z, const float *__restrict__ W3, const float *__restrict__ b3, int64_t w_z,
+                     const float *__restrict__ logp, const float *__restrict__ scalars, float *__restrict__ dz2, float *__restrict__ loss_partial) {
+    __shared__ float sl[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x * 8 + warp;
+    float contrib = 0.f;
+    if (b < B) {
+        const float *h0 = h2 + (int64_t)b * H2, *h1 = h0 + h_z;
+        const float q0 = row_dot(h0, W3, H2, lane) + b3[0], q1 = row_dot(h1, W3 + w_z, H2, lane) + b3[w_z];
+        const bool pick0 = q0 <= q1;
+        contrib = scalars[5] * logp[b] - (pick0 ? q0 : q1);
+        const float g = -1.f / (float)B;
+        for (int z = 0; z < 2; ++z) {
+            const float dq = (z == 0) == pick0 ? g : 0.f;
+            const float *h = z ? h1 : h0, *w = W3 + z * w_z;
+            float *d = dz2 + z * h_z + (int64_t)b * H2;
+            for (int k = lane * 4; k < H2; k += 128) {
+                const float4 a = *reinterpret_cast<const float4 *>(h + k), ww = *reinterpret_cast<const float4 *>(w + k);
+                *reinterpret_cast<float4 *>(d + k) =
+                    make_float4(a.x > 0.f ? dq * ww.x : 0.f, a.y > 0.f ? dq * ww.y : 0.f, a.z > 0.f ? dq * ww.z : 0.f, a.w > 0.f ? dq * ww.w : 0.f);
+            }
+        }
+    }
+    if (lane == 0) sl[warp] = contrib;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += sl[i];
+        loss_partial[blockIdx.x] = t;
+    }
+}
+
+// through the critics' input layers and the squashed Gaussian into the actor head:
+//   da = sum_z dz1c[z] @ W1c[z][:, 4:6];  du = da (1-a^2) + (ent_coef/B) 2a(1-a^2)/(1-a^2+1e-6);  dmean = du;
+//   dlog_std = (du * std*eps - ent_coef/B) * [log_std not clamped];  dz2a = ([dmean, dlog_std] @ W3a) * (h2a > 0)
+__global__ void __launch_bounds__(256)
+sac_actor_bwd_head_kernel(int B, int H1, int H2, const float *__restrict__ dz1c, int64_t dz_z, const float *__restrict__ W1c, int64_t w_z,
+                          const float2 *__restrict__ a_pi, const float2 *__restrict__ std_eps, const float2 *__restrict__ raw, const float *__restrict__ scalars,
+                          const float *__restrict__ W3a, const float *__restrict__ h2a, float4 *__restrict__ dpre_out, float *__restrict__ dz2a) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    float s0 = 0.f, s1 = 0.f;
+    for (int z = 0; z < 2; ++z) {
+        const float *d = dz1c + z * dz_z + (int64_t)b * H1, *W = W1c + z * w_z;
+        for (int j = lane; j < H1; j += 32) {
+            const float v = d[j];
+            s0 = fmaf(v, __ldg(W + j * (OBS + ACT) + OBS), s0);
+            s1 = fmaf(v, __ldg(W + j * (OBS + ACT) + OBS + 1), s1);
+        }
+    }
+    s0 = warp_sum(s0), s1 = warp_sum(s1);
+    const float2 a = a_pi[b], se = std_eps[b], rw = raw[b];
+    const float c = scalars[5] / (float)B;
+    const float om0 = 1.f - a.x * a.x, om1 = 1.f - a.y * a.y;
+    const float du0 = s0 * om0 + c * (2.f * a.x * om0 / (om0 + SAC_SQUASH_EPS)), du1 = s1 * om1 + c * (2.f * a.y * om1 / (om1 + SAC_SQUASH_EPS));
+    const float g0 = (rw.x >= SAC_LOG_STD_MIN && rw.x <= SAC_LOG_STD_MAX) ? du0 * se.x - c : 0.f;
+    const float g1 = (rw.y >= SAC_LOG_STD_MIN && rw.y <= SAC_LOG_STD_MAX) ? du1 * se.y - c : 0.f;
+    if (lane == 0) dpre_out[b] = make_float4(du0, du1, g0, g1);
+    const float p[4] = {du0, du1, g0, g1};
+    const float *h = h2a + (int64_t)b * H2;
+    float *o = dz2a + (int64_t)b * H2;
+    for (int k = lane * 4; k < H2; k += 128) {
+        const float4 hh = *reinterpret_cast<const float4 *>(h + k);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float4 w = *reinterpret_cast<const float4 *>(W3a + (int64_t)r * H2 + k);
+            acc.x = fmaf(p[r], w.x, acc.x), acc.y = fmaf(p[r], w.y, acc.y), acc.z = fmaf(p[r], w.z, acc.z), acc.w = fmaf(p[r], w.w, acc.w);
+        }
+        *reinterpret_cast<float4 *>(o + k) = make_float4(hh.x > 0.f ? acc.x : 0.f, hh.y > 0.f ? acc.y : 0.f, hh.z > 0.f ? acc.z : 0.f, hh.w > 0.f ? acc.w : 0.f);
     }
 }
 
@@ -559,6 +735,7 @@ struct Workspace {  // carved out of the caller's workspace buffer (floats)
     float *t_h1, *t_h2;      // target-critic activations (2 slabs)
     float *a_h1, *a_h2;      // actor / actor-target activations
     float *next_act, *a_pi, *target, *dq, *dpre, *loss_partial, *slabs, *skinny, *scalars;
+    float *logp, *next_logp, *std_eps, *raw_log_std, *dpre4, *lp_partial;  // SAC
     int n_row_blocks;
     bool tensor;  // hidden-layer GEMMs on tcgen05 (cfg->gemm_mode)
     int64_t floats;
@@ -601,6 +778,8 @@ Workspace carve(float *base, int B, int H1, int H2) {
     const int64_t hp = ((int64_t)(H1 > H2 ? H1 : H2) + 31) / 32 * 32;
     w.skinny = take((int64_t)((B + SKINNY_ROWS - 1) / SKINNY_ROWS) * 2 * (OBS + ACT + 1) * hp);
     w.scalars = take(8);
+    w.logp = take(B), w.next_logp = take(B), w.std_eps = take(2 * (int64_t)B), w.raw_log_std = take(2 * (int64_t)B), w.dpre4 = take(4 * (int64_t)B);
+    w.lp_partial = take(w.n_row_blocks);
     w.tensor = false;
     w.floats = o;
     return w;
@@ -774,8 +953,8 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         if (int rc = check_launch("td3_target_head_kernel")) return rc;
         // ---- current Q, loss, backward (td3.py:178-186) ----
         if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st)) return rc;
-        td3_critic_head_kernel<false><<<dim3(rb, 2), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, w.dq, w.dz2,
-                                                                  w.loss_partial);
+        td3_critic_head_kernel<false><<<dim3(rb, 2), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, 2.f / (float)B, w.dq,
+                                                                  w.dz2, w.loss_partial);
         if (int rc = check_launch("td3_critic_head_kernel")) return rc;
         SkinnyArgs s{};  // dW3 = dq^T @ h2, db3 = sum dq
         s.X = w.h2[0], s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
@@ -803,7 +982,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, 0, nullptr, 0.f, 0.f, 0, 0, nullptr, (float2 *)w.a_pi);
         if (int rc = check_launch("td3_actor_head_kernel<pi>")) return rc;
         if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 1, w.h1[0], w.h2[0], w.tensor, st)) return rc;
-        td3_critic_head_kernel<true><<<dim3(rb, 1), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, nullptr, w.dq, w.dz2,
+        td3_critic_head_kernel<true><<<dim3(rb, 1), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, nullptr, 0.f, w.dq, w.dz2,
                                                                  w.loss_partial);
         if (int rc = check_launch("td3_critic_head_kernel<policy>")) return rc;
         if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, g_critic, cz, 1, w.h1[0], w.dz2, w.dz1, w, false, st)) return rc;
@@ -830,6 +1009,138 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         a.loss_partial = w.loss_partial, a.n_loss_partial = rb, a.loss_scale = -1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 2 : nullptr;
         td3_apply_kernel<<<(unsigned)((T.total + 255) / 256), 256, 0, st>>>(a);
         if (int rc = check_launch("td3_apply_kernel<actor+polyak>")) return rc;
+    }
+    return 0;
+}
+
+
+// ---- SAC (core/sac/sac.py:199-296) --------------------------------------------------------------------------------
+static int check_sac_cfg(const cstr_sac_config *c) {
+    if (!c) return fail_arg(CSTR_EINVAL, "sac: null config");
+    if (c->h1 < 4 || c->h2 < 4 || (c->h1 & 3) || (c->h2 & 3) || c->h1 > 4096 || c->h2 > 4096)
+        return fail_arg(CSTR_EINVAL, "sac: hidden sizes must be multiples of 4 in [4, 4096]");
+    if (c->batch < 1 || c->batch > (1 << 22)) return fail_arg(CSTR_EINVAL, "sac: batch must be in [1, 4194304]");
+    if (c->target_update_interval < 1) return fail_arg(CSTR_EINVAL, "sac: target_update_interval must be >= 1");
+    if (c->gemm_mode != CSTR_TD3_GEMM_FP32 && c->gemm_mode != CSTR_TD3_GEMM_TENSOR) return fail_arg(CSTR_EINVAL, "sac: gemm_mode must be 0 or 1");
+    return 0;
+}
+
+int64_t cstr_sac_param_count(int32_t h1, int32_t h2) {
+    if (h1 < 4 || h2 < 4 || (h1 & 3) || (h2 & 3)) return -1;
+    return td3_layout(h1, h2, 2 * ACT).total + 4;  // + the entropy-coefficient slot (log_ent_coef, padded to 4 floats)
+}
+
+int cstr_sac_layout(int32_t h1, int32_t h2, int64_t *offsets) {
+    if (!offsets || h1 < 4 || h2 < 4 || (h1 & 3) || (h2 & 3)) return fail_arg(CSTR_EINVAL, "sac_layout: bad sizes or null output");
+    const Td3Layout T = td3_layout(h1, h2, 2 * ACT);
+    const int64_t base[3] = {T.actor_off, T.critic_off[0], T.critic_off[1]};
+    for (int n = 0; n < 3; ++n) {
+        const NetLayout &L = n == 0 ? T.actor : T.critic;
+        const int64_t o[6] = {L.w1, L.b1, L.w2, L.b2, L.w3, L.b3};
+        for (int k = 0; k < 6; ++k) offsets[n * 6 + k] = base[n] + o[k];
+    }
+    offsets[18] = T.total;      // log_ent_coef
+    offsets[19] = T.total + 4;  // block size
+    return 0;
+}
+
+int64_t cstr_sac_workspace_bytes(const cstr_sac_config *cfg) {
+    if (check_sac_cfg(cfg)) return -1;
+    return carve(nullptr, cfg->batch, cfg->h1, cfg->h2).floats * (int64_t)sizeof(float);
+}
+
+int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const float *obs, const float *actions, const float *next_obs,
+                    const float *dones, const float *rewards, const float *eps_pi, const float *eps_next, int64_t n_updates, int64_t adam_step,
+                    void *stream) {
+    if (int rc = check_sac_cfg(cfg)) return rc;
+    if (!stt || !stt->params || !stt->targets || !stt->grads || !stt->adam_m || !stt->adam_v || !stt->workspace)
+        return fail_arg(CSTR_EINVAL, "sac_update: null state pointer");
+    if (!obs || !actions || !next_obs || !dones || !rewards) return fail_arg(CSTR_EINVAL, "sac_update: null batch pointer");
+    if (!aligned(obs, 16) || !aligned(next_obs, 16) || !aligned(actions, 8) || (eps_pi && !aligned(eps_pi, 8)) || (eps_next && !aligned(eps_next, 8)) ||
+        !aligned(stt->params, 16) || !aligned(stt->targets, 16) || !aligned(stt->grads, 16) || !aligned(stt->adam_m, 16) || !aligned(stt->adam_v, 16) ||
+        !aligned(stt->workspace, 16))
+        return fail_arg(CSTR_EALIGN, "sac_update: 16 B (obs/params/workspace) / 8 B (actions, noise) alignment");
+    const int B = cfg->batch, H1 = cfg->h1, H2 = cfg->h2;
+    Workspace w = carve(stt->workspace, B, H1, H2);
+    w.tensor = cfg->gemm_mode == CSTR_TD3_GEMM_TENSOR;
+    if (stt->workspace_bytes < w.floats * (int64_t)sizeof(float)) return fail_arg(CSTR_EINVAL, "sac_update: workspace too small (cstr_sac_workspace_bytes)");
+    if (n_updates < 1 || adam_step < 1) return fail_arg(CSTR_EINVAL, "sac_update: counters are 1-based (value after this update)");
+    const Td3Layout T = td3_layout(H1, H2, 2 * ACT);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cz = T.critic.size, ent = T.total;
+    const Net actor = net_at(stt->params, T.actor_off, T.actor), critic = net_at(stt->params, T.critic_off[0], T.critic);
+    const Net critic_t = net_at(stt->targets, T.critic_off[0], T.critic);
+    const Net g_actor = net_at(stt->grads, T.actor_off, T.actor), g_critic = net_at(stt->grads, T.critic_off[0], T.critic);
+    const int rb = w.n_row_blocks;
+    const double bc1 = 1.0 - pow((double)cfg->beta1, (double)adam_step), bc2 = 1.0 - pow((double)cfg->beta2, (double)adam_step);
+    const float step_size = (float)((double)cfg->lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+
+    // ---- actions_pi, log_prob of the current actor (sac.py:222-223) and the entropy-coefficient step (:226-243) ----
+    if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st)) return rc;
+    sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, (const float2 *)eps_pi, cfg->seed, (uint32_t)n_updates, 0u, (float2 *)w.a_pi,
+                                             w.logp, (float2 *)w.std_eps, (float2 *)w.raw_log_std, w.lp_partial);
+    if (int rc = check_launch("sac_actor_head_kernel")) return rc;
+    sac_ent_coef_kernel<<<1, 256, 0, st>>>(B, rb, w.lp_partial, cfg->target_entropy, stt->params + ent, stt->adam_m + ent, stt->adam_v + ent, cfg->beta1,
+                                          cfg->beta2, cfg->eps, step_size, bc2_sqrt, w.scalars, stt->losses);
+    if (int rc = check_launch("sac_ent_coef_kernel")) return rc;
+    // ---- target (sac.py:245-254): next action from the CURRENT actor (scratch: the dz slabs are free here) ----
+    if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor, 0, 1, w.dz1, w.dz2, w.tensor, st)) return rc;
+    sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.dz2, actor.w3, actor.b3, (const float2 *)eps_next, cfg->seed, (uint32_t)n_updates, 1u,
+                                             (float2 *)w.next_act, w.next_logp, nullptr, nullptr, nullptr);
+    if (int rc = check_launch("sac_actor_head_kernel<next>")) return rc;
+    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st)) return rc;
+    sac_target_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.t_h2, (int64_t)B * H2, critic_t.w3, critic_t.b3, cz, rewards, dones, w.next_logp, w.scalars,
+                                              cfg->gamma, w.target);
+    if (int rc = check_launch("sac_target_head_kernel")) return rc;
+    // ---- critics (sac.py:256-268): loss = 0.5 * sum_i mse ----
+    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st)) return rc;
+    td3_critic_head_kernel<false><<<dim3(rb, 2), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, 1.f / (float)B, w.dq,
+                                                              w.dz2, w.loss_partial);
+    if (int rc = check_launch("td3_critic_head_kernel<sac>")) return rc;
+    {
+        SkinnyArgs s{};
+        s.X = w.h2[0], s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
+        s.Y0 = w.dq, s.n0 = 1, s.ld0 = 1, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = B;
+        s.out_w = g_critic.w3, s.out_b = g_critic.b3, s.out_z = cz, s.transposed = 1;
+        if (int rc = launch_skinny<1, true>(s, 2, w.skinny, st, "td3_skinny_wgrad_kernel<w3>")) return rc;
+    }
+    if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st)) return rc;
+    {
+        ApplyArgs a{};
+        a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
+        a.adam_lo = T.critic_off[0], a.adam_hi = T.total, a.polyak_lo = a.polyak_hi = 0;
+        a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = step_size, a.bc2_sqrt = bc2_sqrt, a.tau = cfg->tau;
+        a.loss_partial = w.loss_partial, a.n_loss_partial = 2 * rb, a.loss_scale = 0.5f / (float)B, a.loss_acc = stt->losses;
+        td3_apply_kernel<<<(unsigned)((a.adam_hi - a.adam_lo + 255) / 256), 256, 0, st>>>(a);
+        if (int rc = check_launch("td3_apply_kernel<sac critic>")) return rc;
+    }
+    // ---- actor (sac.py:270-281): (ent_coef * log_prob - min_i Q_i(s, a_pi)).mean() with the updated critics ----
+    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st)) return rc;
+    sac_qmin_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.logp, w.scalars, w.dz2, w.loss_partial);
+    if (int rc = check_launch("sac_qmin_head_kernel")) return rc;
+    if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, false, st)) return rc;
+    // the actor's dz2 / dz1 live in the target-activation slabs (free since the target was formed)
+    sac_actor_bwd_head_kernel<<<rb, 256, 0, st>>>(B, H1, H2, w.dz1, (int64_t)B * H1, critic.w1, cz, (const float2 *)w.a_pi, (const float2 *)w.std_eps,
+                                                 (const float2 *)w.raw_log_std, w.scalars, actor.w3, w.a_h2, (float4 *)w.dpre4, w.t_h2);
+    if (int rc = check_launch("sac_actor_bwd_head_kernel")) return rc;
+    {
+        SkinnyArgs s{};  // d[mu; log_std] head = dpre4^T @ h2a, bias = sum dpre4
+        s.X = w.a_h2, s.x_z = 0, s.ldx = H2, s.H = H2, s.B = B;
+        s.Y0 = w.dpre4, s.n0 = 2 * ACT, s.ld0 = 2 * ACT, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = 0;
+        s.out_w = g_actor.w3, s.out_b = g_actor.b3, s.out_z = 0, s.transposed = 1;
+        if (int rc = launch_skinny<2 * ACT, true>(s, 1, w.skinny, st, "td3_skinny_wgrad_kernel<sac head>")) return rc;
+    }
+    if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, w.t_h2, w.t_h1, w, true, st)) return rc;
+    {
+        ApplyArgs a{};
+        a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
+        a.adam_lo = T.actor_off, a.adam_hi = T.actor_off + T.actor.size;
+        const bool sync_targets = ((n_updates - 1) % cfg->target_update_interval) == 0;  // gradient_step % interval == 0 (:284)
+        a.polyak_lo = sync_targets ? T.critic_off[0] : 0, a.polyak_hi = sync_targets ? T.total : 0;
+        a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = step_size, a.bc2_sqrt = bc2_sqrt, a.tau = cfg->tau;
+        a.loss_partial = w.loss_partial, a.n_loss_partial = rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 2 : nullptr;
+        td3_apply_kernel<<<(unsigned)((T.total + 255) / 256), 256, 0, st>>>(a);
+        if (int rc = check_launch("td3_apply_kernel<sac actor+polyak>")) return rc;
     }
     return 0;
 }

@@ -345,3 +345,156 @@ def bind_td3_class(td3_base: type) -> type:
     FusedTD3.__name__ = "TD3"
     FusedTD3.__qualname__ = "TD3"
     return FusedTD3
+
+
+class FusedSACUpdate(FusedTD3Update):
+    """SAC gradient steps on the device: one iteration of the loop body of ``SAC.train`` (``core/sac/sac.py:213-288``) per ``update()``
+    through ``cstr_sac_update`` — squashed-Gaussian actor sample and log-prob, automatic entropy coefficient, soft twin-min target,
+    critics, actor (backward through both critics and the tanh-Gaussian), polyak.  Same flat-block design as :class:`FusedTD3Update`;
+    the actor head is ONE (4, h2) matrix [mu; log_std], ``log_ent_coef`` lives in a slot after the three nets."""
+
+    def __init__(self, net_arch: Sequence[int] = (256, 256), batch_size: int = 256, device: Any = "cuda", gamma: float = 0.99, tau: float = 0.005,
+                 learning_rate: float = 3e-4, target_entropy: float = -2.0, ent_coef_init: float = 1.0, target_update_interval: int = 1,
+                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0, gemm: str = "fp32"):
+        self.target_entropy, self.target_update_interval = float(target_entropy), int(target_update_interval)
+        super().__init__(net_arch, batch_size, device, gamma, tau, learning_rate, 1, 0.0, 0.0, betas, eps, seed, gemm)
+        torch = self._torch
+        offs = (c_int64 * 20)()
+        _lib.check(self._libc.cstr_sac_layout(self.h1, self.h2, offs), "cstr_sac_layout")
+        self.param_count = int(offs[19])
+        self._offsets = {(NET_NAMES[n], _TENSORS[k]): int(offs[n * 6 + k]) for n in range(3) for k in range(6)}
+        self._ent_offset = int(offs[18])
+        self.actor_range = (0, self._offsets[("critic0", "W1")])
+        self.critic_range = (self._offsets[("critic0", "W1")], self._ent_offset)
+        with torch.cuda.device(self.device):
+            z = lambda: torch.zeros(self.param_count, dtype=torch.float32, device=self.device)  # noqa: E731
+            self.params, self.targets, self.grads, self.adam_m, self.adam_v = z(), z(), z(), z(), z()
+            self.loss_sums = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.params[self._ent_offset] = float(np.log(ent_coef_init))
+        self._batch = 0
+        self._set_batch(int(batch_size))
+
+    def _shape(self, net: str, tensor: str):
+        i, o = (4, 4) if net == "actor" else (6, 1)
+        return {"W1": (self.h1, i), "b1": (self.h1,), "W2": (self.h2, self.h1), "b2": (self.h2,), "W3": (o, self.h2), "b3": (o,)}[tensor]
+
+    @property
+    def log_ent_coef(self):
+        return self.params[self._ent_offset:self._ent_offset + 1]
+
+    def _sac_config(self, batch: int) -> "_lib.SacConfig":
+        return _lib.SacConfig(h1=self.h1, h2=self.h2, batch=batch, target_update_interval=self.target_update_interval, gamma=self.gamma, tau=self.tau,
+                              lr=self.learning_rate, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_entropy=self.target_entropy,
+                              seed=self.seed & (2**64 - 1), gemm_mode=int(self.gemm == "tensor"))
+
+    def _set_batch(self, batch: int) -> None:
+        if batch == self._batch or not hasattr(self, "_ent_offset"):
+            return super()._set_batch(batch) if not hasattr(self, "_ent_offset") else None
+        cfg = self._sac_config(batch)
+        need = int(self._libc.cstr_sac_workspace_bytes(byref(cfg)))
+        if need < 0:
+            msg = self._libc.cstr_last_error()
+            raise ValueError(msg.decode() if msg else "bad SAC configuration")
+        with self._torch.cuda.device(self.device):
+            self._workspace = self._torch.empty(need // 4, dtype=self._torch.float32, device=self.device)
+        self._batch = batch
+
+    def load_nets(self, nets: Dict[str, Sequence[Any]]) -> None:
+        """``actor`` (head = [mu; log_std] stacked), ``critic0``, ``critic1`` and optionally ``critic*_target``."""
+        torch = self._torch
+        for block, suffix, names in (("params", "", NET_NAMES), ("targets", "_target", NET_NAMES[1:])):
+            v = self.views(block)
+            for net in names:
+                src = nets.get(net + suffix, nets[net])
+                for dst, s in zip(v[net], src):
+                    dst.copy_(torch.as_tensor(np.asarray(s) if not isinstance(s, torch.Tensor) else s).to(self.device, torch.float32).reshape(dst.shape))
+
+    def nets(self) -> Dict[str, List[np.ndarray]]:
+        out = {net: [t.cpu().numpy() for t in ts] for net, ts in self.views("params").items()}
+        out.update({net + "_target": [t.cpu().numpy() for t in ts] for net, ts in self.views("targets").items() if net != "actor"})
+        return out
+
+    def adopt_policy(self, policy) -> None:
+        """The reference's ``SACPolicy`` (core/sac/policies.py): ``actor.latent_pi`` + ``actor.mu`` + ``actor.log_std``, twin critics."""
+        a, v, t = policy.actor, self.views("params"), self.views("targets")
+        lat = list(a.latent_pi.parameters())
+        pairs = list(zip(v["actor"][:4], lat)) + [(v["actor"][4][0:2], a.mu.weight), (v["actor"][4][2:4], a.log_std.weight),
+                                                 (v["actor"][5][0:2], a.mu.bias), (v["actor"][5][2:4], a.log_std.bias)]
+        for z, q in enumerate(policy.critic.q_networks):
+            pairs += list(zip(v[f"critic{z}"], q.parameters()))
+        for z, q in enumerate(policy.critic_target.q_networks):
+            pairs += list(zip(t[f"critic{z}"], q.parameters()))
+        for view, p in pairs:
+            if tuple(p.shape) != tuple(view.shape):
+                raise ValueError(f"shape mismatch: module {tuple(p.shape)} vs layout {tuple(view.shape)}")
+            view.copy_(p.data.to(self.device, self._torch.float32))
+            p.data = view
+
+    def update(self, batch, eps_pi=None, eps_next=None) -> None:  # type: ignore[override]
+        """One iteration of sac.py:213-288.  ``eps_pi`` / ``eps_next``: explicit standard-normal draws (B,2) of the two rsample() calls
+        (parity tests); default = Philox inside the kernel."""
+        obs, act, nobs, dones, rew = batch
+        self._set_batch(int(obs.shape[0]))
+        obs, act, nobs = self._f32(obs, 4), self._f32(act, 2), self._f32(nobs, 4)
+        dones, rew = self._f32(dones, 1), self._f32(rew, 1)
+        e1 = None if eps_pi is None else self._f32(eps_pi, 2)
+        e2 = None if eps_next is None else self._f32(eps_next, 2)
+        self.n_updates += 1
+        self.critic_step += 1
+        self.actor_step += 1
+        cfg, st = self._sac_config(self._batch), self._state(counters=False)
+        with self._torch.cuda.device(self.device):
+            rc = self._libc.cstr_sac_update(byref(cfg), byref(st), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones), _lib.ptr(rew),
+                                            _lib.ptr(e1), _lib.ptr(e2), self.n_updates, self.critic_step, self._stream())
+        _lib.check(rc, "cstr_sac_update")
+        self.launches += 56
+
+    def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, **_unused) -> None:  # type: ignore[override]
+        bs = int(batch_size or self._batch)
+        for _ in range(gradient_steps):
+            self.update(buffer.sample(bs, env=env))
+
+    def pop_losses(self):
+        """(critic loss, actor loss, ent_coef_loss, ent_coef) means since the last call — the keys SAC.train logs (sac.py:290-296)."""
+        s = self.loss_sums.cpu().numpy().astype(np.float64)
+        self.loss_sums.zero_()
+        return tuple(s[2 * i] / s[2 * i + 1] if s[2 * i + 1] else None for i in range(4))
+
+
+def bind_sac_class(sac_base: type) -> type:
+    """Subclass of the reference's ``SAC`` (``ent_coef="auto"``, no gSDE) whose ``train()`` (core/sac/sac.py:199-296) runs on ``cstr_sac_update``."""
+
+    class FusedSAC(sac_base):  # type: ignore[misc, valid-type]
+        _fused: Optional[FusedSACUpdate] = None
+
+        def train(self, gradient_steps: int, batch_size: int = 64) -> None:
+            if self.use_sde or self.ent_coef_optimizer is None:
+                return super().train(gradient_steps, batch_size)  # gSDE / fixed ent_coef: the reference's torch path
+            self.policy.set_training_mode(True)
+            self._update_learning_rate([self.actor.optimizer, self.critic.optimizer, self.ent_coef_optimizer])
+            if self._fused is None:
+                arch = self.policy.net_arch if isinstance(self.policy.net_arch, (list, tuple)) else self.policy.net_arch["pi"]
+                eng = FusedSACUpdate(arch, batch_size, self.device, self.gamma, self.tau, float(self.lr_schedule(self._current_progress_remaining)),
+                                     float(self.target_entropy), float(self.log_ent_coef.detach().exp().item()), self.target_update_interval,
+                                     seed=int(self.seed or 0))
+                eng.adopt_policy(self.policy)
+                self.log_ent_coef.data = eng.log_ent_coef  # shared storage
+                eng.n_updates = eng.critic_step = eng.actor_step = int(self._n_updates)
+                self._fused = eng
+            eng = self._fused
+            eng.learning_rate = float(self.lr_schedule(self._current_progress_remaining))
+            eng.train(gradient_steps, self.replay_buffer, batch_size, env=self._vec_normalize_env)
+            self._n_updates += gradient_steps
+            critic_loss, actor_loss, ent_loss, ent_coef = eng.pop_losses()
+            self.logger.record("train/n_updates", self._n_updates, exclude="tensorboard")
+            self.logger.record("train/ent_coef", ent_coef)
+            self.logger.record("train/actor_loss", actor_loss)
+            self.logger.record("train/critic_loss", critic_loss)
+            self.logger.record("train/ent_coef_loss", ent_loss)
+
+        def _excluded_save_params(self):
+            return super()._excluded_save_params() + ["_fused"]
+
+    FusedSAC.__name__ = "SAC"
+    FusedSAC.__qualname__ = "SAC"
+    return FusedSAC
