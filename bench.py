@@ -522,6 +522,14 @@ def td3_update_extras(pkg, torch, device, peaks_tflops) -> dict:
         row["tensor_gemm_algorithmic_tflops"] = out["flop_per_sample"] * B / (ms_tc * 1e-3) / 1e12
         out[f"batch_{B}"] = row
         del eng, ref, eng_tc
+    # SAC gradient step (cstr_sac_update), the reference's default [256, 256] nets
+    for B in (256, 4096):
+        sac = pkg.FusedSACUpdate([256, 256], B, device=device)
+        sac.params[:sac._ent_offset].normal_(0, 0.05)
+        sac.targets.copy_(sac.params)
+        ms = R.timed(lambda: sac.update(buf.sample(B)), 200)
+        out[f"sac_batch_{B}"] = {"ms_per_update": ms, "updates_per_s": 1e3 / ms, "samples_per_s": B * 1e3 / ms}
+        del sac
     return out
 
 

@@ -120,6 +120,13 @@ def main() -> None:
         assert len(st) == 12 and float(st[0]["step"]) == m._fused.critic_step
     print(f"[TD3 fused update] n_updates {m._n_updates}, kernel launches {m._fused.launches}; model.save -> TD3.load round trip ok", flush=True)
 
+    # ---- SAC with the gradient steps on the device (bind_sac_class) ----
+    FusedSAC = pkg.bind_sac_class(core.SAC)
+    m = run("SAC fused update", lambda env: FusedSAC("MlpPolicy", env, train_freq=(1, "step"), gradient_steps=4, **common), 6400)
+    assert isinstance(m, core.SAC) and m._fused is not None and m._n_updates == m._fused.n_updates
+    assert m.policy.actor.mu.weight.data_ptr() == m._fused.views("params")["actor"][4].data_ptr() and m.log_ent_coef.data_ptr() == m._fused.log_ent_coef.data_ptr()
+    print(f"[SAC fused update] n_updates {m._n_updates}, ent_coef {float(m.log_ent_coef.detach().exp()):.4f}, kernel launches {m._fused.launches}", flush=True)
+
     # ---- BCQ offline: dataset generated by the GPU tape kernel, handed over in the reference's pickle format -------
     n, T = 2500, 400
     env = pkg.GpuCSTRVecEnv(n, seed=3, monitor=False)
