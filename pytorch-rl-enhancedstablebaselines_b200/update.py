@@ -90,14 +90,16 @@ class FusedTD3Update:
     def _set_batch(self, batch: int) -> None:
         if batch == self._batch:
             return
-        cfg = self._config(batch)
-        need = int(self._libc.cstr_td3_workspace_bytes(byref(cfg)))
+        need = self._workspace_bytes(batch)
         if need < 0:
             msg = self._libc.cstr_last_error()
-            raise ValueError(msg.decode() if msg else "bad TD3 configuration")
+            raise ValueError(msg.decode() if msg else "bad configuration")
         with self._torch.cuda.device(self.device):
             self._workspace = self._torch.empty(need // 4, dtype=self._torch.float32, device=self.device)
         self._batch = batch
+
+    def _workspace_bytes(self, batch: int) -> int:
+        return int(self._libc.cstr_td3_workspace_bytes(byref(self._config(batch))))
 
     def _config(self, batch: int) -> "_lib.Td3Config":
         return _lib.Td3Config(h1=self.h1, h2=self.h2, batch=batch, policy_delay=self.policy_delay, gamma=self.gamma, tau=self.tau, lr=self.learning_rate,
@@ -387,17 +389,8 @@ class FusedSACUpdate(FusedTD3Update):
                               lr=self.learning_rate, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_entropy=self.target_entropy,
                               seed=self.seed & (2**64 - 1), gemm_mode=int(self.gemm == "tensor"))
 
-    def _set_batch(self, batch: int) -> None:
-        if batch == self._batch or not hasattr(self, "_ent_offset"):
-            return super()._set_batch(batch) if not hasattr(self, "_ent_offset") else None
-        cfg = self._sac_config(batch)
-        need = int(self._libc.cstr_sac_workspace_bytes(byref(cfg)))
-        if need < 0:
-            msg = self._libc.cstr_last_error()
-            raise ValueError(msg.decode() if msg else "bad SAC configuration")
-        with self._torch.cuda.device(self.device):
-            self._workspace = self._torch.empty(need // 4, dtype=self._torch.float32, device=self.device)
-        self._batch = batch
+    def _workspace_bytes(self, batch: int) -> int:
+        return int(self._libc.cstr_sac_workspace_bytes(byref(self._sac_config(batch))))
 
     def load_nets(self, nets: Dict[str, Sequence[Any]]) -> None:
         """``actor`` (head = [mu; log_std] stacked), ``critic0``, ``critic1`` and optionally ``critic*_target``."""

@@ -129,3 +129,40 @@ def test_td3_update_ragged_sizes_and_argument_errors(pkg, B, arch, gemm):
     assert lib.cstr_td3_update(byref(cfg), byref(st), *ptrs, None, 0, 1, 1, 15, stream) < 0  # counters are 1-based
     cfg.h1 = 37
     assert lib.cstr_td3_update(byref(cfg), byref(st), *ptrs, None, 1, 1, 1, 15, stream) < 0 and lib.cstr_td3_param_count(37, 20) == -1
+
+
+@pytest.mark.parametrize("B,arch", [(1, [36, 20]), (130, [256, 256]), (641, [132, 260])])
+def test_sac_update_ragged_sizes_and_argument_errors(pkg, B, arch):
+    import gpu_util as G
+
+    lib = G.L.load()
+    eng = pkg.FusedSACUpdate(arch, B)
+    P = eng.param_count
+    blocks = {name: _padded((P,), torch.float32) for name in ("params", "targets", "grads", "adam_m", "adam_v")}
+    ws = _padded((eng._workspace.numel(),), torch.float32)
+    data = {name: _padded(shape, torch.float32) for name, shape in (("obs", (B, 4)), ("act", (B, 2)), ("nobs", (B, 4)), ("done", (B, 1)), ("rew", (B, 1)))}
+    torch.manual_seed(B)
+    blocks["params"][1].copy_(torch.randn(P, device="cuda") * 0.1)
+    blocks["targets"][1].copy_(blocks["params"][1])
+    for name in ("grads", "adam_m", "adam_v"):
+        blocks[name][1].zero_()
+    for name, (_, view, _) in data.items():
+        view.copy_(torch.rand(view.shape, device="cuda") * 2 - 1)
+    data["done"][1].zero_()
+    eng.params, eng.targets, eng.grads, eng.adam_m, eng.adam_v = (blocks[k][1] for k in ("params", "targets", "grads", "adam_m", "adam_v"))
+    eng._workspace = ws[1]
+    for _ in range(2):
+        eng.update(tuple(data[k][1] for k in ("obs", "act", "nobs", "done", "rew")))
+    torch.cuda.synchronize()
+    for name, (full, _, guard) in {**blocks, **data, "workspace": ws}.items():
+        assert _guards_intact(full, guard, torch.float32), name
+    assert bool(torch.isfinite(eng.params).all().item())
+    cfg, st = eng._sac_config(B), eng._state(counters=False)
+    ptrs = [data[k][1].data_ptr() for k in ("obs", "act", "nobs", "done", "rew")]
+    stream = torch.cuda.current_stream().cuda_stream
+    st.workspace_bytes = 16
+    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 1, 1, stream) < 0 and b"workspace" in lib.cstr_last_error()
+    st.workspace_bytes = ws[1].numel() * 4
+    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 0, 1, stream) < 0
+    cfg.target_update_interval = 0
+    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 1, 1, stream) < 0 and lib.cstr_sac_param_count(37, 20) == -1
