@@ -88,3 +88,25 @@ def test_log_std_clamp_and_philox_noise(pkg):
         e.load_nets(nets2)
         e.update(big[:5])
     assert torch.equal(a.params, b.params) and not torch.equal(a.params, c.params)
+
+
+def test_tensor_gemm_mode_tracks_fp32(pkg):
+    """gemm="tensor" (tcgen05, 3-plane bf16 split) for the SAC step: one update from identical weights — losses agree to 1e-4, the
+    gradients to 1e-4 of their norm (ReLU flips at |activation| < 2e-5 excepted, see tests/test_gpu_td3.py), the weights within Adam's
+    first-step bound of 2*lr."""
+    rng = np.random.default_rng(11)
+    nets = U.random_sac_nets(rng, 256, 256)
+    batch = _batches(rng, 1, 512)[0]
+    engs = {}
+    for gemm in ("fp32", "tensor"):
+        e = pkg.FusedSACUpdate([256, 256], 512, gemm=gemm)
+        e.load_nets(nets)
+        e.update(batch[:5], eps_pi=batch[5], eps_next=batch[6])
+        engs[gemm] = e
+    a, b = engs["fp32"], engs["tensor"]
+    la, lb = a.pop_losses(), b.pop_losses()
+    for x, y in zip(la, lb):
+        assert y == pytest.approx(x, rel=1e-4, abs=1e-6)
+    ga, gb = a.grads.cpu().numpy(), b.grads.cpu().numpy()
+    assert np.linalg.norm(ga - gb) <= 2e-3 * np.linalg.norm(ga)
+    assert float((a.params - b.params).abs().max().item()) <= 2.1 * 3e-4
