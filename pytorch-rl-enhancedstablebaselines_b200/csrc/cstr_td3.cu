@@ -118,10 +118,13 @@ struct GemmArgs {
     int M, N, K, lda, ldb, ldc, ldaux;
     int64_t a_z, b_z, c_z, aux_z;  // per-net strides (floats)
     int splits, k_per_split;
-    int64_t c_split;               // WGRAD: slab stride
+    int64_t c_split;               // split-K: slab stride
+    int raw_partials;              // FWD/DGRAD split over K (small batches): store raw partial sums, td3_splitk_finish_kernel applies the epilogue
+    float *split_buf;              // scratch for those partials (NULL: never split)
+    int64_t split_cap;             // its capacity in floats
 };
 
-template <int MODE>
+template <int MODE, bool RAW = false>  // RAW: forward / dgrad split over K, raw partial sums out (compile-time so the main path keeps its registers)
 __global__ void __launch_bounds__(256, 2) td3_gemm_kernel(GemmArgs g) {
     __shared__ __align__(16) float As[2][BK][LDA_S];
     __shared__ __align__(16) float Bs[2][BK][LDB_S];
@@ -130,7 +133,8 @@ __global__ void __launch_bounds__(256, 2) td3_gemm_kernel(GemmArgs g) {
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const float *A = g.A + z * g.a_z, *Bm = g.Bm + z * g.b_z;
     int k_begin = 0, k_end = g.K;
-    if (MODE == G_WGRAD) {
+    constexpr bool partial = MODE == G_WGRAD || RAW;
+    if (partial) {
         k_begin = split * g.k_per_split;
         k_end = min(g.K, k_begin + g.k_per_split);
     }
@@ -224,15 +228,16 @@ __global__ void __launch_bounds__(256, 2) td3_gemm_kernel(GemmArgs g) {
 
     const int n = n0 + tn * 4;
     if (n >= g.N) return;
-    float *C = g.C + z * g.c_z + (MODE == G_WGRAD ? split * g.c_split : 0);
+    float *C = g.C + z * g.c_z + (partial ? split * g.c_split : 0);
     float4 bias = zero4;
-    if (MODE == G_FWD) bias = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + n);
+    if (MODE == G_FWD && !RAW) bias = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + n);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + tm * 8 + i;
         if (m >= g.M) break;
         float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        if (MODE == G_FWD) {
+        if (RAW) {
+        } else if (MODE == G_FWD) {
             v = make_float4(fmaxf(v.x + bias.x, 0.f), fmaxf(v.y + bias.y, 0.f), fmaxf(v.z + bias.z, 0.f), fmaxf(v.w + bias.w, 0.f));
         } else if (MODE == G_DGRAD) {
             const float4 h = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + (int64_t)m * g.ldaux + n);
@@ -240,6 +245,29 @@ __global__ void __launch_bounds__(256, 2) td3_gemm_kernel(GemmArgs g) {
         }
         *reinterpret_cast<float4 *>(C + (int64_t)m * g.ldc + n) = v;
     }
+}
+
+// second stage of a split-K forward / dgrad GEMM: sum the partial slabs in order, then bias+relu or the relu mask
+template <int MODE>
+__global__ void __launch_bounds__(256) td3_splitk_finish_kernel(GemmArgs g, const float *__restrict__ slabs, int splits, int64_t slab_stride, float *__restrict__ out) {
+    const int n4 = g.N >> 2, z = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)g.M * n4) return;
+    const int m = (int)(i / n4), n = (int)(i % n4) * 4;
+    const float *p = slabs + (int64_t)z * g.M * g.N + (int64_t)m * g.N + n;
+    float4 v = *reinterpret_cast<const float4 *>(p);
+    for (int s = 1; s < splits; ++s) {
+        const float4 u = *reinterpret_cast<const float4 *>(p + s * slab_stride);
+        v.x += u.x, v.y += u.y, v.z += u.z, v.w += u.w;
+    }
+    if (MODE == G_FWD) {
+        const float4 b = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + n);
+        v = make_float4(fmaxf(v.x + b.x, 0.f), fmaxf(v.y + b.y, 0.f), fmaxf(v.z + b.z, 0.f), fmaxf(v.w + b.w, 0.f));
+    } else {
+        const float4 h = *reinterpret_cast<const float4 *>(g.aux + z * g.aux_z + (int64_t)m * g.ldaux + n);
+        v = make_float4(h.x > 0.f ? v.x : 0.f, h.y > 0.f ? v.y : 0.f, h.z > 0.f ? v.z : 0.f, h.w > 0.f ? v.w : 0.f);
+    }
+    *reinterpret_cast<float4 *>(out + z * g.c_z + (int64_t)m * g.ldc + n) = v;
 }
 
 }  // namespace cstr
@@ -737,6 +765,7 @@ struct Workspace {  // carved out of the caller's workspace buffer (floats)
     float *next_act, *a_pi, *target, *dq, *dpre, *loss_partial, *slabs, *skinny, *scalars;
     float *logp, *next_logp, *std_eps, *raw_log_std, *dpre4, *lp_partial;  // SAC
     int n_row_blocks;
+    int64_t slab_cap;  // floats in `slabs`
     bool tensor;  // hidden-layer GEMMs on tcgen05 (cfg->gemm_mode)
     int64_t floats;
 };
@@ -774,7 +803,8 @@ Workspace carve(float *base, int B, int H1, int H2) {
     w.next_act = take(2 * (int64_t)B), w.a_pi = take(2 * (int64_t)B), w.target = take(B), w.dq = take(2 * (int64_t)B), w.dpre = take(2 * (int64_t)B);
     w.n_row_blocks = (B + 7) / 8;
     w.loss_partial = take(2 * (int64_t)w.n_row_blocks);
-    w.slabs = take((int64_t)MAX_SPLITS * 2 * pad4((int64_t)H1 * H2));
+    w.slab_cap = (int64_t)MAX_SPLITS * 2 * pad4((int64_t)H1 * H2);
+    w.slabs = take(w.slab_cap);
     const int64_t hp = ((int64_t)(H1 > H2 ? H1 : H2) + 31) / 32 * 32;
     w.skinny = take((int64_t)((B + SKINNY_ROWS - 1) / SKINNY_ROWS) * 2 * (OBS + ACT + 1) * hp);
     w.scalars = take(8);
@@ -821,6 +851,26 @@ int launch_gemm(const GemmArgs &g, int Z, bool tensor, cudaStream_t st, const ch
         td3_gemm_tc_kernel<MODE><<<grid, TC_GEMM_THREADS, t.smem_bytes, st>>>(g, t.n_tile, t.tmem_cols);
         return check_launch(what);
     }
+    if constexpr (MODE != G_WGRAD) if (g.split_buf) {  // small batch: too few tiles for 148 SMs and a 25-iteration serial K loop -> split K
+        const int64_t tiles = (int64_t)((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM) * Z, sms = sm_count();
+        int s = (int)(sms / tiles);
+        const int64_t per = (int64_t)Z * g.M * g.N;
+        if (s > 8) s = 8;
+        if (s > g.K / (2 * BK)) s = g.K / (2 * BK);
+        if (per > 0 && s > g.split_cap / per) s = (int)(g.split_cap / per);
+        if (s >= 2) {
+            const int kps = (((g.K + s - 1) / s) + BK - 1) / BK * BK;
+            s = (g.K + kps - 1) / kps;
+            GemmArgs q = g;
+            q.raw_partials = 1, q.splits = s, q.k_per_split = kps, q.C = g.split_buf, q.c_z = (int64_t)g.M * g.N, q.c_split = per, q.ldc = g.N;
+            dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, Z * s);
+            td3_gemm_kernel<MODE, true><<<grid, 256, 0, st>>>(q);
+            if (int rc = check_launch(what)) return rc;
+            const int64_t n = (int64_t)g.M * (g.N / 4);
+            td3_splitk_finish_kernel<MODE><<<dim3((unsigned)((n + 255) / 256), Z), 256, 0, st>>>(g, g.split_buf, s, per, g.C);
+            return check_launch("td3_splitk_finish_kernel");
+        }
+    }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, Z * g.splits);
     td3_gemm_kernel<MODE><<<grid, 256, 0, st>>>(g);
     return check_launch(what);
@@ -833,7 +883,7 @@ Net net_at(float *base, int64_t off, const NetLayout &L) { return Net{base + off
 
 // h1 = relu(L1(x)), h2 = relu(L2(h1)) for Z nets that are `z_stride` floats apart
 int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float *act, const Net &n, int64_t z_stride, int Z, float *h1, float *h2,
-                   bool tensor, cudaStream_t st) {
+                   bool tensor, cudaStream_t st, float *split_buf = nullptr, int64_t split_cap = 0) {
     const int64_t threads = (int64_t)((B + L1_ROWS - 1) / L1_ROWS) * (H1 / 4);
     dim3 grid((unsigned)((threads + 255) / 256), Z);
     if (in == OBS)
@@ -846,6 +896,7 @@ int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float 
     g.M = B, g.N = H2, g.K = H1, g.lda = H1, g.ldb = H1, g.ldc = H2, g.ldaux = 0;
     g.a_z = (int64_t)B * H1, g.b_z = z_stride, g.c_z = (int64_t)B * H2, g.aux_z = z_stride;
     g.splits = 1, g.k_per_split = H1, g.c_split = 0;
+    g.split_buf = split_buf, g.split_cap = split_cap;
     return launch_gemm<G_FWD>(g, Z, tensor, st, "td3_gemm_kernel<fwd>");
 }
 
@@ -857,6 +908,7 @@ int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float
     g.M = B, g.N = H1, g.K = H2, g.lda = H2, g.ldb = H1, g.ldc = H1, g.ldaux = H1;
     g.a_z = (int64_t)B * H2, g.b_z = z_stride, g.c_z = (int64_t)B * H1, g.aux_z = (int64_t)B * H1;
     g.splits = 1, g.k_per_split = H2, g.c_split = 0;
+    g.split_buf = w.slabs, g.split_cap = w.slab_cap;
     if (int rc = launch_gemm<G_DGRAD>(g, Z, w.tensor, st, "td3_gemm_kernel<dgrad>")) return rc;
     if (!want_weight_grads) return 0;
     // dW2 = dz2^T @ h1, split over the batch into slabs, then summed in order
@@ -944,15 +996,15 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
 
     if (phases & CSTR_TD3_CRITIC_GRAD) {
         // ---- target (td3.py:166-175) ----
-        if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor_t, 0, 1, w.a_h1, w.a_h2, w.tensor, st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor_t, 0, 1, w.a_h1, w.a_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
         td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor_t.w3, actor_t.b3, 1, (const float2 *)noise, cfg->target_policy_noise,
                                                  cfg->target_noise_clip, cfg->seed, (uint32_t)n_updates, dev_sc, (float2 *)w.next_act);
         if (int rc = check_launch("td3_actor_head_kernel")) return rc;
-        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
         td3_target_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.t_h2, (int64_t)B * H2, critic_t.w3, critic_t.b3, cz, rewards, dones, cfg->gamma, w.target);
         if (int rc = check_launch("td3_target_head_kernel")) return rc;
         // ---- current Q, loss, backward (td3.py:178-186) ----
-        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st, w.slabs, w.slab_cap)) return rc;
         td3_critic_head_kernel<false><<<dim3(rb, 2), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, 2.f / (float)B, w.dq,
                                                                   w.dz2, w.loss_partial);
         if (int rc = check_launch("td3_critic_head_kernel")) return rc;
@@ -978,10 +1030,10 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
     }
     if (policy_step && (phases & CSTR_TD3_ACTOR_GRAD)) {
         // ---- actor loss = -Q1(s, pi(s)).mean() and its backward (td3.py:189-196) ----
-        if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
         td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, 0, nullptr, 0.f, 0.f, 0, 0, nullptr, (float2 *)w.a_pi);
         if (int rc = check_launch("td3_actor_head_kernel<pi>")) return rc;
-        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 1, w.h1[0], w.h2[0], w.tensor, st)) return rc;
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 1, w.h1[0], w.h2[0], w.tensor, st, w.slabs, w.slab_cap)) return rc;
         td3_critic_head_kernel<true><<<dim3(rb, 1), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, nullptr, 0.f, w.dq, w.dz2,
                                                                  w.loss_partial);
         if (int rc = check_launch("td3_critic_head_kernel<policy>")) return rc;
@@ -1076,7 +1128,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
     const float step_size = (float)((double)cfg->lr / bc1), bc2_sqrt = (float)sqrt(bc2);
 
     // ---- actions_pi, log_prob of the current actor (sac.py:222-223) and the entropy-coefficient step (:226-243) ----
-    if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st)) return rc;
+    if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
     sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, (const float2 *)eps_pi, cfg->seed, (uint32_t)n_updates, 0u, (float2 *)w.a_pi,
                                              w.logp, (float2 *)w.std_eps, (float2 *)w.raw_log_std, w.lp_partial);
     if (int rc = check_launch("sac_actor_head_kernel")) return rc;
@@ -1084,16 +1136,16 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
                                           cfg->beta2, cfg->eps, step_size, bc2_sqrt, w.scalars, stt->losses);
     if (int rc = check_launch("sac_ent_coef_kernel")) return rc;
     // ---- target (sac.py:245-254): next action from the CURRENT actor (scratch: the dz slabs are free here) ----
-    if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor, 0, 1, w.dz1, w.dz2, w.tensor, st)) return rc;
+    if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor, 0, 1, w.dz1, w.dz2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
     sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.dz2, actor.w3, actor.b3, (const float2 *)eps_next, cfg->seed, (uint32_t)n_updates, 1u,
                                              (float2 *)w.next_act, w.next_logp, nullptr, nullptr, nullptr);
     if (int rc = check_launch("sac_actor_head_kernel<next>")) return rc;
-    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st)) return rc;
+    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
     sac_target_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.t_h2, (int64_t)B * H2, critic_t.w3, critic_t.b3, cz, rewards, dones, w.next_logp, w.scalars,
                                               cfg->gamma, w.target);
     if (int rc = check_launch("sac_target_head_kernel")) return rc;
     // ---- critics (sac.py:256-268): loss = 0.5 * sum_i mse ----
-    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st)) return rc;
+    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st, w.slabs, w.slab_cap)) return rc;
     td3_critic_head_kernel<false><<<dim3(rb, 2), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, 1.f / (float)B, w.dq,
                                                               w.dz2, w.loss_partial);
     if (int rc = check_launch("td3_critic_head_kernel<sac>")) return rc;
@@ -1115,7 +1167,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         if (int rc = check_launch("td3_apply_kernel<sac critic>")) return rc;
     }
     // ---- actor (sac.py:270-281): (ent_coef * log_prob - min_i Q_i(s, a_pi)).mean() with the updated critics ----
-    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st)) return rc;
+    if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st, w.slabs, w.slab_cap)) return rc;
     sac_qmin_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.logp, w.scalars, w.dz2, w.loss_partial);
     if (int rc = check_launch("sac_qmin_head_kernel")) return rc;
     if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, false, st)) return rc;
