@@ -541,7 +541,8 @@ def td3_update_extras(pkg, torch, device, peaks_tflops) -> dict:
         sac.params[:sac._ent_offset].normal_(0, 0.05)
         sac.targets.copy_(sac.params)
         ms = R.timed(lambda: sac.update(buf.sample(B)), 200)
-        out[f"sac_batch_{B}"] = {"ms_per_update": ms, "updates_per_s": 1e3 / ms, "samples_per_s": B * 1e3 / ms}
+        out[f"sac_batch_{B}"] = {"ms_per_update": ms, "updates_per_s": 1e3 / ms, "samples_per_s": B * 1e3 / ms,
+                                 "cuda_graph_ms_per_update": R.timed(lambda: sac.train(2, buf, B, graph=True), 100) / 2}
         del sac
     return out
 

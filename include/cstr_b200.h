@@ -243,7 +243,8 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *state, con
  * rows 2-3 log_std); critics as for TD3.  Flat block = cstr_sac_param_count(h1, h2) floats = [actor | critic0 | critic1 |
  * log_ent_coef(+3 pad)]; cstr_sac_layout writes the 18 tensor offsets, the log_ent_coef offset and the block size.
  * The state struct is cstr_td3_state (targets: only the critic ranges are used; losses: 8 floats = critic, actor,
- * ent_coef_loss, ent_coef as {sum, count} pairs; counters must be NULL).  eps_pi / eps_next: (batch,2) standard-normal draws
+ * ent_coef_loss, ent_coef as {sum, count} pairs; counters as for TD3 — critic_step is the shared Adam step, the target
+ * sync decision uses the by-value n_updates).  eps_pi / eps_next: (batch,2) standard-normal draws
  * of the two rsample() calls, or NULL = Philox (key seed, counter (row, n_updates), stream 5, call 0 / 1).
  * n_updates and adam_step are the values AFTER this update (1-based; all three optimisers share the step count).       */
 typedef struct cstr_sac_config {

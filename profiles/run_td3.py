@@ -113,7 +113,10 @@ def main():
         eng = pkg.FusedSACUpdate([256, 256], B, device=dev, gemm=args.gemm)
         eng.params[:eng._ent_offset].normal_(0, 0.05)
         eng.targets.copy_(eng.params)
-        ms = timed(lambda: eng.update(buf.sample(B)), 4 if args.once else args.steps)
+        if args.graph:
+            ms = timed(lambda: eng.train(2, buf, B, graph=True), args.steps // 2) / 2
+        else:
+            ms = timed(lambda: eng.update(buf.sample(B)), 4 if args.once else args.steps)
         out[f"sac_batch_{B}"] = {"fused_ms_per_update": ms, "fused_updates_per_s": 1e3 / ms}
     print(json.dumps(out))
 

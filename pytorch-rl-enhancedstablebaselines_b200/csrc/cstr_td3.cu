@@ -409,7 +409,8 @@ constexpr float SAC_LOG_STD_MIN = -20.f, SAC_LOG_STD_MAX = 2.f, SAC_SQUASH_EPS =
 // call 0 = actions_pi (keeps what the backward needs), call 1 = next_actions (no grad).
 __global__ void __launch_bounds__(256)
 sac_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *__restrict__ W3, const float *__restrict__ b3, const float2 *__restrict__ eps_in,
-                      uint64_t seed, uint32_t update_index, uint32_t call, float2 *__restrict__ act_out, float *__restrict__ logp_out,
+                      uint64_t seed, uint32_t update_index, const float *__restrict__ dev_scalars, uint32_t call, float2 *__restrict__ act_out,
+                      float *__restrict__ logp_out,
                       float2 *__restrict__ std_eps_out, float2 *__restrict__ raw_out, float *__restrict__ lp_partial) {
     __shared__ float sl[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x * 8 + warp;
@@ -423,7 +424,8 @@ sac_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *
             float2 e;
             if (eps_in) e = eps_in[b];
             else {
-                const uint4 r = philox_env(seed, (uint64_t)b, update_index, STREAM_TD3, call);
+                const uint32_t ui = dev_scalars ? __float_as_uint(dev_scalars[4]) : update_index;
+                const uint4 r = philox_env(seed, (uint64_t)b, ui, STREAM_TD3, call);
                 const float u1 = fmaf(u24(r.x), 1.0f, 5.9604644775390625e-08f), u2 = u24(r.y);
                 const float rad = sqrtf(-2.0f * logf(u1));
                 float sn, cs;
@@ -461,8 +463,8 @@ sac_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *
 // loss = -(log_ent_coef * (log_prob + target_entropy)).mean(), one Adam step on the scalar            sac.py:226-243
 // scalars[5] = ent_coef of this update.  losses: [4] += ent_coef_loss, [5] += 1, [6] += ent_coef, [7] += 1.
 __global__ void sac_ent_coef_kernel(int B, int n_partial, const float *__restrict__ lp_partial, float target_entropy, float *__restrict__ log_ent_coef,
-                                    float *__restrict__ m, float *__restrict__ v, float beta1, float beta2, float eps, float step_size, float bc2_sqrt,
-                                    float *__restrict__ scalars, float *__restrict__ losses) {
+                                    float *__restrict__ m, float *__restrict__ v, float beta1, float beta2, float eps, float step_size_arg, float bc2_sqrt_arg,
+                                    int use_dev_scalars, float *__restrict__ scalars, float *__restrict__ losses) {
     __shared__ float sl[256];
     float s = 0.f;
     for (int k = threadIdx.x; k < n_partial; k += 256) s += lp_partial[k];
@@ -473,6 +475,7 @@ __global__ void sac_ent_coef_kernel(int B, int n_partial, const float *__restric
         __syncthreads();
     }
     if (threadIdx.x) return;
+    const float step_size = use_dev_scalars ? scalars[0] : step_size_arg, bc2_sqrt = use_dev_scalars ? scalars[1] : bc2_sqrt_arg;
     const float mean_term = sl[0] / (float)B + target_entropy;  // mean(log_prob + target_entropy)
     const float le = log_ent_coef[0], g = -mean_term;
     scalars[5] = expf(le);
@@ -1127,17 +1130,22 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
     const double bc1 = 1.0 - pow((double)cfg->beta1, (double)adam_step), bc2 = 1.0 - pow((double)cfg->beta2, (double)adam_step);
     const float step_size = (float)((double)cfg->lr / bc1), bc2_sqrt = (float)sqrt(bc2);
 
+    const float *dev_sc = stt->counters ? w.scalars : nullptr;  // graph mode: per-update scalars live on the device (td3_tick_kernel)
+    if (stt->counters) {
+        td3_tick_kernel<<<1, 32, 0, st>>>(stt->counters, w.scalars, 1, (double)cfg->lr, (double)cfg->beta1, (double)cfg->beta2);
+        if (int rc = check_launch("td3_tick_kernel")) return rc;
+    }
     // ---- actions_pi, log_prob of the current actor (sac.py:222-223) and the entropy-coefficient step (:226-243) ----
     if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
-    sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, (const float2 *)eps_pi, cfg->seed, (uint32_t)n_updates, 0u, (float2 *)w.a_pi,
+    sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, (const float2 *)eps_pi, cfg->seed, (uint32_t)n_updates, dev_sc, 0u, (float2 *)w.a_pi,
                                              w.logp, (float2 *)w.std_eps, (float2 *)w.raw_log_std, w.lp_partial);
     if (int rc = check_launch("sac_actor_head_kernel")) return rc;
     sac_ent_coef_kernel<<<1, 256, 0, st>>>(B, rb, w.lp_partial, cfg->target_entropy, stt->params + ent, stt->adam_m + ent, stt->adam_v + ent, cfg->beta1,
-                                          cfg->beta2, cfg->eps, step_size, bc2_sqrt, w.scalars, stt->losses);
+                                          cfg->beta2, cfg->eps, step_size, bc2_sqrt, dev_sc ? 1 : 0, w.scalars, stt->losses);
     if (int rc = check_launch("sac_ent_coef_kernel")) return rc;
     // ---- target (sac.py:245-254): next action from the CURRENT actor (scratch: the dz slabs are free here) ----
     if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor, 0, 1, w.dz1, w.dz2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
-    sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.dz2, actor.w3, actor.b3, (const float2 *)eps_next, cfg->seed, (uint32_t)n_updates, 1u,
+    sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.dz2, actor.w3, actor.b3, (const float2 *)eps_next, cfg->seed, (uint32_t)n_updates, dev_sc, 1u,
                                              (float2 *)w.next_act, w.next_logp, nullptr, nullptr, nullptr);
     if (int rc = check_launch("sac_actor_head_kernel<next>")) return rc;
     if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
@@ -1162,6 +1170,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
         a.adam_lo = T.critic_off[0], a.adam_hi = T.total, a.polyak_lo = a.polyak_hi = 0;
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = step_size, a.bc2_sqrt = bc2_sqrt, a.tau = cfg->tau;
+        a.dev_scalars = dev_sc;
         a.loss_partial = w.loss_partial, a.n_loss_partial = 2 * rb, a.loss_scale = 0.5f / (float)B, a.loss_acc = stt->losses;
         td3_apply_kernel<<<(unsigned)((a.adam_hi - a.adam_lo + 255) / 256), 256, 0, st>>>(a);
         if (int rc = check_launch("td3_apply_kernel<sac critic>")) return rc;
@@ -1190,6 +1199,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         const bool sync_targets = ((n_updates - 1) % cfg->target_update_interval) == 0;  // gradient_step % interval == 0 (:284)
         a.polyak_lo = sync_targets ? T.critic_off[0] : 0, a.polyak_hi = sync_targets ? T.total : 0;
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = step_size, a.bc2_sqrt = bc2_sqrt, a.tau = cfg->tau;
+        a.dev_scalars = dev_sc;
         a.loss_partial = w.loss_partial, a.n_loss_partial = rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 2 : nullptr;
         td3_apply_kernel<<<(unsigned)((T.total + 255) / 256), 256, 0, st>>>(a);
         if (int rc = check_launch("td3_apply_kernel<sac actor+polyak>")) return rc;

@@ -201,15 +201,13 @@ class FusedTD3Update:
         f32 = dict(dtype=torch.float32, device=self.device)
         out = (torch.empty((batch_size, 4), **f32), torch.empty((batch_size, 2), **f32), torch.empty((batch_size, 4), **f32),
                torch.empty((batch_size, 1), **f32), torch.empty((batch_size, 1), **f32))
-        cfg, st = self._config(batch_size), self._state(counters=True)
+        st = self._state(counters=True)
         draw = self._counters[3:4]
 
         def cycle():
-            for k in range(1, self.policy_delay + 1):  # by-value counters only choose the launch structure: update k of the cycle
+            for k in range(1, self._cycle_len() + 1):  # by-value counters only choose the launch structure: update k of the cycle
                 buffer.sample_into(out, draw, env=env)
-                rc = self._libc.cstr_td3_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
-                                                _lib.ptr(out[4]), None, k, 1, 1, _lib.TD3_ALL, self._stream())
-                _lib.check(rc, "cstr_td3_update (graph capture)")
+                self._graph_launch(batch_size, st, out, k)
 
         snapshot = [t.clone() for t in (self.params, self.targets, self.adam_m, self.adam_v, self.loss_sums, self._counters)]
         side = torch.cuda.Stream(device=self.device)
@@ -226,24 +224,33 @@ class FusedTD3Update:
         self._graph_key = (id(buffer), batch_size, buffer.size(), buffer.n_envs, id(env), self.policy_delay, self.learning_rate, self.params.data_ptr(),
                            self._workspace.data_ptr())
 
+    def _cycle_len(self) -> int:
+        return self.policy_delay
+
+    def _graph_launch(self, batch_size: int, st, out, k: int) -> None:
+        cfg = self._config(batch_size)
+        rc = self._libc.cstr_td3_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(out[4]),
+                                        None, k, 1, 1, _lib.TD3_ALL, self._stream())
+        _lib.check(rc, "cstr_td3_update (graph capture)")
+
     def _train_graph(self, gradient_steps: int, buffer, batch_size: int, env) -> int:
         """Replays whole cycles while the update count is cycle-aligned; returns the number of gradient steps done."""
-        if self.n_updates % self.policy_delay or gradient_steps < self.policy_delay:
+        if self.n_updates % self._cycle_len() or gradient_steps < self._cycle_len():
             return 0
         key = (id(buffer), batch_size, buffer.size(), buffer.n_envs, id(env), self.policy_delay, self.learning_rate, self.params.data_ptr(),
                self._workspace.data_ptr() if self._workspace is not None else 0)
         if self._graph is None or key != self._graph_key:
             self._capture(buffer, batch_size, env)
-        cycles = gradient_steps // self.policy_delay
+        cycles = gradient_steps // self._cycle_len()
         self._counters.copy_(self._torch.tensor([self.n_updates, self.critic_step, self.actor_step, buffer._draw], dtype=self._torch.int64),
                              non_blocking=True)
         with self._torch.cuda.device(self.device):
             for _ in range(cycles):
                 self._graph.replay()
-        done = cycles * self.policy_delay
+        done = cycles * self._cycle_len()
         self.n_updates += done
         self.critic_step += done
-        self.actor_step += cycles
+        self.actor_step += done // self.policy_delay
         buffer._draw += done
         self.launches += cycles * (26 * (self.policy_delay - 1) + 50 + self.policy_delay)
         return done
@@ -442,9 +449,19 @@ class FusedSACUpdate(FusedTD3Update):
         _lib.check(rc, "cstr_sac_update")
         self.launches += 56
 
-    def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, **_unused) -> None:  # type: ignore[override]
+    def _graph_launch(self, batch_size: int, st, out, k: int) -> None:
+        cfg = self._sac_config(batch_size)
+        rc = self._libc.cstr_sac_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(out[4]),
+                                        None, None, 1, 1, self._stream())
+        _lib.check(rc, "cstr_sac_update (graph capture)")
+
+    def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, graph: bool = False, **_unused) -> None:  # type: ignore[override]
+        """``graph=True`` (Philox-index buffer, full ring, target_update_interval 1): every update replays one captured CUDA graph."""
         bs = int(batch_size or self._batch)
-        for _ in range(gradient_steps):
+        done = 0
+        if graph and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1:
+            done = self._train_graph(gradient_steps, buffer, bs, env)
+        for _ in range(gradient_steps - done):
             self.update(buffer.sample(bs, env=env))
 
     def pop_losses(self):
@@ -476,7 +493,7 @@ def bind_sac_class(sac_base: type) -> type:
                 self._fused = eng
             eng = self._fused
             eng.learning_rate = float(self.lr_schedule(self._current_progress_remaining))
-            eng.train(gradient_steps, self.replay_buffer, batch_size, env=self._vec_normalize_env)
+            eng.train(gradient_steps, self.replay_buffer, batch_size, env=self._vec_normalize_env, graph=bool(getattr(self.replay_buffer, "full", False)))
             self._n_updates += gradient_steps
             critic_loss, actor_loss, ent_loss, ent_coef = eng.pop_losses()
             self.logger.record("train/n_updates", self._n_updates, exclude="tensorboard")

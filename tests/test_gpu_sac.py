@@ -110,3 +110,28 @@ def test_tensor_gemm_mode_tracks_fp32(pkg):
     ga, gb = a.grads.cpu().numpy(), b.grads.cpu().numpy()
     assert np.linalg.norm(ga - gb) <= 2e-3 * np.linalg.norm(ga)
     assert float((a.params - b.params).abs().max().item()) <= 2.1 * 3e-4
+
+
+def test_cuda_graph_replay_equals_launch_by_launch(pkg):
+    rng = np.random.default_rng(8)
+    nets = U.random_sac_nets(rng, 256, 256)
+    n_envs = 512
+    buf = pkg.GpuReplayBuffer(32 * n_envs, n_envs=n_envs, index_mode="philox", seed=5)
+    buf.records.uniform_(-1, 1)
+    buf.records[..., 11:13] = 0
+    buf.pos, buf.full = 0, True
+
+    def run(graph):
+        buf._draw = 0
+        eng = pkg.FusedSACUpdate([256, 256], 256, seed=2)
+        eng.load_nets(nets)
+        for steps in (4, 3):
+            eng.train(steps, buf, 256, graph=graph)
+        return eng
+
+    a, b = run(False), run(True)
+    assert a.n_updates == b.n_updates == 7 and b._graph is not None and buf._draw == 7
+    np.testing.assert_allclose(b.params.cpu().numpy(), a.params.cpu().numpy(), rtol=0, atol=3e-7)
+    np.testing.assert_allclose(b.targets.cpu().numpy(), a.targets.cpu().numpy(), rtol=0, atol=3e-7)
+    for x, y in zip(a.pop_losses(), b.pop_losses()):
+        assert y == pytest.approx(x, rel=1e-5)
