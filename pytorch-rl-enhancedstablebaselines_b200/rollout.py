@@ -90,6 +90,14 @@ class ActorWeights:
         if self.packed_bf16 is not None:
             self.pack_bf16()
 
+    def refresh_from_tensors(self, tensors) -> None:
+        """Same, from six tensors ``W1, b1, W2, b2, W3, b3`` — e.g. ``FusedTD3Update.views("params")["actor"]`` (for SAC the head is
+        already the stacked [mu; log_std] matrix)."""
+        for dst, src in zip((self.W1, self.b1, self.W2, self.b2, self.W3, self.b3), tensors):
+            dst.copy_(src.detach(), non_blocking=True)
+        if self.packed_bf16 is not None:
+            self.pack_bf16()
+
     def pack_bf16(self):
         """Build the bf16 UMMA image of W2 for the tensor-core path (cstr_actor_pack_bf16)."""
         torch = _lib.require_cuda()
