@@ -55,7 +55,12 @@ def _worker(rank, world, port, ret):
         torch.nn.functional.mse_loss(ref2(x), y).backward()
         err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(net.parameters(), ref2.parameters()))
         total = d.global_sum(float(rank + 1))
-        ret[rank] = (same, err, bucket.numel(), total)
+        # allreduce_flat: the in-place mean of an already flat gradient range (the hook of FusedTD3Update.update)
+        flat = torch.arange(8, dtype=torch.float32) * (rank + 1)
+        view = flat[2:6]
+        d.allreduce_flat(view)
+        flat_ok = bool(torch.equal(flat[2:6], torch.arange(2, 6, dtype=torch.float32) * 1.5)) and float(flat[0]) == 0.0 and float(flat[7]) == 7.0 * (rank + 1)
+        ret[rank] = (same, err, bucket.numel(), total, flat_ok)
     finally:
         dist.destroy_process_group()
 
@@ -68,7 +73,8 @@ def test_gradient_allreduce_world_size_2():
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     n_params = 4 * 400 + 400 + 400 * 300 + 300 + 300 * 2 + 2
     for rank in (0, 1):
-        same, err, numel, total = ret[rank]
+        same, err, numel, total, flat_ok = ret[rank]
+        assert flat_ok, "allreduce_flat must average the given range in place and leave the rest untouched"
         assert same, "broadcast_parameters did not synchronise the ranks"
         assert err < 1e-6, err  # averaged shard gradients == full-batch gradients
         assert numel == n_params == 122_902  # the TD3 actor: one flat bucket
