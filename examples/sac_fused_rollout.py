@@ -3,7 +3,8 @@
 and the replay write (``FusedRollout``, actor kind "gaussian", tcgen05 hidden layer), Philox replay sampling, and the SAC gradient
 step (``FusedSACUpdate`` = cstr_sac_update: entropy coefficient, soft target, critics, actor, polyak) — no torch autograd anywhere.
 
-    python examples/sac_fused_rollout.py --n-envs 131072 --iters 200
+    python examples/sac_fused_rollout.py                      # 16,384 reactors, 30 episodes, 48,000 updates: learns in ~10 s
+    python examples/sac_fused_rollout.py --n-envs 131072 --iters 200 --steps-per-iter 8 --updates-per-iter 8 --batch 4096   # throughput shape
 """
 from __future__ import annotations
 
@@ -23,11 +24,11 @@ import torch
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n-envs", type=int, default=131072)
-    ap.add_argument("--iters", type=int, default=200)
-    ap.add_argument("--steps-per-iter", type=int, default=8)
-    ap.add_argument("--updates-per-iter", type=int, default=8)
-    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--n-envs", type=int, default=16384)
+    ap.add_argument("--iters", type=int, default=3000)
+    ap.add_argument("--steps-per-iter", type=int, default=4)
+    ap.add_argument("--updates-per-iter", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--rows", type=int, default=64)
     ap.add_argument("--actor-mode", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--seed", type=int, default=0)
@@ -57,16 +58,18 @@ def main():
     log = []
     torch.cuda.synchronize()
     t0 = time.time()
+    window = max(1, 400 // args.steps_per_iter)  # iterations per 400-step episode: report whole episodes
     for it in range(args.iters):
-        rsum.zero_()
         roll.collect(args.steps_per_iter, reward_sum=rsum)
         eng.train(args.updates_per_iter, buf, args.batch, graph=True)  # one CUDA-graph replay per update once the ring is full
         weights.refresh_from_tensors(actor_views)  # device-to-device; repacks the bf16 UMMA image of W2
-        if it % 20 == 0 or it == args.iters - 1:
-            mean_r = float(rsum.item()) / (n * args.steps_per_iter)
+        if (it + 1) % window == 0 or it == args.iters - 1:
+            mean_r = float(rsum.item()) / (n * args.steps_per_iter * ((it % window) + 1))
+            rsum.zero_()
             critic_loss, actor_loss, _, ent_coef = eng.pop_losses()
             log.append(mean_r)
-            print(f"iter {it:3d}  mean reward/step {mean_r:8.4f}  critic loss {critic_loss:.4f}  actor loss {actor_loss:.4f}  ent_coef {ent_coef:.4f}", flush=True)
+            print(f"episode {len(log):3d} (iter {it:4d})  mean reward/step {mean_r:8.4f}  episode return {400 * mean_r:8.1f}  critic loss {critic_loss:.4f}  "
+                  f"actor loss {actor_loss:.4f}  ent_coef {ent_coef:.4f}", flush=True)
     torch.cuda.synchronize()
     dt = time.time() - t0
     transitions = args.iters * args.steps_per_iter * n
