@@ -856,7 +856,7 @@ int launch_gemm(const GemmArgs &g, int Z, bool tensor, cudaStream_t st, const ch
     }
     if constexpr (MODE != G_WGRAD) if (g.split_buf) {  // small batch: too few tiles for 148 SMs and a 25-iteration serial K loop -> split K
         const int64_t tiles = (int64_t)((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM) * Z, sms = sm_count();
-        int s = (int)(sms / tiles);
+        int s = (int)(2 * sms / tiles);  // two CTAs are resident per SM
         const int64_t per = (int64_t)Z * g.M * g.N;
         if (s > 8) s = 8;
         if (s > g.K / (2 * BK)) s = g.K / (2 * BK);
