@@ -58,7 +58,7 @@ def _random_batches(rng, K, B):
             for _ in range(K)]
 
 
-@pytest.mark.parametrize("arch,B,K", [([400, 300], 256, 4), ([36, 20], 100, 4), ([400, 300], 1000, 2), ([128, 256], 7, 3), ([512, 512], 300, 2)])
+@pytest.mark.parametrize("arch,B,K", [([400, 300], 256, 4), ([36, 20], 100, 4), ([400, 300], 1000, 2), ([128, 256], 7, 3), ([512, 512], 300, 2), ([1024, 768], 64, 2)])
 def test_vs_oracle(pkg, arch, B, K):
     rng = np.random.default_rng(B)
     nets = U.random_nets(rng, *arch)
@@ -259,8 +259,8 @@ def test_training_dynamics_track_eager_torch(pkg, gemm):
     assert 0 < critic_loss < 1.0 and actor_loss is not None
 
 
-@pytest.mark.parametrize("gemm", ["fp32", "tensor"])
-def test_cuda_graph_replay_equals_launch_by_launch(pkg, gemm):
+@pytest.mark.parametrize("gemm,delay", [("fp32", 2), ("tensor", 2), ("fp32", 3), ("fp32", 1)])
+def test_cuda_graph_replay_equals_launch_by_launch(pkg, gemm, delay):
     """train(graph=True) replays one captured cycle of policy_delay x (Philox sample + update) with every per-update scalar
     (sample draw counter, smoothing-noise counter, Adam bias corrections) read from device memory: the weights must equal the
     launch-by-launch path (bias corrections from CUDA's double pow instead of the host's: allow 1 ulp of the step size)."""
@@ -274,14 +274,14 @@ def test_cuda_graph_replay_equals_launch_by_launch(pkg, gemm):
 
     def run(graph, steps_list):
         buf._draw = 0
-        eng = _engine(pkg, nets, [400, 300], 256, seed=9, gemm=gemm)
+        eng = _engine(pkg, nets, [400, 300], 256, seed=9, gemm=gemm, policy_delay=delay)
         for s in steps_list:
             eng.train(s, buf, 256, graph=graph)
         return eng
 
     a = run(False, [6, 5])
-    b = run(True, [6, 5])  # 3 cycles, then 2 cycles + 1 launch-by-launch step (odd remainder)
-    assert a.n_updates == b.n_updates == 11 and a.critic_step == b.critic_step == 11 and a.actor_step == b.actor_step == 5
+    b = run(True, [6, 5])  # whole cycles of `delay` updates replay from the graph, the remainder runs launch by launch
+    assert a.n_updates == b.n_updates == 11 and a.critic_step == b.critic_step == 11 and a.actor_step == b.actor_step == 11 // delay
     assert b._graph is not None and buf._draw == 11
     np.testing.assert_allclose(b.params.cpu().numpy(), a.params.cpu().numpy(), rtol=0, atol=3e-7)
     np.testing.assert_allclose(b.targets.cpu().numpy(), a.targets.cpu().numpy(), rtol=0, atol=3e-7)
