@@ -97,3 +97,29 @@ def test_affine_helpers_match_oracle(pkg):
     x = np.random.default_rng(0).uniform(-1, 1, (100, 4)).astype(np.float32)
     assert np.array_equal(env_mod._denormalize_state(x), O.denormalize_state(x))
     assert np.array_equal(env_mod._normalize_state(env_mod._denormalize_state(x)), O.normalize_state(O.denormalize_state(x)))
+
+
+def test_header_is_plain_c_and_struct_sizes_match_the_binding(pkg, tmp_path):
+    """include/cstr_b200.h must be consumable from C (the ABI is `extern "C"`, plain pointers and sizes): compile it as strict C99
+    and compare sizeof() of every struct with the ctypes mirror in _lib.py."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"cstr_env_params": pkg._lib.EnvParams, "cstr_actor_f32": pkg._lib.ActorF32, "cstr_episode_stats": pkg._lib.EpisodeStatsStruct,
+               "cstr_norm_params": pkg._lib.NormParams, "cstr_td3_config": pkg._lib.Td3Config, "cstr_td3_state": pkg._lib.Td3State,
+               "cstr_sac_config": pkg._lib.SacConfig}
+    src = tmp_path / "abi.c"
+    body = "".join(f'    printf("{name} %zu\\n", sizeof({name}));\n' for name in structs)
+    src.write_text('#include <stdio.h>\n#include "cstr_b200.h"\nint main(void) {\n' + body + "    return 0;\n}\n")
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    sizes = dict(line.split() for line in out.splitlines())
+    for name, cls in structs.items():
+        assert int(sizes[name]) == ctypes.sizeof(cls), name
