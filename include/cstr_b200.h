@@ -205,6 +205,7 @@ typedef struct cstr_td3_config {
 } cstr_td3_config;
 #define CSTR_TD3_GEMM_FP32 0
 #define CSTR_TD3_GEMM_TENSOR 1
+#define CSTR_TD3_GEMM_BF16 2 /* tcgen05 with plain bf16 operands (fp32 accumulate): REDUCED precision, opt-in throughput mode */
 
 typedef struct cstr_td3_state {
     float *params, *targets, *grads, *adam_m, *adam_v; /* device, cstr_td3_param_count floats each, 16-byte aligned */

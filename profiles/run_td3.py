@@ -79,7 +79,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--once", action="store_true", help="few launches only (for ncu)")
     ap.add_argument("--no-torch", action="store_true")
-    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor"])
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor", "bf16"])
     ap.add_argument("--sac", action="store_true", help="time the SAC gradient step (cstr_sac_update, [256,256] nets) instead")
     ap.add_argument("--graph", action="store_true", help="time train(graph=True): one CUDA-graph launch per policy_delay updates")
     args = ap.parse_args()

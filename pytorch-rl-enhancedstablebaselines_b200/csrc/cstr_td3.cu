@@ -769,14 +769,14 @@ struct Workspace {  // carved out of the caller's workspace buffer (floats)
     float *logp, *next_logp, *std_eps, *raw_log_std, *dpre4, *lp_partial;  // SAC
     int n_row_blocks;
     int64_t slab_cap;  // floats in `slabs`
-    bool tensor;  // hidden-layer GEMMs on tcgen05 (cfg->gemm_mode)
+    int tensor;  // cfg->gemm_mode: 0 FFMA, 1 tcgen05 bf16x3 split, 2 tcgen05 plain bf16
     int64_t floats;
 };
 
 constexpr int MAX_SPLITS = 16;
 
 // split-K factor of the dW2 GEMM: minimise (CTA rounds per SM) x (k-iterations per CTA) over the 148 SMs
-int choose_splits(int B, int H1, int H2, int Z, bool tc) {
+int choose_splits(int B, int H1, int H2, int Z, int tc) {
     const int64_t tiles = tc ? (int64_t)((H2 + TC_BM - 1) / TC_BM) * tc_tile(H1).n_tiles * Z : (int64_t)((H2 + BM - 1) / BM) * ((H1 + BN - 1) / BN) * Z;
     const int sms = sm_count();
     int best = 1;
@@ -813,7 +813,7 @@ Workspace carve(float *base, int B, int H1, int H2) {
     w.scalars = take(8);
     w.logp = take(B), w.next_logp = take(B), w.std_eps = take(2 * (int64_t)B), w.raw_log_std = take(2 * (int64_t)B), w.dpre4 = take(4 * (int64_t)B);
     w.lp_partial = take(w.n_row_blocks);
-    w.tensor = false;
+    w.tensor = 0;
     w.floats = o;
     return w;
 }
@@ -824,7 +824,7 @@ int check_cfg(const cstr_td3_config *c) {
         return fail_arg(CSTR_EINVAL, "td3: hidden sizes must be multiples of 4 in [4, 4096]");
     if (c->batch < 1 || c->batch > (1 << 22)) return fail_arg(CSTR_EINVAL, "td3: batch must be in [1, 4194304]");
     if (c->policy_delay < 1) return fail_arg(CSTR_EINVAL, "td3: policy_delay must be >= 1");
-    if (c->gemm_mode != CSTR_TD3_GEMM_FP32 && c->gemm_mode != CSTR_TD3_GEMM_TENSOR) return fail_arg(CSTR_EINVAL, "td3: gemm_mode must be 0 (fp32 FFMA) or 1 (bf16x3 tensor)");
+    if (c->gemm_mode < CSTR_TD3_GEMM_FP32 || c->gemm_mode > CSTR_TD3_GEMM_BF16) return fail_arg(CSTR_EINVAL, "td3: gemm_mode must be 0 (fp32 FFMA), 1 (bf16x3 tensor) or 2 (bf16 tensor)");
     return 0;
 }
 
@@ -841,17 +841,20 @@ int launch_skinny(SkinnyArgs s, int Z, float *part, cudaStream_t st, const char 
 }
 
 template <int MODE>
-int launch_gemm(const GemmArgs &g, int Z, bool tensor, cudaStream_t st, const char *what) {
+int launch_gemm(const GemmArgs &g, int Z, int tensor, cudaStream_t st, const char *what) {  // tensor: 0 FFMA, 1 bf16x3 split, 2 plain bf16
     if (tensor) {
         const TcTile t = tc_tile(g.N);
         static bool attr_set[3] = {false, false, false};
         if (!attr_set[MODE]) {
-            if (int rc = check_cuda(cudaFuncSetAttribute(td3_gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "td3_gemm_tc smem attr"))
+            if (int rc = check_cuda(cudaFuncSetAttribute(td3_gemm_tc_kernel<MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "td3_gemm_tc smem attr"))
+                return rc;
+            if (int rc = check_cuda(cudaFuncSetAttribute(td3_gemm_tc_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "td3_gemm_tc smem attr"))
                 return rc;
             attr_set[MODE] = true;
         }
         dim3 grid(t.n_tiles, (g.M + TC_BM - 1) / TC_BM, Z * g.splits);
-        td3_gemm_tc_kernel<MODE><<<grid, TC_GEMM_THREADS, t.smem_bytes, st>>>(g, t.n_tile, t.tmem_cols);
+        if (tensor == CSTR_TD3_GEMM_BF16) td3_gemm_tc_kernel<MODE, 1><<<grid, TC_GEMM_THREADS, t.smem_bytes, st>>>(g, t.n_tile, t.tmem_cols);
+        else td3_gemm_tc_kernel<MODE, 3><<<grid, TC_GEMM_THREADS, t.smem_bytes, st>>>(g, t.n_tile, t.tmem_cols);
         return check_launch(what);
     }
     if constexpr (MODE != G_WGRAD) if (g.split_buf) {  // small batch: too few tiles for 148 SMs and a 25-iteration serial K loop -> split K
@@ -886,7 +889,7 @@ Net net_at(float *base, int64_t off, const NetLayout &L) { return Net{base + off
 
 // h1 = relu(L1(x)), h2 = relu(L2(h1)) for Z nets that are `z_stride` floats apart
 int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float *act, const Net &n, int64_t z_stride, int Z, float *h1, float *h2,
-                   bool tensor, cudaStream_t st, float *split_buf = nullptr, int64_t split_cap = 0) {
+                   int tensor, cudaStream_t st, float *split_buf = nullptr, int64_t split_cap = 0) {
     const int64_t threads = (int64_t)((B + L1_ROWS - 1) / L1_ROWS) * (H1 / 4);
     dim3 grid((unsigned)((threads + 255) / 256), Z);
     if (in == OBS)
@@ -980,7 +983,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         return fail_arg(CSTR_EALIGN, "td3_update: 16 B (obs/params/workspace) / 8 B (actions, noise) alignment");
     const int B = cfg->batch, H1 = cfg->h1, H2 = cfg->h2;
     Workspace w = carve(stt->workspace, B, H1, H2);
-    w.tensor = cfg->gemm_mode == CSTR_TD3_GEMM_TENSOR;
+    w.tensor = cfg->gemm_mode;
     if (stt->workspace_bytes < w.floats * (int64_t)sizeof(float)) return fail_arg(CSTR_EINVAL, "td3_update: workspace too small (cstr_td3_workspace_bytes)");
     if (n_updates < 1 || critic_step < 1 || actor_step < 0) return fail_arg(CSTR_EINVAL, "td3_update: counters are 1-based (value after this update)");
     const Td3Layout T = td3_layout(H1, H2);
@@ -1076,7 +1079,7 @@ static int check_sac_cfg(const cstr_sac_config *c) {
         return fail_arg(CSTR_EINVAL, "sac: hidden sizes must be multiples of 4 in [4, 4096]");
     if (c->batch < 1 || c->batch > (1 << 22)) return fail_arg(CSTR_EINVAL, "sac: batch must be in [1, 4194304]");
     if (c->target_update_interval < 1) return fail_arg(CSTR_EINVAL, "sac: target_update_interval must be >= 1");
-    if (c->gemm_mode != CSTR_TD3_GEMM_FP32 && c->gemm_mode != CSTR_TD3_GEMM_TENSOR) return fail_arg(CSTR_EINVAL, "sac: gemm_mode must be 0 or 1");
+    if (c->gemm_mode < CSTR_TD3_GEMM_FP32 || c->gemm_mode > CSTR_TD3_GEMM_BF16) return fail_arg(CSTR_EINVAL, "sac: gemm_mode must be 0, 1 or 2");
     return 0;
 }
 
@@ -1117,7 +1120,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         return fail_arg(CSTR_EALIGN, "sac_update: 16 B (obs/params/workspace) / 8 B (actions, noise) alignment");
     const int B = cfg->batch, H1 = cfg->h1, H2 = cfg->h2;
     Workspace w = carve(stt->workspace, B, H1, H2);
-    w.tensor = cfg->gemm_mode == CSTR_TD3_GEMM_TENSOR;
+    w.tensor = cfg->gemm_mode;
     if (stt->workspace_bytes < w.floats * (int64_t)sizeof(float)) return fail_arg(CSTR_EINVAL, "sac_update: workspace too small (cstr_sac_workspace_bytes)");
     if (n_updates < 1 || adam_step < 1) return fail_arg(CSTR_EINVAL, "sac_update: counters are 1-based (value after this update)");
     const Td3Layout T = td3_layout(H1, H2, 2 * ACT);

@@ -85,7 +85,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // split 8 consecutive-k floats into the three bf16 planes and store one 16-byte core-matrix row per plane.
 // Planes by truncation (x1 = x & 0xffff0000, r = x - x1 exact, ...): three planes still carry 24 mantissa bits, and the split is
 // LOP/FADD/PRMT only (cvt.rn.bf16x2 runs on the quarter-rate conversion pipe and was the producer bottleneck).
+template <int PLANES>
 __device__ __forceinline__ void split_store(const float v[8], uint32_t addr, uint32_t plane_stride) {
+    if constexpr (PLANES == 1) {  // plain bf16 operands (round to nearest): the reduced-precision throughput mode
+        uint32_t q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]) : "memory");
+    } else {
     uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -100,6 +107,7 @@ __device__ __forceinline__ void split_store(const float v[8], uint32_t addr, uin
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + plane_stride), "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2 * plane_stride), "r"(p3[0]), "r"(p3[1]), "r"(p3[2]), "r"(p3[3]) : "memory");
+    }
 }
 
 }  // namespace tc5
@@ -129,7 +137,7 @@ __device__ __forceinline__ void load_chunk(const float *__restrict__ p, int64_t 
     }
 }
 
-template <int MODE>
+template <int MODE, int PLANES = 3>  // PLANES = 3: fp32-grade split; 1: plain bf16 operands
 __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g, int n_tile, int tmem_cols) {
     using namespace tc5;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -208,10 +216,10 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
     };
     auto store_stage = [&](int s, const float (&v)[TC_SLOTS][8]) {
         const uint32_t st = stage0 + (uint32_t)s * stage_bytes;
-        if (live[0]) split_store(v[0], st + off[0], slot0_is_a ? a_plane : b_plane);
+        if (live[0]) split_store<PLANES>(v[0], st + off[0], slot0_is_a ? a_plane : b_plane);
 #pragma unroll
         for (int c = 1; c < TC_SLOTS; ++c)
-            if (live[c]) split_store(v[c], st + off[c], b_plane);
+            if (live[c]) split_store<PLANES>(v[c], st + off[c], b_plane);
     };
 
     // Warp 16 issues the MMAs; warps 0..15 produce.  Handshake per stage: producers arrive on full[s] after their proxy fence,
@@ -234,6 +242,10 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
                 const uint32_t d0 = tmem_base, d1 = TC_NACC == 3 ? tmem_base + (uint32_t)n_tile : d0, d2 = TC_NACC == 3 ? tmem_base + 2u * (uint32_t)n_tile : d0;
                 const uint32_t acc = it > 0;
                 tc_mma_bf16(d0, da[0], db[0], idesc, acc);
+                if (PLANES == 1) {
+                    tc_commit(bars + 8 * s);
+                    continue;
+                }
                 tc_mma_bf16(d1, da[0], db[1], idesc, TC_NACC == 3 ? acc : 1u);
                 tc_mma_bf16(d2, da[1], db[0], idesc, TC_NACC == 3 ? acc : 1u);
                 tc_mma_bf16(d0, da[1], db[1], idesc, 1);

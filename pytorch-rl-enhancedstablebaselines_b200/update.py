@@ -6,7 +6,8 @@
 delayed actor update, polyak — as hand-written float32 CUDA kernels.  No torch autograd, no cuBLAS.
 
 ``gemm="fp32"`` (default) keeps the reference's float32 FMA arithmetic; ``gemm="tensor"`` runs the three hidden-layer GEMM roles on
-tcgen05 with every fp32 operand split into three bf16 planes (fp32-grade accuracy, see csrc/cstr_td3_tc.cuh).
+tcgen05 with every fp32 operand split into three bf16 planes (fp32-grade accuracy, see csrc/cstr_td3_tc.cuh); ``gemm="bf16"`` uses plain bf16
+operands with fp32 accumulation (reduced precision, throughput mode; no per-step parity bar).
 
 ``adopt_policy`` re-points the parameters of the reference's ``TD3Policy`` modules at views of the flat blocks, so
 ``policy.predict``, ``model.save`` and the fused rollout keep seeing the live weights without copies.
@@ -22,6 +23,7 @@ import numpy as np
 from . import _lib
 
 NET_NAMES = ("actor", "critic0", "critic1")
+_GEMM_MODES = {"fp32": 0, "tensor": 1, "bf16": 2}
 _TENSORS = ("W1", "b1", "W2", "b2", "W3", "b3")
 
 
@@ -45,8 +47,9 @@ class FusedTD3Update:
         self.gamma, self.tau, self.learning_rate = float(gamma), float(tau), float(learning_rate)
         self.policy_delay, self.target_policy_noise, self.target_noise_clip = int(policy_delay), float(target_policy_noise), float(target_noise_clip)
         self.betas, self.eps, self.seed = (float(betas[0]), float(betas[1])), float(eps), int(seed)
-        if gemm not in ("fp32", "tensor"):
-            raise ValueError("gemm must be 'fp32' (FFMA tiles, the reference's arithmetic) or 'tensor' (tcgen05 bf16x3 split, fp32-grade)")
+        if gemm not in _GEMM_MODES:
+            raise ValueError("gemm must be 'fp32' (FFMA tiles, the reference's arithmetic), 'tensor' (tcgen05 bf16x3 split, fp32-grade) or "
+                             "'bf16' (tcgen05, plain bf16 operands: reduced precision)")
         self.gemm = gemm
         offs = (c_int64 * 19)()
         _lib.check(self._libc.cstr_td3_layout(self.h1, self.h2, offs), "cstr_td3_layout")
@@ -104,7 +107,7 @@ class FusedTD3Update:
     def _config(self, batch: int) -> "_lib.Td3Config":
         return _lib.Td3Config(h1=self.h1, h2=self.h2, batch=batch, policy_delay=self.policy_delay, gamma=self.gamma, tau=self.tau, lr=self.learning_rate,
                               beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_policy_noise=self.target_policy_noise,
-                              target_noise_clip=self.target_noise_clip, seed=self.seed & (2**64 - 1), gemm_mode=int(self.gemm == "tensor"))
+                              target_noise_clip=self.target_noise_clip, seed=self.seed & (2**64 - 1), gemm_mode=_GEMM_MODES[self.gemm])
 
     # ---- weights in / out -------------------------------------------------------------------------------------------
     def load_nets(self, nets: Dict[str, Sequence[Any]]) -> None:
@@ -394,7 +397,7 @@ class FusedSACUpdate(FusedTD3Update):
     def _sac_config(self, batch: int) -> "_lib.SacConfig":
         return _lib.SacConfig(h1=self.h1, h2=self.h2, batch=batch, target_update_interval=self.target_update_interval, gamma=self.gamma, tau=self.tau,
                               lr=self.learning_rate, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_entropy=self.target_entropy,
-                              seed=self.seed & (2**64 - 1), gemm_mode=int(self.gemm == "tensor"))
+                              seed=self.seed & (2**64 - 1), gemm_mode=_GEMM_MODES[self.gemm])
 
     def _workspace_bytes(self, batch: int) -> int:
         return int(self._libc.cstr_sac_workspace_bytes(byref(self._sac_config(batch))))

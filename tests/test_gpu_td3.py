@@ -216,11 +216,12 @@ def test_adopts_torch_modules_in_place(pkg):
         pkg.FusedTD3Update([401, 300], 8)
 
 
-@pytest.mark.parametrize("gemm", ["fp32", "tensor"])
+@pytest.mark.parametrize("gemm", ["fp32", "tensor", "bf16"])
 def test_training_dynamics_track_eager_torch(pkg, gemm):
     """300 gradient steps on real CSTR transitions, fused kernels vs the same update in eager torch (fp32 autograd, torch Adam):
     same batches, independent smoothing noise -> the learned critic and actor agree statistically (chaos amplifies ulps, so this
-    is a dynamics check, not a bit check; measured |dq| 0.002 at q = -1.3)."""
+    is a dynamics check, not a bit check; measured |dq| 0.002 at q = -1.3).  gemm="bf16" (plain bf16 operands on tcgen05, fp32 accumulate) is
+    the reduced-precision throughput mode: it has no per-step parity bar, only this one."""
     import os
     import sys
 
