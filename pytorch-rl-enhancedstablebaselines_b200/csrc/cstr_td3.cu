@@ -846,9 +846,9 @@ int launch_gemm(const GemmArgs &g, int Z, int tensor, cudaStream_t st, const cha
         const TcTile t = tc_tile(g.N);
         static bool attr_set[3] = {false, false, false};
         if (!attr_set[MODE]) {
-            if (int rc = check_cuda(cudaFuncSetAttribute(td3_gemm_tc_kernel<MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "td3_gemm_tc smem attr"))
+            if (int rc = check_cuda(cudaFuncSetAttribute(td3_gemm_tc_kernel<MODE, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "td3_gemm_tc smem attr"))
                 return rc;
-            if (int rc = check_cuda(cudaFuncSetAttribute(td3_gemm_tc_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), "td3_gemm_tc smem attr"))
+            if (int rc = check_cuda(cudaFuncSetAttribute(td3_gemm_tc_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "td3_gemm_tc smem attr"))
                 return rc;
             attr_set[MODE] = true;
         }

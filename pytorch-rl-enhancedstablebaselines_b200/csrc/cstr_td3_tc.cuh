@@ -110,6 +110,29 @@ __device__ __forceinline__ void split_store(const float v[8], uint32_t addr, uin
     }
 }
 
+// the same for 4 consecutive-k floats (half a core-matrix row, 8 bytes per plane)
+template <int PLANES>
+__device__ __forceinline__ void split_store4(const float v[4], uint32_t addr, uint32_t plane_stride) {
+    if constexpr (PLANES == 1) {
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(pack_bf16x2(v[0], v[1])), "r"(pack_bf16x2(v[2], v[3])) : "memory");
+    } else {
+        uint32_t p1[2], p2[2], p3[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t a = __float_as_uint(v[2 * i]), b = __float_as_uint(v[2 * i + 1]);
+            p1[i] = __byte_perm(a, b, 0x7632);
+            const float ra = v[2 * i] - __uint_as_float(a & 0xffff0000u), rb = v[2 * i + 1] - __uint_as_float(b & 0xffff0000u);
+            const uint32_t a2 = __float_as_uint(ra), b2 = __float_as_uint(rb);
+            p2[i] = __byte_perm(a2, b2, 0x7632);
+            const float sa = ra - __uint_as_float(a2 & 0xffff0000u), sb = rb - __uint_as_float(b2 & 0xffff0000u);
+            p3[i] = __byte_perm(__float_as_uint(sa), __float_as_uint(sb), 0x7632);
+        }
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(p1[0]), "r"(p1[1]) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + plane_stride), "r"(p2[0]), "r"(p2[1]) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr + 2 * plane_stride), "r"(p3[0]), "r"(p3[1]) : "memory");
+    }
+}
+
 }  // namespace tc5
 
 #ifndef TD3_TC_PRODUCERS
@@ -118,23 +141,44 @@ __device__ __forceinline__ void split_store(const float v[8], uint32_t addr, uin
 #ifndef TD3_TC_ACC
 #define TD3_TC_ACC 1
 #endif
-constexpr int TC_BM = 128, TC_KC = 16, TC_STAGES = 3, TC_PRODUCERS = TD3_TC_PRODUCERS, TC_NACC = TD3_TC_ACC, TC_GEMM_THREADS = TC_PRODUCERS + 32, TC_SLOTS = TC_PRODUCERS == 512 ? 2 : 3;  // 256 A chunks + <= 512 B chunks over 512 threads
+#ifndef TD3_TC_DEPTH
+#define TD3_TC_DEPTH 2
+#endif
+#ifdef CSTR_TD3_TIMING
+__device__ __forceinline__ long long tc5_clock() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#define TC5_T(var) const long long var = tc5_clock();
+#define TC5_ACC(i, a, b) tacc[i] += (b) - (a);
+#else
+#define TC5_T(var)
+#define TC5_ACC(i, a, b)
+#endif
+constexpr int TC_BM = 128, TC_KC = 32, TC_KG = TC_KC / 8, TC_STAGES = 3, TC_PRODUCERS = 512, TC_NACC = TD3_TC_ACC, TC_DEPTH = TD3_TC_DEPTH,
+              TC_GEMM_THREADS = TC_PRODUCERS + 32;
 
-// 8 floats = one (row r, k-group) chunk of an operand tile, through a per-thread pointer that the caller advances by one stage.
-// KMAJ: memory rows are operand rows (k contiguous) -> two float4; otherwise memory rows are k -> 8 loads `ld` apart.
-// k_left = k_end - (k of the chunk's first element): only the last stage of a K range is partial.
+// One producer item.  KMAJ operand (memory rows = operand rows, k contiguous): 4 consecutive k of one row = one float4; consecutive
+// threads take consecutive quarters of the SAME row, so a warp reads four whole 128-byte lines (the first version gave every thread
+// its own row: 32 lines per warp-load, and the L1 tag stage — not the MMAs, not the split — bounded the kernel).
+// MN operand (memory rows = k, operand rows contiguous): 8 consecutive k of one operand row, consecutive threads = consecutive rows.
 template <bool KMAJ>
-__device__ __forceinline__ void load_chunk(const float *__restrict__ p, int64_t ld, bool row_ok, int k_left, float v[8]) {
+__device__ __forceinline__ void load_item(const float *__restrict__ p, int64_t ld, bool ok, int k_left, float *v) {
     if (KMAJ) {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 a = z, b = z;
-        if (row_ok && k_left > 0) a = *reinterpret_cast<const float4 *>(p);
-        if (row_ok && k_left > 4) b = *reinterpret_cast<const float4 *>(p + 4);
-        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && k_left > 0) a = *reinterpret_cast<const float4 *>(p);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (row_ok && j < k_left) ? p[j * ld] : 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = (ok && j < k_left) ? p[j * ld] : 0.f;
     }
+}
+
+template <bool KMAJ, int PLANES>
+__device__ __forceinline__ void store_item(const float *v, uint32_t addr, uint32_t plane_stride) {
+    if (KMAJ) tc5::split_store4<PLANES>(v, addr, plane_stride);
+    else tc5::split_store<PLANES>(v, addr, plane_stride);
 }
 
 template <int MODE, int PLANES = 3>  // PLANES = 3: fp32-grade split; 1: plain bf16 operands
@@ -142,8 +186,10 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
     using namespace tc5;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr bool A_KMAJ = MODE != G_WGRAD, B_KMAJ = MODE == G_FWD;
+    constexpr int A_ITEMS = A_KMAJ ? 2 : 1, A_W = A_KMAJ ? 4 : 8;  // 128 rows: 1024 quarters or 512 chunks over 512 producers
+    constexpr int B_ITEMS = B_KMAJ ? 4 : 2, B_W = B_KMAJ ? 4 : 8;  // n_tile <= 256 rows
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bars = smem_base;  // TC_STAGES mbarriers
+    const uint32_t bars = smem_base;  // empty[TC_STAGES], full[TC_STAGES]
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + 96);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z = blockIdx.z / g.splits, split = blockIdx.z % g.splits;
@@ -155,8 +201,9 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
         k_end = min(g.K, k_begin + g.k_per_split);
     }
     const int n_iter = max(0, (k_end - k_begin + TC_KC - 1) / TC_KC);
-    // one stage: A planes 3 x [2 k-groups][16 row-groups][128 B], then B planes 3 x [2][n_tile/8][128 B]
-    const uint32_t a_plane = 2u * (TC_BM / 8) * 128u, b_plane = 2u * (uint32_t)(n_tile / 8) * 128u;
+    // one stage: A planes 3 x [4 k-groups][16 row-groups][128 B], then B planes 3 x [4][n_tile/8][128 B]
+    const uint32_t lbo_a = (TC_BM / 8) * 128u, lbo_b = (uint32_t)(n_tile / 8) * 128u;
+    const uint32_t a_plane = TC_KG * lbo_a, b_plane = TC_KG * lbo_b;
     const uint32_t stage_bytes = 3u * (a_plane + b_plane), stage0 = smem_base + 128u;
 
     if (tid == 0) {
@@ -177,100 +224,106 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = umma_idesc_bf16(TC_BM, n_tile);
 
-    // Chunk slots.  A tile = 128 rows x 2 k-groups = 256 chunks (threads 0..255, slot 0); B tile = n_tile x 2 <= 512 chunks
-    // (threads 256..511 slot 0, then slot 1 of every thread).  Everything that does not change from stage to stage (global
-    // pointer, row validity, shared-memory offset) is computed once.
-    const int64_t lda = g.lda, ldb = g.ldb;
-    const bool slot0_is_a = tid < 256;  // warp-uniform; chunk id of slot c = tid + c * TC_PRODUCERS: ids 0..255 are A chunks, the rest B chunks
-    const float *ptr[TC_SLOTS];
-    uint32_t off[TC_SLOTS];  // byte offset inside a stage (A planes first, then B planes)
-    bool ok[TC_SLOTS], live[TC_SLOTS];
-    int kg8[TC_SLOTS];
-#pragma unroll
-    for (int c = 0; c < TC_SLOTS; ++c) {
-        const int id = tid + c * TC_PRODUCERS;
-        if (c == 0 && slot0_is_a) {
-            const int r = id & 127, kg = id >> 7;
-            live[c] = true, ok[c] = m0 + r < g.M, kg8[c] = kg * 8;
-            off[c] = (uint32_t)kg * (TC_BM / 8) * 128u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
-            ptr[c] = A_KMAJ ? A + (int64_t)(m0 + r) * lda + (k_begin + kg * 8) : A + (int64_t)(k_begin + kg * 8) * lda + (m0 + r);
-        } else {
-            const int ch = id - 256;
-            const int r = ch % n_tile, kg = ch / n_tile;
-            live[c] = ch < n_tile * 2, ok[c] = live[c] && n0 + r < g.N, kg8[c] = kg * 8;
-            off[c] = 3u * a_plane + (uint32_t)kg * (uint32_t)(n_tile / 8) * 128u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
-            ptr[c] = B_KMAJ ? Bm + (int64_t)(n0 + r) * ldb + (k_begin + kg * 8) : Bm + (int64_t)(k_begin + kg * 8) * ldb + (n0 + r);
-        }
-    }
-    const int64_t a_step = A_KMAJ ? TC_KC : TC_KC * lda, b_step = B_KMAJ ? TC_KC : TC_KC * ldb;
-    // two register sets: the global loads of stage it+2 are issued right after stage it has been written, so they have two
-    // full iterations (split + handshake) to land
-    float v0[TC_SLOTS][8], v1[TC_SLOTS][8];
-    auto load_stage = [&](int it, float (&v)[TC_SLOTS][8]) {
-        const int k_left = k_end - (k_begin + it * TC_KC);
-        if (slot0_is_a) load_chunk<A_KMAJ>(ptr[0] + it * a_step, lda, ok[0], k_left - kg8[0], v[0]);
-        else if (live[0]) load_chunk<B_KMAJ>(ptr[0] + it * b_step, ldb, ok[0], k_left - kg8[0], v[0]);
-#pragma unroll
-        for (int c = 1; c < TC_SLOTS; ++c)
-            if (live[c]) load_chunk<B_KMAJ>(ptr[c] + it * b_step, ldb, ok[c], k_left - kg8[c], v[c]);
-    };
-    auto store_stage = [&](int s, const float (&v)[TC_SLOTS][8]) {
-        const uint32_t st = stage0 + (uint32_t)s * stage_bytes;
-        if (live[0]) split_store<PLANES>(v[0], st + off[0], slot0_is_a ? a_plane : b_plane);
-#pragma unroll
-        for (int c = 1; c < TC_SLOTS; ++c)
-            if (live[c]) split_store<PLANES>(v[c], st + off[c], b_plane);
-    };
-
-    // Warp 16 issues the MMAs; warps 0..15 produce.  Handshake per stage: producers arrive on full[s] after their proxy fence,
-    // the issuer's tcgen05.commit arrives on empty[s] when the MMAs that read the stage have finished.  No CTA-wide barrier in the loop.
     if (warp == TC_PRODUCERS / 32) {
+        // ---- issuer warp: wait for a full stage, issue its MMAs (two K=16 steps), commit to the stage's empty barrier ----
         if (lane == 0) {
             for (int it = 0; it < n_iter; ++it) {
                 const int s = it % TC_STAGES, use = it / TC_STAGES;
                 mbar_wait(bars + 8 * (TC_STAGES + s), (uint32_t)(use & 1));
                 tc_fence_after();
                 const uint32_t sa = stage0 + (uint32_t)s * stage_bytes, sb = sa + 3u * a_plane;
-                uint64_t da[3], db[3];
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    da[p] = umma_desc(sa + p * a_plane, (TC_BM / 8) * 128u, 128u);
-                    db[p] = umma_desc(sb + p * b_plane, (uint32_t)(n_tile / 8) * 128u, 128u);
-                }
-                // three independent accumulators (two products each), summed in the epilogue: the small terms do not have to
-                // survive an addition to the large partial sum inside the tensor core
                 const uint32_t d0 = tmem_base, d1 = TC_NACC == 3 ? tmem_base + (uint32_t)n_tile : d0, d2 = TC_NACC == 3 ? tmem_base + 2u * (uint32_t)n_tile : d0;
-                const uint32_t acc = it > 0;
-                tc_mma_bf16(d0, da[0], db[0], idesc, acc);
-                if (PLANES == 1) {
-                    tc_commit(bars + 8 * s);
-                    continue;
+#pragma unroll
+                for (int ks = 0; ks < TC_KC / 16; ++ks) {
+                    uint64_t da[3], db[3];
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        da[p] = umma_desc(sa + p * a_plane + ks * 2u * lbo_a, lbo_a, 128u);
+                        db[p] = umma_desc(sb + p * b_plane + ks * 2u * lbo_b, lbo_b, 128u);
+                    }
+                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+                    tc_mma_bf16(d0, da[0], db[0], idesc, acc);
+                    if (PLANES == 3) {
+                        tc_mma_bf16(d1, da[0], db[1], idesc, TC_NACC == 3 ? acc : 1u);
+                        tc_mma_bf16(d2, da[1], db[0], idesc, TC_NACC == 3 ? acc : 1u);
+                        tc_mma_bf16(d0, da[1], db[1], idesc, 1);
+                        tc_mma_bf16(d1, da[2], db[0], idesc, 1);
+                        tc_mma_bf16(d2, da[0], db[2], idesc, 1);
+                    }
                 }
-                tc_mma_bf16(d1, da[0], db[1], idesc, TC_NACC == 3 ? acc : 1u);
-                tc_mma_bf16(d2, da[1], db[0], idesc, TC_NACC == 3 ? acc : 1u);
-                tc_mma_bf16(d0, da[1], db[1], idesc, 1);
-                tc_mma_bf16(d1, da[2], db[0], idesc, 1);
-                tc_mma_bf16(d2, da[0], db[2], idesc, 1);
                 tc_commit(bars + 8 * s);
             }
         }
     } else {
-        auto body = [&](int it, float (&v)[TC_SLOTS][8]) {
+        // ---- producers: everything that does not change from stage to stage is computed once per item ----
+        const int64_t lda = g.lda, ldb = g.ldb;
+        const float *a_ptr[A_ITEMS], *b_ptr[B_ITEMS];
+        uint32_t a_off[A_ITEMS], b_off[B_ITEMS];
+        bool a_ok[A_ITEMS], b_ok[B_ITEMS], b_live[B_ITEMS];
+        int a_k[A_ITEMS], b_k[B_ITEMS];
+#pragma unroll
+        for (int i = 0; i < A_ITEMS; ++i) {
+            const int id = tid + i * TC_PRODUCERS;
+            if (A_KMAJ) {
+                const int r = id >> 3, kq = id & 7;
+                a_ok[i] = m0 + r < g.M, a_k[i] = kq * 4;
+                a_off[i] = (uint32_t)(kq >> 1) * lbo_a + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kq & 1) * 8u;
+                a_ptr[i] = A + (int64_t)(m0 + r) * lda + (k_begin + kq * 4);
+            } else {
+                const int r = id & (TC_BM - 1), kg = id >> 7;
+                a_ok[i] = m0 + r < g.M, a_k[i] = kg * 8;
+                a_off[i] = (uint32_t)kg * lbo_a + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+                a_ptr[i] = A + (int64_t)(k_begin + kg * 8) * lda + (m0 + r);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < B_ITEMS; ++i) {
+            const int id = tid + i * TC_PRODUCERS;
+            if (B_KMAJ) {
+                const int r = id >> 3, kq = id & 7;
+                b_live[i] = r < n_tile, b_ok[i] = b_live[i] && n0 + r < g.N, b_k[i] = kq * 4;
+                b_off[i] = 3u * a_plane + (uint32_t)(kq >> 1) * lbo_b + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kq & 1) * 8u;
+                b_ptr[i] = Bm + (int64_t)(n0 + r) * ldb + (k_begin + kq * 4);
+            } else {
+                const int r = id % n_tile, kg = id / n_tile;
+                b_live[i] = kg < TC_KG, b_ok[i] = b_live[i] && n0 + r < g.N, b_k[i] = kg * 8;
+                b_off[i] = 3u * a_plane + (uint32_t)kg * lbo_b + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+                b_ptr[i] = Bm + (int64_t)(k_begin + kg * 8) * ldb + (n0 + r);
+            }
+        }
+        const int64_t a_step = A_KMAJ ? TC_KC : TC_KC * lda, b_step = B_KMAJ ? TC_KC : TC_KC * ldb;
+        float va[TC_DEPTH][A_ITEMS][A_W], vb[TC_DEPTH][B_ITEMS][B_W];  // register sets: loads of stage it+TC_DEPTH are issued once stage it is written
+        auto load_stage = [&](int it, float (&xa)[A_ITEMS][A_W], float (&xb)[B_ITEMS][B_W]) {
+            const int k_left = k_end - (k_begin + it * TC_KC);
+#pragma unroll
+            for (int i = 0; i < A_ITEMS; ++i) load_item<A_KMAJ>(a_ptr[i] + it * a_step, lda, a_ok[i], k_left - a_k[i], xa[i]);
+#pragma unroll
+            for (int i = 0; i < B_ITEMS; ++i)
+                if (b_live[i]) load_item<B_KMAJ>(b_ptr[i] + it * b_step, ldb, b_ok[i], k_left - b_k[i], xb[i]);
+        };
+        auto body = [&](int it, float (&xa)[A_ITEMS][A_W], float (&xb)[B_ITEMS][B_W]) {
             const int s = it % TC_STAGES, use = it / TC_STAGES;
             if (use > 0) {  // the MMAs that read this stage have finished; one lane per warp polls
                 if (lane == 0) mbar_wait(bars + 8 * s, (uint32_t)((use - 1) & 1));
                 __syncwarp();
             }
-            store_stage(s, v);
-            if (it + 2 < n_iter) load_stage(it + 2, v);
+            const uint32_t st = stage0 + (uint32_t)s * stage_bytes;
+#pragma unroll
+            for (int i = 0; i < A_ITEMS; ++i) store_item<A_KMAJ, PLANES>(xa[i], st + a_off[i], a_plane);
+#pragma unroll
+            for (int i = 0; i < B_ITEMS; ++i)
+                if (b_live[i]) store_item<B_KMAJ, PLANES>(xb[i], st + b_off[i], b_plane);
+            if (it + TC_DEPTH < n_iter) load_stage(it + TC_DEPTH, xa, xb);
             fence_proxy_async();
             mbar_arrive(bars + 8 * (TC_STAGES + s));
         };
-        if (n_iter > 0) load_stage(0, v0);
-        if (n_iter > 1) load_stage(1, v1);
-        for (int it = 0; it < n_iter; it += 2) {
-            body(it, v0);
-            if (it + 1 < n_iter) body(it + 1, v1);
+#pragma unroll
+        for (int d = 0; d < TC_DEPTH; ++d)
+            if (d < n_iter) load_stage(d, va[d], vb[d]);
+        for (int it = 0; it < n_iter; it += TC_DEPTH) {
+#pragma unroll
+            for (int d = 0; d < TC_DEPTH; ++d)
+                if (it + d < n_iter) body(it + d, va[d], vb[d]);
         }
     }
     if (n_iter > 0) {
@@ -346,7 +399,7 @@ inline TcTile tc_tile(int N) {
     t.n_tile = (((N + t.n_tiles - 1) / t.n_tiles) + 15) & ~15;
     t.tmem_cols = 32;
     while (t.tmem_cols < TC_NACC * t.n_tile) t.tmem_cols <<= 1;
-    const uint32_t a_plane = 2u * (TC_BM / 8) * 128u, b_plane = 2u * (uint32_t)(t.n_tile / 8) * 128u;
+    const uint32_t a_plane = TC_KG * (TC_BM / 8) * 128u, b_plane = TC_KG * (uint32_t)(t.n_tile / 8) * 128u;
     t.smem_bytes = 128u + TC_STAGES * 3u * (a_plane + b_plane);
     return t;
 }
