@@ -9,10 +9,10 @@
 // here), split, and store the planes into shared memory in the UMMA no-swizzle K-major core-matrix layout
 // ([k-group of 8][row-group of 8][8 rows x 16 B]); they arrive on the stage's `full` mbarrier after a proxy fence.  Lane 0 of
 // the issuer warp waits for `full`, issues the six MMAs of the stage and commits them to the stage's `empty` mbarrier, which
-// frees the stage for reuse (3 stages of K=16, global loads two stages ahead in registers).  Epilogue: tcgen05.ld ->
+// frees the stage for reuse (3 stages of K=32, global loads TD3_TC_DEPTH stages ahead in registers).  Epilogue: tcgen05.ld ->
 // bias+relu / relu-mask / slab store, 32-byte row pieces straight to global.
-// Build-time switches: -DTD3_TC_PRODUCERS=256|512 (producer threads), -DTD3_TC_ACC=1|3 (one accumulator, or one per product
-// pair summed in the epilogue: n_tile <= 160 then).  Measured: both within 10 % of each other; defaults 512 / 1.
+// Build-time switches: -DTD3_TC_ACC=1|3 (one accumulator, or one per product pair summed in the epilogue: n_tile <= 160 then),
+// -DTD3_TC_DEPTH=2|3 (register prefetch depth).  Measured within 10 % of each other; defaults 1 / 2.
 #pragma once
 #include <cuda_bf16.h>
 
