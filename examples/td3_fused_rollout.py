@@ -64,7 +64,7 @@ def main():
     ap.add_argument("--lr", type=float, default=1e-3, help="Adam learning rate (the reference's TD3 default)")
     ap.add_argument("--sigma", type=float, default=0.1, help="exploration noise of the rollout (NormalActionNoise)")
     ap.add_argument("--update", default="fused", choices=["fused", "torch"])
-    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor"], help="hidden-layer GEMMs of the fused update")
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor", "bf16"], help="hidden-layer GEMMs of the fused update")
     args = ap.parse_args()
 
     pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
