@@ -134,20 +134,22 @@ def test_tc_rollout_multi_tile_many_steps(pkg, golden):
 
 
 def test_td3_example_learns_end_to_end():
-    """examples/td3_fused_rollout.py: fused tcgen05 rollout -> GPU replay -> TD3 update -> weights back to the kernel.
-    The mean reward per step must improve within a few hundred updates (it does so by ~0.13 in 30 iterations)."""
+    """examples/td3_fused_rollout.py: fused tcgen05 rollout -> GPU replay (Philox sample) -> fused TD3 update (CUDA graph) -> weights back
+    to the rollout kernel, nothing on the host.  Rewards depend on the episode phase, so the example reports whole 400-step episodes: the
+    episode return must improve from the random-policy level (about -290) by more than 120 within 15 episodes (measured: -281 -> -34;
+    the best constant action reaches -75)."""
     import json
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "examples", "td3_fused_rollout.py"), "--n-envs", "32768", "--iters", "30"],
-                         capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "td3_fused_rollout.py"), "--n-envs", "16384", "--iters", "1500"],
+                         capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
-    assert res["updates"] == 240 and res["transitions"] == 30 * 8 * 32768
-    assert res["mean_reward_last"] > res["mean_reward_first"] + 0.05, res
+    assert res["updates"] == 1500 * 16 and res["transitions"] == 1500 * 4 * 16384 and res["update"] == "fused"
+    assert 400 * res["mean_reward_last"] > 400 * res["mean_reward_first"] + 120, res
 
 
 @pytest.mark.parametrize("actor_mode,atol", [("fp32", 3e-6), ("tc", 5e-3)])
