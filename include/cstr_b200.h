@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 12
+#define CSTR_B200_ABI_VERSION 13
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -201,7 +201,8 @@ typedef struct cstr_td3_config {
     float gamma, tau, lr, beta1, beta2, eps, target_policy_noise, target_noise_clip;
     uint64_t seed;
     int32_t gemm_mode;    /* CSTR_TD3_GEMM_FP32: FFMA tiles (the reference's float32 arithmetic);                      */
-    int32_t reserved;     /* CSTR_TD3_GEMM_TENSOR: tcgen05 bf16x3 split (3 bf16 planes per operand, 6 MMAs, fp32-grade)  */
+    int32_t n_critics;    /* 2 (or 0) = TD3's twin critics; 1 = DDPG (core/ddpg/ddpg.py:100-109: TD3 with one critic,
+                             policy_delay 1, target_noise_clip 0) — critic1's block of the layout stays unused              */
 } cstr_td3_config;
 #define CSTR_TD3_GEMM_FP32 0
 #define CSTR_TD3_GEMM_TENSOR 1

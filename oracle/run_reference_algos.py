@@ -120,6 +120,11 @@ def main() -> None:
         assert len(st) == 12 and float(st[0]["step"]) == m._fused.critic_step
     print(f"[TD3 fused update] n_updates {m._n_updates}, kernel launches {m._fused.launches}; model.save -> TD3.load round trip ok", flush=True)
 
+    # ---- DDPG (TD3 with one critic, core/ddpg/ddpg.py) through the same fused update ----
+    FusedDDPG = pkg.bind_td3_class(core.DDPG)
+    m = run("DDPG fused update", lambda env: FusedDDPG("MlpPolicy", env, action_noise=noise(), train_freq=(1, "step"), gradient_steps=4, **common), 6400)
+    assert isinstance(m, core.DDPG) and m._fused is not None and m._fused.n_critics == 1 and m._fused.policy_delay == 1
+
     # ---- SAC with the gradient steps on the device (bind_sac_class) ----
     FusedSAC = pkg.bind_sac_class(core.SAC)
     m = run("SAC fused update", lambda env: FusedSAC("MlpPolicy", env, train_freq=(1, "step"), gradient_steps=4, **common), 6400)

@@ -98,7 +98,7 @@ class TD3UpdateOracle:
         na, _ = mlp_forward(self.actor_target, next_obs, True)
         next_actions = np.clip(na + nz, F32(-1), F32(1))  # :170
         xin = np.concatenate([next_obs, next_actions], 1)
-        q_next = np.minimum(*[mlp_forward(c, xin, False)[0] for c in self.critic_targets])  # :173-174
+        q_next = np.minimum.reduce([mlp_forward(c, xin, False)[0] for c in self.critic_targets])  # :173-174 (one critic: DDPG)
         target = (rewards + (F32(1) - dones) * F32(self.gamma) * q_next).astype(F32)  # :175
         x = np.concatenate([obs, actions], 1)
         grads, loss, hidden = [], 0.0, []

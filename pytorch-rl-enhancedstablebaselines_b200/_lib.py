@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -62,7 +62,7 @@ class Td3Config(Structure):
 
     _fields_ = [("h1", c_int32), ("h2", c_int32), ("batch", c_int32), ("policy_delay", c_int32), ("gamma", c_float), ("tau", c_float),
                 ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("target_policy_noise", c_float),
-                ("target_noise_clip", c_float), ("seed", c_uint64), ("gemm_mode", c_int32), ("reserved", c_int32)]
+                ("target_noise_clip", c_float), ("seed", c_uint64), ("gemm_mode", c_int32), ("n_critics", c_int32)]
 
 
 class Td3State(Structure):

@@ -324,12 +324,12 @@ td3_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *
 // target head: target = r + (1 - done) * gamma * min(q1_target, q2_target)                         td3.py:173-175
 __global__ void __launch_bounds__(256)
 td3_target_head_kernel(int B, int H2, const float *__restrict__ h2, int64_t h_z, const float *__restrict__ W3, const float *__restrict__ b3, int64_t w_z,
-                       const float *__restrict__ rewards, const float *__restrict__ dones, float gamma, float *__restrict__ target) {
+                       const float *__restrict__ rewards, const float *__restrict__ dones, float gamma, int n_critics, float *__restrict__ target) {
     const int lane = threadIdx.x & 31, b = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= B) return;
-    const float q0 = row_dot(h2 + (int64_t)b * H2, W3, H2, lane) + b3[0];
-    const float q1 = row_dot(h2 + h_z + (int64_t)b * H2, W3 + w_z, H2, lane) + b3[w_z];
-    if (lane == 0) target[b] = rewards[b] + (1.f - dones[b]) * gamma * fminf(q0, q1);
+    float q = row_dot(h2 + (int64_t)b * H2, W3, H2, lane) + b3[0];
+    if (n_critics > 1) q = fminf(q, row_dot(h2 + h_z + (int64_t)b * H2, W3 + w_z, H2, lane) + b3[w_z]);  // DDPG (n_critics = 1): no min
+    if (lane == 0) target[b] = rewards[b] + (1.f - dones[b]) * gamma * q;
 }
 
 // critic head (z = critic): q = h2 . w3 + b3; loss += (q-target)^2; dq = 2 (q-target)/B; dz2 = dq * w3 * (h2 > 0)   td3.py:178-186
@@ -824,6 +824,7 @@ int check_cfg(const cstr_td3_config *c) {
         return fail_arg(CSTR_EINVAL, "td3: hidden sizes must be multiples of 4 in [4, 4096]");
     if (c->batch < 1 || c->batch > (1 << 22)) return fail_arg(CSTR_EINVAL, "td3: batch must be in [1, 4194304]");
     if (c->policy_delay < 1) return fail_arg(CSTR_EINVAL, "td3: policy_delay must be >= 1");
+    if (c->n_critics < 0 || c->n_critics > 2) return fail_arg(CSTR_EINVAL, "td3: n_critics must be 1 or 2 (0 = 2)");
     if (c->gemm_mode < CSTR_TD3_GEMM_FP32 || c->gemm_mode > CSTR_TD3_GEMM_BF16) return fail_arg(CSTR_EINVAL, "td3: gemm_mode must be 0 (fp32 FFMA), 1 (bf16x3 tensor) or 2 (bf16 tensor)");
     return 0;
 }
@@ -994,6 +995,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
     const Net g_actor = net_at(stt->grads, T.actor_off, T.actor), g_critic = net_at(stt->grads, T.critic_off[0], T.critic);
     const int rb = w.n_row_blocks;
     const bool policy_step = (n_updates % cfg->policy_delay) == 0;
+    const int ZC = cfg->n_critics == 1 ? 1 : 2;  // DDPG = TD3 with one critic (core/ddpg/ddpg.py:100-109); its block 1 stays unused
     const float *dev_sc = stt->counters ? w.scalars : nullptr;  // graph mode (see td3_tick_kernel)
     if (stt->counters && (phases & CSTR_TD3_CRITIC_GRAD)) {
         td3_tick_kernel<<<1, 32, 0, st>>>(stt->counters, w.scalars, policy_step ? 1 : 0, (double)cfg->lr, (double)cfg->beta1, (double)cfg->beta2);
@@ -1006,30 +1008,30 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         td3_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor_t.w3, actor_t.b3, 1, (const float2 *)noise, cfg->target_policy_noise,
                                                  cfg->target_noise_clip, cfg->seed, (uint32_t)n_updates, dev_sc, (float2 *)w.next_act);
         if (int rc = check_launch("td3_actor_head_kernel")) return rc;
-        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, 2, w.t_h1, w.t_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
-        td3_target_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.t_h2, (int64_t)B * H2, critic_t.w3, critic_t.b3, cz, rewards, dones, cfg->gamma, w.target);
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, next_obs, w.next_act, critic_t, cz, ZC, w.t_h1, w.t_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
+        td3_target_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.t_h2, (int64_t)B * H2, critic_t.w3, critic_t.b3, cz, rewards, dones, cfg->gamma, ZC, w.target);
         if (int rc = check_launch("td3_target_head_kernel")) return rc;
         // ---- current Q, loss, backward (td3.py:178-186) ----
-        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st, w.slabs, w.slab_cap)) return rc;
-        td3_critic_head_kernel<false><<<dim3(rb, 2), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, 2.f / (float)B, w.dq,
+        if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, cz, ZC, w.h1[0], w.h2[0], w.tensor, st, w.slabs, w.slab_cap)) return rc;
+        td3_critic_head_kernel<false><<<dim3(rb, ZC), 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.target, 2.f / (float)B, w.dq,
                                                                   w.dz2, w.loss_partial);
         if (int rc = check_launch("td3_critic_head_kernel")) return rc;
         SkinnyArgs s{};  // dW3 = dq^T @ h2, db3 = sum dq
         s.X = w.h2[0], s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
         s.Y0 = w.dq, s.n0 = 1, s.ld0 = 1, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = B;
         s.out_w = g_critic.w3, s.out_b = g_critic.b3, s.out_z = cz, s.transposed = 1;
-        if (int rc = launch_skinny<1, true>(s, 2, w.skinny, st, "td3_skinny_wgrad_kernel<w3>")) return rc;
-        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st)) return rc;
+        if (int rc = launch_skinny<1, true>(s, ZC, w.skinny, st, "td3_skinny_wgrad_kernel<w3>")) return rc;
+        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, ZC, w.h1[0], w.dz2, w.dz1, w, true, st)) return rc;
     }
     if (phases & CSTR_TD3_CRITIC_APPLY) {
         ApplyArgs a{};
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
-        a.adam_lo = T.critic_off[0], a.adam_hi = T.total, a.polyak_lo = a.polyak_hi = 0;
+        a.adam_lo = T.critic_off[0], a.adam_hi = T.critic_off[0] + ZC * cz, a.polyak_lo = a.polyak_hi = 0;
         const double bc1 = 1.0 - pow((double)cfg->beta1, (double)critic_step), bc2 = 1.0 - pow((double)cfg->beta2, (double)critic_step);
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = (float)((double)cfg->lr / bc1), a.bc2_sqrt = (float)sqrt(bc2);
         a.tau = cfg->tau;
         a.dev_scalars = dev_sc;
-        a.loss_partial = w.loss_partial, a.n_loss_partial = 2 * rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses;
+        a.loss_partial = w.loss_partial, a.n_loss_partial = ZC * rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses;
         const int64_t n = a.adam_hi - a.adam_lo;
         td3_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
         if (int rc = check_launch("td3_apply_kernel<critic>")) return rc;

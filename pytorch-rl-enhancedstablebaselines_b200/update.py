@@ -30,7 +30,7 @@ _TENSORS = ("W1", "b1", "W2", "b2", "W3", "b3")
 class FusedTD3Update:
     def __init__(self, net_arch: Sequence[int] = (400, 300), batch_size: int = 256, device: Any = "cuda", gamma: float = 0.99, tau: float = 0.005,
                  learning_rate: float = 1e-3, policy_delay: int = 2, target_policy_noise: float = 0.2, target_noise_clip: float = 0.5,
-                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0, gemm: str = "fp32"):
+                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0, gemm: str = "fp32", n_critics: int = 2):
         torch = _lib.require_cuda()
         self._torch = torch
         self._libc = _lib.load()
@@ -51,6 +51,9 @@ class FusedTD3Update:
             raise ValueError("gemm must be 'fp32' (FFMA tiles, the reference's arithmetic), 'tensor' (tcgen05 bf16x3 split, fp32-grade) or "
                              "'bf16' (tcgen05, plain bf16 operands: reduced precision)")
         self.gemm = gemm
+        if n_critics not in (1, 2):
+            raise ValueError("n_critics must be 2 (TD3) or 1 (DDPG)")
+        self.n_critics = int(n_critics)
         offs = (c_int64 * 19)()
         _lib.check(self._libc.cstr_td3_layout(self.h1, self.h2, offs), "cstr_td3_layout")
         self.param_count = int(offs[18])
@@ -107,7 +110,8 @@ class FusedTD3Update:
     def _config(self, batch: int) -> "_lib.Td3Config":
         return _lib.Td3Config(h1=self.h1, h2=self.h2, batch=batch, policy_delay=self.policy_delay, gamma=self.gamma, tau=self.tau, lr=self.learning_rate,
                               beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_policy_noise=self.target_policy_noise,
-                              target_noise_clip=self.target_noise_clip, seed=self.seed & (2**64 - 1), gemm_mode=_GEMM_MODES[self.gemm])
+                              target_noise_clip=self.target_noise_clip, seed=self.seed & (2**64 - 1), gemm_mode=_GEMM_MODES[self.gemm],
+                              n_critics=getattr(self, "n_critics", 2))
 
     # ---- weights in / out -------------------------------------------------------------------------------------------
     def load_nets(self, nets: Dict[str, Sequence[Any]]) -> None:
@@ -115,7 +119,7 @@ class FusedTD3Update:
         torch = self._torch
         for block, suffix in (("params", ""), ("targets", "_target")):
             v = self.views(block)
-            for net in NET_NAMES:
+            for net in NET_NAMES[:1 + self.n_critics]:
                 src = nets.get(net + suffix, nets[net] if suffix else None)
                 for dst, s in zip(v[net], src):
                     dst.copy_(torch.as_tensor(np.asarray(s) if not isinstance(s, torch.Tensor) else s).to(self.device, torch.float32).reshape(dst.shape))
@@ -130,8 +134,11 @@ class FusedTD3Update:
     def adopt_modules(self, actor, critics: Sequence[Any], actor_target, critic_targets: Sequence[Any]) -> None:
         """Copy the weights of ``nn.Sequential(Linear, ReLU, Linear, ReLU, Linear[, Tanh])`` modules in and re-point their
         parameters at the flat blocks (zero-copy sharing from then on)."""
-        pairs = [("params", "actor", actor), ("params", "critic0", critics[0]), ("params", "critic1", critics[1]),
-                 ("targets", "actor", actor_target), ("targets", "critic0", critic_targets[0]), ("targets", "critic1", critic_targets[1])]
+        if len(critics) != self.n_critics or len(critic_targets) != self.n_critics:
+            raise ValueError(f"expected {self.n_critics} critic network(s)")
+        pairs = [("params", "actor", actor), ("targets", "actor", actor_target)]
+        for z in range(self.n_critics):
+            pairs += [("params", f"critic{z}", critics[z]), ("targets", f"critic{z}", critic_targets[z])]
         for block, net, module in pairs:
             ps = list(module.parameters())
             if len(ps) != 6:
@@ -144,14 +151,14 @@ class FusedTD3Update:
 
     def adopt_policy(self, policy) -> None:
         """The reference's ``TD3Policy`` (core/td3/policies.py:172-210): ``actor.mu``, ``critic.q_networks`` and the targets."""
-        if len(policy.critic.q_networks) != 2:
-            raise ValueError("FusedTD3Update implements the twin-critic TD3 (n_critics=2)")
+        if len(policy.critic.q_networks) != self.n_critics:
+            raise ValueError(f"this engine was built for n_critics={self.n_critics}, the policy has {len(policy.critic.q_networks)}")
         self.adopt_modules(policy.actor.mu, list(policy.critic.q_networks), policy.actor_target.mu, list(policy.critic_target.q_networks))
         self._opt_params = {"actor": list(policy.actor.mu.parameters()), "critic": [p for q in policy.critic.q_networks for p in q.parameters()]}
 
     def import_optimizer_state(self, actor_optimizer, critic_optimizer) -> None:
         """Take over Adam moments / step counts of ``torch.optim.Adam`` optimisers created over the adopted modules."""
-        for tag, opt, nets in (("actor", actor_optimizer, ("actor",)), ("critic", critic_optimizer, ("critic0", "critic1"))):
+        for tag, opt, nets in (("actor", actor_optimizer, ("actor",)), ("critic", critic_optimizer, ("critic0", "critic1")[:self.n_critics])):
             group = opt.param_groups[0]
             self.betas, self.eps = (float(group["betas"][0]), float(group["betas"][1])), float(group["eps"])
             m = [t for n in nets for t in self.views("adam_m")[n]]
@@ -171,7 +178,7 @@ class FusedTD3Update:
     def export_optimizer_state(self, actor_optimizer, critic_optimizer) -> None:
         """Write moments / step counts back so ``model.save`` and a later torch ``optimizer.step()`` continue from here."""
         torch = self._torch
-        for opt, nets, step in ((actor_optimizer, ("actor",), self.actor_step), (critic_optimizer, ("critic0", "critic1"), self.critic_step)):
+        for opt, nets, step in ((actor_optimizer, ("actor",), self.actor_step), (critic_optimizer, ("critic0", "critic1")[:self.n_critics], self.critic_step)):
             if step == 0:
                 continue
             m = [t for n in nets for t in self.views("adam_m")[n]]
@@ -314,7 +321,8 @@ class FusedTD3Update:
 
 
 def bind_td3_class(td3_base: type) -> type:
-    """Return a subclass of the reference's ``TD3`` whose ``train()`` (core/td3/td3.py:154-211) runs on ``cstr_td3_update``.
+    """Return a subclass of the reference's ``TD3`` (or of ``DDPG``, which is TD3 with one critic, core/ddpg/ddpg.py) whose ``train()``
+    (core/td3/td3.py:154-211) runs on ``cstr_td3_update``.
     Rollout collection, logging, saving and ``predict`` stay the reference's code; the policy modules share memory with the
     flat parameter blocks."""
 
@@ -325,7 +333,8 @@ def bind_td3_class(td3_base: type) -> type:
             if self._fused is None:
                 arch = self.policy.net_arch if isinstance(self.policy.net_arch, (list, tuple)) else self.policy.net_arch["pi"]
                 eng = FusedTD3Update(arch, batch_size, self.device, self.gamma, self.tau, float(self.lr_schedule(self._current_progress_remaining)),
-                                     self.policy_delay, self.target_policy_noise, self.target_noise_clip, seed=int(self.seed or 0))
+                                     self.policy_delay, self.target_policy_noise, self.target_noise_clip, seed=int(self.seed or 0),
+                                     n_critics=len(self.policy.critic.q_networks))  # DDPG (a TD3 subclass) has one
                 eng.adopt_policy(self.policy)
                 eng.import_optimizer_state(self.actor.optimizer, self.critic.optimizer)
                 eng.n_updates = int(self._n_updates)

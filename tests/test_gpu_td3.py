@@ -288,3 +288,28 @@ def test_cuda_graph_replay_equals_launch_by_launch(pkg, gemm, delay):
     np.testing.assert_allclose(b.targets.cpu().numpy(), a.targets.cpu().numpy(), rtol=0, atol=3e-7)
     la, lb = a.pop_losses(), b.pop_losses()
     assert lb[0] == pytest.approx(la[0], rel=1e-5) and lb[1] == pytest.approx(la[1], rel=1e-4)
+
+
+def test_ddpg_single_critic(pkg):
+    """DDPG = TD3 with one critic, policy_delay 1 and no target smoothing (core/ddpg/ddpg.py:100-109): n_critics=1."""
+    rng = np.random.default_rng(12)
+    nets = U.random_nets(rng, 400, 300)
+    o = T.TD3UpdateOracle(nets["actor"], [nets["critic0"]], policy_delay=1, target_noise_clip=0.0)
+    eng = _engine(pkg, nets, [400, 300], 256, policy_delay=1, target_noise_clip=0.0, target_policy_noise=0.1, n_critics=1)
+    for batch in _random_batches(rng, 3, 256):
+        out = o.step(*batch)
+        eng.update(batch[:5], noise=batch[5])
+        gv = eng.views("grads")
+        for k in range(6):
+            for name, want in (("critic0", out["critic_grads"][k]), ("actor", out["actor_grads"][k])):
+                np.testing.assert_allclose(gv[name][k].cpu().numpy(), want, rtol=0, atol=2e-5 * max(np.abs(want).max(), 1e-3), err_msg=f"{name} grad {k}")
+    got = eng.nets()
+    for name, want in (("actor", o.actor), ("critic0", o.critics[0]), ("actor_target", o.actor_target), ("critic0_target", o.critic_targets[0])):
+        for a, b in zip(got[name], want):
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+    for a, b in zip(got["critic1"], nets["critic1"]):  # the unused block is left alone... it was never loaded: zeros
+        assert np.all(a == 0)
+    critic_loss, actor_loss = eng.pop_losses()
+    assert critic_loss == pytest.approx(np.mean(o.critic_losses), rel=1e-5) and actor_loss == pytest.approx(np.mean(o.actor_losses), rel=1e-4, abs=1e-6)
+    with pytest.raises(ValueError):
+        pkg.FusedTD3Update([400, 300], 8, n_critics=3)
