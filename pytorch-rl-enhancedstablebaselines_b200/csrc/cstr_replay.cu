@@ -40,12 +40,20 @@ __device__ __forceinline__ float4 norm4(float4 o, const NormArgs &na) {
                        normalize_obs_value(o.z, s[2], s[6], na.eps, na.clip_obs), normalize_obs_value(o.w, s[3], s[7], na.eps, na.clip_obs));
 }
 
+// 16-byte read-only load that asks L2 to fetch only the 64 bytes around it on a miss (one record = 64 bytes; the default prefetch
+// size pulls a whole 128-byte line from DRAM for every random record)
+__device__ __forceinline__ float4 ldg64(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::64B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ void gather_one(const float4 *__restrict__ records, int64_t flat, int64_t i, float4 *out_obs, float2 *out_act,
                                            float4 *out_next_obs, float *out_dones, float *out_rewards, const NormArgs &na) {
     const float4 *rec = records + 4 * flat;
-    float4 o = __ldg(rec), no = __ldg(rec + 1);
-    const float4 ar = __ldg(rec + 2);
-    const float to = __ldg(reinterpret_cast<const float *>(rec + 3));
+    float4 o = ldg64(rec), no = ldg64(rec + 1);
+    const float4 ar = ldg64(rec + 2);
+    const float to = ldg64(rec + 3).x;
     float rew = ar.z;
     if (na.stats) {  // VecNormalize inside the gather (buffers.py:314-323)
         if (na.norm_obs) { o = norm4(o, na); no = norm4(no, na); }
