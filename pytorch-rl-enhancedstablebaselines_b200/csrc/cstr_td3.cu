@@ -666,19 +666,60 @@ __global__ void __launch_bounds__(256) td3_skinny_reduce_kernel(SkinnyArgs s, in
     }
 }
 
-// dW2 = sum of the split-K slabs (fixed order)
-__global__ void __launch_bounds__(256)
-td3_sum_slabs_kernel(int64_t n4, int splits, const float4 *__restrict__ slabs, int64_t slab_stride4, int64_t z_stride4, float4 *__restrict__ out,
-                     int64_t out_z4) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const int z = blockIdx.y;
-    float4 s = slabs[z * z_stride4 + i];
-    for (int k = 1; k < splits; ++k) {
-        const float4 v = slabs[k * slab_stride4 + z * z_stride4 + i];
-        s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+// One node instead of four: the second stages of up to three skinny weight gradients and the dW2 slab sum of a backward pass run as
+// jobs of ONE launch (blockIdx.z = job).  Fewer graph nodes is what the small-batch update time is made of.
+struct FinJob {
+    SkinnyArgs s;
+    int ny, ybias, hp, Z;
+};
+struct FinJobs {
+    FinJob job[3];
+    int n;  // skinny jobs; job index n (if slab_splits > 0) is the slab sum
+    int64_t slab_n4, slab_stride4, slab_z4, slab_out_z4;
+    int slab_splits, slab_Z;
+    const float4 *slabs;
+    float4 *slab_out;
+};
+
+__global__ void __launch_bounds__(256) td3_finalize_kernel(FinJobs J) {
+    const int jb = blockIdx.z, z = blockIdx.y;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (jb == J.n) {  // dW2 = sum of the split-K slabs (fixed order)
+        if (z >= J.slab_Z || e >= J.slab_n4) return;
+        float4 acc = J.slabs[z * J.slab_z4 + e];
+        for (int k = 1; k < J.slab_splits; ++k) {
+            const float4 v = J.slabs[k * J.slab_stride4 + z * J.slab_z4 + e];
+            acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+        J.slab_out[z * J.slab_out_z4 + e] = acc;
+        return;
     }
-    out[z * out_z4 + i] = s;
+    const FinJob &f = J.job[jb];
+    const SkinnyArgs &s = f.s;
+    const int NY = f.ny, Hp = f.hp;
+    if (z >= f.Z || e >= (int64_t)(NY + 1) * Hp) return;
+    const int i = (int)(e / Hp), jj = (int)(e % Hp);
+    if (i == NY) {
+        if (!s.out_b || (f.ybias ? jj >= NY : jj >= s.H)) return;
+    } else if (jj >= s.H || !s.out_w) return;
+    const int64_t stride = (int64_t)f.Z * (NY + 1) * Hp;
+    const float *pp = s.part + (int64_t)z * (NY + 1) * Hp + e;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // four loads in flight; the combination order is fixed
+    int c = 0;
+    for (; c + 4 <= s.chunks; c += 4) {
+        a0 += pp[(c + 0) * stride];
+        a1 += pp[(c + 1) * stride];
+        a2 += pp[(c + 2) * stride];
+        a3 += pp[(c + 3) * stride];
+    }
+    for (; c < s.chunks; ++c) a0 += pp[c * stride];
+    const float v = (a0 + a1) + (a2 + a3);
+    if (i < NY) {
+        if (s.transposed) s.out_w[z * s.out_z + (int64_t)i * s.H + jj] = v;
+        else s.out_w[z * s.out_z + (int64_t)jj * NY + i] = v;
+    } else {
+        s.out_b[z * s.out_z + jj] = v;
+    }
 }
 
 // graph mode: the per-update scalars (Philox counter of the smoothing noise, Adam bias corrections) cannot be baked into a captured
@@ -769,6 +810,7 @@ struct Workspace {  // carved out of the caller's workspace buffer (floats)
     float *logp, *next_logp, *std_eps, *raw_log_std, *dpre4, *lp_partial;  // SAC
     int n_row_blocks;
     int64_t slab_cap;  // floats in `slabs`
+    int64_t skinny_region;
     int tensor;  // cfg->gemm_mode: 0 FFMA, 1 tcgen05 bf16x3 split, 2 tcgen05 plain bf16
     int64_t floats;
 };
@@ -809,7 +851,8 @@ Workspace carve(float *base, int B, int H1, int H2) {
     w.slab_cap = (int64_t)MAX_SPLITS * 2 * pad4((int64_t)H1 * H2);
     w.slabs = take(w.slab_cap);
     const int64_t hp = ((int64_t)(H1 > H2 ? H1 : H2) + 31) / 32 * 32;
-    w.skinny = take((int64_t)((B + SKINNY_ROWS - 1) / SKINNY_ROWS) * 2 * (OBS + ACT + 1) * hp);
+    w.skinny_region = (int64_t)((B + SKINNY_ROWS - 1) / SKINNY_ROWS) * 2 * (OBS + ACT + 1) * hp;
+    w.skinny = take(3 * w.skinny_region);  // one region per deferred job of a backward pass
     w.scalars = take(8);
     w.logp = take(B), w.next_logp = take(B), w.std_eps = take(2 * (int64_t)B), w.raw_log_std = take(2 * (int64_t)B), w.dpre4 = take(4 * (int64_t)B);
     w.lp_partial = take(w.n_row_blocks);
@@ -830,15 +873,34 @@ int check_cfg(const cstr_td3_config *c) {
 }
 
 template <int NY, bool YBIAS>
-int launch_skinny(SkinnyArgs s, int Z, float *part, cudaStream_t st, const char *what) {
+int launch_skinny(SkinnyArgs s, int Z, float *part, cudaStream_t st, const char *what, FinJobs *defer = nullptr) {
     s.part = part;
     s.rows_per_chunk = SKINNY_ROWS;
     s.chunks = (s.B + SKINNY_ROWS - 1) / SKINNY_ROWS;
     const int cols = (s.H + 31) / 32, Hp = cols * 32;
     td3_skinny_wgrad_kernel<NY, YBIAS><<<dim3(cols, s.chunks, Z), 256, 0, st>>>(s);
     if (int rc = check_launch(what)) return rc;
+    if (defer) {  // the second stage runs as a job of the backward pass's finalize launch
+        FinJob &f = defer->job[defer->n++];
+        f.s = s, f.ny = NY, f.ybias = YBIAS ? 1 : 0, f.hp = Hp, f.Z = Z;
+        return 0;
+    }
     td3_skinny_reduce_kernel<NY, YBIAS><<<dim3(((NY + 1) * Hp + 255) / 256, Z), 256, 0, st>>>(s, Hp, Z);
     return check_launch(what);
+}
+
+int launch_finalize(const FinJobs &J, cudaStream_t st) {
+    int64_t elems = J.slab_splits > 0 ? J.slab_n4 : 0;
+    int Z = J.slab_splits > 0 ? J.slab_Z : 1;
+    for (int k = 0; k < J.n; ++k) {
+        const int64_t e = (int64_t)(J.job[k].ny + 1) * J.job[k].hp;
+        if (e > elems) elems = e;
+        if (J.job[k].Z > Z) Z = J.job[k].Z;
+    }
+    const int jobs = J.n + (J.slab_splits > 0 ? 1 : 0);
+    if (jobs == 0) return 0;
+    td3_finalize_kernel<<<dim3((unsigned)((elems + 255) / 256), Z, jobs), 256, 0, st>>>(J);
+    return check_launch("td3_finalize_kernel");
 }
 
 template <int MODE>
@@ -909,7 +971,8 @@ int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float 
 
 // given dz2 (and h1, x): dz1 (optional), then every weight gradient of the hidden and input layers into the flat grads
 int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float *act, const Net &n, const Net &gn, int64_t z_stride, int Z,
-                    const float *h1, const float *dz2, float *dz1, const Workspace &w, bool want_weight_grads, cudaStream_t st) {
+                    const float *h1, const float *dz2, float *dz1, const Workspace &w, bool want_weight_grads, cudaStream_t st,
+                    FinJobs *pending = nullptr) {
     GemmArgs g{};
     g.A = dz2, g.Bm = n.w2, g.aux = h1, g.C = dz1;
     g.M = B, g.N = H1, g.K = H2, g.lda = H2, g.ldb = H1, g.ldc = H1, g.ldaux = H1;
@@ -927,22 +990,24 @@ int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float
     const int splits = choose_splits(B, H1, H2, Z, w.tensor);
     q.splits = splits, q.k_per_split = (B + splits - 1) / splits, q.c_split = 2 * w2n;
     if (int rc = launch_gemm<G_WGRAD>(q, Z, w.tensor, st, "td3_gemm_kernel<wgrad>")) return rc;
-    const int64_t n4 = (int64_t)H1 * H2 / 4;
-    td3_sum_slabs_kernel<<<dim3((unsigned)((n4 + 255) / 256), Z), 256, 0, st>>>(n4, splits, (const float4 *)w.slabs, 2 * w2n / 4, w2n / 4, (float4 *)gn.w2,
-                                                                              z_stride / 4);
-    if (int rc = check_launch("td3_sum_slabs_kernel")) return rc;
+    FinJobs local{};
+    FinJobs &J = pending ? *pending : local;  // the caller's layer-3 job (region 2) rides along
+    J.slab_n4 = (int64_t)H1 * H2 / 4, J.slab_splits = splits, J.slabs = (const float4 *)w.slabs, J.slab_stride4 = 2 * w2n / 4, J.slab_z4 = w2n / 4;
+    J.slab_out = (float4 *)gn.w2, J.slab_out_z4 = z_stride / 4, J.slab_Z = Z;
     // db2 = colsum(dz2)
     SkinnyArgs s{};
     s.X = dz2, s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
     s.out_w = nullptr, s.out_b = gn.b2, s.out_z = z_stride;
-    if (int rc = launch_skinny<0, false>(s, Z, w.skinny, st, "td3_skinny_wgrad_kernel<b2>")) return rc;
+    if (int rc = launch_skinny<0, false>(s, Z, w.skinny, st, "td3_skinny_wgrad_kernel<b2>", &J)) return rc;
     // dW1 = dz1^T @ [obs | act], db1 = colsum(dz1)
     SkinnyArgs t{};
     t.X = dz1, t.x_z = (int64_t)B * H1, t.ldx = H1, t.H = H1, t.B = B;
     t.Y0 = obs, t.n0 = OBS, t.ld0 = OBS, t.Y1 = act, t.n1 = in - OBS, t.ld1 = ACT, t.y_z = 0;
     t.out_w = gn.w1, t.out_b = gn.b1, t.out_z = z_stride;
-    if (in == OBS) return launch_skinny<OBS, false>(t, Z, w.skinny, st, "td3_skinny_wgrad_kernel<w1>");
-    return launch_skinny<OBS + ACT, false>(t, Z, w.skinny, st, "td3_skinny_wgrad_kernel<w1>");
+    if (in == OBS) {
+        if (int rc = launch_skinny<OBS, false>(t, Z, w.skinny + w.skinny_region, st, "td3_skinny_wgrad_kernel<w1>", &J)) return rc;
+    } else if (int rc = launch_skinny<OBS + ACT, false>(t, Z, w.skinny + w.skinny_region, st, "td3_skinny_wgrad_kernel<w1>", &J)) return rc;
+    return launch_finalize(J, st);
 }
 
 }  // namespace
@@ -1020,8 +1085,9 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         s.X = w.h2[0], s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
         s.Y0 = w.dq, s.n0 = 1, s.ld0 = 1, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = B;
         s.out_w = g_critic.w3, s.out_b = g_critic.b3, s.out_z = cz, s.transposed = 1;
-        if (int rc = launch_skinny<1, true>(s, ZC, w.skinny, st, "td3_skinny_wgrad_kernel<w3>")) return rc;
-        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, ZC, w.h1[0], w.dz2, w.dz1, w, true, st)) return rc;
+        FinJobs J{};
+        if (int rc = launch_skinny<1, true>(s, ZC, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<w3>", &J)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, ZC, w.h1[0], w.dz2, w.dz1, w, true, st, &J)) return rc;
     }
     if (phases & CSTR_TD3_CRITIC_APPLY) {
         ApplyArgs a{};
@@ -1054,8 +1120,9 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         s.X = w.a_h2, s.x_z = 0, s.ldx = H2, s.H = H2, s.B = B;
         s.Y0 = w.dpre, s.n0 = ACT, s.ld0 = ACT, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = 0;
         s.out_w = g_actor.w3, s.out_b = g_actor.b3, s.out_z = 0, s.transposed = 1;
-        if (int rc = launch_skinny<ACT, true>(s, 1, w.skinny, st, "td3_skinny_wgrad_kernel<actor w3>")) return rc;
-        if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, dz2a, dz1a, w, true, st)) return rc;
+        FinJobs J{};
+        if (int rc = launch_skinny<ACT, true>(s, 1, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<actor w3>", &J)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, dz2a, dz1a, w, true, st, &J)) return rc;
     }
     if (policy_step && (phases & CSTR_TD3_ACTOR_APPLY)) {
         if (actor_step < 1) return fail_arg(CSTR_EINVAL, "td3_update: actor_step must be >= 1 on a policy step");
@@ -1167,9 +1234,10 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         s.X = w.h2[0], s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
         s.Y0 = w.dq, s.n0 = 1, s.ld0 = 1, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = B;
         s.out_w = g_critic.w3, s.out_b = g_critic.b3, s.out_z = cz, s.transposed = 1;
-        if (int rc = launch_skinny<1, true>(s, 2, w.skinny, st, "td3_skinny_wgrad_kernel<w3>")) return rc;
+        FinJobs J{};
+        if (int rc = launch_skinny<1, true>(s, 2, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<w3>", &J)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st, &J)) return rc;
     }
-    if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st)) return rc;
     {
         ApplyArgs a{};
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
@@ -1194,9 +1262,10 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         s.X = w.a_h2, s.x_z = 0, s.ldx = H2, s.H = H2, s.B = B;
         s.Y0 = w.dpre4, s.n0 = 2 * ACT, s.ld0 = 2 * ACT, s.Y1 = nullptr, s.n1 = 0, s.ld1 = 0, s.y_z = 0;
         s.out_w = g_actor.w3, s.out_b = g_actor.b3, s.out_z = 0, s.transposed = 1;
-        if (int rc = launch_skinny<2 * ACT, true>(s, 1, w.skinny, st, "td3_skinny_wgrad_kernel<sac head>")) return rc;
+        FinJobs J{};
+        if (int rc = launch_skinny<2 * ACT, true>(s, 1, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<sac head>", &J)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, w.t_h2, w.t_h1, w, true, st, &J)) return rc;
     }
-    if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, w.t_h2, w.t_h1, w, true, st)) return rc;
     {
         ApplyArgs a{};
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
