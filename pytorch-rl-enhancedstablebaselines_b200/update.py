@@ -262,7 +262,7 @@ class FusedTD3Update:
         self.critic_step += done
         self.actor_step += done // self.policy_delay
         buffer._draw += done
-        self.launches += cycles * (26 * (self.policy_delay - 1) + 50 + self.policy_delay)
+        self.launches += cycles * (23 * (self.policy_delay - 1) + 44 + self.policy_delay)
         return done
 
     def update(self, batch, noise=None, allreduce: Optional[Callable[[Any], None]] = None) -> None:
@@ -297,12 +297,12 @@ class FusedTD3Update:
                 if policy_step:
                     allreduce(self.grads[self.actor_range[0]:self.actor_range[1]])
                 run(_lib.TD3_ACTOR_APPLY)
-        self.launches += 26 if not policy_step else 50
+        self.launches += 23 if not policy_step else 44  # without the split-K finish kernels of small batches
 
     def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, allreduce=None, graph: bool = False) -> None:
         """``TD3.train(gradient_steps, batch_size)`` (td3.py:154-206): sample + update, ``gradient_steps`` times.
         ``graph=True`` (single-GPU, Philox-index buffer): whole cycles of ``policy_delay`` updates are replayed from ONE captured CUDA
-        graph (27-51 launches per update become one graph launch per cycle); the remainder runs launch by launch."""
+        graph (24-45 launches per update become one graph launch per cycle); the remainder runs launch by launch."""
         bs = int(batch_size or self._batch)
         done = 0
         # a captured cycle bakes the sampling range in: only worth capturing once the ring is full (its range is constant from then on)
@@ -459,7 +459,7 @@ class FusedSACUpdate(FusedTD3Update):
             rc = self._libc.cstr_sac_update(byref(cfg), byref(st), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones), _lib.ptr(rew),
                                             _lib.ptr(e1), _lib.ptr(e2), self.n_updates, self.critic_step, self._stream())
         _lib.check(rc, "cstr_sac_update")
-        self.launches += 56
+        self.launches += 50
 
     def _graph_launch(self, batch_size: int, st, out, k: int) -> None:
         cfg = self._sac_config(batch_size)
