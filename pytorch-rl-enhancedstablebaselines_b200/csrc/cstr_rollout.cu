@@ -8,8 +8,8 @@
 //   VecEnv.step -> TwoSeriesCSTREnv.step core/common/vec_env/dummy_vec_env.py:56-73, twoseriescstr.py:394-454
 //   _store_transition + ReplayBuffer.add core/common/off_policy_algorithm.py:445-508, core/common/buffers.py:247-283
 //
-// actor_mode 0 (this file, fp32 CUDA cores): the parity path.  One CTA = 128 reactors, one thread
-// per reactor.  Layer 1 (K=4) is computed per thread and parked in shared memory k-major
+// actor_mode 0 (this file, fp32 CUDA cores): the parity path.  One CTA = 128 reactors, four threads
+// per reactor.  Layer 1 (K=4) is computed by the reactor's threads and parked in shared memory k-major
 // (h1[k][m]: conflict-free); layer 2 is a register-tiled contraction, 12 outputs per pass with the
 // W2 rows fetched as warp-uniform 16-byte loads (L1-resident, 480 KB total streams from L2); layer 3
 // (N=2) and tanh are folded into the layer-2 epilogue so h2 never exists in memory.
@@ -20,56 +20,64 @@
 
 namespace cstr {
 
-constexpr int ROLL_M = 128;  // reactors per CTA
-constexpr int ROLL_NB = 12;  // layer-2 outputs per register pass
+constexpr int ROLL_M = 128;    // reactors per CTA
+constexpr int ROLL_NB = 12;    // layer-2 outputs per register pass
+constexpr int ROLL_PARTS = 4;  // threads per reactor: h1 of 128 reactors fills shared memory, so one thread per reactor leaves ONE
+                               // warp per scheduler; four threads share a reactor's h1 column and split the hidden units
+constexpr int ROLL_THREADS = ROLL_M * ROLL_PARTS;
 
 template <int MODE, int KIND>
-__global__ void __launch_bounds__(ROLL_M)
+__global__ void __launch_bounds__(ROLL_THREADS, 1)
 rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, float sigma, const float2 *__restrict__ noise, int warmup,
                    uint32_t t_base, float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode,
                    double *static_base, int64_t rows, int64_t pos0, float4 *__restrict__ records, double *reward_sum, cstr_episode_stats stats,
                    int has_stats) {
-    extern __shared__ float h1[];  // [H1][ROLL_M]
-    const int m = threadIdx.x;
+    extern __shared__ float h1[];  // [H1][ROLL_M], then the state column [ROLL_M] float4 and the partial heads [PARTS][4][ROLL_M]
+    constexpr int NOUT = KIND == CSTR_ACTOR_GAUSSIAN ? 4 : 2;
+    const int m = threadIdx.x & (ROLL_M - 1), part = threadIdx.x >> 7;  // part is warp-uniform
+    const bool owner = part == 0;  // owns the reactor: state registers, head, env step, record
     const int64_t i = (int64_t)blockIdx.x * ROLL_M + m;
     const bool live = i < n;
     const int H1 = actor.H1, H2 = actor.H2;
-    float4 s = live ? state[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    int sc = live ? step_count[i] : 0, ep = live ? episode[i] : 0;
+    float4 *s_state = reinterpret_cast<float4 *>(h1 + (size_t)H1 * ROLL_M);
+    float *s_o = reinterpret_cast<float *>(s_state + ROLL_M);
+    float4 s = (live && owner) ? state[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int sc = (live && owner) ? step_count[i] : 0, ep = (live && owner) ? episode[i] : 0;
     const uint64_t env = (uint64_t)(p.env_offset + i);
     double acc_r = 0.0;
-    double ep_ret = (has_stats && live) ? stats.ep_return[i] : 0.0;
+    double ep_ret = (has_stats && live && owner) ? stats.ep_return[i] : 0.0;
     uint4 cache = make_uint4(0, 0, 0, 0);
 
     for (int64_t k = 0; k < K; ++k) {
         const uint32_t g = t_base + (uint32_t)k;
-        float2 env_a, buf_a;
+        float2 env_a = make_float2(0.f, 0.f), buf_a = make_float2(0.f, 0.f);
         if (warmup) {
-            // learning_starts phase: uniform action from the space (:386-388), then scale (:398)
-            const float2 a = philox_action(p.seed, env, g, cache, k == 0 || (g & 1u) == 0);
-            env_a = a;
-            buf_a = make_float2(__fadd_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn(a.x, 1.0f), 0.5f)), -1.0f),
-                                __fadd_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn(a.y, 1.0f), 0.5f)), -1.0f));
-            env_a = make_float2(__fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(buf_a.x, 1.0f)), 2.0f)),
-                                __fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(buf_a.y, 1.0f)), 2.0f)));
+            if (owner) {
+                // learning_starts phase: uniform action from the space (:386-388), then scale (:398)
+                const float2 a = philox_action(p.seed, env, g, cache, k == 0 || (g & 1u) == 0);
+                buf_a = make_float2(__fadd_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn(a.x, 1.0f), 0.5f)), -1.0f),
+                                    __fadd_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn(a.y, 1.0f), 0.5f)), -1.0f));
+                env_a = make_float2(__fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(buf_a.x, 1.0f)), 2.0f)),
+                                    __fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(buf_a.y, 1.0f)), 2.0f)));
+            }
         } else {
-            // ---- layer 1: h1 = relu(W1 s + b1), parked k-major in shared memory (column m is private to thread m: no barrier)
-            for (int j = 0; j < H1; ++j) {
+            if (owner) s_state[m] = s;
+            __syncthreads();
+            const float4 sv = s_state[m];
+            // ---- layer 1: h1 = relu(W1 s + b1), parked k-major in shared memory; part p computes every 4th hidden unit
+            for (int j = part; j < H1; j += ROLL_PARTS) {
                 const float4 w = __ldg(reinterpret_cast<const float4 *>(actor.W1) + j);
                 float v = __ldg(actor.b1 + j);
-                v = fmaf(w.x, s.x, v);
-                v = fmaf(w.y, s.y, v);
-                v = fmaf(w.z, s.z, v);
-                v = fmaf(w.w, s.w, v);
+                v = fmaf(w.x, sv.x, v);
+                v = fmaf(w.y, sv.y, v);
+                v = fmaf(w.z, sv.z, v);
+                v = fmaf(w.w, sv.w, v);
                 h1[j * ROLL_M + m] = fmaxf(v, 0.0f);
             }
-            // each thread only reads back its own column m: no barrier needed between layers
-            // ---- layer 2 + 3: out = W3 relu(W2 h1 + b2) + b3, 12 hidden units per pass
-            constexpr int NOUT = KIND == CSTR_ACTOR_GAUSSIAN ? 4 : 2;
+            __syncthreads();
+            // ---- layer 2 + 3: out = W3 relu(W2 h1 + b2) + b3, 12 hidden units per pass, passes dealt round-robin to the parts
             float o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int r = 0; r < NOUT; ++r) o[r] = __ldg(actor.b3 + r);
-            for (int nb = 0; nb < H2; nb += ROLL_NB) {
+            for (int nb = part * ROLL_NB; nb < H2; nb += ROLL_PARTS * ROLL_NB) {
                 float acc[ROLL_NB];
 #pragma unroll
                 for (int q = 0; q < ROLL_NB; ++q) acc[q] = 0.0f;
@@ -101,17 +109,30 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
                     }
                 }
             }
-            float2 nz;
-            if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
-            else if (KIND == CSTR_ACTOR_GAUSSIAN) nz = philox_normal2(p.seed, env, g);
-            else if (sigma != 0.0f) { nz = philox_normal2(p.seed, env, g); nz.x *= sigma; nz.y *= sigma; }
-            else nz = make_float2(0.f, 0.f);
-            float mu0, mu1;
-            float2 add;
-            actor_head<KIND>(o, nz, mu0, mu1, add);
-            action_maps(mu0, add.x, env_a.x, buf_a.x);
-            action_maps(mu1, add.y, env_a.y, buf_a.y);
+#pragma unroll
+            for (int r = 0; r < NOUT; ++r) s_o[(part * 4 + r) * ROLL_M + m] = o[r];
+            __syncthreads();
+            if (owner) {
+#pragma unroll
+                for (int r = 0; r < NOUT; ++r) {  // fixed order: bias, then parts 0..3
+                    float v = __ldg(actor.b3 + r);
+#pragma unroll
+                    for (int q = 0; q < ROLL_PARTS; ++q) v += s_o[(q * 4 + r) * ROLL_M + m];
+                    o[r] = v;
+                }
+                float2 nz;
+                if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
+                else if (KIND == CSTR_ACTOR_GAUSSIAN) nz = philox_normal2(p.seed, env, g);
+                else if (sigma != 0.0f) { nz = philox_normal2(p.seed, env, g); nz.x *= sigma; nz.y *= sigma; }
+                else nz = make_float2(0.f, 0.f);
+                float mu0, mu1;
+                float2 add;
+                actor_head<KIND>(o, nz, mu0, mu1, add);
+                action_maps(mu0, add.x, env_a.x, buf_a.x);
+                action_maps(mu1, add.y, env_a.y, buf_a.y);
+            }
         }
+        if (!owner) continue;  // (the barriers above are reached by every thread on every step before this point)
         // ---- env step + transition record
         const float4 obs = s;
         const StepResult r = (MODE == CSTR_MATH_STRICT) ? step_strict_f32(s, env_a, sc, (float)p.target_c2, p.max_steps)
@@ -127,6 +148,7 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
             sc = 0;
         }
     }
+    if (!owner) return;
     if (live) {
         state[i] = s;
         step_count[i] = sc;
@@ -174,8 +196,8 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
     if (actor_mode != 0 && actor_mode != 1) return fail_arg(CSTR_EINVAL, "rollout: unknown actor_mode");
     cstr_actor_f32 a = {};
     if (actor) a = *actor;
-    const size_t smem = warmup ? 0 : (size_t)a.H1 * ROLL_M * sizeof(float);
-    if (smem > 227 * 1024) return fail_arg(CSTR_EINVAL, "rollout: H1 too large for the fp32 path (max 452)");
+    const size_t smem = warmup ? 0 : (size_t)a.H1 * ROLL_M * sizeof(float) + ROLL_M * sizeof(float4) + (size_t)ROLL_PARTS * 4 * ROLL_M * sizeof(float);
+    if (smem > 227 * 1024) return fail_arg(CSTR_EINVAL, "rollout: H1 too large for the fp32 path (max 432)");
     const int grid = (int)((n + ROLL_M - 1) / ROLL_M);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
@@ -183,7 +205,7 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
     do {                                                                                                                                   \
         rc = check_cuda(cudaFuncSetAttribute(rollout_f32_kernel<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
         if (!rc)                                                                                                                           \
-            rollout_f32_kernel<MODE, KIND><<<grid, ROLL_M, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state, \
+            rollout_f32_kernel<MODE, KIND><<<grid, ROLL_THREADS, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state, \
                                                                        step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum, st_copy, has_stats); \
     } while (0)
     cstr_episode_stats st_copy = {};
