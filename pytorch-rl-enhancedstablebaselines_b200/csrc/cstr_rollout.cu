@@ -20,21 +20,33 @@
 
 namespace cstr {
 
-constexpr int ROLL_M = 128;    // reactors per CTA
-constexpr int ROLL_NB = 12;    // layer-2 outputs per register pass
-constexpr int ROLL_PARTS = 4;  // threads per reactor: h1 of 128 reactors fills shared memory, so one thread per reactor leaves ONE
+#ifndef ROLL_M_LOG2
+#define ROLL_M_LOG2 7
+#endif
+#ifndef ROLL_PARTS_
+#define ROLL_PARTS_ 4
+#endif
+#ifndef ROLL_NB_
+#define ROLL_NB_ 12
+#endif
+#ifndef ROLL_MINB
+#define ROLL_MINB 1
+#endif
+constexpr int ROLL_M = 1 << ROLL_M_LOG2;  // reactors per CTA
+constexpr int ROLL_NB = ROLL_NB_;    // layer-2 outputs per register pass
+constexpr int ROLL_PARTS = ROLL_PARTS_;  // threads per reactor: h1 of 128 reactors fills shared memory, so one thread per reactor leaves ONE
                                // warp per scheduler; four threads share a reactor's h1 column and split the hidden units
 constexpr int ROLL_THREADS = ROLL_M * ROLL_PARTS;
 
 template <int MODE, int KIND>
-__global__ void __launch_bounds__(ROLL_THREADS, 1)
+__global__ void __launch_bounds__(ROLL_THREADS, ROLL_MINB)
 rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, float sigma, const float2 *__restrict__ noise, int warmup,
                    uint32_t t_base, float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode,
                    double *static_base, int64_t rows, int64_t pos0, float4 *__restrict__ records, double *reward_sum, cstr_episode_stats stats,
                    int has_stats) {
     extern __shared__ float h1[];  // [H1][ROLL_M], then the state column [ROLL_M] float4 and the partial heads [PARTS][4][ROLL_M]
     constexpr int NOUT = KIND == CSTR_ACTOR_GAUSSIAN ? 4 : 2;
-    const int m = threadIdx.x & (ROLL_M - 1), part = threadIdx.x >> 7;  // part is warp-uniform
+    const int m = threadIdx.x & (ROLL_M - 1), part = threadIdx.x >> ROLL_M_LOG2;  // part is warp-uniform
     const bool owner = part == 0;  // owns the reactor: state registers, head, env step, record
     const int64_t i = (int64_t)blockIdx.x * ROLL_M + m;
     const bool live = i < n;
