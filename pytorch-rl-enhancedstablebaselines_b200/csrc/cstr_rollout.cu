@@ -8,8 +8,8 @@
 //   VecEnv.step -> TwoSeriesCSTREnv.step core/common/vec_env/dummy_vec_env.py:56-73, twoseriescstr.py:394-454
 //   _store_transition + ReplayBuffer.add core/common/off_policy_algorithm.py:445-508, core/common/buffers.py:247-283
 //
-// actor_mode 0 (this file, fp32 CUDA cores): the parity path.  One CTA = 128 reactors, four threads
-// per reactor.  Layer 1 (K=4) is computed by the reactor's threads and parked in shared memory k-major
+// actor_mode 0 (this file, fp32 CUDA cores): the parity path.  One CTA = 128 reactors and 16 warps; every lane works on
+// four reactors.  Layer 1 (K=4) is computed by the reactor's threads and parked in shared memory k-major
 // (h1[k][m]: conflict-free); layer 2 is a register-tiled contraction, 12 outputs per pass with the
 // W2 rows fetched as warp-uniform 16-byte loads (L1-resident, 480 KB total streams from L2); layer 3
 // (N=2) and tanh are folded into the layer-2 epilogue so h2 never exists in memory.
@@ -20,44 +20,37 @@
 
 namespace cstr {
 
-#ifndef ROLL_M_LOG2
-#define ROLL_M_LOG2 7
-#endif
-#ifndef ROLL_PARTS_
-#define ROLL_PARTS_ 4
-#endif
-#ifndef ROLL_NB_
-#define ROLL_NB_ 12
-#endif
-#ifndef ROLL_MINB
-#define ROLL_MINB 1
-#endif
-constexpr int ROLL_M = 1 << ROLL_M_LOG2;  // reactors per CTA
-constexpr int ROLL_NB = ROLL_NB_;    // layer-2 outputs per register pass
-constexpr int ROLL_PARTS = ROLL_PARTS_;  // threads per reactor: h1 of 128 reactors fills shared memory, so one thread per reactor leaves ONE
-                               // warp per scheduler; four threads share a reactor's h1 column and split the hidden units
-constexpr int ROLL_THREADS = ROLL_M * ROLL_PARTS;
+constexpr int ROLL_M = 128;     // reactors per CTA (their h1 columns fill shared memory)
+constexpr int ROLL_R = 4;       // reactors per thread in the actor: lane l works on reactors l, l+32, l+64, l+96
+constexpr int ROLL_NB = 12;     // layer-2 outputs per register pass
+constexpr int ROLL_PARTS = 16;  // warps per CTA; warp p takes the hidden units / output blocks p, p+16, ...
+constexpr int ROLL_THREADS = ROLL_PARTS * 32;
+// The kernel is bound by the L1 data pipe (ncu: 87 % of its wavefronts, FMA pipe 32 % with one reactor per thread): every
+// warp-uniform 16-byte load of a W2 row piece and every h1 read is one wavefront.  Register-blocking FOUR reactors per thread
+// makes one W2 load feed 16 FMAs per lane instead of 4: 28 wavefronts per 192 FMA instructions instead of 64.
 
 template <int MODE, int KIND>
-__global__ void __launch_bounds__(ROLL_THREADS, ROLL_MINB)
+__global__ void __launch_bounds__(ROLL_THREADS, 1)
 rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, float sigma, const float2 *__restrict__ noise, int warmup,
                    uint32_t t_base, float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode,
                    double *static_base, int64_t rows, int64_t pos0, float4 *__restrict__ records, double *reward_sum, cstr_episode_stats stats,
                    int has_stats) {
-    extern __shared__ float h1[];  // [H1][ROLL_M], then the state column [ROLL_M] float4 and the partial heads [PARTS][4][ROLL_M]
+    extern __shared__ float h1[];  // [H1][ROLL_M] (reused for the partial heads [PARTS][4][ROLL_M] once layer 2 is done), then the state column
     constexpr int NOUT = KIND == CSTR_ACTOR_GAUSSIAN ? 4 : 2;
-    const int m = threadIdx.x & (ROLL_M - 1), part = threadIdx.x >> ROLL_M_LOG2;  // part is warp-uniform
-    const bool owner = part == 0;  // owns the reactor: state registers, head, env step, record
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const bool owner = part < ROLL_M / 32;  // warps 0..3 own one reactor per lane: state registers, head, env step, record
+    const int m = part * 32 + lane;         // the owned reactor (owners only)
     const int64_t i = (int64_t)blockIdx.x * ROLL_M + m;
-    const bool live = i < n;
+    const bool live = owner && i < n;
     const int H1 = actor.H1, H2 = actor.H2;
-    float4 *s_state = reinterpret_cast<float4 *>(h1 + (size_t)H1 * ROLL_M);
-    float *s_o = reinterpret_cast<float *>(s_state + ROLL_M);
-    float4 s = (live && owner) ? state[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    int sc = (live && owner) ? step_count[i] : 0, ep = (live && owner) ? episode[i] : 0;
+    const size_t h1_floats = max((size_t)H1 * ROLL_M, (size_t)ROLL_PARTS * 4 * ROLL_M);
+    float4 *s_state = reinterpret_cast<float4 *>(h1 + h1_floats);
+    float *s_o = h1;
+    float4 s = live ? state[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    int sc = live ? step_count[i] : 0, ep = live ? episode[i] : 0;
     const uint64_t env = (uint64_t)(p.env_offset + i);
     double acc_r = 0.0;
-    double ep_ret = (has_stats && live && owner) ? stats.ep_return[i] : 0.0;
+    double ep_ret = (has_stats && live) ? stats.ep_return[i] : 0.0;
     uint4 cache = make_uint4(0, 0, 0, 0);
 
     for (int64_t k = 0; k < K; ++k) {
@@ -75,62 +68,91 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
         } else {
             if (owner) s_state[m] = s;
             __syncthreads();
-            const float4 sv = s_state[m];
-            // ---- layer 1: h1 = relu(W1 s + b1), parked k-major in shared memory; part p computes every 4th hidden unit
+            float4 sv[ROLL_R];
+#pragma unroll
+            for (int r = 0; r < ROLL_R; ++r) sv[r] = s_state[lane + 32 * r];
+            // ---- layer 1: h1 = relu(W1 s + b1), parked k-major in shared memory; warp p computes the hidden units p, p+16, ...
             for (int j = part; j < H1; j += ROLL_PARTS) {
                 const float4 w = __ldg(reinterpret_cast<const float4 *>(actor.W1) + j);
-                float v = __ldg(actor.b1 + j);
-                v = fmaf(w.x, sv.x, v);
-                v = fmaf(w.y, sv.y, v);
-                v = fmaf(w.z, sv.z, v);
-                v = fmaf(w.w, sv.w, v);
-                h1[j * ROLL_M + m] = fmaxf(v, 0.0f);
+                const float bj = __ldg(actor.b1 + j);
+#pragma unroll
+                for (int r = 0; r < ROLL_R; ++r) {
+                    float v = bj;
+                    v = fmaf(w.x, sv[r].x, v);
+                    v = fmaf(w.y, sv[r].y, v);
+                    v = fmaf(w.z, sv[r].z, v);
+                    v = fmaf(w.w, sv[r].w, v);
+                    h1[j * ROLL_M + lane + 32 * r] = fmaxf(v, 0.0f);
+                }
             }
             __syncthreads();
-            // ---- layer 2 + 3: out = W3 relu(W2 h1 + b2) + b3, 12 hidden units per pass, passes dealt round-robin to the parts
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int nb = part * ROLL_NB; nb < H2; nb += ROLL_PARTS * ROLL_NB) {
-                float acc[ROLL_NB];
+            // ---- layer 2 + 3: out = W3 relu(W2 h1 + b2) + b3, 12 hidden units x 4 reactors per pass, passes dealt round-robin to the warps
+            float o[ROLL_R][4];
 #pragma unroll
-                for (int q = 0; q < ROLL_NB; ++q) acc[q] = 0.0f;
+            for (int r = 0; r < ROLL_R; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[r][c] = 0.f;
+            for (int nb = part * ROLL_NB; nb < H2; nb += ROLL_PARTS * ROLL_NB) {
+                float acc[ROLL_NB][ROLL_R];
+#pragma unroll
+                for (int q = 0; q < ROLL_NB; ++q)
+#pragma unroll
+                    for (int r = 0; r < ROLL_R; ++r) acc[q][r] = 0.0f;
                 const int H1v = H1 & ~3;
                 for (int kk = 0; kk < H1v; kk += 4) {
-                    const float a0 = h1[(kk + 0) * ROLL_M + m], a1 = h1[(kk + 1) * ROLL_M + m];
-                    const float a2 = h1[(kk + 2) * ROLL_M + m], a3 = h1[(kk + 3) * ROLL_M + m];
+                    float a[4][ROLL_R];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int r = 0; r < ROLL_R; ++r) a[c][r] = h1[(kk + c) * ROLL_M + lane + 32 * r];
 #pragma unroll
                     for (int q = 0; q < ROLL_NB; ++q) {
                         const int row = min(nb + q, H2 - 1);  // clamp: tail lanes recompute the last row, discarded below
                         const float4 w = __ldg(reinterpret_cast<const float4 *>(actor.W2 + (size_t)row * H1 + kk));
-                        acc[q] = fmaf(w.x, a0, acc[q]);
-                        acc[q] = fmaf(w.y, a1, acc[q]);
-                        acc[q] = fmaf(w.z, a2, acc[q]);
-                        acc[q] = fmaf(w.w, a3, acc[q]);
+#pragma unroll
+                        for (int r = 0; r < ROLL_R; ++r) {  // same summation order per reactor as the one-reactor version
+                            acc[q][r] = fmaf(w.x, a[0][r], acc[q][r]);
+                            acc[q][r] = fmaf(w.y, a[1][r], acc[q][r]);
+                            acc[q][r] = fmaf(w.z, a[2][r], acc[q][r]);
+                            acc[q][r] = fmaf(w.w, a[3][r], acc[q][r]);
+                        }
                     }
                 }
                 for (int kk = H1v; kk < H1; ++kk) {
-                    const float a0 = h1[kk * ROLL_M + m];
 #pragma unroll
-                    for (int q = 0; q < ROLL_NB; ++q) acc[q] = fmaf(__ldg(actor.W2 + (size_t)min(nb + q, H2 - 1) * H1 + kk), a0, acc[q]);
+                    for (int q = 0; q < ROLL_NB; ++q) {
+                        const float w = __ldg(actor.W2 + (size_t)min(nb + q, H2 - 1) * H1 + kk);
+#pragma unroll
+                        for (int r = 0; r < ROLL_R; ++r) acc[q][r] = fmaf(w, h1[kk * ROLL_M + lane + 32 * r], acc[q][r]);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < ROLL_NB; ++q) {
                     if (nb + q < H2) {
-                        const float h = fmaxf(acc[q] + __ldg(actor.b2 + nb + q), 0.0f);
+                        const float b2 = __ldg(actor.b2 + nb + q);
 #pragma unroll
-                        for (int r = 0; r < NOUT; ++r) o[r] = fmaf(__ldg(actor.W3 + (size_t)r * H2 + nb + q), h, o[r]);
+                        for (int c = 0; c < NOUT; ++c) {
+                            const float w3 = __ldg(actor.W3 + (size_t)c * H2 + nb + q);
+#pragma unroll
+                            for (int r = 0; r < ROLL_R; ++r) o[r][c] = fmaf(w3, fmaxf(acc[q][r] + b2, 0.0f), o[r][c]);
+                        }
                     }
                 }
             }
+            __syncthreads();  // every warp is done with h1: its memory now carries the partial heads
 #pragma unroll
-            for (int r = 0; r < NOUT; ++r) s_o[(part * 4 + r) * ROLL_M + m] = o[r];
+            for (int r = 0; r < ROLL_R; ++r)
+#pragma unroll
+                for (int c = 0; c < NOUT; ++c) s_o[(part * 4 + c) * ROLL_M + lane + 32 * r] = o[r][c];
             __syncthreads();
             if (owner) {
+                float oo[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int r = 0; r < NOUT; ++r) {  // fixed order: bias, then parts 0..3
-                    float v = __ldg(actor.b3 + r);
+                for (int c = 0; c < NOUT; ++c) {  // fixed order: bias, then warps 0..15
+                    float v = __ldg(actor.b3 + c);
 #pragma unroll
-                    for (int q = 0; q < ROLL_PARTS; ++q) v += s_o[(q * 4 + r) * ROLL_M + m];
-                    o[r] = v;
+                    for (int q = 0; q < ROLL_PARTS; ++q) v += s_o[(q * 4 + c) * ROLL_M + m];
+                    oo[c] = v;
                 }
                 float2 nz;
                 if (noise) nz = live ? noise[k * n + i] : make_float2(0.f, 0.f);
@@ -139,12 +161,12 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
                 else nz = make_float2(0.f, 0.f);
                 float mu0, mu1;
                 float2 add;
-                actor_head<KIND>(o, nz, mu0, mu1, add);
+                actor_head<KIND>(oo, nz, mu0, mu1, add);
                 action_maps(mu0, add.x, env_a.x, buf_a.x);
                 action_maps(mu1, add.y, env_a.y, buf_a.y);
             }
         }
-        if (!owner) continue;  // (the barriers above are reached by every thread on every step before this point)
+        if (!owner) continue;  // (every thread has passed this step's barriers by now)
         // ---- env step + transition record
         const float4 obs = s;
         const StepResult r = (MODE == CSTR_MATH_STRICT) ? step_strict_f32(s, env_a, sc, (float)p.target_c2, p.max_steps)
@@ -170,7 +192,7 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
     if (reward_sum) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc_r += __shfl_down_sync(0xffffffffu, acc_r, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(reward_sum, acc_r);
+        if (lane == 0) atomicAdd(reward_sum, acc_r);
     }
 }
 
@@ -208,8 +230,9 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
     if (actor_mode != 0 && actor_mode != 1) return fail_arg(CSTR_EINVAL, "rollout: unknown actor_mode");
     cstr_actor_f32 a = {};
     if (actor) a = *actor;
-    const size_t smem = warmup ? 0 : (size_t)a.H1 * ROLL_M * sizeof(float) + ROLL_M * sizeof(float4) + (size_t)ROLL_PARTS * 4 * ROLL_M * sizeof(float);
-    if (smem > 227 * 1024) return fail_arg(CSTR_EINVAL, "rollout: H1 too large for the fp32 path (max 432)");
+    const size_t h1_floats = (size_t)a.H1 * ROLL_M > (size_t)ROLL_PARTS * 4 * ROLL_M ? (size_t)a.H1 * ROLL_M : (size_t)ROLL_PARTS * 4 * ROLL_M;
+    const size_t smem = warmup ? 0 : h1_floats * sizeof(float) + ROLL_M * sizeof(float4);
+    if (smem > 227 * 1024) return fail_arg(CSTR_EINVAL, "rollout: H1 too large for the fp32 path (max 448)");
     const int grid = (int)((n + ROLL_M - 1) / ROLL_M);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = 0;
