@@ -30,8 +30,13 @@
 namespace cstr {
 
 constexpr int TC_M = 128;             // reactors per CTA = UMMA M
-constexpr int TC_ENV_THREADS = 256;   // two threads per reactor
-constexpr int TC_THREADS = 352;       // + loader warp + two MMA-issuer warps
+#ifndef TC_PER_
+#define TC_PER_ 2
+#endif
+constexpr int TC_PER = TC_PER_;                 // env threads per reactor (2 or 4): they split the accumulator columns
+constexpr int TC_ENV_THREADS = TC_M * TC_PER;
+constexpr int TC_ENV_WARPS = TC_ENV_THREADS / 32;
+constexpr int TC_THREADS = TC_ENV_THREADS + 96;  // + loader warp + two MMA-issuer warps
 constexpr int TC_WSTAGES = 3;
 constexpr int TC_ASTAGES = 2;
 
@@ -71,7 +76,7 @@ static bool make_geometry(int H1, int H2, TcGeometry &g) {
     g.off_a1 = up(g.off_w1 + 2u * H1 * 16);                     // W1 split-bf16 UMMA image [2][H1][8 x bf16]
     g.off_ep = up(g.off_a1 + 2u * TC_M * 16);                   // layer-1 A operand [2][128][8 x bf16]
     g.off_part = up(g.off_ep + 5u * g.NP * 4);                  // b2 and up to four W3 rows (zero padded)
-    g.off_a = up(g.off_part + 2 * 2 * TC_M * 4 * 4);            // layer-3 partial sums [step parity][half][m] x float4
+    g.off_a = up(g.off_part + 2 * TC_PER * TC_M * 4 * 4);            // layer-3 partial sums [step parity][half][m] x float4
     g.off_w = up(g.off_a + TC_ASTAGES * g.a_chunk_bytes);
     g.smem_bytes = up(g.off_w + TC_WSTAGES * g.w_chunk_bytes);
     return g.smem_bytes <= 227u * 1024u;
@@ -198,7 +203,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         for (int b = 0; b < 2; ++b) { mbar_init(bars + 8 * (BAR_D1_FULL + b), 1); mbar_init(bars + 8 * (BAR_D1_EMPTY + b), TC_ENV_THREADS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {  // TMEM allocation is warp-collective; the same warp frees it at the end
+    if (warp == TC_ENV_WARPS + 1) {  // TMEM allocation is warp-collective; the same warp frees it at the end
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
                      "r"((uint32_t)g.tmem_cols)
                      : "memory");
@@ -235,7 +240,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
 
     const int kgroups = g.KC / 8;  // 16-byte K groups per chunk
 
-    if (warp < 8) {
+    if (warp < TC_ENV_WARPS) {
         // =========================== env warps ===========================================================
         const int m = tid & (TC_M - 1), half = tid >> 7;
         const int64_t i = (int64_t)blockIdx.x * TC_M + m;
@@ -255,7 +260,6 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         }
         uint32_t gchunk = 0;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        const int cols_per_half = NP / 2;
 
 #ifdef CSTR_TC_TIMING
         long long T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0;
@@ -276,10 +280,12 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                 __nv_bfloat162 p0 = __halves2bfloat162(hi[0], hi[1]), p1 = __halves2bfloat162(hi[2], hi[3]);
                 __nv_bfloat162 p2 = half == 0 ? __halves2bfloat162(lo[0], lo[1]) : __halves2bfloat162(one, one);
                 __nv_bfloat162 p3 = half == 0 ? __halves2bfloat162(lo[2], lo[3]) : __halves2bfloat162(z, z);
+                if (half < 2) {  // the layer-1 A operand has two K groups: parts 0 and 1 publish them
                 uint4 pk;
                 pk.x = *reinterpret_cast<uint32_t *>(&p0); pk.y = *reinterpret_cast<uint32_t *>(&p1);
                 pk.z = *reinterpret_cast<uint32_t *>(&p2); pk.w = *reinterpret_cast<uint32_t *>(&p3);
                 *reinterpret_cast<uint4 *>(smem + g.off_a1 + (size_t)half * (TC_M * 16) + m * 16) = pk;  // K group = half
+                }
                 fence_proxy_async();
                 mbar_arrive(bars + 8 * BAR_A1_FULL);
             }
@@ -295,10 +301,11 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                 mbar_wait(bars + 8 * (BAR_D1_FULL + db), duse & 1u);
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + lane_base + (uint32_t)(g.d1_col + (int)db * g.KC);
-                float v[5][8];  // up to 5 K-groups per thread and chunk (KC <= 80, two threads per reactor); static indices only
+                constexpr int KGT = (10 + TC_PER - 1) / TC_PER;  // K-groups per thread and chunk (KC <= 80); static indices only
+                float v[KGT][8];
 #pragma unroll
-                for (int c5 = 0; c5 < 5; ++c5) {
-                    const int kg = half + 2 * c5;
+                for (int c5 = 0; c5 < KGT; ++c5) {
+                    const int kg = half + TC_PER * c5;
                     if (kg < kgroups) tmem_ld8(d1 + (uint32_t)(kg * 8), v[c5]);
                 }
                 tmem_ld_wait();
@@ -309,8 +316,8 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
                 // completion of everything issued before it — so the buffer is already free.
                 uint8_t *abuf = smem + g.off_a + ab * g.a_chunk_bytes;
 #pragma unroll
-                for (int c5 = 0; c5 < 5; ++c5) {
-                    const int kg = half + 2 * c5;
+                for (int c5 = 0; c5 < KGT; ++c5) {
+                    const int kg = half + TC_PER * c5;
                     if (kg < kgroups) {
                         __nv_bfloat162 h01 = __floats2bfloat162_rn(fmaxf(v[c5][0], 0.f), fmaxf(v[c5][1], 0.f));
                         __nv_bfloat162 h23 = __floats2bfloat162_rn(fmaxf(v[c5][2], 0.f), fmaxf(v[c5][3], 0.f));
@@ -331,28 +338,35 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             CSTR_TICK(T2);
             tc_fence_after();
             float o[4] = {0.f, 0.f, 0.f, 0.f};
-            const int c_begin = half * cols_per_half;
-            const uint32_t d2 = tmem_base + lane_base + (uint32_t)c_begin;
+            // the NP/8 eight-column groups of the row are dealt round-robin to the reactor's threads: group index = half + TC_PER * j
+            const uint32_t d2 = tmem_base + lane_base;
+            const int my_groups = (NP / 8 - half + TC_PER - 1) / TC_PER;
             float va[8], vb[8];
-            tmem_ld8(d2, va);
-            for (int c = 0; c < cols_per_half; c += 16) {  // two 8-column groups per trip, loads one group ahead of the math
+            if (my_groups > 0) tmem_ld8(d2 + (uint32_t)(half * 8), va);
+            for (int j = 0; j < my_groups; j += 2) {  // two groups per trip, loads one group ahead of the math
+                const int c0 = (half + TC_PER * j) * 8, c1 = c0 + TC_PER * 8, c2 = c1 + TC_PER * 8;
                 tmem_ld_wait();
-                if (c + 8 < cols_per_half) tmem_ld8(d2 + (uint32_t)(c + 8), vb);
+                if (j + 1 < my_groups) tmem_ld8(d2 + (uint32_t)c1, vb);
                 // constants come as 16-byte broadcast loads (scalar LDS made the epilogue shared-memory-issue bound)
-                epi8<NOUT>(va, sep, NP, c_begin + c, o);
-                if (c + 8 < cols_per_half) {
+                epi8<NOUT>(va, sep, NP, c0, o);
+                if (j + 1 < my_groups) {
                     tmem_ld_wait();
-                    if (c + 16 < cols_per_half) tmem_ld8(d2 + (uint32_t)(c + 16), va);
-                    epi8<NOUT>(vb, sep, NP, c_begin + c + 8, o);
+                    if (j + 2 < my_groups) tmem_ld8(d2 + (uint32_t)c2, va);
+                    epi8<NOUT>(vb, sep, NP, c1, o);
                 }
             }
             CSTR_TICK(T3);
             tc_fence_before();  // TMEM reads are complete before anybody re-arms the accumulator
-            float4 *sp = spart + (size_t)(k & 1) * (2 * TC_M);  // double-buffered by step parity: one barrier per step
+            float4 *sp = spart + (size_t)(k & 1) * (TC_PER * TC_M);  // double-buffered by step parity: one barrier per step
             sp[half * TC_M + m] = make_float4(o[0], o[1], o[2], o[3]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float4 p0 = sp[m], p1 = sp[TC_M + m];
-            const float head[4] = {(p0.x + p1.x) + b3[0], (p0.y + p1.y) + b3[1], (p0.z + p1.z) + b3[2], (p0.w + p1.w) + b3[3]};  // same order in both threads
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_ENV_THREADS) : "memory");
+            float4 ps = sp[m];
+#pragma unroll
+            for (int q = 1; q < TC_PER; ++q) {  // same order in every thread of the reactor
+                const float4 pq = sp[q * TC_M + m];
+                ps.x += pq.x, ps.y += pq.y, ps.z += pq.z, ps.w += pq.w;
+            }
+            const float head[4] = {ps.x + b3[0], ps.y + b3[1], ps.z + b3[2], ps.w + b3[3]};
             float mu0, mu1;
             float2 add;
             actor_head<KIND>(head, nz, mu0, mu1, add);
@@ -397,7 +411,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
             for (int o = 16; o > 0; o >>= 1) acc_r += __shfl_down_sync(0xffffffffu, acc_r, o);
             if (lane == 0 && half == 0) atomicAdd(reward_sum, acc_r);
         }
-    } else if (warp == 8) {
+    } else if (warp == TC_ENV_WARPS) {
         // =========================== W2 loader ===========================================================
         if (lane == 0) {
             const uint32_t total = (uint32_t)(K * g.NKC);
@@ -417,7 +431,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
         // thread's commits, waits and layer-1 MMA overlap the other thread's layer-2 MMAs.  Pipe order between the two
         // threads is the ORDER token (tcgen05.fence::before_thread_sync + mbarrier arrive / wait + fence::after).
         if (lane == 0) {
-            const uint32_t me = (uint32_t)(warp - 9);  // chunk gc is issued by thread (gc & 1)
+            const uint32_t me = (uint32_t)(warp - (TC_ENV_WARPS + 1));  // chunk gc is issued by thread (gc & 1)
             const uint32_t idesc0 = umma_idesc_bf16(TC_M, g.N0), idesc1 = g.N1 ? umma_idesc_bf16(TC_M, g.N1) : 0;
             const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)NP * 16, sbo = 128;
             const uint64_t a_step = (uint64_t)((2u * lbo_a) >> 4), b_step = (uint64_t)((2u * lbo_b) >> 4);  // one K=16 step, in 16-byte units
@@ -485,7 +499,7 @@ rollout_tc_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor,
     // ---- teardown ---------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == TC_ENV_WARPS + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
     }
