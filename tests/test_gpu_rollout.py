@@ -224,3 +224,28 @@ def test_device_episode_stats(pkg, golden, actor_mode):
     assert len(stats.pop()) == 0
     roll.collect(3, stats=stats)
     assert len(stats.pop()) == 0  # nobody finishes in the next 3 steps
+
+
+def test_actor_weights_refresh_from_tensors(pkg, golden):
+    """ActorWeights.refresh_from_tensors (the hand-over from a FusedTD3Update / FusedSACUpdate flat block to the rollout kernel): the
+    fp32 tensors are copied in place and the bf16 UMMA image of W2 is rebuilt, so the next collect() acts with the new weights."""
+    g, _ = _actor(golden)
+    n = 256
+    actor = pkg.ActorWeights(g["W1"], g["b1"], g["W2"], g["b2"], g["W3"], g["b3"])
+    env = pkg.GpuCSTRVecEnv(n, seed=3, monitor=False)
+    env.reset()
+    buf = pkg.GpuReplayBuffer(8 * n, device="cuda", n_envs=n)
+    roll = pkg.FusedRollout(env, buf, actor, sigma=0.0, actor_mode="tc")
+    roll.collect(1)
+    a_old = buf.records[0, :, 8:10].clone()
+    packed_old = actor.packed_bf16.clone()
+    new = [torch.as_tensor(g[k]).cuda() for k in ("W1", "b1", "W2", "b2", "W3", "b3")]
+    new[2] = -new[2]  # flip the hidden layer: a different policy
+    ptrs = [t.data_ptr() for t in (actor.W1, actor.W2, actor.packed_bf16)]
+    actor.refresh_from_tensors(new)
+    assert ptrs == [t.data_ptr() for t in (actor.W1, actor.W2, actor.packed_bf16)]  # in place: the kernel's pointers stay valid
+    assert torch.equal(actor.W2, new[2]) and not torch.equal(actor.packed_bf16, packed_old)
+    env.reset()
+    buf.reset()
+    roll.collect(1)
+    assert not torch.allclose(buf.records[0, :, 8:10], a_old, atol=1e-3)
