@@ -320,6 +320,45 @@ class FusedTD3Update:
         return critic, actor
 
 
+def fused_update_unsupported(model, max_critics: int = 2) -> Optional[str]:
+    """Why the fused kernels can NOT stand in for ``model.train()`` — or None when they can.  The kernels are specialised to what the
+    reference's TD3/DDPG/SAC build by default for the CSTR task (core/td3/policies.py:117-170, core/sac/policies.py:218-262): a flat
+    4-value observation, a 2-value action, two ReLU hidden layers shared by actor and critics (multiples of 4), 1-2 critics and plain
+    Adam.  Anything else keeps the reference's own torch ``train()``."""
+    import torch.nn as nn
+    import torch.optim as optim
+    pol = model.policy
+    if tuple(model.observation_space.shape or ()) != (4,) or tuple(model.action_space.shape or ()) != (2,):
+        return f"spaces {model.observation_space.shape} -> {model.action_space.shape} are not the CSTR's (4,) -> (2,)"
+    if getattr(pol, "activation_fn", nn.ReLU) is not nn.ReLU:
+        return f"activation_fn {pol.activation_fn.__name__} (kernels are ReLU)"
+    arch = pol.net_arch
+    if isinstance(arch, dict):
+        if list(arch.get("pi", [])) != list(arch.get("qf", [])):
+            return "different actor and critic net_arch"
+        arch = arch["pi"]
+    arch = list(arch)
+    if len(arch) != 2 or any(int(h) < 4 or int(h) > 4096 or int(h) % 4 for h in arch):
+        return f"net_arch {arch}: two hidden layers, multiples of 4 in [4, 4096]"
+    n_critics = len(pol.critic.q_networks)
+    if not 1 <= n_critics <= max_critics:
+        return f"n_critics={n_critics}"
+    if type(pol.actor.features_extractor).__name__ != "FlattenExtractor":
+        return f"features extractor {type(pol.actor.features_extractor).__name__}"
+    for opt in (pol.actor.optimizer, pol.critic.optimizer):
+        g = opt.param_groups[0]
+        if type(opt) is not optim.Adam or g.get("weight_decay", 0) or g.get("amsgrad", False) or g.get("maximize", False):
+            return f"optimizer {type(opt).__name__} {({k: v for k, v in g.items() if k in ('weight_decay', 'amsgrad', 'maximize')})} (kernels are plain Adam)"
+    return None
+
+
+def _fallback_once(model, why: str) -> None:
+    if not getattr(model, "_fused_fallback_warned", False):
+        import warnings
+        warnings.warn(f"fused update not used, the reference's torch train() runs instead: {why}", RuntimeWarning, stacklevel=3)
+        model._fused_fallback_warned = True
+
+
 def bind_td3_class(td3_base: type) -> type:
     """Return a subclass of the reference's ``TD3`` (or of ``DDPG``, which is TD3 with one critic, core/ddpg/ddpg.py) whose ``train()``
     (core/td3/td3.py:154-211) runs on ``cstr_td3_update``.
@@ -342,6 +381,10 @@ def bind_td3_class(td3_base: type) -> type:
             return self._fused
 
         def train(self, gradient_steps: int, batch_size: int = 100) -> None:
+            why = fused_update_unsupported(self) if self._fused is None else None
+            if why:
+                _fallback_once(self, why)
+                return super().train(gradient_steps, batch_size)
             self.policy.set_training_mode(True)
             self._update_learning_rate([self.actor.optimizer, self.critic.optimizer])
             eng = self._fused_engine(batch_size)
@@ -490,8 +533,13 @@ def bind_sac_class(sac_base: type) -> type:
         _fused: Optional[FusedSACUpdate] = None
 
         def train(self, gradient_steps: int, batch_size: int = 64) -> None:
-            if self.use_sde or self.ent_coef_optimizer is None:
-                return super().train(gradient_steps, batch_size)  # gSDE / fixed ent_coef: the reference's torch path
+            why = None
+            if self._fused is None:
+                why = ("use_sde" if self.use_sde else "fixed ent_coef" if self.ent_coef_optimizer is None else
+                       "n_critics != 2" if len(self.policy.critic.q_networks) != 2 else fused_update_unsupported(self))
+            if why:  # the reference's torch path
+                _fallback_once(self, why)
+                return super().train(gradient_steps, batch_size)
             self.policy.set_training_mode(True)
             self._update_learning_rate([self.actor.optimizer, self.critic.optimizer, self.ent_coef_optimizer])
             if self._fused is None:

@@ -128,3 +128,40 @@ def test_sac_update_default_arch_live(ref_env_module):
         for a, b in zip(final[name], ref[name]):
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)
     assert np.mean(o.actor_losses) == pytest.approx(float(g["actor_loss_mean"]), rel=1e-5)
+
+
+def test_fused_update_support_check_live(ref_env_module):
+    """``fused_update_unsupported`` on live reference models: the defaults qualify, anything the kernels do not implement is named —
+    and a bound class then runs the reference's own torch ``train()`` (here on CPU, where the fused engine could not even be built)."""
+    import importlib
+    import warnings
+
+    import torch
+
+    core = refload.load_core()  # mirrors the tree first (the bare reference package cannot be imported from a read-only mount)
+    from core.common.vec_env import DummyVecEnv
+
+    pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
+    upd = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200.update")
+    torch.set_num_threads(1)
+    venv = DummyVecEnv([lambda: ref_env_module.TwoSeriesCSTREnv(init_mode="random")])
+    mk = lambda cls, **kw: cls("MlpPolicy", venv, buffer_size=500, batch_size=16, learning_starts=0, device="cpu", seed=1, **kw)  # noqa: E731
+    assert upd.fused_update_unsupported(mk(core.TD3)) is None
+    assert upd.fused_update_unsupported(mk(core.DDPG)) is None
+    assert upd.fused_update_unsupported(mk(core.SAC)) is None
+    assert "activation_fn" in upd.fused_update_unsupported(mk(core.TD3, policy_kwargs=dict(activation_fn=torch.nn.Tanh)))
+    assert "net_arch" in upd.fused_update_unsupported(mk(core.TD3, policy_kwargs=dict(net_arch=[64])))
+    assert "net_arch" in upd.fused_update_unsupported(mk(core.TD3, policy_kwargs=dict(net_arch=[64, 30])))
+    assert "different" in upd.fused_update_unsupported(mk(core.SAC, policy_kwargs=dict(net_arch=dict(pi=[64, 64], qf=[32, 32]))))
+    assert "n_critics" in upd.fused_update_unsupported(mk(core.TD3, policy_kwargs=dict(n_critics=3)))
+    assert "optimizer" in upd.fused_update_unsupported(mk(core.TD3, policy_kwargs=dict(optimizer_class=torch.optim.SGD)))
+    assert "optimizer" in upd.fused_update_unsupported(mk(core.TD3, policy_kwargs=dict(optimizer_kwargs=dict(weight_decay=1e-2))))
+    # an unsupported model under the bound class trains through the reference's code path
+    model = mk(pkg.bind_td3_class(core.TD3), policy_kwargs=dict(activation_fn=torch.nn.Tanh, net_arch=[32, 32]))
+    before = [p.detach().clone() for p in model.critic.parameters()]
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        model.learn(total_timesteps=40)
+    assert any("fused update not used" in str(x.message) for x in w)
+    assert model._fused is None and model._n_updates > 0
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.critic.parameters()))
