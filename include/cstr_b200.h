@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 13
+#define CSTR_B200_ABI_VERSION 14
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -248,7 +248,11 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *state, con
  * ent_coef_loss, ent_coef as {sum, count} pairs; counters as for TD3 — critic_step is the shared Adam step, the target
  * sync decision uses the by-value n_updates).  eps_pi / eps_next: (batch,2) standard-normal draws
  * of the two rsample() calls, or NULL = Philox (key seed, counter (row, n_updates), stream 5, call 0 / 1).
- * n_updates and adam_step are the values AFTER this update (1-based; all three optimisers share the step count).       */
+ * n_updates and adam_step are the values AFTER this update (1-based; all three optimisers share the step count).
+ * phases: the CSTR_TD3_* bits.  CRITIC_GRAD = actor sample, d loss / d log_ent_coef (-> grads[log_ent_coef]), target,
+ * critic gradients; CRITIC_APPLY = Adam on log_ent_coef and the critics; ACTOR_GRAD = actor loss backward; ACTOR_APPLY = actor
+ * Adam + polyak.  A data-parallel caller all-reduces grads[critic0 .. log_ent_coef] after CRITIC_GRAD and grads[actor] after
+ * ACTOR_GRAD; the intermediate activations of the earlier phases stay in the workspace.                               */
 typedef struct cstr_sac_config {
     int32_t h1, h2, batch, target_update_interval;
     float gamma, tau, lr, beta1, beta2, eps, target_entropy, reserved0;
@@ -261,7 +265,7 @@ int cstr_sac_layout(int32_t h1, int32_t h2, int64_t *offsets /* 20 */);
 int64_t cstr_sac_workspace_bytes(const cstr_sac_config *cfg);
 int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *state, const float *obs, const float *actions,
                     const float *next_obs, const float *dones, const float *rewards, const float *eps_pi,
-                    const float *eps_next, int64_t n_updates, int64_t adam_step, void *stream);
+                    const float *eps_next, int64_t n_updates, int64_t adam_step, int32_t phases, void *stream);
 
 /* ---- fused rollout --------------------------------------------------------------------------------
  * Replaces, for K consecutive env steps of N reactors, OffPolicyAlgorithm._sample_action +

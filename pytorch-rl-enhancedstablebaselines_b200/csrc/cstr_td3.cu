@@ -462,27 +462,36 @@ sac_actor_head_kernel(int B, int H2, const float *__restrict__ h2, const float *
 // entropy coefficient: ent_coef = exp(log_ent_coef) BEFORE the step (used by this update's target and actor loss),
 // loss = -(log_ent_coef * (log_prob + target_entropy)).mean(), one Adam step on the scalar            sac.py:226-243
 // scalars[5] = ent_coef of this update.  losses: [4] += ent_coef_loss, [5] += 1, [6] += ent_coef, [7] += 1.
+// mode bit 0: form the gradient (-> grad[0]); bit 1: Adam step from grad[0] (split for the data-parallel all-reduce in between).
 __global__ void sac_ent_coef_kernel(int B, int n_partial, const float *__restrict__ lp_partial, float target_entropy, float *__restrict__ log_ent_coef,
-                                    float *__restrict__ m, float *__restrict__ v, float beta1, float beta2, float eps, float step_size_arg, float bc2_sqrt_arg,
-                                    int use_dev_scalars, float *__restrict__ scalars, float *__restrict__ losses) {
+                                    float *__restrict__ grad, float *__restrict__ m, float *__restrict__ v, float beta1, float beta2, float eps,
+                                    float step_size_arg, float bc2_sqrt_arg, int use_dev_scalars, float *__restrict__ scalars, float *__restrict__ losses,
+                                    int mode) {
     __shared__ float sl[256];
-    float s = 0.f;
-    for (int k = threadIdx.x; k < n_partial; k += 256) s += lp_partial[k];
-    sl[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) sl[threadIdx.x] += sl[threadIdx.x + o];
+    if (mode & 1) {
+        float s = 0.f;
+        for (int k = threadIdx.x; k < n_partial; k += 256) s += lp_partial[k];
+        sl[threadIdx.x] = s;
         __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sl[threadIdx.x] += sl[threadIdx.x + o];
+            __syncthreads();
+        }
     }
     if (threadIdx.x) return;
     const float step_size = use_dev_scalars ? scalars[0] : step_size_arg, bc2_sqrt = use_dev_scalars ? scalars[1] : bc2_sqrt_arg;
-    const float mean_term = sl[0] / (float)B + target_entropy;  // mean(log_prob + target_entropy)
-    const float le = log_ent_coef[0], g = -mean_term;
-    scalars[5] = expf(le);
-    if (losses) {
-        losses[4] += -(le * mean_term), losses[5] += 1.f;
-        losses[6] += scalars[5], losses[7] += 1.f;
+    const float le = log_ent_coef[0];
+    if (mode & 1) {
+        const float mean_term = sl[0] / (float)B + target_entropy;  // mean(log_prob + target_entropy)
+        grad[0] = -mean_term;
+        scalars[5] = expf(le);
+        if (losses) {
+            losses[4] += -(le * mean_term), losses[5] += 1.f;
+            losses[6] += scalars[5], losses[7] += 1.f;
+        }
     }
+    if (!(mode & 2)) return;
+    const float g = grad[0];
     float mm = m[0], vv = v[0];
     mm = mm + (g - mm) * (1.f - beta1);
     vv = vv * beta2 + (1.f - beta2) * g * g;
@@ -1178,8 +1187,9 @@ int64_t cstr_sac_workspace_bytes(const cstr_sac_config *cfg) {
 
 int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const float *obs, const float *actions, const float *next_obs,
                     const float *dones, const float *rewards, const float *eps_pi, const float *eps_next, int64_t n_updates, int64_t adam_step,
-                    void *stream) {
+                    int32_t phases, void *stream) {
     if (int rc = check_sac_cfg(cfg)) return rc;
+    if (!(phases & CSTR_TD3_ALL) || (phases & ~CSTR_TD3_ALL)) return fail_arg(CSTR_EINVAL, "sac_update: phases must be a non-empty subset of CSTR_TD3_ALL");
     if (!stt || !stt->params || !stt->targets || !stt->grads || !stt->adam_m || !stt->adam_v || !stt->workspace)
         return fail_arg(CSTR_EINVAL, "sac_update: null state pointer");
     if (!obs || !actions || !next_obs || !dones || !rewards) return fail_arg(CSTR_EINVAL, "sac_update: null batch pointer");
@@ -1203,18 +1213,25 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
     const float step_size = (float)((double)cfg->lr / bc1), bc2_sqrt = (float)sqrt(bc2);
 
     const float *dev_sc = stt->counters ? w.scalars : nullptr;  // graph mode: per-update scalars live on the device (td3_tick_kernel)
-    if (stt->counters) {
+    const bool fused_ent = (phases & (CSTR_TD3_CRITIC_GRAD | CSTR_TD3_CRITIC_APPLY)) == (CSTR_TD3_CRITIC_GRAD | CSTR_TD3_CRITIC_APPLY);
+    auto ent_coef = [&](int mode) {
+        sac_ent_coef_kernel<<<1, 256, 0, st>>>(B, rb, w.lp_partial, cfg->target_entropy, stt->params + ent, stt->grads + ent, stt->adam_m + ent,
+                                              stt->adam_v + ent, cfg->beta1, cfg->beta2, cfg->eps, step_size, bc2_sqrt, dev_sc ? 1 : 0, w.scalars,
+                                              stt->losses, mode);
+        return check_launch("sac_ent_coef_kernel");
+    };
+    if (stt->counters && (phases & CSTR_TD3_CRITIC_GRAD)) {
         td3_tick_kernel<<<1, 32, 0, st>>>(stt->counters, w.scalars, 1, (double)cfg->lr, (double)cfg->beta1, (double)cfg->beta2);
         if (int rc = check_launch("td3_tick_kernel")) return rc;
     }
+    if (phases & CSTR_TD3_CRITIC_GRAD) {
     // ---- actions_pi, log_prob of the current actor (sac.py:222-223) and the entropy-coefficient step (:226-243) ----
     if (int rc = forward_hidden(B, H1, H2, OBS, obs, nullptr, actor, 0, 1, w.a_h1, w.a_h2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
     sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.a_h2, actor.w3, actor.b3, (const float2 *)eps_pi, cfg->seed, (uint32_t)n_updates, dev_sc, 0u, (float2 *)w.a_pi,
                                              w.logp, (float2 *)w.std_eps, (float2 *)w.raw_log_std, w.lp_partial);
     if (int rc = check_launch("sac_actor_head_kernel")) return rc;
-    sac_ent_coef_kernel<<<1, 256, 0, st>>>(B, rb, w.lp_partial, cfg->target_entropy, stt->params + ent, stt->adam_m + ent, stt->adam_v + ent, cfg->beta1,
-                                          cfg->beta2, cfg->eps, step_size, bc2_sqrt, dev_sc ? 1 : 0, w.scalars, stt->losses);
-    if (int rc = check_launch("sac_ent_coef_kernel")) return rc;
+    // one launch when nothing sits between gradient and step; split around the caller's all-reduce of grads[critics .. log_ent_coef] otherwise
+    if (int rc = ent_coef(fused_ent ? 3 : 1)) return rc;
     // ---- target (sac.py:245-254): next action from the CURRENT actor (scratch: the dz slabs are free here) ----
     if (int rc = forward_hidden(B, H1, H2, OBS, next_obs, nullptr, actor, 0, 1, w.dz1, w.dz2, w.tensor, st, w.slabs, w.slab_cap)) return rc;
     sac_actor_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.dz2, actor.w3, actor.b3, (const float2 *)eps_next, cfg->seed, (uint32_t)n_updates, dev_sc, 1u,
@@ -1238,7 +1255,10 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         if (int rc = launch_skinny<1, true>(s, 2, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<w3>", &J)) return rc;
         if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st, &J)) return rc;
     }
-    {
+    }  // CRITIC_GRAD
+    if (phases & CSTR_TD3_CRITIC_APPLY) {
+        if (!fused_ent)
+            if (int rc = ent_coef(2)) return rc;
         ApplyArgs a{};
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
         a.adam_lo = T.critic_off[0], a.adam_hi = T.total, a.polyak_lo = a.polyak_hi = 0;
@@ -1248,6 +1268,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         td3_apply_kernel<<<(unsigned)((a.adam_hi - a.adam_lo + 255) / 256), 256, 0, st>>>(a);
         if (int rc = check_launch("td3_apply_kernel<sac critic>")) return rc;
     }
+    if (phases & CSTR_TD3_ACTOR_GRAD) {
     // ---- actor (sac.py:270-281): (ent_coef * log_prob - min_i Q_i(s, a_pi)).mean() with the updated critics ----
     if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st, w.slabs, w.slab_cap)) return rc;
     sac_qmin_head_kernel<<<rb, 256, 0, st>>>(B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.logp, w.scalars, w.dz2, w.loss_partial);
@@ -1266,7 +1287,8 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         if (int rc = launch_skinny<2 * ACT, true>(s, 1, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<sac head>", &J)) return rc;
         if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, w.t_h2, w.t_h1, w, true, st, &J)) return rc;
     }
-    {
+    }  // ACTOR_GRAD
+    if (phases & CSTR_TD3_ACTOR_APPLY) {
         ApplyArgs a{};
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
         a.adam_lo = T.actor_off, a.adam_hi = T.actor_off + T.actor.size;

@@ -485,9 +485,10 @@ class FusedSACUpdate(FusedTD3Update):
             view.copy_(p.data.to(self.device, self._torch.float32))
             p.data = view
 
-    def update(self, batch, eps_pi=None, eps_next=None) -> None:  # type: ignore[override]
+    def update(self, batch, eps_pi=None, eps_next=None, allreduce: Optional[Callable[[Any], None]] = None) -> None:  # type: ignore[override]
         """One iteration of sac.py:213-288.  ``eps_pi`` / ``eps_next``: explicit standard-normal draws (B,2) of the two rsample() calls
-        (parity tests); default = Philox inside the kernel."""
+        (parity tests); default = Philox inside the kernel.  ``allreduce``: called on grads[critics .. log_ent_coef] and on grads[actor]
+        between backward and Adam (data-parallel training: every rank ends with the gradient of the global batch)."""
         obs, act, nobs, dones, rew = batch
         self._set_batch(int(obs.shape[0]))
         obs, act, nobs = self._f32(obs, 4), self._f32(act, 2), self._f32(nobs, 4)
@@ -498,26 +499,37 @@ class FusedSACUpdate(FusedTD3Update):
         self.critic_step += 1
         self.actor_step += 1
         cfg, st = self._sac_config(self._batch), self._state(counters=False)
-        with self._torch.cuda.device(self.device):
+
+        def run(phases):
             rc = self._libc.cstr_sac_update(byref(cfg), byref(st), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones), _lib.ptr(rew),
-                                            _lib.ptr(e1), _lib.ptr(e2), self.n_updates, self.critic_step, self._stream())
-        _lib.check(rc, "cstr_sac_update")
+                                            _lib.ptr(e1), _lib.ptr(e2), self.n_updates, self.critic_step, phases, self._stream())
+            _lib.check(rc, "cstr_sac_update")
+
+        with self._torch.cuda.device(self.device):
+            if allreduce is None:
+                run(_lib.TD3_ALL)
+            else:
+                run(_lib.TD3_CRITIC_GRAD)
+                allreduce(self.grads[self.critic_range[0]:self._ent_offset + 4])  # both critics and the log_ent_coef slot, contiguous
+                run(_lib.TD3_CRITIC_APPLY | _lib.TD3_ACTOR_GRAD)
+                allreduce(self.grads[self.actor_range[0]:self.actor_range[1]])
+                run(_lib.TD3_ACTOR_APPLY)
         self.launches += 50
 
     def _graph_launch(self, batch_size: int, st, out, k: int) -> None:
         cfg = self._sac_config(batch_size)
         rc = self._libc.cstr_sac_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(out[4]),
-                                        None, None, 1, 1, self._stream())
+                                        None, None, 1, 1, _lib.TD3_ALL, self._stream())
         _lib.check(rc, "cstr_sac_update (graph capture)")
 
-    def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, graph: bool = False, **_unused) -> None:  # type: ignore[override]
-        """``graph=True`` (Philox-index buffer, full ring, target_update_interval 1): every update replays one captured CUDA graph."""
+    def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, allreduce=None, graph: bool = False) -> None:  # type: ignore[override]
+        """``graph=True`` (single GPU, Philox-index buffer, full ring, target_update_interval 1): every update replays one captured CUDA graph."""
         bs = int(batch_size or self._batch)
         done = 0
-        if graph and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1:
+        if graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1:
             done = self._train_graph(gradient_steps, buffer, bs, env)
         for _ in range(gradient_steps - done):
-            self.update(buffer.sample(bs, env=env))
+            self.update(buffer.sample(bs, env=env), allreduce=allreduce)
 
     def pop_losses(self):
         """(critic loss, actor loss, ent_coef_loss, ent_coef) means since the last call — the keys SAC.train logs (sac.py:290-296)."""

@@ -161,8 +161,10 @@ def test_sac_update_ragged_sizes_and_argument_errors(pkg, B, arch):
     ptrs = [data[k][1].data_ptr() for k in ("obs", "act", "nobs", "done", "rew")]
     stream = torch.cuda.current_stream().cuda_stream
     st.workspace_bytes = 16
-    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 1, 1, stream) < 0 and b"workspace" in lib.cstr_last_error()
+    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 1, 1, 15, stream) < 0 and b"workspace" in lib.cstr_last_error()
     st.workspace_bytes = ws[1].numel() * 4
-    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 0, 1, stream) < 0
+    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 0, 1, 15, stream) < 0
+    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 1, 1, 0, stream) < 0 and b"phases" in lib.cstr_last_error()
+    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 1, 1, 16, stream) < 0
     cfg.target_update_interval = 0
-    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 1, 1, stream) < 0 and lib.cstr_sac_param_count(37, 20) == -1
+    assert lib.cstr_sac_update(byref(cfg), byref(st), *ptrs, None, None, 1, 1, 15, stream) < 0 and lib.cstr_sac_param_count(37, 20) == -1

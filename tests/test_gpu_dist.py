@@ -72,8 +72,33 @@ if rank == 0:
         full.update(b[:5], noise=b[5])
     td3_err = max(float((full.params - dp.params).abs().max()), float((full.targets - dp.targets).abs().max()))
     td3_same = all(bool(torch.equal(p.to(dev), dp.params)) for p in peers)
+# (4) the same for SAC: the log_ent_coef gradient travels with the critics' range, the actor range follows
+def mlp_sac(i, o):
+    out = []
+    for fi, fo in ((i, 256), (256, 256), (256, o)):
+        out += [rng.uniform(-1, 1, (fo, fi)).astype(np.float32) / np.sqrt(fi), rng.uniform(-0.05, 0.05, fo).astype(np.float32)]
+    return out
+sac_nets = {"actor": mlp_sac(4, 4), "critic0": mlp_sac(6, 1), "critic1": mlp_sac(6, 1)}
+sac_nets["actor"][5][2:4] -= np.float32(1.0)
+sac_batches = [b[:5] + (rng.normal(size=(B, 2)).astype(np.float32), rng.normal(size=(B, 2)).astype(np.float32)) for b in batches]
+sdp = pkg.FusedSACUpdate([256, 256], B // world, device=dev, ent_coef_init=0.7)
+sdp.load_nets(sac_nets)
+for b in sac_batches:
+    sdp.update(tuple(t[sl] for t in b[:5]), eps_pi=b[5][sl], eps_next=b[6][sl], allreduce=pkg.dist.allreduce_flat)
+sac_err = sac_same = None
+peers = [torch.empty_like(sdp.params) for _ in range(world)]
+dist.all_gather(peers, sdp.params)
 if rank == 0:
-    print(json.dumps({"ok_shard": ok_shard, "grad_err": err, "bucket": bucket.numel(), "world": world, "td3_err": td3_err, "td3_ranks_equal": td3_same}))
+    full = pkg.FusedSACUpdate([256, 256], B, device=dev, ent_coef_init=0.7)
+    full.load_nets(sac_nets)
+    for b in sac_batches:
+        full.update(b[:5], eps_pi=b[5], eps_next=b[6])
+    sac_err = max(float((full.params - sdp.params).abs().max()), float((full.targets - sdp.targets).abs().max()))
+    sac_same = all(bool(torch.equal(p.to(dev), sdp.params)) for p in peers)
+    sac_ent_moved = abs(float(sdp.log_ent_coef.item()) - float(np.log(0.7))) > 1e-4
+if rank == 0:
+    print(json.dumps({"ok_shard": ok_shard, "grad_err": err, "bucket": bucket.numel(), "world": world, "td3_err": td3_err, "td3_ranks_equal": td3_same,
+                      "sac_err": sac_err, "sac_ranks_equal": sac_same, "sac_ent_moved": sac_ent_moved}))
 dist.destroy_process_group()
 '''
 
@@ -90,3 +115,4 @@ def test_nccl_allreduce_and_shard_invariance(tmp_path):
     assert res["ok_shard"] is True
     assert res["grad_err"] < 1e-6 and res["bucket"] == 122_902 and res["world"] == 2
     assert res["td3_ranks_equal"] is True and res["td3_err"] < 2e-5  # DP TD3 update == single-device update on the whole batch
+    assert res["sac_ranks_equal"] is True and res["sac_err"] < 2e-5 and res["sac_ent_moved"] is True  # and the DP SAC update

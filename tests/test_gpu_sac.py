@@ -63,6 +63,27 @@ def test_vs_oracle(pkg, arch, B, K):
     assert ent_coef == pytest.approx(np.mean(o.ent_coefs), rel=1e-6)
 
 
+def test_phases_split_equals_one_call(pkg):
+    """GRAD / APPLY phases with a no-op all-reduce in between (the data-parallel call pattern) = the single call, bit for bit."""
+    rng = np.random.default_rng(12)
+    nets = U.random_sac_nets(rng, 256, 256)
+    batches = _batches(rng, 4, 300)
+
+    def run(split):
+        eng = pkg.FusedSACUpdate([256, 256], 300, ent_coef_init=0.5, seed=4)
+        eng.load_nets(nets)
+        seen = []
+        for b in batches:
+            eng.update(b[:5], allreduce=(lambda flat: seen.append(flat.numel())) if split else None)
+        return eng.params.clone(), eng.targets.clone(), eng.adam_m.clone(), eng.pop_losses(), seen
+
+    a, b = run(False), run(True)
+    assert all(torch.equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] == b[3]
+    eng = pkg.FusedSACUpdate([256, 256], 300)
+    n_critics_ent = eng._ent_offset + 4 - eng.critic_range[0]
+    assert b[4] == [n_critics_ent, eng.actor_range[1] - eng.actor_range[0]] * 4  # critics + log_ent_coef slot, then the actor
+
+
 def test_log_std_clamp_and_philox_noise(pkg):
     """Rows whose raw log_std is outside [-20, 2] take the clamped value and pass no gradient to the log_std head; the Philox
     draws are standard normal (checked through log_prob statistics) and reproducible."""
