@@ -130,7 +130,20 @@ def main() -> None:
     m = run("SAC fused update", lambda env: FusedSAC("MlpPolicy", env, train_freq=(1, "step"), gradient_steps=4, **common), 6400)
     assert isinstance(m, core.SAC) and m._fused is not None and m._n_updates == m._fused.n_updates
     assert m.policy.actor.mu.weight.data_ptr() == m._fused.views("params")["actor"][4].data_ptr() and m.log_ent_coef.data_ptr() == m._fused.log_ent_coef.data_ptr()
-    print(f"[SAC fused update] n_updates {m._n_updates}, ent_coef {float(m.log_ent_coef.detach().exp()):.4f}, kernel launches {m._fused.launches}", flush=True)
+    with tempfile.TemporaryDirectory() as tmp:  # save -> SAC.load (plain reference class): weights, log_ent_coef and all three Adam states
+        m.save(os.path.join(tmp, "sac"))
+        back = core.SAC.load(os.path.join(tmp, "sac"), device="cuda")
+        assert torch.equal(back.policy.actor.log_std.weight, m.policy.actor.log_std.weight) and torch.equal(back.log_ent_coef, m.log_ent_coef)
+        for opt, count in ((back.actor.optimizer, 8), (back.critic.optimizer, 12), (back.ent_coef_optimizer, 1)):
+            st = opt.state_dict()["state"]
+            assert len(st) == count and float(st[0]["step"]) == m._fused.critic_step == m._n_updates
+        assert torch.equal(back.actor.optimizer.state_dict()["state"][5]["exp_avg"], m._fused.views("adam_m")["actor"][5][0:2])  # mu.bias moments
+        # ... and back into a fused model: the engine takes the moments and the step count over and keeps going
+        again = FusedSAC.load(os.path.join(tmp, "sac"), env=m.get_env(), device="cuda")
+        again.learn(total_timesteps=64, reset_num_timesteps=False)
+        assert again._fused is not None and again._fused.critic_step == again._n_updates > m._n_updates
+    print(f"[SAC fused update] n_updates {m._n_updates}, ent_coef {float(m.log_ent_coef.detach().exp()):.4f}, kernel launches {m._fused.launches}; "
+          f"model.save -> SAC.load -> fused continue ok", flush=True)
 
     # ---- BCQ offline: dataset generated by the GPU tape kernel, handed over in the reference's pickle format -------
     n, T = 2500, 400

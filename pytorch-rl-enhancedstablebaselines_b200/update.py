@@ -484,6 +484,52 @@ class FusedSACUpdate(FusedTD3Update):
                 raise ValueError(f"shape mismatch: module {tuple(p.shape)} vs layout {tuple(view.shape)}")
             view.copy_(p.data.to(self.device, self._torch.float32))
             p.data = view
+        # Adam moment views per module parameter (same slicing as the weights), for import/export_optimizer_state
+        am, av = self.views("adam_m"), self.views("adam_v")
+        head = lambda blk: [blk["actor"][4][0:2], blk["actor"][4][2:4], blk["actor"][5][0:2], blk["actor"][5][2:4]]  # noqa: E731
+        actor_params = lat + [a.mu.weight, a.log_std.weight, a.mu.bias, a.log_std.bias]
+        critic_params = [p for q in policy.critic.q_networks for p in q.parameters()]
+        self._moments = {id(p): mv for p, mv in zip(actor_params, zip(am["actor"][:4] + head(am), av["actor"][:4] + head(av)))}
+        self._moments.update({id(p): mv for p, mv in zip(critic_params, zip(am["critic0"] + am["critic1"], av["critic0"] + av["critic1"]))})
+
+    def import_optimizer_state(self, actor_optimizer, critic_optimizer, ent_coef_optimizer=None) -> None:  # type: ignore[override]
+        """Take over Adam moments / the step count of the reference's three optimisers (sac.py:187, policies.py:264-284) after ``adopt_policy``.
+        One step count serves all three: the reference steps each exactly once per gradient step."""
+        step = 0
+        for opt in (actor_optimizer, critic_optimizer):
+            group = opt.param_groups[0]
+            self.betas, self.eps = (float(group["betas"][0]), float(group["betas"][1])), float(group["eps"])
+            for p in group["params"]:
+                st = opt.state.get(p)
+                if st and id(p) in self._moments:
+                    m, v = self._moments[id(p)]
+                    m.copy_(st["exp_avg"])
+                    v.copy_(st["exp_avg_sq"])
+                    step = max(step, int(float(st["step"])))
+        if ent_coef_optimizer is not None:
+            for p in ent_coef_optimizer.param_groups[0]["params"]:
+                st = ent_coef_optimizer.state.get(p)
+                if st:
+                    self.adam_m[self._ent_offset] = float(st["exp_avg"])
+                    self.adam_v[self._ent_offset] = float(st["exp_avg_sq"])
+                    step = max(step, int(float(st["step"])))
+        self.critic_step = self.actor_step = step
+
+    def export_optimizer_state(self, actor_optimizer, critic_optimizer, ent_coef_optimizer=None) -> None:  # type: ignore[override]
+        """Write moments / step count back so ``model.save`` and a later torch ``optimizer.step()`` continue from here."""
+        torch = self._torch
+        if self.critic_step == 0:
+            return
+        step = lambda: torch.tensor(float(self.critic_step))  # noqa: E731
+        for opt in (actor_optimizer, critic_optimizer):
+            for p in opt.param_groups[0]["params"]:
+                if id(p) in self._moments:
+                    m, v = self._moments[id(p)]
+                    opt.state[p] = {"step": step(), "exp_avg": m, "exp_avg_sq": v}
+        if ent_coef_optimizer is not None:
+            e = self._ent_offset
+            for p in ent_coef_optimizer.param_groups[0]["params"]:
+                ent_coef_optimizer.state[p] = {"step": step(), "exp_avg": self.adam_m[e:e + 1].reshape(p.shape), "exp_avg_sq": self.adam_v[e:e + 1].reshape(p.shape)}
 
     def update(self, batch, eps_pi=None, eps_next=None, allreduce: Optional[Callable[[Any], None]] = None) -> None:  # type: ignore[override]
         """One iteration of sac.py:213-288.  ``eps_pi`` / ``eps_next``: explicit standard-normal draws (B,2) of the two rsample() calls
@@ -561,7 +607,8 @@ def bind_sac_class(sac_base: type) -> type:
                                      seed=int(self.seed or 0))
                 eng.adopt_policy(self.policy)
                 self.log_ent_coef.data = eng.log_ent_coef  # shared storage
-                eng.n_updates = eng.critic_step = eng.actor_step = int(self._n_updates)
+                eng.import_optimizer_state(self.actor.optimizer, self.critic.optimizer, self.ent_coef_optimizer)
+                eng.n_updates = int(self._n_updates)
                 self._fused = eng
             eng = self._fused
             eng.learning_rate = float(self.lr_schedule(self._current_progress_remaining))
@@ -576,6 +623,11 @@ def bind_sac_class(sac_base: type) -> type:
 
         def _excluded_save_params(self):
             return super()._excluded_save_params() + ["_fused"]
+
+        def save(self, *args, **kwargs):
+            if self._fused is not None:
+                self._fused.export_optimizer_state(self.actor.optimizer, self.critic.optimizer, self.ent_coef_optimizer)
+            return super().save(*args, **kwargs)
 
     FusedSAC.__name__ = "SAC"
     FusedSAC.__qualname__ = "SAC"

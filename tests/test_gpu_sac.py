@@ -156,3 +156,90 @@ def test_cuda_graph_replay_equals_launch_by_launch(pkg):
     np.testing.assert_allclose(b.targets.cpu().numpy(), a.targets.cpu().numpy(), rtol=0, atol=3e-7)
     for x, y in zip(a.pop_losses(), b.pop_losses()):
         assert y == pytest.approx(x, rel=1e-5)
+
+
+def _torch_sac_twin(seed, H=64, lr=3e-4):
+    """A stand-in for the reference's SACPolicy (same attribute names) with torch.optim.Adam optimisers, and one gradient step of
+    sac.py:213-288 written with torch autograd — an independent check of the fused step and of the optimiser-state hand-over."""
+    import torch.nn as nn
+    from types import SimpleNamespace as NS
+
+    torch.manual_seed(seed)
+
+    def mlp(i, o=None):
+        return nn.Sequential(*([nn.Linear(i, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU()] + ([nn.Linear(H, o)] if o else []))).cuda()
+
+    actor = NS(latent_pi=mlp(4), mu=nn.Linear(H, 2).cuda(), log_std=nn.Linear(H, 2).cuda())
+    critic, critic_t = NS(q_networks=[mlp(6, 1), mlp(6, 1)]), NS(q_networks=[mlp(6, 1), mlp(6, 1)])
+    for a, b in zip(critic.q_networks, critic_t.q_networks):
+        b.load_state_dict(a.state_dict())
+    tw = NS(policy=NS(actor=actor, critic=critic, critic_target=critic_t), H=H)
+    tw.actor_params = list(actor.latent_pi.parameters()) + list(actor.mu.parameters()) + list(actor.log_std.parameters())
+    tw.critic_params = [p for q in critic.q_networks for p in q.parameters()]
+    tw.log_ent = torch.log(torch.ones(1, device="cuda") * 0.8).requires_grad_(True)
+    tw.opt_a, tw.opt_c, tw.opt_e = (torch.optim.Adam(ps, lr=lr) for ps in (tw.actor_params, tw.critic_params, [tw.log_ent]))
+
+    def pi(obs, eps):
+        lat = actor.latent_pi(obs)
+        mu, std = actor.mu(lat), actor.log_std(lat).clamp(-20, 2).exp()
+        g = mu + std * eps
+        a = torch.tanh(g)
+        return a, torch.distributions.Normal(mu, std).log_prob(g).sum(1) - torch.log(1 - a ** 2 + 1e-6).sum(1)
+
+    def step(batch, gamma=0.99, tau=0.005, target_entropy=-2.0):
+        obs, act, nobs, dones, rew, e1, e2 = (torch.as_tensor(x, device="cuda") for x in batch)
+        a_pi, logp = pi(obs, e1)
+        ent_coef = tw.log_ent.detach().exp()
+        ent_loss = -(tw.log_ent * (logp.reshape(-1, 1) + target_entropy).detach()).mean()
+        tw.opt_e.zero_grad(); ent_loss.backward(); tw.opt_e.step()
+        with torch.no_grad():
+            na, nlogp = pi(nobs, e2)
+            nq = torch.cat([q(torch.cat([nobs, na], 1)) for q in critic_t.q_networks], 1).min(1, keepdim=True)[0] - ent_coef * nlogp.reshape(-1, 1)
+            target = rew + (1 - dones) * gamma * nq
+        closs = 0.5 * sum(torch.nn.functional.mse_loss(q(torch.cat([obs, act], 1)), target) for q in critic.q_networks)
+        tw.opt_c.zero_grad(); closs.backward(); tw.opt_c.step()
+        qpi = torch.cat([q(torch.cat([obs, a_pi], 1)) for q in critic.q_networks], 1).min(1, keepdim=True)[0]
+        aloss = (ent_coef * logp.reshape(-1, 1) - qpi).mean()
+        tw.opt_a.zero_grad(); aloss.backward(); tw.opt_a.step()
+        with torch.no_grad():
+            for q, qt in zip(critic.q_networks, critic_t.q_networks):
+                for p, t in zip(q.parameters(), qt.parameters()):
+                    t.mul_(1 - tau).add_(p, alpha=tau)
+
+    tw.step = step
+    return tw
+
+
+def test_adopt_policy_and_optimizer_state_hand_over(pkg):
+    """Two torch steps, then the engine adopts the modules AND the three Adam states and does two more: same weights as four torch
+    steps; exporting writes the moments and the step count back into the torch optimisers."""
+    rng = np.random.default_rng(21)
+    batches = _batches(rng, 4, 192)
+    a, b = _torch_sac_twin(5), _torch_sac_twin(5)
+    for batch in batches:
+        a.step(batch)
+    for batch in batches[:2]:
+        b.step(batch)
+    eng = pkg.FusedSACUpdate([b.H, b.H], 192, ent_coef_init=1.0)
+    eng.adopt_policy(b.policy)
+    eng.log_ent_coef.copy_(b.log_ent.detach())
+    b.log_ent.data = eng.log_ent_coef
+    eng.import_optimizer_state(b.opt_a, b.opt_c, b.opt_e)
+    assert eng.critic_step == 2 and torch.equal(eng.views("adam_m")["actor"][4][2:4], b.opt_a.state[b.policy.actor.log_std.weight]["exp_avg"])
+    eng.n_updates = 2
+    for batch in batches[2:]:
+        eng.update(batch[:5], eps_pi=batch[5], eps_next=batch[6])
+    for pa, pb in zip(a.actor_params + a.critic_params + [a.log_ent], b.actor_params + b.critic_params + [b.log_ent]):
+        np.testing.assert_allclose(pb.detach().cpu().numpy(), pa.detach().cpu().numpy(), rtol=0, atol=2e-5)  # b's modules are views of the engine's block
+    for qa, qb in zip(a.policy.critic_target.q_networks, b.policy.critic_target.q_networks):
+        for pa, pb in zip(qa.parameters(), qb.parameters()):
+            np.testing.assert_allclose(pb.detach().cpu().numpy(), pa.detach().cpu().numpy(), rtol=0, atol=2e-5)
+    eng.export_optimizer_state(b.opt_a, b.opt_c, b.opt_e)
+    for oa, ob in ((a.opt_a, b.opt_a), (a.opt_c, b.opt_c), (a.opt_e, b.opt_e)):
+        for pa, pb in zip(oa.param_groups[0]["params"], ob.param_groups[0]["params"]):
+            sa, sb = oa.state[pa], ob.state[pb]
+            assert float(sb["step"]) == float(sa["step"]) == 4
+            scale = max(float(sa["exp_avg"].abs().max()), 1e-6)
+            np.testing.assert_allclose(sb["exp_avg"].cpu().numpy(), sa["exp_avg"].cpu().numpy(), rtol=0, atol=2e-4 * scale)
+    b.step(batches[0])  # and torch can carry on from the exported state (moments are views of the engine's blocks)
+    assert float(b.opt_c.state[b.critic_params[0]]["step"]) == 5
