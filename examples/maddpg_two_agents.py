@@ -19,8 +19,8 @@ Agent 0 sees (C1, T1) and sets the coolant flow of reactor 1, agent 1 sees (C2, 
 The multi-agent update itself stays torch (the fused update engine is specialised to the single-agent 4 -> 2 shapes); the hot
 path exercised here is the env step, the buffer write and the sample.  What to expect (``profiles/r01_maddpg_two_agents.log``): 5.1e6
 transitions/s on one B200 and 9.0e6 on two, bounded by the torch updates; the return does NOT improve — neither here nor in the
-reference's own ``MADDPG.learn`` on this task (``profiles/r01_reference_algos.log``: eval return -678) — because two agents that each see
-half the state and share one reward chase each other; ``--own-observations`` reaches -140 after two episodes and then diverges the same way.
+reference's own ``MADDPG.learn`` on this task (``profiles/r01_reference_algos.log``: eval return -678); ``--own-observations`` reaches
+-140 after two episodes and then diverges as well.  This example is about the data path, not about tuning MADDPG.
 """
 from __future__ import annotations
 
