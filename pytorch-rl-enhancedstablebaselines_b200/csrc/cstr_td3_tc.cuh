@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(TC_GEMM_THREADS) td3_gemm_tc_kernel(GemmArgs g
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_enter();  // barrier init and the TMEM allocation above overlap the tail of the previous kernel; operands are read below
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = umma_idesc_bf16(TC_BM, n_tile);
 
