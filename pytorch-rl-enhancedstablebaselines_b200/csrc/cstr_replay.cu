@@ -10,41 +10,22 @@
 
 namespace cstr {
 
-// One transition per thread on the load side (every array is read with full-sector coalesced vector loads); the 64-byte records
-// are then staged through shared memory so that each warp store instruction writes 512 contiguous bytes (8 whole records) instead
-// of 32 sixteen-byte pieces at a 64-byte stride (half-filled sectors, twice the L2 write transactions).  The staging slot of float4
-// c of record j is rotated by j/2 so that both the per-record stores and the linear reads are free of bank conflicts.
 __global__ void __launch_bounds__(256)
 replay_add_kernel(int64_t n, const float4 *__restrict__ obs, const float4 *__restrict__ next_obs, const float2 *__restrict__ action,
                   const float *__restrict__ reward, const uint8_t *__restrict__ done, const uint8_t *__restrict__ timeout,
                   float4 *__restrict__ row /* records + pos*n*4 float4 */) {
-    __shared__ float4 tile[8][32 * 4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32;  // first transition of this warp
-    if (base >= n) return;
-    const int64_t i = base + lane;
-    float4 *t = tile[warp];
-    if (i < n) {
-        const float4 o = obs[i], no = next_obs[i];
-        const float2 a = action[i];
-        const float r = reward[i];
-        const float d = done[i] ? 1.0f : 0.0f;
-        const float to = (timeout && timeout[i]) ? 1.0f : 0.0f;
-        const int rot = lane >> 1;
-        t[lane * 4 + ((0 + rot) & 3)] = o;
-        t[lane * 4 + ((1 + rot) & 3)] = no;
-        t[lane * 4 + ((2 + rot) & 3)] = make_float4(a.x, a.y, r, d);
-        t[lane * 4 + ((3 + rot) & 3)] = make_float4(to, 0.0f, 0.0f, 0.0f);
-    }
-    __syncwarp();
-    const int cnt4 = (int)((n - base < 32 ? n - base : 32) * 4);  // float4 slots of this warp that hold data
-    float4 *dst = row + 4 * base;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int slot = q * 32 + lane;  // physical slot: record slot/4, rotated component
-        const int rec = slot >> 2, c = ((slot & 3) - (rec >> 1)) & 3;
-        if (slot < cnt4) dst[rec * 4 + c] = t[slot];
-    }
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = obs[i], no = next_obs[i];
+    const float2 a = action[i];
+    const float r = reward[i];
+    const float d = done[i] ? 1.0f : 0.0f;
+    const float to = (timeout && timeout[i]) ? 1.0f : 0.0f;
+    float4 *rec = row + 4 * i;
+    rec[0] = o;
+    rec[1] = no;
+    rec[2] = make_float4(a.x, a.y, r, d);
+    rec[3] = make_float4(to, 0.0f, 0.0f, 0.0f);
 }
 
 struct NormArgs {  // by-value copy of cstr_norm_params (stats == nullptr: off)
