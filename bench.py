@@ -399,8 +399,14 @@ def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict
     def rate_of(fn, env_steps, reps=5):
         for _ in range(2):
             fn()
-        ms, per = time_launches(torch, fn, reps)
-        return env_steps / (statistics.mean(per) * 1e-3)
+        # ONE event pair around the reps: an event between launches puts host gaps into the time of kernels shorter than a Python call
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return env_steps / (e0.elapsed_time(e1) / reps * 1e-3)
 
     try:
         for math, mode in (("strict", 0), ("fast", 1)):
