@@ -11,8 +11,10 @@
 2. Every gradient step samples with the Philox gather kernel (``GpuReplayBuffer.sample``) straight into the float32 tensors the
    update consumes.
 3. The update follows ``core/bcq/bcq.py:129-213`` (VAE reconstruction + 0.5 KL, 10 candidate actions from the target VAE +
-   perturbation net, twin-critic min then max over candidates, delayed perturbation-actor step, polyak) in plain torch — the
-   BCQ update kernels are not built; the hot path here is 1-2.
+   perturbation net, twin-critic min then the max over the reference's (B, 10) reshape, delayed perturbation-actor step, polyak) in
+   plain torch — the BCQ update kernels are not built (DESIGN.md §7; their oracle is: ``oracle/td3_oracle.py::BCQUpdateOracle``,
+   pinned against the reference in ``tests/golden/bcq_update.npz``); the hot path here is 1-2.  Network sizes default to
+   ``BCQPolicy``'s (core/bcq/policies.py:305-307).
 """
 from __future__ import annotations
 
@@ -40,7 +42,7 @@ def mlp(i, hs, o):
 
 
 class VAE(nn.Module):  # core/bcq/policies.py: encoder (s,a) -> (mean, log_std), decoder (s,z) -> a
-    def __init__(self, latent=32, hidden=720):
+    def __init__(self, latent=32, hidden=64):
         super().__init__()
         self.enc, self.dec, self.latent = mlp(6, [hidden, hidden], 2 * latent), mlp(4 + latent, [hidden, hidden], 2), latent
 
@@ -56,9 +58,9 @@ class VAE(nn.Module):  # core/bcq/policies.py: encoder (s,a) -> (mean, log_std),
 
 
 class Actor(nn.Module):  # VAE proposal + perturbation net: a + phi * tanh(xi(s, a)), clipped to the action box
-    def __init__(self, phi=0.05):
+    def __init__(self, phi=0.05, latent=32, vae_hidden=64, pert_hidden=64):
         super().__init__()
-        self.vae, self.xi, self.phi = VAE(), mlp(6, [400, 300], 2), phi
+        self.vae, self.xi, self.phi = VAE(latent, vae_hidden), mlp(6, [pert_hidden, pert_hidden], 2), phi
 
     def forward(self, s, num_samples=1):
         s = s.repeat(num_samples, 1)
@@ -72,6 +74,9 @@ def main():
     ap.add_argument("--updates", type=int, default=300)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--latent", type=int, default=32)
+    ap.add_argument("--vae-hidden", type=int, default=64)
+    ap.add_argument("--pert-hidden", type=int, default=64)
     args = ap.parse_args()
     pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
     dev = torch.device("cuda", 0)
@@ -89,7 +94,8 @@ def main():
     torch.cuda.synchronize()
     t_data = time.time() - t0
     assert buf.full and buf.size() * n == T * n
-    actor, actor_t = Actor().to(dev), Actor().to(dev)
+    mk = lambda: Actor(0.05, args.latent, args.vae_hidden, args.pert_hidden).to(dev)  # noqa: E731
+    actor, actor_t = mk(), mk()
     critics = nn.ModuleList([mlp(6, [400, 300], 1) for _ in range(2)]).to(dev)
     critics_t = nn.ModuleList([mlp(6, [400, 300], 1) for _ in range(2)]).to(dev)
     actor_t.load_state_dict(actor.state_dict())
@@ -111,7 +117,8 @@ def main():
             actor_t.vae.load_state_dict(actor.vae.state_dict())
             cand = actor_t(b.next_observations, ncand)
             nobs = b.next_observations.repeat(ncand, 1)
-            q = torch.min(*[c(torch.cat([nobs, cand], 1)) for c in critics_t]).reshape(ncand, B).max(0)[0].unsqueeze(1)
+            # bcq.py:170-171 as written: the candidate-major (10 B, 1) column reshaped row-major to (B, 10) before the max
+            q = torch.min(*[c(torch.cat([nobs, cand], 1)) for c in critics_t]).reshape(B, ncand).max(1)[0].unsqueeze(1)
             target = b.rewards + (1 - b.dones) * gamma * q
         critic_loss = sum(F.mse_loss(c(torch.cat([b.observations, b.actions], 1)), target) for c in critics)
         opt_c.zero_grad(set_to_none=True)

@@ -374,6 +374,105 @@ def gen_sac_update(m, core) -> None:
     np.savez_compressed(os.path.join(OUT, "sac_update.npz"), **sac_update_reference_run(m, core, [64, 48]))
 
 
+def bcq_update_reference_run(m, core, K=5, B=32, arch=None, critic_arch=(36, 20)) -> dict:
+    """Run the reference's BCQ.train for K gradient steps on CPU torch, recording every random draw, and return what replays it."""
+    import pickle
+    import tempfile
+
+    import torch
+    from types import SimpleNamespace
+    from core.common.buffers import ReplayBuffer
+    from core.common.vec_env import DummyVecEnv
+
+    torch.set_num_threads(1)
+    arch = dict(arch or dict(vae_latent_dim=8, vae_hidden_dim=48, perturbation_hidden_dim=40, max_perturbation=0.05))
+    venv = DummyVecEnv([lambda: m.TwoSeriesCSTREnv(init_mode="random")])
+    rng = np.random.default_rng(51)
+    n = 600
+    data = ReplayBuffer(n, venv.observation_space, venv.action_space, device="cpu", n_envs=1)
+    data.observations[:, 0] = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+    data.next_observations[:, 0] = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+    data.actions[:, 0] = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    data.rewards[:, 0] = rng.normal(-1, 1, n).astype(np.float32)
+    data.dones[:, 0] = (rng.random(n) < 0.05).astype(np.float32)
+    data.full, data.pos = True, 0
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "dataset.pkl")
+        with open(path, "wb") as fh:
+            pickle.dump(data, fh)
+        model = core.BCQ("MlpPolicy", venv, dataset=path, batch_size=B, device="cpu", seed=9,
+                         policy_kwargs=dict(actor_net_arch=arch, critic_net_arch=list(critic_arch)))
+    logged = {}
+    model._logger = SimpleNamespace(record=lambda k, v, **kw: logged.__setitem__(k, v))
+
+    def nets():
+        pol = model.policy
+        get = lambda seq: [t.detach().numpy().copy() for t in seq.parameters()]  # noqa: E731
+
+        def vae(v):
+            enc = get(v.encoder)
+            head_w = np.concatenate([v.mean.weight.detach().numpy(), v.log_std.weight.detach().numpy()], 0)
+            head_b = np.concatenate([v.mean.bias.detach().numpy(), v.log_std.bias.detach().numpy()], 0)
+            return enc + [head_w, head_b], get(v.decoder)
+
+        enc, dec = vae(pol.actor.vae)
+        enc_t, dec_t = vae(pol.actor_target.vae)
+        return {"vae_enc": enc, "vae_dec": dec, "pert": get(pol.actor.perturbation.model), "critic0": get(pol.critic.q_networks[0]),
+                "critic1": get(pol.critic.q_networks[1]), "vae_enc_target": enc_t, "vae_dec_target": dec_t,
+                "pert_target": get(pol.actor_target.perturbation.model), "critic0_target": get(pol.critic_target.q_networks[0]),
+                "critic1_target": get(pol.critic_target.q_networks[1])}
+
+    out = {}
+    for name, ps in nets().items():
+        for i, t in enumerate(ps):
+            out[f"init_{name}_{i}"] = t
+    np.random.seed(23)
+    batches = [model.replay_buffer.sample(B) for _ in range(K)]
+    draws = []
+    orig_randn, orig_like = torch.randn, torch.randn_like
+
+    def rec_randn(*a, **k):
+        t = orig_randn(*a, **k)
+        draws.append(t.numpy().copy())
+        return t
+
+    def rec_like(x, **k):
+        t = orig_like(x, **k)
+        draws.append(t.numpy().copy())
+        return t
+
+    np.random.seed(23)
+    torch.manual_seed(33)
+    torch.randn, torch.randn_like = rec_randn, rec_like
+    try:
+        model.train(gradient_steps=K, batch_size=B)
+    finally:
+        torch.randn, torch.randn_like = orig_randn, orig_like
+    for name, ps in nets().items():
+        for i, t in enumerate(ps):
+            out[f"final_{name}_{i}"] = t
+    for k, f in zip(("obs", "act", "next_obs", "dones", "rewards"), ("observations", "actions", "next_observations", "dones", "rewards")):
+        out["batch_" + k] = np.stack([getattr(b, f).numpy() for b in batches])
+    # draw order per gradient step: randn_like (B, L); randn (10 B, L); on actor steps randn (B, L)
+    it = iter(draws)
+    L = arch["vae_latent_dim"]
+    eps_vae, z_next, z_actor = [], [], []
+    for k in range(1, K + 1):
+        eps_vae.append(next(it))
+        z_next.append(next(it))
+        z_actor.append(next(it) if k % model.actor_delay == 0 else np.zeros((B, L), np.float32))
+    assert next(it, None) is None and eps_vae[0].shape == (B, L) and z_next[0].shape == (10 * B, L)
+    out["eps_vae"], out["z_next"], out["z_actor"] = np.stack(eps_vae), np.stack(z_next), np.stack(z_actor)
+    for k in ("critic_loss", "actor_loss", "vae_loss"):
+        out[k + "_mean"] = np.array(logged["train/" + k])
+    out["hyper"] = np.array([model.gamma, model.tau, arch["max_perturbation"], model.lr_schedule(1), model.actor_delay])
+    return out
+
+
+def gen_bcq_update(m, core) -> None:
+    np.savez_compressed(os.path.join(OUT, "bcq_update.npz"), **bcq_update_reference_run(m, core))
+
+
 def main() -> None:
     if not refload.available():
         raise SystemExit("reference tree not found; fixtures can only be generated in the build container")
@@ -389,6 +488,7 @@ def main() -> None:
     gen_vecnorm(m, core)
     gen_td3_update(m, core)
     gen_sac_update(m, core)
+    gen_bcq_update(m, core)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

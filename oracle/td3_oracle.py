@@ -6,6 +6,8 @@ Follows, line by line:
   create_mlp / Actor / critic    core/common/torch_layers.py:110-183, core/td3/policies.py:58,75-78, core/common/policies.py:966-987
   polyak_update                  core/common/utils.py:457-481
   torch.optim.Adam (defaults)    betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad  (torch/optim/adam.py, single-tensor path)
+Further down: SACUpdateOracle (core/sac/sac.py:199-296) and BCQUpdateOracle (core/bcq/bcq.py:129-205, pinned by
+tests/golden/bcq_update.npz; its CUDA counterpart is not built yet).
 Everything is float32 NumPy with hand-written backward passes.  Pinned against the unmodified reference running on CPU torch
 (tests/golden/td3_update.npz, made by oracle/make_golden.py::gen_td3_update): weights agree to ~1e-6 after 6 gradient steps
 (GEMM summation order is the only difference), tolerance written in tests/test_golden.py.
@@ -210,3 +212,104 @@ class SACUpdateOracle:
                 polyak(c, t, self.tau)
         self.gradient_step += 1
         return {"target_q": target, "critic_grads": grads, "actor_grads": ag, "log_prob": logp, "a_pi": a_pi}
+
+
+class BCQUpdateOracle:
+    """The loop body of ``BCQ.train`` (core/bcq/bcq.py:137-205) with the networks of core/bcq/policies.py:
+
+      vae_enc  [W1,b1,W2,b2,Wh,bh]   encoder (obs+act -> H -> H) and the two heads stacked, Wh = [mean; log_std] (2L, H)   policies.py:47-55
+      vae_dec  [W1..b3]              decoder (obs+L -> H -> H -> act, Tanh)                                                 :58-65
+      pert     [W1..b3]              perturbation net (obs+act -> P -> P -> act, Tanh) * max_perturbation, clamp(-1, 1)     :147-160
+      critics  2 x [W1..b3]          ContinuousCritic q-networks (obs+act -> h1 -> h2 -> 1)
+
+    Three Adam optimisers (policies.py:357-382): the VAE's (every actor parameter that is not the perturbation net's), the
+    perturbation net's, the critics'.  Targets: perturbation net and critics by polyak on actor steps; the target VAE is a plain copy of the
+    VAE, refreshed after every VAE step (bcq.py:158-159, 198).  The random draws are arguments (standard normal, UNclamped):
+    ``eps_vae`` (B, L) of :76 randn_like; ``z_next`` (n_candidates*B, L) of sample_action's randn (:122, clamped to +-0.5 there);
+    ``z_actor`` (B, L) of the actor step's randn.  NOTE bcq.py:170-171 reshapes the (n_candidates*B, 1) q column — whose rows are ordered
+    candidate-major by ``repeat`` — to (B, n_candidates) row-major, so the max runs over n_candidates CONSECUTIVE rows of the tiled batch,
+    not over the candidates of one observation; restated as written."""
+
+    def __init__(self, vae_enc: Params, vae_dec: Params, pert: Params, critics: Sequence[Params], lr: float = 1e-3, gamma: float = 0.99,
+                 tau: float = 0.005, max_perturbation: float = 0.05, actor_delay: int = 2, n_candidates: int = 10):
+        cp = lambda ps: [np.array(a, F32, copy=True) for a in ps]  # noqa: E731
+        self.vae_enc, self.vae_dec, self.pert, self.critics = cp(vae_enc), cp(vae_dec), cp(pert), [cp(c) for c in critics]
+        self.pert_target, self.critic_targets = cp(pert), [cp(c) for c in critics]
+        self.L = self.vae_enc[4].shape[0] // 2
+        self.gamma, self.tau, self.phi, self.actor_delay, self.n_candidates = gamma, tau, F32(max_perturbation), actor_delay, n_candidates
+        self.vae_opt = Adam(self.vae_enc + self.vae_dec, lr)
+        self.pert_opt = Adam(self.pert, lr)
+        self.critic_opt = Adam([t for c in self.critics for t in c], lr)
+        self.n_updates = 0
+        self.vae_losses: List[float] = []
+        self.critic_losses: List[float] = []
+        self.actor_losses: List[float] = []
+
+    def _decode(self, dec: Params, s, z_raw):
+        z = np.clip(z_raw, F32(-0.5), F32(0.5))  # policies.py:111,122
+        return mlp_forward(dec, np.concatenate([s, z], 1), True)
+
+    def _perturb(self, pert: Params, s, a):
+        xi, cache = mlp_forward(pert, np.concatenate([s, a], 1), True)
+        pre = a + xi * self.phi
+        return np.clip(pre, F32(-1), F32(1)).astype(F32), (cache, pre)
+
+    def step(self, obs, actions, next_obs, dones, rewards, eps_vae, z_next, z_actor=None) -> Dict[str, np.ndarray]:
+        self.n_updates += 1
+        B, L = obs.shape[0], self.L
+        # ---- VAE (bcq.py:142-155): recon MSE + 0.5 * KL ----
+        enc_out, ecache = mlp_forward(self.vae_enc, np.concatenate([obs, actions], 1), False)
+        mean, raw_ls = enc_out[:, :L], enc_out[:, L:]
+        log_std = np.clip(raw_ls, F32(-4), F32(15))
+        std = np.exp(log_std).astype(F32)
+        z = (mean + std * eps_vae).astype(F32)
+        recon, dcache = mlp_forward(self.vae_dec, np.concatenate([obs, z], 1), True)
+        diff = recon - actions
+        recon_loss = np.mean(diff * diff, dtype=F32)
+        kl = F32(-0.5) * np.mean(F32(1) + np.log(std * std) - mean * mean - std * std, dtype=F32)
+        self.vae_losses.append(float(recon_loss + F32(0.5) * kl))
+        dgrads, dx = mlp_backward(self.vae_dec, dcache, (F32(2) / F32(diff.size)) * diff, True, need_dx=True)
+        dz = dx[:, obs.shape[1]:]
+        n = F32(B * L)
+        dmean = dz + F32(0.5) * mean / n
+        dstd = dz * eps_vae + F32(0.5) * (std - F32(1) / std) / n
+        draw = dstd * std * ((raw_ls >= F32(-4)) & (raw_ls <= F32(15)))  # clamp passes the gradient inside (and at) the bounds
+        egrads, _ = mlp_backward(self.vae_enc, ecache, np.concatenate([dmean, draw], 1).astype(F32), False)
+        self.vae_opt.step(egrads + dgrads)
+        out = {"vae_grads": egrads + dgrads}
+        # ---- target (bcq.py:157-172): candidates from the (just refreshed) target VAE + target perturbation net ----
+        K = self.n_candidates
+        s_rep = np.tile(next_obs, (K, 1))
+        cand, _ = self._decode(self.vae_dec, s_rep, z_next)
+        cand_p, _ = self._perturb(self.pert_target, s_rep, cand)
+        xin = np.concatenate([s_rep, cand_p], 1)
+        q = np.minimum.reduce([mlp_forward(c, xin, False)[0] for c in self.critic_targets])
+        q = q.reshape(B, K).max(1)[:, None]  # as written at :170-171 (see the class docstring)
+        target = (rewards + (F32(1) - dones) * F32(self.gamma) * q).astype(F32)
+        # ---- critics (bcq.py:174-186) ----
+        x = np.concatenate([obs, actions], 1)
+        grads, loss = [], 0.0
+        for c in self.critics:
+            qc, cache = mlp_forward(c, x, False)
+            d = qc - target
+            loss += float(np.mean(d * d, dtype=F32))
+            g, _ = mlp_backward(c, cache, (F32(2) / F32(B)) * d, False)
+            grads += g
+        self.critic_losses.append(loss)
+        self.critic_opt.step(grads)
+        out.update(target_q=target, critic_grads=grads)
+        # ---- delayed perturbation-actor step (bcq.py:188-203) ----
+        if self.n_updates % self.actor_delay == 0:
+            a0, _ = self._decode(self.vae_dec, obs, z_actor)
+            a, (pcache, pre) = self._perturb(self.pert, obs, a0)
+            q1, ccache = mlp_forward(self.critics[0], np.concatenate([obs, a], 1), False)
+            self.actor_losses.append(float(-np.mean(q1, dtype=F32)))
+            _, dx = mlp_backward(self.critics[0], ccache, np.full_like(q1, F32(-1) / F32(B)), False, need_dx=True)
+            da = dx[:, obs.shape[1]:] * ((pre >= F32(-1)) & (pre <= F32(1)))
+            pg, _ = mlp_backward(self.pert, pcache, (da * self.phi).astype(F32), True)  # only the perturbation optimiser steps (:196)
+            self.pert_opt.step(pg)
+            for c, t in zip(self.critics, self.critic_targets):
+                polyak(c, t, self.tau)
+            polyak(self.pert, self.pert_target, self.tau)  # the VAE half of polyak_update(actor) is overwritten by the copy at :198
+            out["pert_grads"] = pg
+        return out

@@ -61,3 +61,26 @@ def random_sac_nets(rng, h1, h2):
     n["actor"][4] = rng.uniform(-b, b, (4, h2)).astype(np.float32)  # [mu; log_std] head
     n["actor"][5] = rng.uniform(-b, b, 4).astype(np.float32)
     return {k: n[k] for k in SAC_NETS}
+
+
+BCQ_NETS = ("vae_enc", "vae_dec", "pert", "critic0", "critic1", "vae_enc_target", "vae_dec_target", "pert_target", "critic0_target", "critic1_target")
+
+
+def bcq_nets_from(g, prefix):
+    return {name: [np.asarray(g[f"{prefix}_{name}_{i}"]) for i in range(6)] for name in BCQ_NETS}
+
+
+def make_bcq_oracle(T, g):
+    n = bcq_nets_from(g, "init")
+    gamma, tau, phi, lr, delay = [float(x) for x in g["hyper"]]
+    return T.BCQUpdateOracle(n["vae_enc"], n["vae_dec"], n["pert"], [n["critic0"], n["critic1"]], lr=lr, gamma=gamma, tau=tau,
+                             max_perturbation=phi, actor_delay=int(delay))
+
+
+def replay_bcq(o, g):
+    for k in range(g["eps_vae"].shape[0]):
+        o.step(g["batch_obs"][k], g["batch_act"][k], g["batch_next_obs"][k], g["batch_dones"][k], g["batch_rewards"][k], g["eps_vae"][k],
+               g["z_next"][k], g["z_actor"][k])
+    return {"vae_enc": o.vae_enc, "vae_dec": o.vae_dec, "pert": o.pert, "critic0": o.critics[0], "critic1": o.critics[1],
+            "vae_enc_target": o.vae_enc, "vae_dec_target": o.vae_dec,  # the target VAE is a copy of the VAE (bcq.py:158-159)
+            "pert_target": o.pert_target, "critic0_target": o.critic_targets[0], "critic1_target": o.critic_targets[1]}

@@ -182,3 +182,27 @@ def test_sac_update_oracle_vs_reference_fixture(golden):
     for got, key in ((o.critic_losses, "critic_loss_mean"), (o.actor_losses, "actor_loss_mean"), (o.ent_coefs, "ent_coef_mean"),
                      (o.ent_coef_losses, "ent_coef_loss_mean")):
         assert np.mean(got) == pytest.approx(float(g[key]), rel=1e-5)
+
+
+def test_bcq_update_oracle_vs_reference_fixture(golden):
+    """BCQUpdateOracle replays 5 gradient steps of the reference's BCQ.train (bcq.py:129-205): VAE step, candidate target through the
+    refreshed target VAE + target perturbation net (with the reference's (B, 10) reshape as written), twin critics, delayed perturbation
+    step, polyak — on the recorded batches and the recorded randn / randn_like draws.  This pins the oracle for the BCQ update kernels
+    (SURVEY §8f-1), which are not built yet: there is no CUDA counterpart of this test."""
+    import td3_oracle as T
+    import td3_util as U
+
+    g = golden("bcq_update.npz")
+    o = U.make_bcq_oracle(T, g)
+    final = U.replay_bcq(o, g)
+    ref = U.bcq_nets_from(g, "final")
+    for name in U.BCQ_NETS:
+        for a, b in zip(final[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=5e-6, err_msg=name)  # measured 2.4e-7
+    for got, key in ((o.vae_losses, "vae_loss_mean"), (o.critic_losses, "critic_loss_mean"), (o.actor_losses, "actor_loss_mean")):
+        assert np.mean(got) == pytest.approx(float(g[key]), rel=1e-5)
+    assert o.vae_opt.step_count == o.critic_opt.step_count == 5 and o.pert_opt.step_count == 2
+    # the max over "candidates" is the reference's row-major reshape of a candidate-major column: not a per-observation max
+    B = g["batch_obs"].shape[1]
+    col = np.arange(10 * B).reshape(10 * B, 1)
+    assert not np.array_equal(col.reshape(B, 10).max(1), col.reshape(10, B).max(0))

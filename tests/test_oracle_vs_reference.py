@@ -165,3 +165,21 @@ def test_fused_update_support_check_live(ref_env_module):
     assert any("fused update not used" in str(x.message) for x in w)
     assert model._fused is None and model._n_updates > 0
     assert any(not torch.equal(a, b) for a, b in zip(before, model.critic.parameters()))
+
+
+def test_bcq_update_default_arch_live(ref_env_module):
+    """The BCQ gradient-step restatement against the reference's BCQ.train at BCQPolicy's default architecture
+    (VAE 6-64-64-(32+32) / 36-64-64-2, perturbation 6-64-64-2, critics 6-400-300-1)."""
+    import make_golden
+    import td3_oracle as T
+    import td3_util as U
+
+    arch = dict(vae_latent_dim=32, vae_hidden_dim=64, perturbation_hidden_dim=64, max_perturbation=0.05)
+    g = make_golden.bcq_update_reference_run(ref_env_module, refload.load_core(), K=4, B=24, arch=arch, critic_arch=(400, 300))
+    o = U.make_bcq_oracle(T, g)
+    final = U.replay_bcq(o, g)
+    ref = U.bcq_nets_from(g, "final")
+    for name in U.BCQ_NETS:
+        for a, b in zip(final[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-5, err_msg=name)
+    assert np.mean(o.vae_losses) == pytest.approx(float(g["vae_loss_mean"]), rel=1e-5)
