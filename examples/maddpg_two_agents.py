@@ -16,7 +16,8 @@ Agent 0 sees (C1, T1) and sets the coolant flow of reactor 1, agent 1 sees (C2, 
    with a clipped-noise target from the target actors and the twin minimum, delayed actor step through Q_i's first critic, polyak.
    Multi-GPU: gradients are all-reduced (one flat NCCL bucket per optimiser) so every rank holds the same agents.
 
-The multi-agent update itself stays torch (the fused update engine is specialised to the single-agent 4 -> 2 shapes); the hot
+The multi-agent update itself stays torch (the fused update engine is specialised to the single-agent 4 -> 2 shapes; its oracle,
+``oracle/td3_oracle.py::MultiAgentDDPGOracle``, is pinned against the reference in ``tests/golden/maddpg_update.npz``); the hot
 path exercised here is the env step, the buffer write and the sample.  What to expect (``profiles/r01_maddpg_two_agents.log``): 5.1e6
 transitions/s on one B200 and 9.0e6 on two, bounded by the torch updates; the return does NOT improve — neither here nor in the
 reference's own ``MADDPG.learn`` on this task (``profiles/r01_reference_algos.log``: eval return -678); ``--own-observations`` reaches

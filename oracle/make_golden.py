@@ -473,6 +473,66 @@ def gen_bcq_update(m, core) -> None:
     np.savez_compressed(os.path.join(OUT, "bcq_update.npz"), **bcq_update_reference_run(m, core))
 
 
+def multi_agent_reference_run(m, core, algo="MADDPG", K=4, B=32, arch=(24, 16)) -> dict:
+    """Run the reference's MADDPG.train / IDDPG.train (two agents = the two reactors) for K gradient steps on CPU torch."""
+    import torch
+    from types import SimpleNamespace
+    from core.common.vec_env import DummyVecEnv
+
+    torch.set_num_threads(1)
+    venv = DummyVecEnv([(lambda: m.TwoSeriesCSTREnv(init_mode="random")) for _ in range(4)])
+    splits = dict(n_agents=2, observation_splits=[[0, 1], [2, 3]], action_splits=[[0], [1]], learning_rate_list=[1e-3, 5e-4])
+    model = getattr(core, algo)(policy="MlpPolicy", env=venv, buffer_size=4000, batch_size=B, learning_starts=0, device="cpu", seed=13,
+                                policy_kwargs=dict(net_arch=[list(arch), list(arch)]), **splits)
+    logged = {}
+    model._logger = SimpleNamespace(record=lambda k, v, **kw: logged.__setitem__(k, v))
+    rng = np.random.default_rng(61)
+    buf = model.replay_buffer
+    for _ in range(200):
+        d = rng.random(4) < 0.05
+        buf.add(rng.uniform(-1, 1, (4, 4)).astype(np.float32), rng.uniform(-1, 1, (4, 4)).astype(np.float32), rng.uniform(-1, 1, (4, 2)).astype(np.float32),
+                rng.normal(-1, 1, 4).astype(np.float32), d, [{"TimeLimit.truncated": False} for _ in d])
+
+    def nets():
+        pol = model.policy
+        get = lambda seq: [t.detach().numpy().copy() for t in seq.parameters()]  # noqa: E731
+        out = {}
+        for i in range(2):
+            out[f"actor{i}"], out[f"actor{i}_target"] = get(pol.actor.mu_list[i]), get(pol.actor_target.mu_list[i])
+            for k in range(2):
+                out[f"critic{i}_{k}"] = get(pol.critic.q_networks_list[i][k])
+                out[f"critic{i}_{k}_target"] = get(pol.critic_target.q_networks_list[i][k])
+        return out
+
+    out = {}
+    for name, ps in nets().items():
+        for j, t in enumerate(ps):
+            out[f"init_{name}_{j}"] = t
+    np.random.seed(27)
+    batches = [buf.sample(B) for _ in range(K)]
+    torch.manual_seed(37)
+    noise = [[torch.empty(B, 1).normal_(0, model.target_policy_noise).numpy().copy() for _ in range(2)] for _ in range(K)]  # :139, agent order
+    np.random.seed(27)
+    torch.manual_seed(37)
+    model.train(gradient_steps=K, batch_size=B)
+    for name, ps in nets().items():
+        for j, t in enumerate(ps):
+            out[f"final_{name}_{j}"] = t
+    for k, f in zip(("obs", "act", "next_obs", "dones", "rewards"), ("observations", "actions", "next_observations", "dones", "rewards")):
+        out["batch_" + k] = np.stack([getattr(b, f).numpy() for b in batches])
+    out["noise"] = np.asarray(noise)  # (K, agent, B, 1)
+    for i in range(2):
+        out[f"critic_loss_mean_{i}"] = np.array(logged[f"train/agent_{i}_critic_loss"])
+        out[f"actor_loss_mean_{i}"] = np.array(logged[f"train/agent_{i}_actor_loss"])
+    out["hyper"] = np.array([model.gamma, model.tau, model.policy_delay, model.target_noise_clip, 1e-3, 5e-4])
+    return out
+
+
+def gen_multi_agent_update(m, core) -> None:
+    np.savez_compressed(os.path.join(OUT, "maddpg_update.npz"), **multi_agent_reference_run(m, core, "MADDPG"))
+    np.savez_compressed(os.path.join(OUT, "iddpg_update.npz"), **multi_agent_reference_run(m, core, "IDDPG"))
+
+
 def main() -> None:
     if not refload.available():
         raise SystemExit("reference tree not found; fixtures can only be generated in the build container")
@@ -489,6 +549,7 @@ def main() -> None:
     gen_td3_update(m, core)
     gen_sac_update(m, core)
     gen_bcq_update(m, core)
+    gen_multi_agent_update(m, core)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

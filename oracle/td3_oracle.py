@@ -7,7 +7,8 @@ Follows, line by line:
   polyak_update                  core/common/utils.py:457-481
   torch.optim.Adam (defaults)    betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad  (torch/optim/adam.py, single-tensor path)
 Further down: SACUpdateOracle (core/sac/sac.py:199-296) and BCQUpdateOracle (core/bcq/bcq.py:129-205, pinned by
-tests/golden/bcq_update.npz; its CUDA counterpart is not built yet).
+tests/golden/bcq_update.npz) and MultiAgentDDPGOracle (core/maddpg/maddpg.py, core/iddpg/iddpg.py :131-185, pinned by
+tests/golden/{maddpg,iddpg}_update.npz); their CUDA counterparts are not built yet.
 Everything is float32 NumPy with hand-written backward passes.  Pinned against the unmodified reference running on CPU torch
 (tests/golden/td3_update.npz, made by oracle/make_golden.py::gen_td3_update): weights agree to ~1e-6 after 6 gradient steps
 (GEMM summation order is the only difference), tolerance written in tests/test_golden.py.
@@ -313,3 +314,82 @@ class BCQUpdateOracle:
             polyak(self.pert, self.pert_target, self.tau)  # the VAE half of polyak_update(actor) is overwritten by the copy at :198
             out["pert_grads"] = pg
         return out
+
+
+class MultiAgentDDPGOracle:
+    """The loop body of ``MADDPG.train`` (core/maddpg/maddpg.py:131-185; ``centralised=True``) and of ``IDDPG.train``
+    (core/iddpg/iddpg.py:131-185, the same text; ``centralised=False``).  Per agent i: an actor on the agent's observation slice
+    (policies.py:64-72) and ``n_critics`` q-networks — over ALL observations and ALL actions for MADDPG (maddpg/policies.py:236-241), over the
+    agent's own slices for IDDPG (iddpg/policies.py:135) — each with targets; one Adam per agent for the actor and one for its critics.
+
+    Restated as written, including: the target actions of every agent are formed once, before the agent loop (:132-144); the polyak update of
+    ALL actors and critics sits inside the agent loop (:181-182), so it runs once per agent on an actor step and agent i+1's critic target
+    already sees it; the actor step evaluates EVERY actor on agent i's observation slice (:169-171 ``mu_list[id](agent_observations)``).
+    Learning rates: ``train()`` calls ``_update_learning_rate([actor_opt_i, critic_opt_i])`` per agent (:121-123) and that method
+    (core/common/base_class.py:1112-1136) pairs the k-th list entry with ``lr_schedule_list[k]`` — so with two agents EVERY actor runs at
+    ``learning_rate_list[0]`` and EVERY critic at ``learning_rate_list[1]``; ``reference_lrs`` returns that assignment."""
+
+    @staticmethod
+    def reference_lrs(learning_rate_list: Sequence[float]):
+        n = len(learning_rate_list)
+        return [learning_rate_list[0]] * n, [learning_rate_list[1]] * n
+
+    def __init__(self, actors: Sequence[Params], critics: Sequence[Sequence[Params]], obs_splits, act_splits, centralised: bool,
+                 actor_lrs: Sequence[float], critic_lrs: Sequence[float], gamma: float = 0.99, tau: float = 0.005, policy_delay: int = 2,
+                 target_noise_clip: float = 0.5):
+        cp = lambda ps: [np.array(a, F32, copy=True) for a in ps]  # noqa: E731
+        self.actors, self.critics = [cp(a) for a in actors], [[cp(q) for q in qs] for qs in critics]
+        self.actor_targets, self.critic_targets = [cp(a) for a in actors], [[cp(q) for q in qs] for qs in critics]
+        self.obs_splits, self.act_splits, self.centralised = [list(s) for s in obs_splits], [list(s) for s in act_splits], centralised
+        self.gamma, self.tau, self.policy_delay, self.noise_clip = gamma, tau, policy_delay, target_noise_clip
+        self.actor_opts = [Adam(a, lr) for a, lr in zip(self.actors, actor_lrs)]
+        self.critic_opts = [Adam([t for q in qs for t in q], lr) for qs, lr in zip(self.critics, critic_lrs)]
+        self.n = len(self.actors)
+        self.n_updates = 0
+        self.critic_losses: List[List[float]] = [[] for _ in range(self.n)]
+        self.actor_losses: List[List[float]] = [[] for _ in range(self.n)]
+
+    def _critic_input(self, i, obs, acts):
+        if self.centralised:
+            return np.concatenate([obs, acts], 1), obs.shape[1] + self.act_splits[i][0]
+        return np.concatenate([obs[:, self.obs_splits[i]], acts[:, self.act_splits[i]]], 1), len(self.obs_splits[i])
+
+    def step(self, obs, actions, next_obs, dones, rewards, noises: Sequence[np.ndarray]) -> None:
+        self.n_updates += 1
+        B = obs.shape[0]
+        nxt = []
+        for i in range(self.n):  # :132-144
+            nz = np.clip(noises[i], F32(-self.noise_clip), F32(self.noise_clip))
+            a, _ = mlp_forward(self.actor_targets[i], next_obs[:, self.obs_splits[i]], True)
+            nxt.append(np.clip(a + nz, F32(-1), F32(1)))
+        next_actions = np.concatenate(nxt, 1).astype(F32)
+        for i in range(self.n):
+            xin, _ = self._critic_input(i, next_obs, next_actions)
+            q_next = np.minimum.reduce([mlp_forward(q, xin, False)[0] for q in self.critic_targets[i]])  # :147-151
+            target = (rewards + (F32(1) - dones) * F32(self.gamma) * q_next).astype(F32)
+            x, _ = self._critic_input(i, obs, actions)
+            grads, loss = [], 0.0
+            for q in self.critics[i]:
+                qv, cache = mlp_forward(q, x, False)
+                d = qv - target
+                loss += float(np.mean(d * d, dtype=F32))
+                g, _ = mlp_backward(q, cache, (F32(2) / F32(B)) * d, False)
+                grads += g
+            self.critic_losses[i].append(loss)
+            self.critic_opts[i].step(grads)
+            if self.n_updates % self.policy_delay == 0:  # :166
+                oi = obs[:, self.obs_splits[i]]
+                outs = [mlp_forward(a, oi, True) for a in self.actors]  # every actor on agent i's slice (:169-171)
+                joint = np.concatenate([o[0] for o in outs], 1).astype(F32)
+                xa, col = self._critic_input(i, obs, joint)
+                q1, ccache = mlp_forward(self.critics[i][0], xa, False)
+                self.actor_losses[i].append(float(-np.mean(q1, dtype=F32)))
+                _, dx = mlp_backward(self.critics[i][0], ccache, np.full_like(q1, F32(-1) / F32(B)), False, need_dx=True)
+                width = len(self.act_splits[i])
+                ag, _ = mlp_backward(self.actors[i], outs[i][1], dx[:, col:col + width].astype(F32), True)
+                self.actor_opts[i].step(ag)  # only agent i's optimiser steps (:177-179)
+                for qs, ts in zip(self.critics, self.critic_targets):  # :181-182, all agents
+                    for q, t in zip(qs, ts):
+                        polyak(q, t, self.tau)
+                for a, t in zip(self.actors, self.actor_targets):
+                    polyak(a, t, self.tau)

@@ -84,3 +84,29 @@ def replay_bcq(o, g):
     return {"vae_enc": o.vae_enc, "vae_dec": o.vae_dec, "pert": o.pert, "critic0": o.critics[0], "critic1": o.critics[1],
             "vae_enc_target": o.vae_enc, "vae_dec_target": o.vae_dec,  # the target VAE is a copy of the VAE (bcq.py:158-159)
             "pert_target": o.pert_target, "critic0_target": o.critic_targets[0], "critic1_target": o.critic_targets[1]}
+
+
+MA_NETS = tuple(f"{n}{t}" for n in ("actor0", "actor1", "critic0_0", "critic0_1", "critic1_0", "critic1_1") for t in ("", "_target"))
+
+
+def ma_nets_from(g, prefix):
+    return {name: [np.asarray(g[f"{prefix}_{name}_{i}"]) for i in range(6)] for name in MA_NETS}
+
+
+def make_ma_oracle(T, g, centralised):
+    n = ma_nets_from(g, "init")
+    gamma, tau, delay, clip, lr0, lr1 = [float(x) for x in g["hyper"]]
+    return T.MultiAgentDDPGOracle([n["actor0"], n["actor1"]], [[n["critic0_0"], n["critic0_1"]], [n["critic1_0"], n["critic1_1"]]],
+                                  [[0, 1], [2, 3]], [[0], [1]], centralised, *T.MultiAgentDDPGOracle.reference_lrs([lr0, lr1]), gamma=gamma, tau=tau, policy_delay=int(delay),
+                                  target_noise_clip=clip)
+
+
+def replay_ma(o, g):
+    for k in range(g["noise"].shape[0]):
+        o.step(g["batch_obs"][k], g["batch_act"][k], g["batch_next_obs"][k], g["batch_dones"][k], g["batch_rewards"][k], list(g["noise"][k]))
+    out = {}
+    for i in range(2):
+        out[f"actor{i}"], out[f"actor{i}_target"] = o.actors[i], o.actor_targets[i]
+        for k in range(2):
+            out[f"critic{i}_{k}"], out[f"critic{i}_{k}_target"] = o.critics[i][k], o.critic_targets[i][k]
+    return out

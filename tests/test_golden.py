@@ -206,3 +206,31 @@ def test_bcq_update_oracle_vs_reference_fixture(golden):
     B = g["batch_obs"].shape[1]
     col = np.arange(10 * B).reshape(10 * B, 1)
     assert not np.array_equal(col.reshape(B, 10).max(1), col.reshape(10, B).max(0))
+
+
+@pytest.mark.parametrize("algo,centralised", [("maddpg", True), ("iddpg", False)])
+def test_multi_agent_update_oracle_vs_reference_fixture(golden, algo, centralised):
+    """MultiAgentDDPGOracle replays 4 gradient steps of the reference's MADDPG.train / IDDPG.train (two agents = the two reactors, unequal
+    learning rates so the reference's actor/critic learning-rate pairing shows) on the recorded batches and target-noise draws.  Pins the
+    oracle for the multi-agent update kernels, which are not built yet: there is no CUDA counterpart of this test."""
+    import td3_oracle as T
+    import td3_util as U
+
+    g = golden(f"{algo}_update.npz")
+    o = U.make_ma_oracle(T, g, centralised)
+    final = U.replay_ma(o, g)
+    ref = U.ma_nets_from(g, "final")
+    for name in U.MA_NETS:
+        for a, b in zip(final[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-6, err_msg=name)  # measured 6e-8
+    for i in range(2):
+        assert np.mean(o.critic_losses[i]) == pytest.approx(float(g[f"critic_loss_mean_{i}"]), rel=1e-5)
+        assert np.mean(o.actor_losses[i]) == pytest.approx(float(g[f"actor_loss_mean_{i}"]), rel=1e-5, abs=1e-7)
+    # the naive reading (agent i trains at learning_rate_list[i]) does NOT reproduce the reference
+    n = U.ma_nets_from(g, "init")
+    lr0, lr1 = float(g["hyper"][4]), float(g["hyper"][5])
+    naive = T.MultiAgentDDPGOracle([n["actor0"], n["actor1"]], [[n["critic0_0"], n["critic0_1"]], [n["critic1_0"], n["critic1_1"]]],
+                                   [[0, 1], [2, 3]], [[0], [1]], centralised, [lr0, lr1], [lr0, lr1], gamma=float(g["hyper"][0]),
+                                   tau=float(g["hyper"][1]), policy_delay=int(g["hyper"][2]), target_noise_clip=float(g["hyper"][3]))
+    U.replay_ma(naive, g)
+    assert np.abs(naive.critics[0][0][0] - ref["critic0_0"][0]).max() > 1e-4

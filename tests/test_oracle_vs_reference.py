@@ -183,3 +183,19 @@ def test_bcq_update_default_arch_live(ref_env_module):
         for a, b in zip(final[name], ref[name]):
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-5, err_msg=name)
     assert np.mean(o.vae_losses) == pytest.approx(float(g["vae_loss_mean"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("algo,centralised", [("MADDPG", True), ("IDDPG", False)])
+def test_multi_agent_update_default_arch_live(ref_env_module, algo, centralised):
+    """The MADDPG / IDDPG gradient-step restatement against the reference's own train() at the default [400, 300] per-agent architecture."""
+    import make_golden
+    import td3_oracle as T
+    import td3_util as U
+
+    g = make_golden.multi_agent_reference_run(ref_env_module, refload.load_core(), algo, K=4, B=24, arch=(400, 300))
+    o = U.make_ma_oracle(T, g, centralised)
+    final = U.replay_ma(o, g)
+    ref = U.ma_nets_from(g, "final")
+    for name in U.MA_NETS:
+        for a, b in zip(final[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-5, err_msg=name)
