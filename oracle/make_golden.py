@@ -254,15 +254,17 @@ def gen_vecnorm(m, core) -> None:
     np.savez_compressed(os.path.join(OUT, "vecnorm.npz"), **out)
 
 
-def td3_update_reference_run(m, core, net_arch, K=6, B=64) -> dict:
-    """Run the reference's TD3.train for K gradient steps on CPU torch and return everything needed to replay it."""
+def td3_update_reference_run(m, core, net_arch, K=6, B=64, algo="TD3") -> dict:
+    """Run the reference's TD3.train (``algo="DDPG"``: the subclass with one critic, delay 1, no target noise, core/ddpg/ddpg.py:100-109) for K
+    gradient steps on CPU torch and return everything needed to replay it."""
     import torch
     from types import SimpleNamespace
     from core.common.vec_env import DummyVecEnv
 
     torch.set_num_threads(1)
     venv = DummyVecEnv([(lambda: m.TwoSeriesCSTREnv(init_mode="random")) for _ in range(4)])
-    model = core.TD3("MlpPolicy", venv, buffer_size=4000, batch_size=B, learning_starts=0, device="cpu", seed=5, policy_kwargs=dict(net_arch=list(net_arch)))
+    model = getattr(core, algo)("MlpPolicy", venv, buffer_size=4000, batch_size=B, learning_starts=0, device="cpu", seed=5,
+                                policy_kwargs=dict(net_arch=list(net_arch)))
     logged = {}
     model._logger = SimpleNamespace(record=lambda k, v, **kw: logged.__setitem__(k, v))
     rng = np.random.default_rng(31)
@@ -278,9 +280,10 @@ def td3_update_reference_run(m, core, net_arch, K=6, B=64) -> dict:
     def nets():
         pol = model.policy
         get = lambda seq: [t.detach().numpy().copy() for t in seq.parameters()]  # noqa: E731
+        single = len(pol.critic.q_networks) == 1  # DDPG: the second critic slot of the fixture repeats the first
         return {"actor": get(pol.actor.mu), "actor_target": get(pol.actor_target.mu), "critic0": get(pol.critic.q_networks[0]),
-                "critic1": get(pol.critic.q_networks[1]), "critic0_target": get(pol.critic_target.q_networks[0]),
-                "critic1_target": get(pol.critic_target.q_networks[1])}
+                "critic1": get(pol.critic.q_networks[0 if single else 1]), "critic0_target": get(pol.critic_target.q_networks[0]),
+                "critic1_target": get(pol.critic_target.q_networks[0 if single else 1])}
 
     out = {}
     for name, ps in nets().items():
@@ -307,6 +310,12 @@ def td3_update_reference_run(m, core, net_arch, K=6, B=64) -> dict:
     out["critic_loss_mean"], out["actor_loss_mean"] = np.array(logged["train/critic_loss"]), np.array(logged["train/actor_loss"])
     out["hyper"] = np.array([model.gamma, model.tau, model.policy_delay, model.target_policy_noise, model.target_noise_clip, model.lr_schedule(1)])
     return out
+
+
+def gen_ddpg_update(m, core) -> None:
+    g = td3_update_reference_run(m, core, [64, 48], K=4, algo="DDPG")
+    g["n_critics"] = np.array(1)
+    np.savez_compressed(os.path.join(OUT, "ddpg_update.npz"), **g)
 
 
 def gen_td3_update(m, core) -> None:
@@ -547,6 +556,7 @@ def main() -> None:
     gen_actor(m, core)
     gen_vecnorm(m, core)
     gen_td3_update(m, core)
+    gen_ddpg_update(m, core)
     gen_sac_update(m, core)
     gen_bcq_update(m, core)
     gen_multi_agent_update(m, core)

@@ -234,3 +234,25 @@ def test_multi_agent_update_oracle_vs_reference_fixture(golden, algo, centralise
                                    tau=float(g["hyper"][1]), policy_delay=int(g["hyper"][2]), target_noise_clip=float(g["hyper"][3]))
     U.replay_ma(naive, g)
     assert np.abs(naive.critics[0][0][0] - ref["critic0_0"][0]).max() > 1e-4
+
+
+def test_ddpg_update_oracle_vs_reference_fixture(golden):
+    """The one-critic path of TD3UpdateOracle against the reference's DDPG (core/ddpg/ddpg.py: TD3 with n_critics=1, policy_delay=1,
+    target_noise_clip=0 — the smoothing noise is still drawn, then clamped to zero), 4 gradient steps."""
+    import td3_oracle as T
+    import td3_util as U
+
+    g = golden("ddpg_update.npz")
+    gamma, tau, delay, _sigma, clip, lr = [float(x) for x in g["hyper"]]
+    assert int(g["n_critics"]) == 1 and int(delay) == 1 and clip == 0.0
+    n = U.nets_from(g, "init")
+    o = T.TD3UpdateOracle(n["actor"], [n["critic0"]], n["actor_target"], [n["critic0_target"]], lr=lr, gamma=gamma, tau=tau, policy_delay=1,
+                          target_noise_clip=clip)
+    for k in range(g["noise"].shape[0]):
+        o.step(g["batch_obs"][k], g["batch_act"][k], g["batch_next_obs"][k], g["batch_dones"][k], g["batch_rewards"][k], g["noise"][k])
+    ref = U.nets_from(g, "final")
+    for name, got in (("actor", o.actor), ("critic0", o.critics[0]), ("actor_target", o.actor_target), ("critic0_target", o.critic_targets[0])):
+        for a, b in zip(got, ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-6, err_msg=name)  # measured 3e-8
+    assert np.mean(o.critic_losses) == pytest.approx(float(g["critic_loss_mean"]), rel=1e-5)
+    assert np.mean(o.actor_losses) == pytest.approx(float(g["actor_loss_mean"]), rel=1e-5)

@@ -290,6 +290,23 @@ def test_cuda_graph_replay_equals_launch_by_launch(pkg, gemm, delay):
     assert lb[0] == pytest.approx(la[0], rel=1e-5) and lb[1] == pytest.approx(la[1], rel=1e-4)
 
 
+def test_ddpg_four_steps_vs_reference_fixture(pkg, golden):
+    """n_critics=1 against the reference's DDPG.train (fixture recorded from the unmodified reference on CPU torch)."""
+    g = golden("ddpg_update.npz")
+    gamma, tau, delay, sigma, clip, lr = [float(x) for x in g["hyper"]]
+    eng = pkg.FusedTD3Update([64, 48], 64, gamma=gamma, tau=tau, policy_delay=int(delay), target_policy_noise=sigma, target_noise_clip=clip,
+                             learning_rate=lr, n_critics=1)
+    eng.load_nets(U.nets_from(g, "init"))
+    for k in range(g["noise"].shape[0]):
+        eng.update(tuple(g[f"batch_{f}"][k] for f in ("obs", "act", "next_obs", "dones", "rewards")), noise=g["noise"][k])
+    got, ref = eng.nets(), U.nets_from(g, "final")
+    for name in ("actor", "critic0", "actor_target", "critic0_target"):
+        for a, b in zip(got[name], ref[name]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=5e-6, err_msg=name)
+    critic_loss, actor_loss = eng.pop_losses()
+    assert critic_loss == pytest.approx(float(g["critic_loss_mean"]), rel=1e-5) and actor_loss == pytest.approx(float(g["actor_loss_mean"]), rel=1e-4)
+
+
 def test_ddpg_single_critic(pkg):
     """DDPG = TD3 with one critic, policy_delay 1 and no target smoothing (core/ddpg/ddpg.py:100-109): n_critics=1."""
     rng = np.random.default_rng(12)
