@@ -257,7 +257,10 @@ typedef struct cstr_sac_config {
     int32_t h1, h2, batch, target_update_interval;
     float gamma, tau, lr, beta1, beta2, eps, target_entropy, reserved0;
     uint64_t seed;
-    int32_t gemm_mode, reserved1;
+    int32_t gemm_mode;
+    int32_t local_step;   /* which gradient step of the current SAC.train() call this is, 1-based: the reference's target sync tests the LOOP
+                             index (`gradient_step % target_update_interval == 0`, core/sac/sac.py:284), which restarts at 0 on every
+                             train() call.  0 = unknown: fall back to the global counter ((n_updates - 1) % interval)              */
 } cstr_sac_config;
 
 int64_t cstr_sac_param_count(int32_t h1, int32_t h2);

@@ -4,7 +4,7 @@ Only usable where the reference tree exists (this build container: ``/root/refer
 override with ``CSTR_REFERENCE_ROOT``).  It is used by
   * ``oracle/make_golden.py``   – to generate the committed fixtures under ``tests/golden/``;
   * ``tests/test_oracle_vs_reference.py`` – to pin the oracle restatement (skipped when absent);
-  * ``tests/test_reference_algos.py`` – reference TD3/SAC/BCQ/... on top of the GPU classes (skipped when absent).
+  * ``oracle/run_reference_algos.py`` – reference TD3/SAC/BCQ/... on top of the GPU classes (staged for ``gpurun``).
 
 What it does:
   1. puts the stand-in ``gymnasium`` / ``matplotlib`` packages of ``oracle/shim`` on ``sys.path``

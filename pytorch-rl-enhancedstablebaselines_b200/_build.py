@@ -18,6 +18,10 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-shared",
+    # link the CUDA runtime dynamically (the same libcudart.so.12 torch has loaded, else the toolkit's): the artefact then carries only
+    # the runtime entry points this code calls instead of a private copy of the whole runtime and its symbol table
+    "-cudart", "shared",
+    "-Xlinker", "-rpath=/usr/local/cuda/lib64",
 ]
 
 

@@ -77,7 +77,7 @@ class SacConfig(Structure):
 
     _fields_ = [("h1", c_int32), ("h2", c_int32), ("batch", c_int32), ("target_update_interval", c_int32), ("gamma", c_float), ("tau", c_float),
                 ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("target_entropy", c_float), ("reserved0", c_float),
-                ("seed", c_uint64), ("gemm_mode", c_int32), ("reserved1", c_int32)]
+                ("seed", c_uint64), ("gemm_mode", c_int32), ("local_step", c_int32)]
 
 
 TD3_CRITIC_GRAD, TD3_CRITIC_APPLY, TD3_ACTOR_GRAD, TD3_ACTOR_APPLY, TD3_ALL = 1, 2, 4, 8, 15
@@ -132,9 +132,13 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     if build_if_missing and _build.is_stale():
         try:
             _build.build()
-        except Exception as exc:  # stale-but-present library is still usable; missing is fatal
+        except Exception as exc:  # a missing library is fatal; a present-but-older one is used, loudly (the ABI check below still applies)
             if not os.path.exists(path):
                 raise CstrLibraryError(f"libcstr_b200.so is missing and could not be built: {exc}") from exc
+            import warnings
+
+            warnings.warn(f"libcstr_b200.so is older than its sources and the rebuild failed ({exc}); loading the stale library",
+                          RuntimeWarning, stacklevel=2)
     if not os.path.exists(path):
         raise CstrLibraryError(f"{path} not found — run `python __graft_entry__.py build` (no CPU fallback exists)")
     try:

@@ -233,6 +233,9 @@ class GpuReplayBuffer:
         sit inside a CUDA graph (``FusedTD3Update.train(..., graph=True)``).  The caller advances the counter."""
         if self.index_mode != "philox":
             raise ValueError("sample_into needs index_mode='philox' (indices drawn inside the kernel)")
+        if env is not None and getattr(env, "norm_params", None) is None:
+            raise ValueError("sample_into normalises inside the kernel: env must be a GpuVecNormalize (device statistics); a host-side "
+                             "VecNormalize needs sample(), or GpuVecNormalize.from_reference(env)")
         upper_bound = self.buffer_size if self.full else self.pos
         if upper_bound <= 0:
             raise ValueError("cannot sample from an empty replay buffer")
@@ -333,6 +336,12 @@ class GpuReplayBuffer:
         ref.pos, ref.full = self.pos, self.full
         return ref
 
+    def __reduce__(self):
+        # classes made by bind_replay_buffer_class are function-local: pickle names the reference base instead and the bound class is
+        # rebuilt on load (so `isinstance(buffer, ReplayBuffer)` in load_replay_buffer, off_policy_algorithm.py:239, still holds)
+        base = getattr(type(self), "_bound_base", None)
+        return (_unpickle_buffer, (getattr(base, "__module__", None), getattr(base, "__qualname__", None), self.__getstate__()))
+
     def __getstate__(self):
         state = {k: v for k, v in self.__dict__.items() if k not in ("records", "_torch", "_libc", "_device", "_norm_keepalive")}
         state.update(self.to_numpy_arrays())
@@ -351,13 +360,37 @@ class GpuReplayBuffer:
         self.load_numpy_arrays(arrays, self.pos, self.full)
 
 
+_BOUND_CLASSES: dict = {}
+
+
+def _unpickle_buffer(base_module: Optional[str], base_qualname: Optional[str], state: dict) -> GpuReplayBuffer:
+    cls = GpuReplayBuffer
+    if base_module and base_qualname:
+        try:
+            import importlib
+
+            base = importlib.import_module(base_module)
+            for part in base_qualname.split("."):
+                base = getattr(base, part)
+            cls = bind_replay_buffer_class(base)
+        except Exception:  # the reference is not importable here: the plain class carries the same data
+            cls = GpuReplayBuffer
+    obj = cls.__new__(cls)
+    obj.__setstate__(state)
+    return obj
+
+
 def bind_replay_buffer_class(replay_buffer_base: type) -> type:
     """``class GpuReplayBuffer(GpuReplayBuffer, <reference ReplayBuffer>)`` for ``isinstance`` checks in
-    the unchanged reference (e.g. ``isinstance(self.replay_buffer, ReplayBuffer)`` when loading)."""
+    the unchanged reference (e.g. ``isinstance(self.replay_buffer, ReplayBuffer)`` when loading).  One class per base (cached), and
+    instances pickle through ``_unpickle_buffer`` (``save_replay_buffer`` / ``load_replay_buffer``, save_util.py:339-373)."""
+    if replay_buffer_base in _BOUND_CLASSES:
+        return _BOUND_CLASSES[replay_buffer_base]
 
     class BoundGpuReplayBuffer(GpuReplayBuffer, replay_buffer_base):  # type: ignore[misc, valid-type]
-        pass
+        _bound_base = replay_buffer_base
 
     BoundGpuReplayBuffer.__name__ = "GpuReplayBuffer"
     BoundGpuReplayBuffer.__qualname__ = "GpuReplayBuffer"
+    _BOUND_CLASSES[replay_buffer_base] = BoundGpuReplayBuffer
     return BoundGpuReplayBuffer

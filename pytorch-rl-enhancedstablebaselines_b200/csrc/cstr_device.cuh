@@ -7,7 +7,7 @@
 //               FMA), IEEE division, and the documented "shared exp"  instead of NumPy's
 //               host-dependent SIMD exp.  x/c with a compile-time constant c uses the Markstein
 //               sequence (1 mul + 2 fma) which is correctly rounded — validated exhaustively per
-//               constant by tests/test_div_const.py.
+//               constant on the device by cstr_selftest (tests/test_gpu_selftest.py).
 //   FastF32   — same scheme, free association: FMA contraction, reciprocal multiplies, ex2.approx.
 //   F64       — the same scheme in double (oracle: reference _dynamics fed float64).
 #pragma once

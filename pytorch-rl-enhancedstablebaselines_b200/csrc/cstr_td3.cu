@@ -1216,6 +1216,7 @@ static int check_sac_cfg(const cstr_sac_config *c) {
         return fail_arg(CSTR_EINVAL, "sac: hidden sizes must be multiples of 4 in [4, 4096]");
     if (c->batch < 1 || c->batch > (1 << 22)) return fail_arg(CSTR_EINVAL, "sac: batch must be in [1, 4194304]");
     if (c->target_update_interval < 1) return fail_arg(CSTR_EINVAL, "sac: target_update_interval must be >= 1");
+    if (c->local_step < 0) return fail_arg(CSTR_EINVAL, "sac: local_step must be >= 0 (0 = use the global update counter)");
     if (c->gemm_mode < CSTR_TD3_GEMM_FP32 || c->gemm_mode > CSTR_TD3_GEMM_BF16) return fail_arg(CSTR_EINVAL, "sac: gemm_mode must be 0, 1 or 2");
     return 0;
 }
@@ -1351,7 +1352,9 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         ApplyArgs a{};
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
         a.adam_lo = T.actor_off, a.adam_hi = T.actor_off + T.actor.size;
-        const bool sync_targets = ((n_updates - 1) % cfg->target_update_interval) == 0;  // gradient_step % interval == 0 (:284)
+        // `gradient_step % target_update_interval == 0` (:284) with gradient_step the index inside the current train() call
+        const int64_t loop_index = cfg->local_step > 0 ? (int64_t)cfg->local_step - 1 : n_updates - 1;
+        const bool sync_targets = (loop_index % cfg->target_update_interval) == 0;
         a.polyak_lo = sync_targets ? T.critic_off[0] : 0, a.polyak_hi = sync_targets ? T.total : 0;
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = step_size, a.bc2_sqrt = bc2_sqrt, a.tau = cfg->tau;
         a.dev_scalars = dev_sc;

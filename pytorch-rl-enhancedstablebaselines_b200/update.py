@@ -30,7 +30,7 @@ _TENSORS = ("W1", "b1", "W2", "b2", "W3", "b3")
 class FusedTD3Update:
     def __init__(self, net_arch: Sequence[int] = (400, 300), batch_size: int = 256, device: Any = "cuda", gamma: float = 0.99, tau: float = 0.005,
                  learning_rate: float = 1e-3, policy_delay: int = 2, target_policy_noise: float = 0.2, target_noise_clip: float = 0.5,
-                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0, gemm: str = "fp32", n_critics: int = 2):
+                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0, gemm: str = "fp32", n_critics: int = 2, dp_rank: int = 0):
         torch = _lib.require_cuda()
         self._torch = torch
         self._libc = _lib.load()
@@ -47,6 +47,9 @@ class FusedTD3Update:
         self.gamma, self.tau, self.learning_rate = float(gamma), float(tau), float(learning_rate)
         self.policy_delay, self.target_policy_noise, self.target_noise_clip = int(policy_delay), float(target_policy_noise), float(target_noise_clip)
         self.betas, self.eps, self.seed = (float(betas[0]), float(betas[1])), float(eps), int(seed)
+        # data-parallel training: every rank holds the same `seed`, and the in-kernel noise is keyed by (seed, batch row, update), so
+        # without the rank in the key row b of every shard would draw the same smoothing noise / eps (perfectly correlated global batch)
+        self.dp_rank = int(dp_rank)
         if gemm not in _GEMM_MODES:
             raise ValueError("gemm must be 'fp32' (FFMA tiles, the reference's arithmetic), 'tensor' (tcgen05 bf16x3 split, fp32-grade) or "
                              "'bf16' (tcgen05, plain bf16 operands: reduced precision)")
@@ -107,10 +110,13 @@ class FusedTD3Update:
     def _workspace_bytes(self, batch: int) -> int:
         return int(self._libc.cstr_td3_workspace_bytes(byref(self._config(batch))))
 
+    def _keyed_seed(self) -> int:
+        return (self.seed + 0x9E3779B97F4A7C15 * self.dp_rank) & (2**64 - 1)
+
     def _config(self, batch: int) -> "_lib.Td3Config":
         return _lib.Td3Config(h1=self.h1, h2=self.h2, batch=batch, policy_delay=self.policy_delay, gamma=self.gamma, tau=self.tau, lr=self.learning_rate,
                               beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_policy_noise=self.target_policy_noise,
-                              target_noise_clip=self.target_noise_clip, seed=self.seed & (2**64 - 1), gemm_mode=_GEMM_MODES[self.gemm],
+                              target_noise_clip=self.target_noise_clip, seed=self._keyed_seed(), gemm_mode=_GEMM_MODES[self.gemm],
                               n_critics=getattr(self, "n_critics", 2))
 
     # ---- weights in / out -------------------------------------------------------------------------------------------
@@ -306,7 +312,7 @@ class FusedTD3Update:
         bs = int(batch_size or self._batch)
         done = 0
         # a captured cycle bakes the sampling range in: only worth capturing once the ring is full (its range is constant from then on)
-        if graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox" and buffer.full:
+        if graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox" and buffer.full and _graph_env_ok(env):
             done = self._train_graph(gradient_steps, buffer, bs, env)
         for _ in range(gradient_steps - done):
             self.update(buffer.sample(bs, env=env), allreduce=allreduce)
@@ -318,6 +324,22 @@ class FusedTD3Update:
         critic = s[0] / s[1] if s[1] else None
         actor = s[2] / s[3] if s[3] else None
         return critic, actor
+
+
+def _dist_rank() -> int:
+    """Rank of this process in the default process group (0 when torch.distributed is not initialised)."""
+    try:
+        import torch.distributed as dist
+
+        return int(dist.get_rank()) if dist.is_available() and dist.is_initialized() else 0
+    except Exception:
+        return 0
+
+
+def _graph_env_ok(env) -> bool:
+    """A captured sample can only normalise on the device (``GpuVecNormalize.norm_params``); the reference's host-side ``VecNormalize``
+    needs the launch-by-launch path, whose ``sample()`` round-trips through ``env.normalize_obs`` (buffer.py ``_finish``)."""
+    return env is None or getattr(env, "norm_params", None) is not None
 
 
 def fused_update_unsupported(model, max_critics: int = 2) -> Optional[str]:
@@ -373,7 +395,8 @@ def bind_td3_class(td3_base: type) -> type:
                 arch = self.policy.net_arch if isinstance(self.policy.net_arch, (list, tuple)) else self.policy.net_arch["pi"]
                 eng = FusedTD3Update(arch, batch_size, self.device, self.gamma, self.tau, float(self.lr_schedule(self._current_progress_remaining)),
                                      self.policy_delay, self.target_policy_noise, self.target_noise_clip, seed=int(self.seed or 0),
-                                     n_critics=len(self.policy.critic.q_networks))  # DDPG (a TD3 subclass) has one
+                                     n_critics=len(self.policy.critic.q_networks),  # DDPG (a TD3 subclass) has one
+                                     dp_rank=_dist_rank())
                 eng.adopt_policy(self.policy)
                 eng.import_optimizer_state(self.actor.optimizer, self.critic.optimizer)
                 eng.n_updates = int(self._n_updates)
@@ -419,9 +442,9 @@ class FusedSACUpdate(FusedTD3Update):
 
     def __init__(self, net_arch: Sequence[int] = (256, 256), batch_size: int = 256, device: Any = "cuda", gamma: float = 0.99, tau: float = 0.005,
                  learning_rate: float = 3e-4, target_entropy: float = -2.0, ent_coef_init: float = 1.0, target_update_interval: int = 1,
-                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0, gemm: str = "fp32"):
+                 betas=(0.9, 0.999), eps: float = 1e-8, seed: int = 0, gemm: str = "fp32", dp_rank: int = 0):
         self.target_entropy, self.target_update_interval = float(target_entropy), int(target_update_interval)
-        super().__init__(net_arch, batch_size, device, gamma, tau, learning_rate, 1, 0.0, 0.0, betas, eps, seed, gemm)
+        super().__init__(net_arch, batch_size, device, gamma, tau, learning_rate, 1, 0.0, 0.0, betas, eps, seed, gemm, dp_rank=dp_rank)
         torch = self._torch
         offs = (c_int64 * 20)()
         _lib.check(self._libc.cstr_sac_layout(self.h1, self.h2, offs), "cstr_sac_layout")
@@ -449,7 +472,7 @@ class FusedSACUpdate(FusedTD3Update):
     def _sac_config(self, batch: int) -> "_lib.SacConfig":
         return _lib.SacConfig(h1=self.h1, h2=self.h2, batch=batch, target_update_interval=self.target_update_interval, gamma=self.gamma, tau=self.tau,
                               lr=self.learning_rate, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, target_entropy=self.target_entropy,
-                              seed=self.seed & (2**64 - 1), gemm_mode=_GEMM_MODES[self.gemm])
+                              seed=self._keyed_seed(), gemm_mode=_GEMM_MODES[self.gemm])
 
     def _workspace_bytes(self, batch: int) -> int:
         return int(self._libc.cstr_sac_workspace_bytes(byref(self._sac_config(batch))))
@@ -531,10 +554,13 @@ class FusedSACUpdate(FusedTD3Update):
             for p in ent_coef_optimizer.param_groups[0]["params"]:
                 ent_coef_optimizer.state[p] = {"step": step(), "exp_avg": self.adam_m[e:e + 1].reshape(p.shape), "exp_avg_sq": self.adam_v[e:e + 1].reshape(p.shape)}
 
-    def update(self, batch, eps_pi=None, eps_next=None, allreduce: Optional[Callable[[Any], None]] = None) -> None:  # type: ignore[override]
+    def update(self, batch, eps_pi=None, eps_next=None, allreduce: Optional[Callable[[Any], None]] = None,  # type: ignore[override]
+               gradient_step: Optional[int] = None) -> None:
         """One iteration of sac.py:213-288.  ``eps_pi`` / ``eps_next``: explicit standard-normal draws (B,2) of the two rsample() calls
         (parity tests); default = Philox inside the kernel.  ``allreduce``: called on grads[critics .. log_ent_coef] and on grads[actor]
-        between backward and Adam (data-parallel training: every rank ends with the gradient of the global batch)."""
+        between backward and Adam (data-parallel training: every rank ends with the gradient of the global batch).
+        ``gradient_step``: the index of this step inside the current ``train()`` call — what the reference's target sync tests
+        (``gradient_step % target_update_interval``, sac.py:284); None = the engine's own running count of updates."""
         obs, act, nobs, dones, rew = batch
         self._set_batch(int(obs.shape[0]))
         obs, act, nobs = self._f32(obs, 4), self._f32(act, 2), self._f32(nobs, 4)
@@ -545,6 +571,7 @@ class FusedSACUpdate(FusedTD3Update):
         self.critic_step += 1
         self.actor_step += 1
         cfg, st = self._sac_config(self._batch), self._state(counters=False)
+        cfg.local_step = 0 if gradient_step is None else int(gradient_step) + 1
 
         def run(phases):
             rc = self._libc.cstr_sac_update(byref(cfg), byref(st), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones), _lib.ptr(rew),
@@ -572,10 +599,11 @@ class FusedSACUpdate(FusedTD3Update):
         """``graph=True`` (single GPU, Philox-index buffer, full ring, target_update_interval 1): every update replays one captured CUDA graph."""
         bs = int(batch_size or self._batch)
         done = 0
-        if graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1:
+        if (graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1
+                and _graph_env_ok(env)):
             done = self._train_graph(gradient_steps, buffer, bs, env)
-        for _ in range(gradient_steps - done):
-            self.update(buffer.sample(bs, env=env), allreduce=allreduce)
+        for g in range(done, gradient_steps):  # g = the reference's loop index: the target sync tests `g % target_update_interval` (sac.py:284)
+            self.update(buffer.sample(bs, env=env), allreduce=allreduce, gradient_step=g)
 
     def pop_losses(self):
         """(critic loss, actor loss, ent_coef_loss, ent_coef) means since the last call — the keys SAC.train logs (sac.py:290-296)."""
@@ -604,7 +632,7 @@ def bind_sac_class(sac_base: type) -> type:
                 arch = self.policy.net_arch if isinstance(self.policy.net_arch, (list, tuple)) else self.policy.net_arch["pi"]
                 eng = FusedSACUpdate(arch, batch_size, self.device, self.gamma, self.tau, float(self.lr_schedule(self._current_progress_remaining)),
                                      float(self.target_entropy), float(self.log_ent_coef.detach().exp().item()), self.target_update_interval,
-                                     seed=int(self.seed or 0))
+                                     seed=int(self.seed or 0), dp_rank=_dist_rank())
                 eng.adopt_policy(self.policy)
                 self.log_ent_coef.data = eng.log_ent_coef  # shared storage
                 eng.import_optimizer_state(self.actor.optimizer, self.critic.optimizer, self.ent_coef_optimizer)

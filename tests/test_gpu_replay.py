@@ -166,3 +166,31 @@ def test_bcq_dataset_10m_transitions(pkg):
     assert np.array_equal(r[same], s.rewards.cpu().numpy()[same, 0])
     small = buf.sample(256)  # the reference's batch size
     assert small.actions.shape == (256, 2)
+
+
+class ReferenceLikeReplayBuffer:
+    """Stands in for the reference's ``core.common.buffers.ReplayBuffer`` as the base of a bound class (module-level: importable)."""
+
+
+def test_bound_class_pickles_and_stays_an_instance_of_the_reference_base(pkg, golden, tmp_path):
+    """``model.save_replay_buffer`` pickles the bound buffer (save_util.py:339-373) and ``load_replay_buffer`` asserts
+    ``isinstance(buffer, ReplayBuffer)`` (off_policy_algorithm.py:239): the dynamic class must survive the round trip."""
+    g = golden("replay.npz")
+    size, n_envs, n_add, batch = (int(v) for v in g["a_cfg"])
+    Bound = pkg.bind_replay_buffer_class(ReferenceLikeReplayBuffer)
+    assert pkg.bind_replay_buffer_class(ReferenceLikeReplayBuffer) is Bound
+    buf = Bound(size, device="cuda", n_envs=n_envs)
+    _fill(buf, g, "a", n_add)
+    path = tmp_path / "replay.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(buf, f)
+    with open(path, "rb") as f:
+        back = pickle.load(f)
+    assert isinstance(back, ReferenceLikeReplayBuffer) and isinstance(back, pkg.GpuReplayBuffer) and type(back) is Bound
+    assert torch.equal(back.records, buf.records) and (back.pos, back.full) == (buf.pos, buf.full)
+    back.device = "cuda"
+    np.random.seed(3)
+    s1 = buf.sample(32)
+    np.random.seed(3)
+    s2 = back.sample(32)
+    assert torch.equal(s1.observations, s2.observations) and torch.equal(s1.rewards, s2.rewards)

@@ -243,3 +243,33 @@ def test_adopt_policy_and_optimizer_state_hand_over(pkg):
             np.testing.assert_allclose(sb["exp_avg"].cpu().numpy(), sa["exp_avg"].cpu().numpy(), rtol=0, atol=2e-4 * scale)
     b.step(batches[0])  # and torch can carry on from the exported state (moments are views of the engine's blocks)
     assert float(b.opt_c.state[b.critic_params[0]]["step"]) == 5
+
+
+def test_target_sync_follows_the_loop_index_of_train(pkg):
+    """sac.py:284 tests `gradient_step % target_update_interval` with the LOOP index, which restarts at 0 in every train() call: with
+    interval 2 and one gradient step per call (the usual train_freq=1, gradient_steps=1) the reference polyaks on EVERY call."""
+    rng = np.random.default_rng(3)
+    nets = U.random_sac_nets(rng, 64, 48)
+    n_envs = 256
+    buf = pkg.GpuReplayBuffer(16 * n_envs, n_envs=n_envs, index_mode="philox", seed=5)
+    buf.records.uniform_(-1, 1)
+    buf.records[..., 11:13] = 0
+    buf.pos, buf.full = 0, True
+    eng = pkg.FusedSACUpdate([64, 48], 128, seed=2, target_update_interval=2)
+    eng.load_nets(nets)
+    orc = T.SACUpdateOracle(nets["actor"], [nets["critic0"], nets["critic1"]], [nets["critic0_target"], nets["critic1_target"]],
+                            target_update_interval=2)
+    for call in range(3):  # three train() calls of (1, then 3, then 1) gradient steps
+        steps = (1, 3, 1)[call]
+        orc.gradient_step = 0  # the reference's loop variable
+        for g in range(steps):
+            b = buf.sample(128)
+            e1, e2 = rng.normal(size=(128, 2)).astype(np.float32), rng.normal(size=(128, 2)).astype(np.float32)
+            before = eng.targets.clone()
+            eng.update(b, eps_pi=e1, eps_next=e2, gradient_step=g)
+            orc.step(*[t.cpu().numpy() for t in b], e1, e2)
+            assert (not torch.equal(before, eng.targets)) == (g % 2 == 0)
+    got = eng.nets()
+    for name, want in (("critic0_target", orc.critic_targets[0]), ("critic1_target", orc.critic_targets[1]), ("actor", orc.actor)):
+        for a, w in zip(got[name], want):
+            np.testing.assert_allclose(a, w, rtol=0, atol=2e-5)

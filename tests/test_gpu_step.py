@@ -322,3 +322,61 @@ def test_host_tape_entry_matches_device_tape(G, pkg):
     assert np.array_equal(h_state.numpy(), env.state.cpu().numpy())
     assert np.array_equal(h_sc.numpy(), env.step_count.cpu().numpy()) and np.array_equal(h_ep.numpy(), env.episode.cpu().numpy())
     assert h_done.numpy()[29].all()  # 370 + 30 = 400: the truncation row
+
+
+def _fast_tape_vs_oracle(pkg, n, T, seed, start_steps):
+    """tape_f32_kernel<fast> fed from an HBM action tape with obs + rewards + dones all requested (the instance bench.py times),
+    against the C oracle (libm expf / powf: the reference's arithmetic) on the same initial states, counters and actions."""
+    B.use_all_cores()
+    rng = np.random.default_rng(seed)
+    env = pkg.GpuCSTRVecEnv(n, seed=seed, math="fast", monitor=False)
+    st0 = env.reset().copy()
+    sc0 = np.asarray(start_steps, np.int32)
+    env.step_count.copy_(torch.as_tensor(sc0, device="cuda"))
+    acts = rng.uniform(-1, 1, (T, n, 2)).astype(np.float32)
+    ep0 = env.episode.cpu().numpy().copy()
+    res = env.tape(T, torch.as_tensor(acts, device="cuda"), want_obs=True, want_rewards=True, want_dones=True)
+    obs, rew, done = res["obs"].cpu().numpy(), res["rewards"].cpu().numpy(), res["dones"].cpu().numpy().astype(bool)
+    # the exact template instance bench.py launches (no observation tape) returns the same rewards / dones / final state, bit for bit
+    e2 = pkg.GpuCSTRVecEnv(n, seed=seed, math="fast", monitor=False)
+    e2.reset()
+    e2.step_count.copy_(torch.as_tensor(sc0, device="cuda"))
+    r2 = e2.tape(T, torch.as_tensor(acts, device="cuda"), want_obs=False, want_rewards=True, want_dones=True)
+    assert torch.equal(r2["rewards"], res["rewards"]) and torch.equal(r2["dones"], res["dones"]) and torch.equal(e2.state, env.state)
+    ref = B.tape_f32(st0, sc0, ep0, acts, 0, seed, 0, want_obs=True)
+    out = {"dones_equal": bool(np.array_equal(done, ref["dones"]))}
+    # (i) the whole trajectory, auto-resets included (reset rows are pure Philox + float64 math: bit-equal on both sides)
+    out["traj_obs"] = float(np.abs(obs - ref["obs"]).max())
+    out["traj_reward"] = float(np.abs(rew - ref["rewards"]).max())
+    # (ii) per step from IDENTICAL states: the oracle steps once from the kernel's own previous observation
+    prev = np.concatenate([st0[None], obs[:-1]], 0).reshape(-1, 4)
+    sc = (sc0[None, :] + np.arange(T, dtype=np.int32)[:, None]) % 400  # counter before each step (wraps at the truncation row)
+    s1, r1, tr1, _, _ = B.step_f32(prev, acts.reshape(-1, 2), sc.reshape(-1))
+    keep = ~tr1  # the truncation row returns the post-reset observation; its terminal state is covered by (i) through the reward
+    out["step_obs"] = float(np.abs(obs.reshape(-1, 4)[keep] - s1[keep]).max())
+    out["step_reward"] = float(np.abs(rew.reshape(-1) - r1).max())
+    out["step_dones_equal"] = bool(np.array_equal(done.reshape(-1), tr1))
+    return out
+
+
+def test_fast_tape_hbm_actions_rewards_dones_vs_oracle(pkg):
+    """The benchmarked kernel instance (bench.py: fast math, HBM action tape, rewards + dones out) has its own oracle test, at the
+    benchmark's size (65,536 x 400 = BASELINE config #2) and at a ragged size with resets inside the tape.
+    Bars: per step from identical states |dobs| <= 2e-6, |dreward| <= 1e-5; dones equal; over the 400-step trajectory
+    |dobs| <= 1e-5 (the dynamics are contractive: rounding differences do not accumulate) and |dreward| <= 5e-5."""
+    import json
+    import os
+
+    measured = {}
+    for name, n, T, starts in (("config2_65536x400", 65_536, 400, np.zeros(65_536, np.int32)),
+                               ("ragged_1037x403", 1037, 403, np.random.default_rng(5).integers(0, 400, 1037).astype(np.int32))):
+        m = _fast_tape_vs_oracle(pkg, n, T, seed=11, start_steps=starts)
+        measured[name] = m
+        assert m["dones_equal"] and m["step_dones_equal"], m
+        assert m["step_obs"] <= 2e-6 and m["step_reward"] <= 1e-5, m
+        assert m["traj_obs"] <= 1e-5 and m["traj_reward"] <= 5e-5, m
+    print("fast tape vs oracle, measured maxima:", json.dumps(measured))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "fast_tape_parity.json"), "w") as f:
+            json.dump(measured, f, indent=1)

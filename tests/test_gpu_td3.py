@@ -330,3 +330,43 @@ def test_ddpg_single_critic(pkg):
     assert critic_loss == pytest.approx(np.mean(o.critic_losses), rel=1e-5) and actor_loss == pytest.approx(np.mean(o.actor_losses), rel=1e-4, abs=1e-6)
     with pytest.raises(ValueError):
         pkg.FusedTD3Update([400, 300], 8, n_critics=3)
+
+
+class _HostVecNormalize:
+    """Stands in for the reference's host-side VecNormalize (vec_normalize.py:225-259): NumPy in, NumPy out, no device statistics."""
+
+    def normalize_obs(self, obs):
+        return (obs * np.float32(0.5) + np.float32(0.25)).astype(np.float32)
+
+    def normalize_reward(self, reward):
+        return (reward * np.float32(0.1)).astype(np.float32)
+
+
+def test_graph_path_is_not_taken_under_a_host_vecnormalize(pkg):
+    """A captured sample normalises inside the gather kernel, which needs device statistics.  With the reference's host VecNormalize the
+    graph path must be skipped (every update then samples through the normalising `sample()`), and `sample_into` must refuse."""
+    rng = np.random.default_rng(4)
+    nets = U.random_nets(rng, 64, 48)
+    n_envs = 256
+    buf = pkg.GpuReplayBuffer(16 * n_envs, n_envs=n_envs, index_mode="philox", seed=5)
+    buf.records.uniform_(-1, 1)
+    buf.records[..., 11:13] = 0
+    buf.pos, buf.full = 0, True
+    host_env = _HostVecNormalize()
+
+    def run(graph):
+        buf._draw = 0
+        eng = _engine(pkg, nets, [64, 48], 128, seed=9, policy_delay=2)
+        eng.train(6, buf, 128, env=host_env, graph=graph)
+        return eng
+
+    a, b = run(False), run(True)
+    assert b._graph is None  # the guard, not a silently un-normalised replay
+    assert torch.equal(a.params, b.params)
+    raw = _engine(pkg, nets, [64, 48], 128, seed=9, policy_delay=2)
+    buf._draw = 0
+    raw.train(6, buf, 128, env=None, graph=False)
+    assert not torch.equal(raw.params, a.params)  # the normalisation did reach the updates
+    out = buf._alloc_out(128)
+    with pytest.raises(ValueError):
+        buf.sample_into(out, torch.zeros(1, dtype=torch.int64, device="cuda"), env=host_env)
