@@ -183,7 +183,7 @@ def measure_pipe_peaks(pkg, torch, device) -> dict:
     res = {"sm_count": sms}
     stream = torch.cuda.current_stream(device).cuda_stream
     for kind, name, flop in ((0, "fp32_ffma_tflops", 2), (1, "fp64_dfma_tflops", 2), (2, "fp32_fmul_fadd_tflops", 2), (3, "mufu_ex2_tops", 1)):
-        best = 0.0
+        best, mhz = 0.0, None
         for rep in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -191,9 +191,14 @@ def measure_pipe_peaks(pkg, torch, device) -> dict:
             e1.record()
             e1.synchronize()
             ms = e0.elapsed_time(e1)
-            if rep:
-                best = max(best, grid * block * iters * 8 * flop / (ms * 1e-3) / 1e12)
+            rate = grid * block * iters * 8 * flop / (ms * 1e-3) / 1e12
+            if rep and rate > best:
+                best, mhz = rate, float(out[0].item())  # out[0]: the SM clock block 0 ran at (clock64 / globaltimer)
         res[name] = best
+        res[name.rsplit("_", 1)[0] + "_sm_mhz"] = mhz
+    res["sm_clock_khz_max"] = info[1].value
+    # the clock-derived FP32 peak (SMs x 128 lanes x 2 flop x f_clk) at the device's maximum SM clock
+    res["fp32_clock_derived_tflops"] = sms * 128 * 2 * info[1].value * 1e3 / 1e12
     return res
 
 
@@ -327,6 +332,14 @@ def run_ours(args) -> None:
     assert int(h_done.sum().item()) == n
     clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
 
+    # ---- the other half of the metric and the only collective, at EVERY N (all ranks take part) -------------------------------
+    multi = {}
+    if not args.no_extras:
+        try:
+            multi = run_multi_rank_sections(pkg, torch, device, dist, rank, world, args)
+        except Exception as exc:  # must never take the headline down
+            multi = {"error": repr(exc)}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -350,14 +363,20 @@ def run_ours(args) -> None:
     kernel_ms = statistics.mean(per)
     achieved = FLOP_PER_ENV_STEP * n * T / (kernel_ms * 1e-3) / 1e12
     peak = peaks["fp32_ffma_tflops"]
-    traffic = None  # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            key = "tape_f32_kernel<0, 0, 0, 0>" if args.math == "strict" else "tape_f32_kernel<1, 0, 0, 0>"
-            traffic = json.load(open(tpath)).get(key, {}).get("dram_bytes")
-        except Exception:
-            traffic = None
+    # dram__bytes_read + dram__bytes_write of one launch: STATIC, from the committed ncu --set full capture (ncu cannot run inside the bench)
+    traffic, traffic_source = None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                key = "tape_f32_kernel<0, 0, 0, 0>" if args.math == "strict" else "tape_f32_kernel<1, 0, 0, 0>"
+                traffic = tj.get(key, {}).get("dram_bytes")
+                traffic_source = f"static: ncu --set full capture in profiles/{name} (commit {tj.get('_commit', 'unrecorded')}), not measured in this run"
+            except Exception:
+                traffic = None
+            if traffic is not None:
+                break
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -368,7 +387,10 @@ def run_ours(args) -> None:
                    "l2": "inputs larger than L2 (210 MB tape vs 126 MB): no flush needed", "parallelism": f"env-shard x{world}", "per_rank_ms_per_step": [round(t / args.steps, 5) for t in per_rank_ms],
                    "parity": "fast: |dobs|<=2e-6 per step vs the reference arithmetic (tests/test_gpu_step.py); strict: bit-exact vs oracle"},
         "roofline": {"bound": "fp32-pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": traffic, "kernel": f"tape_f32_kernel<{args.math}>", "kernel_ms": kernel_ms,
+                     "traffic": traffic, "traffic_source": traffic_source, "kernel": f"tape_f32_kernel<{args.math}>", "kernel_ms": kernel_ms,
+                     "frac_of_clock_derived_peak": achieved / peaks["fp32_clock_derived_tflops"],
+                     "peak_note": "the FFMA probe (64 FFMA per loop branch, SASS-checked) runs at the SM clock it reports (fp32_ffma_sm_mhz) — "
+                                  "the clock-derived figure assumes the nominal maximum clock",
                      "flop_per_env_step": FLOP_PER_ENV_STEP, "peak_source": "measured in this run: cstr_probe_pipe FFMA chains (2 flop/FMA)",
                      "other_peaks": peaks,
                      "hbm_algorithmic_gbs": n * T * (8 + 4 + 1) / (kernel_ms * 1e-3) / 1e9},
@@ -378,12 +400,113 @@ def run_ours(args) -> None:
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "call": "cstr_tape_f32_host (pinned host buffers -> H2D -> tape kernel -> D2H, synchronous)"},
-        "gpu_launches": args.steps, "clocks": clocks, "extras": extras,
+        "gpu_launches": args.steps, "clocks": clocks, "rollout": multi.get("rollout"), "dp_update": multi.get("dp_update"),
+        "multi_rank_error": multi.get("error"), "extras": extras,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_multi_rank_sections(pkg, torch, device, dist, rank, world, args) -> dict:
+    """BASELINE metric, second half ("rollout transitions/sec at 1/2/4/8 B200") and SURVEY 8e's only collective, measured at every N:
+
+    rollout   config #3: TD3 actor 4-400-300-2 on tcgen05 fused with noise, bounds, CSTR step, reward/done and the replay record
+              (cstr_rollout_fused, 16 steps per launch, ring of 64 rows per GPU).  strong: 1,048,576 reactors sharded over the N
+              ranks; weak: 131,072 reactors per rank.  No collective on this path.  value = transitions of ALL ranks / max-over-ranks time.
+    dp_update TD3 [400,300] gradient step, data-parallel over the N ranks, per-rank batch 4096 and 256, replayed from ONE CUDA graph
+              per policy_delay cycle (Philox sample -> GRAD -> gradient mean over ranks -> Adam/polyak): "peer" = the mean is taken
+              inside the Adam kernels over NVLink peer memory (cstr_peer_comm), "nccl" = ncclAllReduce(avg) captured between the
+              phases, "nccl_eager" = the round-1 path (launch by launch, dist.all_reduce between the phases), "local" = the same
+              graph without any exchange (what one GPU does alone).  ms per update, max over ranks."""
+    import numpy as np
+
+    def max_over_ranks(ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return max_over_ranks(e0.elapsed_time(e1) / reps)
+
+    out = {"rollout": {}, "dp_update": {}}
+    torch.manual_seed(0)
+    lin = [torch.nn.Linear(4, 400), torch.nn.Linear(400, 300), torch.nn.Linear(300, 2)]
+    K, rows = 16, 64
+    for name, n_total in (("strong_1048576_total", 1 << 20), ("weak_131072_per_gpu", (1 << 17) * world)):
+        off, cnt = pkg.dist.shard_range(n_total, rank, world)
+        er = pkg.GpuCSTRVecEnv(cnt, device=device, math="strict", seed=4, env_offset=off, monitor=False)
+        er.reset()
+        buf = pkg.GpuReplayBuffer(rows * cnt, device=device, n_envs=cnt, index_mode="philox", seed=rank)
+        actor = pkg.ActorWeights(lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias, device=device)
+        roll = pkg.FusedRollout(er, buf, actor, sigma=0.1, actor_mode="tc")
+        ms = timed(lambda: roll.collect(K), reps=8, warm=4)
+        out["rollout"][name] = {"transitions_per_s": n_total * K / (ms * 1e-3), "ms_per_launch": ms, "steps_per_launch": K,
+                                "reactors_total": n_total, "reactors_this_rank": cnt, "actor": "TD3 4-400-300-2, bf16 tcgen05 hidden layer",
+                                "algorithmic_tflops_per_gpu": (244_400 + 176) * cnt * K / (ms * 1e-3) / 1e12}
+        del roll, actor, buf, er
+    out["rollout"]["scaling"] = {"strong_1048576_total": "strong", "weak_131072_per_gpu": "weak"}
+
+    n_envs = 65536
+    buf = pkg.GpuReplayBuffer(16 * n_envs, device=device, n_envs=n_envs, index_mode="philox", seed=1000 + rank)
+    buf.records.uniform_(-1, 1)
+    buf.records[..., 11:13] = 0
+    buf.pos, buf.full = 0, True
+    rng = np.random.default_rng(0)
+
+    def nets():
+        def mlp(i, o):
+            t = []
+            for fi, fo in ((i, 400), (400, 300), (300, o)):
+                b = 1.0 / np.sqrt(fi)
+                t += [rng.uniform(-b, b, (fo, fi)).astype(np.float32), rng.uniform(-b, b, fo).astype(np.float32)]
+            return t
+        return {"actor": mlp(4, 2), "critic0": mlp(6, 1), "critic1": mlp(6, 1)}
+
+    weights = nets()
+    hook = pkg.dist.allreduce_flat if world > 1 else None
+    for B in (4096, 256):
+        row = {"per_rank_batch": B, "global_batch": B * world, "net_arch": [400, 300], "gradient_bucket_bytes": None}
+        reps = 50 if B == 4096 else 100
+        for mode in ("local", "peer", "nccl", "nccl_eager"):
+            if world == 1 and mode != "local":
+                continue
+            eng = pkg.FusedTD3Update([400, 300], B, device=device, seed=7, dp_rank=rank)
+            eng.load_nets(weights)
+            row["gradient_bucket_bytes"] = eng.param_count * 4
+            if mode == "peer":
+                eng.enable_peer_allreduce()
+            ar = hook if mode in ("nccl", "nccl_eager") else None
+            graph = mode != "nccl_eager"
+            ms = timed(lambda: eng.train(2, buf, B, graph=graph, allreduce=ar), reps=reps, warm=5) / 2
+            row[f"{mode}_ms_per_update"] = ms
+            if mode == "peer":
+                row["peer_error_word"] = eng.peer_error()
+            eng.close_peer_allreduce()
+            del eng
+        if world > 1:
+            row["peer_over_local"] = row["peer_ms_per_update"] / row["local_ms_per_update"]
+            row["nccl_graph_over_local"] = row["nccl_ms_per_update"] / row["local_ms_per_update"]
+        out["dp_update"][f"per_rank_batch_{B}"] = row
+    out["dp_update"]["collective"] = ("gradient mean over ranks: critics' range every update, actor's range on policy steps (the actor loss needs the "
+                                      "UPDATED critic, td3.py:189-191, so the two ranges cannot share one exchange)")
+    return out
 
 
 def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict:

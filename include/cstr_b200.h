@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 14
+#define CSTR_B200_ABI_VERSION 15
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -208,6 +208,32 @@ typedef struct cstr_td3_config {
 #define CSTR_TD3_GEMM_TENSOR 1
 #define CSTR_TD3_GEMM_BF16 2 /* tcgen05 with plain bf16 operands (fp32 accumulate): REDUCED precision, opt-in throughput mode */
 
+/* ---- gradient all-reduce fused into the Adam step (multi-GPU) -----------------------------------------
+ * The data-parallel update's only collective is the mean of the flat gradient block over the ranks.  With a
+ * cstr_peer_comm the APPLY phases do it themselves: every rank's `grads` block lives in memory the other ranks have mapped
+ * (CUDA IPC, one process per GPU on one NVSwitch node), and the Adam kernel of rank r reads element i of ALL `world`
+ * blocks over NVLink, sums them in rank order 0..world-1 (bit-identical result on every rank, no atomics), scales by
+ * 1/world and goes straight into the Adam update — no separate collective launch, no second pass over the bucket.
+ * Cross-GPU ordering: a per-CTA flag barrier over peer memory before the reads (every peer's backward pass has finished)
+ * and after them (nobody overwrites its block while a peer still reads it); flags carry a per-launch epoch kept on the
+ * device, so the launches can sit inside a CUDA graph.  A rank that waits longer than ~4 s (a dead peer) stops waiting,
+ * raises the error word (cstr_peer_error) and skips the update instead of hanging the GPU.
+ * cstr_peer_alloc returns device memory (cudaMalloc, zeroed) and its 64-byte IPC handle; cstr_peer_open maps a peer's
+ * handle.  Layout of one rank's allocation, chosen by the caller: [grads block | pad to 256 B | cstr_peer_flag_bytes()]. */
+#define CSTR_PEER_MAX_WORLD 8
+typedef struct cstr_peer_comm {
+    int32_t world, rank;
+    float *grads[CSTR_PEER_MAX_WORLD];    /* grads[r]: rank r's flat gradient block as mapped in THIS process (grads[rank] = the local block) */
+    uint32_t *flags[CSTR_PEER_MAX_WORLD]; /* flags[r]: rank r's barrier block (cstr_peer_flag_bytes() bytes, zero before the first update)  */
+} cstr_peer_comm;
+int64_t cstr_peer_flag_bytes(void);
+int cstr_peer_alloc(int64_t bytes, void **ptr, void *handle64 /* 64 bytes out */);
+int cstr_peer_open(const void *handle64, void **ptr);
+int cstr_peer_close(void *ptr);
+int cstr_peer_free(void *ptr);
+/* non-zero after a peer wait timed out; *error is read from the local flag block (synchronises the stream)            */
+int cstr_peer_error(const cstr_peer_comm *comm, uint32_t *error, void *stream);
+
 typedef struct cstr_td3_state {
     float *params, *targets, *grads, *adam_m, *adam_v; /* device, cstr_td3_param_count floats each, 16-byte aligned */
     float *workspace;                                  /* device, >= cstr_td3_workspace_bytes(cfg)                  */
@@ -220,6 +246,9 @@ typedef struct cstr_td3_state {
                                                           update is baked into a launch and a cycle of policy_delay updates can be captured
                                                           in a CUDA graph and replayed (the by-value counters then only decide which
                                                           kernels are launched, i.e. whether this is a policy step)                     */
+    const cstr_peer_comm *peer;                        /* NULL: single GPU, or the caller all-reduces `grads` between the GRAD and APPLY
+                                                          phases itself.  Non-NULL: `grads` must be peer->grads[peer->rank] and the APPLY
+                                                          phases average the gradient over the ranks inside the Adam kernel (see above)  */
 } cstr_td3_state;
 
 #define CSTR_TD3_CRITIC_GRAD 1
@@ -323,7 +352,8 @@ int64_t cstr_actor_pack_bf16(const cstr_actor_f32 *actor, void *dst, void *strea
 /* ---- measurement probes (bench.py roofline denominators) ------------------------------------------
  * FMA-chain microbenchmarks: every thread runs `iters` iterations of 8 independent FMA chains.
  * kind 0: fp32 FFMA, 1: fp64 DFMA, 2: fp32 separate FMUL+FADD (the non-contractible op mix),
- * 3: MUFU.EX2.  out: one value per thread (keeps the chains live).  flops/launch =
+ * 3: MUFU.EX2.  out: one value per thread (keeps the chains live); out[0] instead holds the SM clock in MHz that
+ * thread 0 of block 0 observed over its own loop (clock64 cycles per globaltimer ns).  flops/launch =
  * grid*block*iters*8*(2 for kinds 0,1,2; 1 for kind 3).                                            */
 int cstr_probe_pipe(int kind, int64_t iters, int grid, int block, float *out, void *stream);
 

@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -69,7 +69,16 @@ class Td3State(Structure):
     """struct cstr_td3_state"""
 
     _fields_ = [("params", c_void_p), ("targets", c_void_p), ("grads", c_void_p), ("adam_m", c_void_p), ("adam_v", c_void_p),
-                ("workspace", c_void_p), ("workspace_bytes", c_int64), ("losses", c_void_p), ("counters", c_void_p)]
+                ("workspace", c_void_p), ("workspace_bytes", c_int64), ("losses", c_void_p), ("counters", c_void_p), ("peer", c_void_p)]
+
+
+PEER_MAX_WORLD = 8
+
+
+class PeerComm(Structure):
+    """struct cstr_peer_comm"""
+
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("grads", c_void_p * PEER_MAX_WORLD), ("flags", c_void_p * PEER_MAX_WORLD)]
 
 
 class SacConfig(Structure):
@@ -108,6 +117,12 @@ _SIGNATURES = {
     "cstr_sac_layout": (c_int, [c_int32, c_int32, POINTER(c_int64)]),
     "cstr_sac_workspace_bytes": (c_int64, [POINTER(SacConfig)]),
     "cstr_sac_update": (c_int, [POINTER(SacConfig), POINTER(Td3State), P, P, P, P, P, P, P, c_int64, c_int64, c_int32, P]),
+    "cstr_peer_flag_bytes": (c_int64, []),
+    "cstr_peer_alloc": (c_int, [c_int64, POINTER(c_void_p), P]),
+    "cstr_peer_open": (c_int, [P, POINTER(c_void_p)]),
+    "cstr_peer_close": (c_int, [P]),
+    "cstr_peer_free": (c_int, [P]),
+    "cstr_peer_error": (c_int, [POINTER(PeerComm), POINTER(c_uint32), P]),
     "cstr_rollout_fused": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, c_int, POINTER(ActorF32), P, c_float, P, c_int,
                                    c_uint32, P, P, P, P, c_int64, c_int64, P, P, POINTER(EpisodeStatsStruct), P]),
     "cstr_actor_pack_bf16": (c_int64, [POINTER(ActorF32), P, P]),

@@ -6,9 +6,20 @@
 
 namespace cstr {
 
+__device__ __forceinline__ uint64_t probe_globaltimer() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// out[0] (thread 0 of block 0) additionally carries the SM clock the chains actually ran at, in MHz: clock64 cycles / globaltimer ns
+// over the thread's own loop — the pipe peak a launch can reach is SMs x lanes x 2 x THIS clock, not the nominal maximum
 template <int KIND>
 __global__ void __launch_bounds__(256) probe_kernel(int64_t iters, float *out) {
     const float seed = (float)(threadIdx.x & 7) * 1e-3f;
+    const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+    const uint64_t t0 = timer ? probe_globaltimer() : 0;
+    const long long c0 = timer ? clock64() : 0;
     if (KIND == 1) {
         double a[8], b = 1.0000001, c = 1e-9 + seed;
 #pragma unroll
@@ -23,6 +34,11 @@ __global__ void __launch_bounds__(256) probe_kernel(int64_t iters, float *out) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += a[j];
         out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
+        if (timer) {
+            const long long c1 = clock64();
+            const uint64_t t1 = probe_globaltimer();
+            out[0] = (s != s ? 1.f : 0.f) + (float)(1e3 * (double)(c1 - c0) / (double)(t1 - t0 ? t1 - t0 : 1));
+        }
     } else {
         float a[8], b = 1.0000001f + seed * 1e-3f, c = 1e-9f + seed;
 #pragma unroll
@@ -42,6 +58,11 @@ __global__ void __launch_bounds__(256) probe_kernel(int64_t iters, float *out) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += a[j];
         out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+        if (timer) {
+            const long long c1 = clock64();
+            const uint64_t t1 = probe_globaltimer();
+            out[0] = (s != s ? 1.f : 0.f) + (float)(1e3 * (double)(c1 - c0) / (double)(t1 - t0 ? t1 - t0 : 1));
+        }
     }
 }
 

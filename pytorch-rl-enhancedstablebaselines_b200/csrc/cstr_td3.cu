@@ -18,7 +18,9 @@
 #include "cstr_abi.cuh"
 #include "cstr_device.cuh"
 
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace cstr {
 
@@ -860,6 +862,137 @@ __global__ void __launch_bounds__(256) td3_apply_kernel(ApplyArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// data-parallel variant of td3_apply_kernel: the gradient all-reduce is INSIDE the Adam step (include/cstr_b200.h,
+// cstr_peer_comm).  Every rank's gradient block is mapped in every process; thread i reads element group i of all `world`
+// blocks over NVLink, adds them in rank order (the same order on every rank: bit-identical weights without a broadcast),
+// scales by 1/world and continues with exactly the arithmetic of td3_apply_kernel.
+// Barrier block of one rank (uint32): [phase 0|1][PEER_MAX_BLOCKS][8 ranks] flags, then {epoch, done-ticket, error, pad}.
+// CTA b of rank r: writes `epoch` into slot [phase][b][r] of EVERY rank's block, then spins on its own slots [phase][b][*].
+// phase 0 (before the reads): the peer's CTA b has started, hence its stream reached this kernel, hence its backward pass is complete
+// and visible (kernel boundary + the release/acquire pair).  phase 1 (after the reads): every peer's CTA b has finished reading
+// region b of my block, so the kernels after this one may overwrite it.  The grid never exceeds the resident-CTA capacity, so every
+// CTA of every rank is running and the waits cannot deadlock; a dead peer is a bounded wait (error word), not a hang.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PEER_MAX_BLOCKS = 592;  // 148 SMs x 4 CTAs of 256 threads: always co-resident
+constexpr int PEER_FLAG_WORDS = 2 * PEER_MAX_BLOCKS * CSTR_PEER_MAX_WORLD;
+constexpr int PEER_EPOCH = PEER_FLAG_WORDS, PEER_TICKET = PEER_FLAG_WORDS + 1, PEER_ERROR = PEER_FLAG_WORDS + 2;
+constexpr long long PEER_WAIT_CYCLES = 8000000000LL;  // ~4 s at 2 GHz
+
+struct PeerArgs {
+    int world, rank;
+    const float *g[CSTR_PEER_MAX_WORLD];
+    uint32_t *flags[CSTR_PEER_MAX_WORLD];
+    float scale;  // 1 / world
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float *p) {  // peer memory written by another GPU: never from this SM's L1
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// returns false when a peer never arrived (error word raised)
+__device__ __forceinline__ bool peer_barrier(const PeerArgs &pa, int phase, uint32_t epoch) {
+    __shared__ int ok_s;
+    __syncthreads();
+    if (threadIdx.x == 0) ok_s = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < pa.world) {
+        const int slot = (phase * PEER_MAX_BLOCKS + blockIdx.x) * CSTR_PEER_MAX_WORLD;
+        st_release_sys(pa.flags[threadIdx.x] + slot + pa.rank, epoch);
+        const uint32_t *mine = pa.flags[pa.rank] + slot + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (clock64() - t0 > PEER_WAIT_CYCLES) {
+                pa.flags[pa.rank][PEER_ERROR] = 1u + (uint32_t)threadIdx.x;
+                ok_s = 0;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    return ok_s != 0;
+}
+
+__global__ void __launch_bounds__(256) td3_apply_peer_kernel(ApplyArgs a, PeerArgs pa) {
+    pdl_enter();
+    uint32_t *my = pa.flags[pa.rank];
+    const uint32_t epoch = *(volatile uint32_t *)(my + PEER_EPOCH) + 1u;
+    const bool alive = peer_barrier(pa, 0, epoch);
+    if (blockIdx.x == 0 && a.loss_acc) {  // as td3_apply_kernel: per-CTA loss partials -> running sums (the LOCAL shard's loss)
+        __shared__ float sl[256];
+        float s = 0.f;
+        for (int k = threadIdx.x; k < a.n_loss_partial; k += 256) s += a.loss_partial[k];
+        sl[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) sl[threadIdx.x] += sl[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            a.loss_acc[0] += sl[0] * a.loss_scale;
+            a.loss_acc[1] += 1.f;
+        }
+    }
+    const float step_size = a.dev_scalars ? a.dev_scalars[0] : a.step_size, bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
+    const int64_t lo = min(a.adam_lo, a.polyak_lo < a.polyak_hi ? a.polyak_lo : a.adam_lo), hi = max(a.adam_hi, a.polyak_hi);
+    if (alive)  // every range boundary is a multiple of 4 floats (pad4 layout): one float4 group per thread and trip
+        for (int64_t i = lo + 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 4 * (int64_t)gridDim.x * blockDim.x) {
+            float p[4];
+            bool have = false;
+            if (i >= a.adam_lo && i < a.adam_hi) {
+                float4 g4 = ld_peer_f4(pa.g[0] + i);
+                for (int r = 1; r < pa.world; ++r) {
+                    const float4 u = ld_peer_f4(pa.g[r] + i);
+                    g4.x += u.x, g4.y += u.y, g4.z += u.z, g4.w += u.w;
+                }
+                const float g[4] = {g4.x * pa.scale, g4.y * pa.scale, g4.z * pa.scale, g4.w * pa.scale};
+                const float4 p4 = *reinterpret_cast<const float4 *>(a.p + i), m4 = *reinterpret_cast<const float4 *>(a.m + i),
+                             v4 = *reinterpret_cast<const float4 *>(a.v + i);
+                float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+                p[0] = p4.x, p[1] = p4.y, p[2] = p4.z, p[3] = p4.w;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    m[c] = m[c] + (g[c] - m[c]) * (1.f - a.beta1);
+                    v[c] = v[c] * a.beta2 + (1.f - a.beta2) * g[c] * g[c];
+                    const float denom = sqrtf(v[c]) / bc2_sqrt + a.eps;
+                    p[c] = p[c] - step_size * (m[c] / denom);
+                }
+                *reinterpret_cast<float4 *>(a.p + i) = make_float4(p[0], p[1], p[2], p[3]);
+                *reinterpret_cast<float4 *>(a.m + i) = make_float4(m[0], m[1], m[2], m[3]);
+                *reinterpret_cast<float4 *>(a.v + i) = make_float4(v[0], v[1], v[2], v[3]);
+                have = true;
+            }
+            if (i >= a.polyak_lo && i < a.polyak_hi) {
+                if (!have) {
+                    const float4 p4 = *reinterpret_cast<const float4 *>(a.p + i);
+                    p[0] = p4.x, p[1] = p4.y, p[2] = p4.z, p[3] = p4.w;
+                }
+                float4 t = *reinterpret_cast<const float4 *>(a.t + i);
+                t.x = t.x * (1.f - a.tau) + a.tau * p[0], t.y = t.y * (1.f - a.tau) + a.tau * p[1];
+                t.z = t.z * (1.f - a.tau) + a.tau * p[2], t.w = t.w * (1.f - a.tau) + a.tau * p[3];
+                *reinterpret_cast<float4 *>(a.t + i) = t;
+            }
+        }
+    if (alive) peer_barrier(pa, 1, epoch);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the last CTA to get here publishes the epoch for the next launch (every CTA has read it by now)
+        __threadfence();
+        if (atomicAdd(my + PEER_TICKET, 1u) == gridDim.x - 1) {
+            my[PEER_TICKET] = 0u;
+            *(volatile uint32_t *)(my + PEER_EPOCH) = epoch;
+        }
+    }
+}
+
 }  // namespace cstr
 
 using namespace cstr;
@@ -1010,6 +1143,30 @@ int launch_gemm(const GemmArgs &g, int Z, int tensor, cudaStream_t st, const cha
     }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, Z * g.splits);
     launch_k(td3_gemm_kernel<MODE>, grid, 256, 0, st, g);
+    return check_launch(what);
+}
+
+// Adam (+ polyak) over flat ranges; with a peer communicator the gradient is averaged over the ranks inside the kernel
+int launch_apply(const ApplyArgs &a, const cstr_peer_comm *peer, const float *local_grads, cudaStream_t st, const char *what) {
+    const int64_t lo = std::min(a.adam_lo, a.polyak_lo < a.polyak_hi ? a.polyak_lo : a.adam_lo), hi = std::max(a.adam_hi, a.polyak_hi);
+    if (!peer) {
+        launch_k(td3_apply_kernel, (unsigned)((hi - lo + 255) / 256), 256, 0, st, a);
+        return check_launch(what);
+    }
+    if (peer->world < 1 || peer->world > CSTR_PEER_MAX_WORLD || peer->rank < 0 || peer->rank >= peer->world)
+        return fail_arg(CSTR_EINVAL, "peer comm: world must be in [1, 8] and rank in [0, world)");
+    if (peer->grads[peer->rank] != local_grads) return fail_arg(CSTR_EINVAL, "peer comm: state.grads must be peer->grads[rank]");
+    if ((lo | hi | a.adam_lo | a.adam_hi | a.polyak_lo | a.polyak_hi) & 3) return fail_arg(CSTR_EINVAL, "peer apply: ranges must be multiples of 4 floats");
+    PeerArgs pa{};
+    pa.world = peer->world, pa.rank = peer->rank, pa.scale = 1.f / (float)peer->world;
+    for (int r = 0; r < peer->world; ++r) {
+        if (!peer->grads[r] || !peer->flags[r] || !aligned(peer->grads[r], 16)) return fail_arg(CSTR_EINVAL, "peer comm: null or misaligned peer pointer");
+        pa.g[r] = peer->grads[r], pa.flags[r] = peer->flags[r];
+    }
+    int64_t blocks = ((hi - lo) / 4 + 255) / 256;
+    if (blocks > PEER_MAX_BLOCKS) blocks = PEER_MAX_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    launch_k(td3_apply_peer_kernel, (unsigned)blocks, 256, 0, st, a, pa);
     return check_launch(what);
 }
 
@@ -1166,9 +1323,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         a.tau = cfg->tau;
         a.dev_scalars = dev_sc;
         a.loss_partial = w.loss_partial, a.n_loss_partial = ZC * rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses;
-        const int64_t n = a.adam_hi - a.adam_lo;
-        launch_k(td3_apply_kernel, (unsigned)((n + 255) / 256), 256, 0, st, a);
-        if (int rc = check_launch("td3_apply_kernel<critic>")) return rc;
+        if (int rc = launch_apply(a, stt->peer, stt->grads, st, "td3_apply_kernel<critic>")) return rc;
     }
     if (policy_step && (phases & CSTR_TD3_ACTOR_GRAD)) {
         // ---- actor loss = -Q1(s, pi(s)).mean() and its backward (td3.py:189-196) ----
@@ -1202,8 +1357,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         a.tau = cfg->tau;
         a.dev_scalars = dev_sc ? dev_sc + 2 : nullptr;
         a.loss_partial = w.loss_partial, a.n_loss_partial = rb, a.loss_scale = -1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 2 : nullptr;
-        launch_k(td3_apply_kernel, (unsigned)((T.total + 255) / 256), 256, 0, st, a);
-        if (int rc = check_launch("td3_apply_kernel<actor+polyak>")) return rc;
+        if (int rc = launch_apply(a, stt->peer, stt->grads, st, "td3_apply_kernel<actor+polyak>")) return rc;
     }
     return 0;
 }
@@ -1273,7 +1427,9 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
     const float step_size = (float)((double)cfg->lr / bc1), bc2_sqrt = (float)sqrt(bc2);
 
     const float *dev_sc = stt->counters ? w.scalars : nullptr;  // graph mode: per-update scalars live on the device (td3_tick_kernel)
-    const bool fused_ent = (phases & (CSTR_TD3_CRITIC_GRAD | CSTR_TD3_CRITIC_APPLY)) == (CSTR_TD3_CRITIC_GRAD | CSTR_TD3_CRITIC_APPLY);
+    // log_ent_coef: gradient and Adam step in one launch when nothing sits between them; gradient only when the caller all-reduces
+    // between the phases, or when a peer communicator averages it inside the critic apply (its slot joins that Adam range)
+    const bool fused_ent = !stt->peer && (phases & (CSTR_TD3_CRITIC_GRAD | CSTR_TD3_CRITIC_APPLY)) == (CSTR_TD3_CRITIC_GRAD | CSTR_TD3_CRITIC_APPLY);
     auto ent_coef = [&](int mode) {
         launch_k(sac_ent_coef_kernel, 1, 256, 0, st, B, rb, w.lp_partial, cfg->target_entropy, stt->params + ent, stt->grads + ent, stt->adam_m + ent,
                                               stt->adam_v + ent, cfg->beta1, cfg->beta2, cfg->eps, step_size, bc2_sqrt, dev_sc ? 1 : 0, w.scalars,
@@ -1317,7 +1473,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
     }
     }  // CRITIC_GRAD
     if (phases & CSTR_TD3_CRITIC_APPLY) {
-        if (!fused_ent)
+        if (!fused_ent && !stt->peer)
             if (int rc = ent_coef(2)) return rc;
         ApplyArgs a{};
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
@@ -1325,8 +1481,8 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = step_size, a.bc2_sqrt = bc2_sqrt, a.tau = cfg->tau;
         a.dev_scalars = dev_sc;
         a.loss_partial = w.loss_partial, a.n_loss_partial = 2 * rb, a.loss_scale = 0.5f / (float)B, a.loss_acc = stt->losses;
-        launch_k(td3_apply_kernel, (unsigned)((a.adam_hi - a.adam_lo + 255) / 256), 256, 0, st, a);
-        if (int rc = check_launch("td3_apply_kernel<sac critic>")) return rc;
+        if (stt->peer) a.adam_hi = T.total + 4;  // the log_ent_coef slot rides in the same averaged Adam range (same formulas, same step size)
+        if (int rc = launch_apply(a, stt->peer, stt->grads, st, "td3_apply_kernel<sac critic>")) return rc;
     }
     if (phases & CSTR_TD3_ACTOR_GRAD) {
     // ---- actor (sac.py:270-281): (ent_coef * log_prob - min_i Q_i(s, a_pi)).mean() with the updated critics ----
@@ -1359,10 +1515,47 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = step_size, a.bc2_sqrt = bc2_sqrt, a.tau = cfg->tau;
         a.dev_scalars = dev_sc;
         a.loss_partial = w.loss_partial, a.n_loss_partial = rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 2 : nullptr;
-        launch_k(td3_apply_kernel, (unsigned)((T.total + 255) / 256), 256, 0, st, a);
-        if (int rc = check_launch("td3_apply_kernel<sac actor+polyak>")) return rc;
+        if (int rc = launch_apply(a, stt->peer, stt->grads, st, "td3_apply_kernel<sac actor+polyak>")) return rc;
     }
     return 0;
+}
+
+// ---- peer memory for the fused gradient all-reduce (include/cstr_b200.h, cstr_peer_comm) ---------------------------------
+int64_t cstr_peer_flag_bytes(void) { return (int64_t)(PEER_FLAG_WORDS + 4) * (int64_t)sizeof(uint32_t); }
+
+int cstr_peer_alloc(int64_t bytes, void **ptr, void *handle64) {
+    if (bytes <= 0 || !ptr || !handle64) return fail_arg(CSTR_EINVAL, "peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    if (int rc = check_cuda(cudaMalloc(&p, (size_t)bytes), "peer_alloc: cudaMalloc")) return rc;
+    if (int rc = check_cuda(cudaMemset(p, 0, (size_t)bytes), "peer_alloc: cudaMemset")) return rc;
+    cudaIpcMemHandle_t h;
+    if (int rc = check_cuda(cudaIpcGetMemHandle(&h, p), "peer_alloc: cudaIpcGetMemHandle")) {
+        cudaFree(p);
+        return rc;
+    }
+    if (int rc = check_cuda(cudaDeviceSynchronize(), "peer_alloc: sync")) return rc;
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return 0;
+}
+
+int cstr_peer_open(const void *handle64, void **ptr) {
+    if (!handle64 || !ptr) return fail_arg(CSTR_EINVAL, "peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    return check_cuda(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), "peer_open: cudaIpcOpenMemHandle");
+}
+
+int cstr_peer_close(void *ptr) { return ptr ? check_cuda(cudaIpcCloseMemHandle(ptr), "peer_close") : 0; }
+
+int cstr_peer_free(void *ptr) { return ptr ? check_cuda(cudaFree(ptr), "peer_free") : 0; }
+
+int cstr_peer_error(const cstr_peer_comm *comm, uint32_t *error, void *stream) {
+    if (!comm || !error || comm->rank < 0 || comm->rank >= CSTR_PEER_MAX_WORLD || !comm->flags[comm->rank]) return fail_arg(CSTR_EINVAL, "peer_error: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = check_cuda(cudaMemcpyAsync(error, comm->flags[comm->rank] + PEER_ERROR, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "peer_error: copy")) return rc;
+    return check_cuda(cudaStreamSynchronize(st), "peer_error: sync");
 }
 
 }  // extern "C"

@@ -70,9 +70,12 @@ def allreduce_flat(flat, group=None, average: bool = True):
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            flat.div_(dist.get_world_size(group))
+        if average and flat.is_cuda:  # NCCL averages inside the collective: no extra scaling launch (and none to capture in a graph)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat.div_(dist.get_world_size(group))
     return flat
 
 

@@ -15,6 +15,7 @@ operands with fp32 accumulation (reduced precision, throughput mode; no per-step
 """
 from __future__ import annotations
 
+import ctypes
 from ctypes import byref, c_int64
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
@@ -71,6 +72,7 @@ class FusedTD3Update:
         self._graph = None
         self._graph_key = None
         self._graph_out = None
+        self._peer = None  # cstr_peer_comm of enable_peer_allreduce()
         self._workspace = None
         self._batch = 0
         self._set_batch(int(batch_size))
@@ -208,10 +210,81 @@ class FusedTD3Update:
     def _state(self, counters: bool) -> "_lib.Td3State":
         return _lib.Td3State(params=self.params.data_ptr(), targets=self.targets.data_ptr(), grads=self.grads.data_ptr(), adam_m=self.adam_m.data_ptr(),
                              adam_v=self.adam_v.data_ptr(), workspace=self._workspace.data_ptr(), workspace_bytes=self._workspace.numel() * 4,
-                             losses=self.loss_sums.data_ptr(), counters=self._counters.data_ptr() if counters else None)
+                             losses=self.loss_sums.data_ptr(), counters=self._counters.data_ptr() if counters else None,
+                             peer=ctypes.addressof(self._peer) if self._peer is not None else None)
+
+    # ---- data-parallel training: the gradient all-reduce inside the Adam kernel (include/cstr_b200.h, cstr_peer_comm) ---------------
+    def enable_peer_allreduce(self, group=None) -> bool:
+        """Move the flat gradient block into memory every rank of ``group`` maps (CUDA IPC over NVLink/NVSwitch, one process per GPU on one
+        node) so that the APPLY phases average the gradient over the ranks inside the Adam kernel — no collective launch at all, and the
+        update stays capturable as one CUDA graph.  Every rank must then call ``update``/``train`` in lockstep (same number of updates, same
+        policy steps).  Returns False (and changes nothing) for a single-process group."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return False
+        torch, lib = self._torch, self._libc
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > _lib.PEER_MAX_WORLD:
+            raise ValueError(f"peer all-reduce spans one NVSwitch node: world size {world} > {_lib.PEER_MAX_WORLD}")
+        grad_bytes = (self.param_count * 4 + 255) // 256 * 256
+        total = grad_bytes + int(lib.cstr_peer_flag_bytes())
+        base, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.cstr_peer_alloc(total, byref(base), handle), "cstr_peer_alloc")
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            bases = []
+            for r in range(world):
+                if r == rank:
+                    bases.append(base.value)
+                else:
+                    p = ctypes.c_void_p()
+                    _lib.check(lib.cstr_peer_open(handles[r], byref(p)), f"cstr_peer_open(rank {r})")
+                    bases.append(p.value)
+            comm = _lib.PeerComm(world=world, rank=rank)
+            for r in range(world):
+                comm.grads[r], comm.flags[r] = bases[r], bases[r] + grad_bytes
+            local = torch.as_tensor(_DeviceMemory(base.value, self.param_count), device=self.device)
+            local.copy_(self.grads)
+            torch.cuda.synchronize(self.device)
+        self.grads, self._peer, self._peer_bases, self._peer_group = local, comm, bases, group
+        self._graph = None
+        dist.barrier(group)  # nobody starts an update before every rank has mapped every block
+        return True
+
+    def peer_error(self) -> int:
+        """Non-zero after a rank waited in vain for a peer inside the fused all-reduce (the update of that step was skipped)."""
+        if self._peer is None:
+            return 0
+        err = ctypes.c_uint32(0)
+        with self._torch.cuda.device(self.device):
+            _lib.check(self._libc.cstr_peer_error(byref(self._peer), byref(err), self._stream()), "cstr_peer_error")
+        return int(err.value)
+
+    def close_peer_allreduce(self) -> None:
+        """Unmap the peers' blocks and free the local one (collective: every rank calls it)."""
+        if self._peer is None:
+            return
+        import torch.distributed as dist
+
+        torch = self._torch
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self._peer_group)
+        keep = torch.empty(self.param_count, dtype=torch.float32, device=self.device)
+        keep.copy_(self.grads)
+        rank = self._peer.rank
+        self.grads, self._graph = keep, None
+        torch.cuda.synchronize(self.device)
+        for r, b in enumerate(self._peer_bases):
+            if r != rank:
+                self._libc.cstr_peer_close(b)
+        dist.barrier(self._peer_group)  # a block is freed only after every peer has unmapped it
+        self._libc.cstr_peer_free(self._peer_bases[rank])
+        self._peer = None
 
     # ---- CUDA-graph path: one captured cycle of policy_delay x (sample + update), replayed ------------------------------------
-    def _capture(self, buffer, batch_size: int, env) -> None:
+    def _capture(self, buffer, batch_size: int, env, allreduce=None) -> None:
         torch = self._torch
         self._set_batch(batch_size)
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -223,7 +296,7 @@ class FusedTD3Update:
         def cycle():
             for k in range(1, self._cycle_len() + 1):  # by-value counters only choose the launch structure: update k of the cycle
                 buffer.sample_into(out, draw, env=env)
-                self._graph_launch(batch_size, st, out, k)
+                self._graph_launch(batch_size, st, out, k, allreduce)
 
         snapshot = [t.clone() for t in (self.params, self.targets, self.adam_m, self.adam_v, self.loss_sums, self._counters)]
         side = torch.cuda.Stream(device=self.device)
@@ -232,31 +305,46 @@ class FusedTD3Update:
             cycle()
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
+        # thread_local: a collective inside the cycle keeps NCCL's watchdog thread polling events while this thread captures
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
             cycle()
         for dst, src in zip((self.params, self.targets, self.adam_m, self.adam_v, self.loss_sums, self._counters), snapshot):
             dst.copy_(src)  # the warm-up cycle was a real update: undo it
         self._graph, self._graph_out = graph, out
-        self._graph_key = (id(buffer), batch_size, buffer.size(), buffer.n_envs, id(env), self.policy_delay, self.learning_rate, self.params.data_ptr(),
-                           self._workspace.data_ptr())
+        self._graph_key = self._make_graph_key(buffer, batch_size, env, allreduce)
+
+    def _make_graph_key(self, buffer, batch_size: int, env, allreduce):
+        return (id(buffer), batch_size, buffer.size(), buffer.n_envs, id(env), self.policy_delay, self.learning_rate, self.params.data_ptr(),
+                self._workspace.data_ptr() if self._workspace is not None else 0, self.grads.data_ptr(), id(allreduce) if allreduce is not None else 0)
 
     def _cycle_len(self) -> int:
         return self.policy_delay
 
-    def _graph_launch(self, batch_size: int, st, out, k: int) -> None:
+    def _graph_launch(self, batch_size: int, st, out, k: int, allreduce=None) -> None:
         cfg = self._config(batch_size)
-        rc = self._libc.cstr_td3_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(out[4]),
-                                        None, k, 1, 1, _lib.TD3_ALL, self._stream())
-        _lib.check(rc, "cstr_td3_update (graph capture)")
 
-    def _train_graph(self, gradient_steps: int, buffer, batch_size: int, env) -> int:
+        def run(phases):
+            rc = self._libc.cstr_td3_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+                                            _lib.ptr(out[4]), None, k, 1, 1, phases, self._stream())
+            _lib.check(rc, "cstr_td3_update (graph capture)")
+
+        if allreduce is None:
+            run(_lib.TD3_ALL)
+        else:  # the collective is captured between the phases: GRAD -> all-reduce -> APPLY is ONE graph
+            run(_lib.TD3_CRITIC_GRAD)
+            allreduce(self.grads[self.critic_range[0]:self.critic_range[1]])
+            run(_lib.TD3_CRITIC_APPLY | _lib.TD3_ACTOR_GRAD)
+            if k % self.policy_delay == 0:
+                allreduce(self.grads[self.actor_range[0]:self.actor_range[1]])
+            run(_lib.TD3_ACTOR_APPLY)
+
+    def _train_graph(self, gradient_steps: int, buffer, batch_size: int, env, allreduce=None) -> int:
         """Replays whole cycles while the update count is cycle-aligned; returns the number of gradient steps done."""
         if self.n_updates % self._cycle_len() or gradient_steps < self._cycle_len():
             return 0
-        key = (id(buffer), batch_size, buffer.size(), buffer.n_envs, id(env), self.policy_delay, self.learning_rate, self.params.data_ptr(),
-               self._workspace.data_ptr() if self._workspace is not None else 0)
+        key = self._make_graph_key(buffer, batch_size, env, allreduce)
         if self._graph is None or key != self._graph_key:
-            self._capture(buffer, batch_size, env)
+            self._capture(buffer, batch_size, env, allreduce)
         cycles = gradient_steps // self._cycle_len()
         self._counters.copy_(self._torch.tensor([self.n_updates, self.critic_step, self.actor_step, buffer._draw], dtype=self._torch.int64),
                              non_blocking=True)
@@ -294,7 +382,7 @@ class FusedTD3Update:
             _lib.check(rc, "cstr_td3_update")
 
         with self._torch.cuda.device(self.device):
-            if allreduce is None:
+            if allreduce is None or self._peer is not None:  # a peer communicator averages inside the APPLY kernels
                 run(_lib.TD3_ALL)
             else:
                 run(_lib.TD3_CRITIC_GRAD)
@@ -307,13 +395,17 @@ class FusedTD3Update:
 
     def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, allreduce=None, graph: bool = False) -> None:
         """``TD3.train(gradient_steps, batch_size)`` (td3.py:154-206): sample + update, ``gradient_steps`` times.
-        ``graph=True`` (single-GPU, Philox-index buffer): whole cycles of ``policy_delay`` updates are replayed from ONE captured CUDA
-        graph (24-45 launches per update become one graph launch per cycle); the remainder runs launch by launch."""
+        ``graph=True`` (Philox-index buffer): whole cycles of ``policy_delay`` updates are replayed from ONE captured CUDA graph (24-45
+        launches per update become one graph launch per cycle); the remainder runs launch by launch.  Data-parallel training is captured
+        too: with ``enable_peer_allreduce`` the averaging is part of the Adam kernels, and an ``allreduce=`` hook (``dist.all_reduce``
+        over NCCL) is captured between the phases, so GRAD -> all-reduce -> APPLY is one graph on every rank."""
         bs = int(batch_size or self._batch)
         done = 0
+        if self._peer is not None:
+            allreduce = None
         # a captured cycle bakes the sampling range in: only worth capturing once the ring is full (its range is constant from then on)
-        if graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox" and buffer.full and _graph_env_ok(env):
-            done = self._train_graph(gradient_steps, buffer, bs, env)
+        if graph and getattr(buffer, "index_mode", None) == "philox" and buffer.full and _graph_env_ok(env):
+            done = self._train_graph(gradient_steps, buffer, bs, env, allreduce)
         for _ in range(gradient_steps - done):
             self.update(buffer.sample(bs, env=env), allreduce=allreduce)
 
@@ -324,6 +416,13 @@ class FusedTD3Update:
         critic = s[0] / s[1] if s[1] else None
         actor = s[2] / s[3] if s[3] else None
         return critic, actor
+
+
+class _DeviceMemory:
+    """``__cuda_array_interface__`` view of float32 device memory the library allocated (``cstr_peer_alloc``), for ``torch.as_tensor``."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
 def _dist_rank() -> int:
@@ -579,7 +678,7 @@ class FusedSACUpdate(FusedTD3Update):
             _lib.check(rc, "cstr_sac_update")
 
         with self._torch.cuda.device(self.device):
-            if allreduce is None:
+            if allreduce is None or self._peer is not None:
                 run(_lib.TD3_ALL)
             else:
                 run(_lib.TD3_CRITIC_GRAD)
@@ -589,19 +688,31 @@ class FusedSACUpdate(FusedTD3Update):
                 run(_lib.TD3_ACTOR_APPLY)
         self.launches += 50
 
-    def _graph_launch(self, batch_size: int, st, out, k: int) -> None:
+    def _graph_launch(self, batch_size: int, st, out, k: int, allreduce=None) -> None:
         cfg = self._sac_config(batch_size)
-        rc = self._libc.cstr_sac_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]), _lib.ptr(out[4]),
-                                        None, None, 1, 1, _lib.TD3_ALL, self._stream())
-        _lib.check(rc, "cstr_sac_update (graph capture)")
+
+        def run(phases):
+            rc = self._libc.cstr_sac_update(byref(cfg), byref(st), _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(out[3]),
+                                            _lib.ptr(out[4]), None, None, 1, 1, phases, self._stream())
+            _lib.check(rc, "cstr_sac_update (graph capture)")
+
+        if allreduce is None:
+            run(_lib.TD3_ALL)
+        else:
+            run(_lib.TD3_CRITIC_GRAD)
+            allreduce(self.grads[self.critic_range[0]:self._ent_offset + 4])
+            run(_lib.TD3_CRITIC_APPLY | _lib.TD3_ACTOR_GRAD)
+            allreduce(self.grads[self.actor_range[0]:self.actor_range[1]])
+            run(_lib.TD3_ACTOR_APPLY)
 
     def train(self, gradient_steps: int, buffer, batch_size: Optional[int] = None, env=None, allreduce=None, graph: bool = False) -> None:  # type: ignore[override]
         """``graph=True`` (single GPU, Philox-index buffer, full ring, target_update_interval 1): every update replays one captured CUDA graph."""
         bs = int(batch_size or self._batch)
         done = 0
-        if (graph and allreduce is None and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1
-                and _graph_env_ok(env)):
-            done = self._train_graph(gradient_steps, buffer, bs, env)
+        if self._peer is not None:
+            allreduce = None
+        if graph and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1 and _graph_env_ok(env):
+            done = self._train_graph(gradient_steps, buffer, bs, env, allreduce)
         for g in range(done, gradient_steps):  # g = the reference's loop index: the target sync tests `g % target_update_interval` (sac.py:284)
             self.update(buffer.sample(bs, env=env), allreduce=allreduce, gradient_step=g)
 

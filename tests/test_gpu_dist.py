@@ -96,7 +96,60 @@ if rank == 0:
     sac_err = max(float((full.params - sdp.params).abs().max()), float((full.targets - sdp.targets).abs().max()))
     sac_same = all(bool(torch.equal(p.to(dev), sdp.params)) for p in peers)
     sac_ent_moved = abs(float(sdp.log_ent_coef.item()) - float(np.log(0.7))) > 1e-4
+# (5) the all-reduce fused INTO the Adam kernels over peer memory (cstr_peer_comm, CUDA IPC over NVLink): no collective call at all
+pf = pkg.FusedTD3Update([400, 300], B // world, device=dev)
+pf.load_nets(nets)
+assert pf.enable_peer_allreduce()
+for b in batches:
+    pf.update(tuple(t[sl] for t in b[:5]), noise=b[5][sl])
+peers = [torch.empty_like(pf.params) for _ in range(world)]
+dist.all_gather(peers, pf.params)
+peer_same = all(bool(torch.equal(p.to(dev), pf.params)) for p in peers)
+peer_vs_nccl = max(float((pf.params - dp.params).abs().max()), float((pf.targets - dp.targets).abs().max()))
+peer_error_word = pf.peer_error()
+spf = pkg.FusedSACUpdate([256, 256], B // world, device=dev, ent_coef_init=0.7)
+spf.load_nets(sac_nets)
+assert spf.enable_peer_allreduce()
+for b in sac_batches:
+    spf.update(tuple(t[sl] for t in b[:5]), eps_pi=b[5][sl], eps_next=b[6][sl])
+peers = [torch.empty_like(spf.params) for _ in range(world)]
+dist.all_gather(peers, spf.params)
+sac_peer_same = all(bool(torch.equal(p.to(dev), spf.params)) for p in peers)
+sac_peer_vs_nccl = max(float((spf.params - sdp.params).abs().max()), float((spf.targets - sdp.targets).abs().max()))
+# (6) the data-parallel update as ONE CUDA graph per cycle: sample -> GRAD -> all-reduce -> APPLY captured, for the NCCL hook and for
+#     the peer-fused kernels; the replayed weights must equal the launch-by-launch data-parallel run
+n_envs = 512
+buf = pkg.GpuReplayBuffer(32 * n_envs, device=dev, n_envs=n_envs, index_mode="philox", seed=100 + rank)
+buf.records.uniform_(-1, 1)
+buf.records[..., 11:13] = 0
+buf.pos, buf.full = 0, True
+def run(mode, graph, cls=pkg.FusedTD3Update, arch=(400, 300), src=nets):
+    buf._draw = 0
+    eng = cls(list(arch), 128, device=dev, seed=3, dp_rank=rank)
+    eng.load_nets(src)
+    if mode == "peer":
+        eng.enable_peer_allreduce()
+    for steps in (6, 5):
+        eng.train(steps, buf, 128, graph=graph, allreduce=pkg.dist.allreduce_flat if mode == "nccl" else None)
+    torch.cuda.synchronize()
+    out = (eng.params.clone(), eng.targets.clone(), eng._graph is not None, eng.peer_error())
+    eng.close_peer_allreduce()
+    return out
+g = {}
+for name, cls, arch, src in (("td3", pkg.FusedTD3Update, (400, 300), nets), ("sac", pkg.FusedSACUpdate, (256, 256), sac_nets)):
+    for mode in ("nccl", "peer"):
+        a, b = run(mode, False, cls, arch, src), run(mode, True, cls, arch, src)
+        g[f"{name}_{mode}_graph_err"] = max(float((a[0] - b[0]).abs().max()), float((a[1] - b[1]).abs().max()))
+        g[f"{name}_{mode}_graph_used"] = bool(b[2]) and not a[2]
+        g[f"{name}_{mode}_peer_error"] = a[3] + b[3]
+        peers = [torch.empty_like(b[0]) for _ in range(world)]
+        dist.all_gather(peers, b[0])
+        g[f"{name}_{mode}_ranks_equal"] = all(bool(torch.equal(p.to(dev), b[0])) for p in peers)
+pf.close_peer_allreduce()
+spf.close_peer_allreduce()
 if rank == 0:
+    print(json.dumps({"peer_same": peer_same, "peer_vs_nccl": peer_vs_nccl, "peer_error_word": peer_error_word, "sac_peer_same": sac_peer_same,
+                      "sac_peer_vs_nccl": sac_peer_vs_nccl, "graph": g}))
     print(json.dumps({"ok_shard": ok_shard, "grad_err": err, "bucket": bucket.numel(), "world": world, "td3_err": td3_err, "td3_ranks_equal": td3_same,
                       "sac_err": sac_err, "sac_ranks_equal": sac_same, "sac_ent_moved": sac_ent_moved}))
 dist.destroy_process_group()
@@ -109,9 +162,20 @@ def test_nccl_allreduce_and_shard_invariance(tmp_path):
     script.write_text(WORKER)
     env = dict(os.environ, CSTR_ROOT=ROOT)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29541", str(script)], capture_output=True, text=True, timeout=600, env=env)
+                          "--master-port", "29541", str(script)], capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stderr[-3000:]
-    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    res, peer = lines[-1], lines[-2]
+    print(json.dumps(peer))
+    # the all-reduce fused into the Adam kernels (peer memory): every rank bit-identical, same weights as the NCCL path up to the
+    # summation order of the mean (NCCL's ring vs rank order), no timeout raised
+    assert peer["peer_same"] is True and peer["peer_vs_nccl"] < 2e-6 and peer["peer_error_word"] == 0
+    assert peer["sac_peer_same"] is True and peer["sac_peer_vs_nccl"] < 2e-6
+    for name in ("td3", "sac"):
+        for mode in ("nccl", "peer"):  # sample -> GRAD -> all-reduce -> APPLY replayed from one CUDA graph == launch by launch
+            assert peer["graph"][f"{name}_{mode}_graph_used"] is True
+            assert peer["graph"][f"{name}_{mode}_graph_err"] <= 3e-7 and peer["graph"][f"{name}_{mode}_ranks_equal"] is True
+            assert peer["graph"][f"{name}_{mode}_peer_error"] == 0
     assert res["ok_shard"] is True
     assert res["grad_err"] < 1e-6 and res["bucket"] == 122_902 and res["world"] == 2
     assert res["td3_ranks_equal"] is True and res["td3_err"] < 2e-5  # DP TD3 update == single-device update on the whole batch
