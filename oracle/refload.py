@@ -30,8 +30,12 @@ _scratch: Optional[str] = None
 
 
 def reference_root() -> Optional[str]:
-    root = os.environ.get("CSTR_REFERENCE_ROOT", "/root/reference")
-    return root if os.path.isfile(os.path.join(root, "twoseriescstr.py")) else None
+    """``CSTR_REFERENCE_ROOT``, else /root/reference (the build container), else the git-ignored staging copy ``baseline/_ref`` that
+    travels to a GPU box with the repository snapshot."""
+    for root in (os.environ.get("CSTR_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")):
+        if root and os.path.isfile(os.path.join(root, "twoseriescstr.py")):
+            return root
+    return None
 
 
 def available() -> bool:

@@ -12,7 +12,7 @@ from .buffer import GpuReplayBuffer, ReplayBufferSamples, bind_replay_buffer_cla
 from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
 from .normalize import GpuVecNormalize, bind_vec_normalize_class
 from .update import FusedSACUpdate, FusedTD3Update, bind_sac_class, bind_td3_class
-from .rollout import ActorWeights, EpisodeStats, FusedRollout
+from .rollout import ActorWeights, EpisodeStats, FusedRollout, bind_offpolicy_rollout, fused_rollout_unsupported
 
 __all__ = [
     "ActorWeights",
@@ -24,6 +24,7 @@ __all__ = [
     "GpuVecNormalize",
     "FusedTD3Update",
     "FusedSACUpdate",
+    "bind_offpolicy_rollout",
     "bind_sac_class",
     "bind_td3_class",
     "bind_vec_normalize_class",
@@ -34,6 +35,7 @@ __all__ = [
     "bind_vec_env_class",
     "build",
     "dist",
+    "fused_rollout_unsupported",
 ]
 
 

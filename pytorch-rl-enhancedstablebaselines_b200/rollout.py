@@ -198,3 +198,166 @@ class FusedRollout:
         self.launches += 1
         self.t += K
         buf.advance(K)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the fused rollout behind the reference's own learn()
+# ---------------------------------------------------------------------------------------------------------------------
+def _noise_sigma(action_noise):
+    """sigma of a zero-mean ``NormalActionNoise`` (noise.py:29-48), possibly wrapped in ``VectorizedActionNoise``; None if the noise is
+    something the kernel does not draw (Ornstein-Uhlenbeck, non-zero mean, per-dimension sigmas)."""
+    import numpy as np
+
+    if action_noise is None:
+        return 0.0
+    base = getattr(action_noise, "base_noise", action_noise)
+    if type(base).__name__ != "NormalActionNoise":
+        return None
+    mu, sigma = np.asarray(base._mu, np.float64).ravel(), np.asarray(base._sigma, np.float64).ravel()
+    if np.any(mu != 0.0) or np.any(sigma != sigma[0]):
+        return None
+    return float(sigma[0])
+
+
+def fused_rollout_unsupported(model, env, replay_buffer, train_freq, action_noise) -> Optional[str]:
+    """Why ``cstr_rollout_fused`` can NOT stand in for this ``collect_rollouts`` call — or None when it can."""
+    if not isinstance(env, GpuCSTRVecEnv):
+        return f"env is a {type(env).__name__}, not a GpuCSTRVecEnv (wrappers step through the NumPy protocol)"
+    if env.dtype != "fp32" or env.reset_rng != "philox":
+        return "the fused rollout needs GpuCSTRVecEnv(dtype='fp32', reset_rng='philox')"
+    if not isinstance(replay_buffer, GpuReplayBuffer) or replay_buffer.n_envs != env.num_envs or replay_buffer.device != env.device:
+        return "replay buffer is not a GpuReplayBuffer on the env's device with n_envs == env.num_envs"
+    if getattr(train_freq.unit, "value", train_freq.unit) != "step":
+        return "train_freq counts episodes (one kernel launch collects a fixed number of steps)"
+    if getattr(model, "use_sde", False):
+        return "use_sde (state-dependent exploration matrices)"
+    if getattr(model, "_vec_normalize_env", None) is not None:
+        return "VecNormalize wraps the env (the actor would need normalised observations)"
+    if _noise_sigma(action_noise) is None:
+        return f"action noise {action_noise!r} is not a zero-mean NormalActionNoise with one sigma"
+    actor = getattr(model, "actor", None)
+    if actor is None or not (hasattr(actor, "mu") and (hasattr(actor.mu, "__len__") or hasattr(actor, "latent_pi"))):
+        return "the policy has no TD3/DDPG `actor.mu` Sequential or SAC `actor.latent_pi/mu/log_std`"
+    return None
+
+
+def bind_offpolicy_rollout(algo_base: type, actor_mode: str = "fp32") -> type:
+    """Return a subclass of a reference off-policy algorithm (``core.TD3 / DDPG / SAC``, or what ``bind_td3_class`` / ``bind_sac_class``
+    returned) whose ``collect_rollouts`` (core/common/off_policy_algorithm.py:510-605) is ONE ``cstr_rollout_fused`` launch per call:
+    ``train_freq.frequency`` steps of ``_sample_action`` (:364-411) + ``env.step`` (:564) + ``_store_transition`` (:445-508) +
+    ``ReplayBuffer.add`` for every reactor, with the bookkeeping the rest of ``learn()`` (:309-355) relies on kept intact:
+
+    * ``num_timesteps += n_envs`` per step, the warm-up switch at ``learning_starts`` (a launch that straddles it is split there),
+      ``_update_current_progress_remaining``, ``_on_step``;
+    * finished episodes come from the device-side Monitor (:class:`EpisodeStats`) into ``ep_info_buffer`` (``rollout/ep_rew_mean`` /
+      ``ep_len_mean``), ``_episode_num`` advances by their number, ``_dump_logs`` runs when it crosses a multiple of ``log_interval``;
+    * callbacks: ``on_rollout_start`` / ``on_step`` / ``on_rollout_end`` once per launch (``on_step`` sees ``num_timesteps`` advanced by
+      the whole launch); a False from ``on_step`` stops training as in the reference.
+
+    Nothing per-env runs in Python and nothing leaves the device except the finished-episode list.  Models the kernel does not cover
+    (see :func:`fused_rollout_unsupported`) keep the reference's own ``collect_rollouts`` with a one-time warning.
+    ``actor_mode``: ``"fp32"`` (exact float32 actor) or ``"tc"`` (bf16 tcgen05 hidden layer)."""
+    if actor_mode not in ("fp32", "tc"):
+        raise ValueError("actor_mode must be 'fp32' or 'tc'")
+    import importlib
+    import time
+    import warnings
+
+    root = algo_base.__module__.split(".")[0]
+    for klass in algo_base.__mro__:  # the reference package the algorithm comes from ("core", or upstream "stable_baselines3")
+        mod = klass.__module__.split(".")[0]
+        if klass.__name__ == "OffPolicyAlgorithm":
+            root = mod
+            break
+    RolloutReturn = importlib.import_module(root + ".common.type_aliases").RolloutReturn
+
+    class FusedRolloutAlgorithm(algo_base):  # type: ignore[misc, valid-type]
+        _fused_roll: Optional[FusedRollout] = None
+        _fused_stats: Optional[EpisodeStats] = None
+        _fused_rollout_warned = False
+        fused_rollout_launches = 0
+
+        # _setup_learn wraps the noise in VectorizedActionNoise = one deepcopy per env (off_policy_algorithm.py:293-299): skip it when the
+        # kernel draws the noise itself
+        def _setup_learn(self, *args, **kwargs):
+            noise = self.action_noise
+            if noise is not None and isinstance(self.env, GpuCSTRVecEnv) and _noise_sigma(noise) is not None and self.env.num_envs > 1:
+                self.action_noise = None
+            try:
+                return super()._setup_learn(*args, **kwargs)
+            finally:
+                self.action_noise = noise
+
+        def _fused_actor_modules(self):
+            a = self.actor
+            if hasattr(a, "latent_pi"):  # SAC
+                return "gaussian", (a.latent_pi, a.mu, a.log_std)
+            return "tanh", (a.mu,)
+
+        def _fused_rollout_engine(self, env, replay_buffer, sigma: float) -> FusedRollout:
+            kind, modules = self._fused_actor_modules()
+            roll = self._fused_roll
+            if roll is None or roll.env is not env or roll.buffer is not replay_buffer:
+                actor = (ActorWeights.from_sac_actor(*modules, device=env.device) if kind == "gaussian"
+                         else ActorWeights.from_module(modules[0], device=env.device))
+                roll = FusedRollout(env, replay_buffer, actor, sigma=sigma, actor_mode=actor_mode)
+                roll.t = int(self.num_timesteps // max(env.num_envs, 1))
+                self._fused_roll, self._fused_stats = roll, EpisodeStats(env.num_envs, device=env.device)
+            roll.sigma = sigma
+            return roll
+
+        def collect_rollouts(self, env, callback, train_freq, replay_buffer, action_noise=None, learning_starts: int = 0, log_interval=None):
+            noise = action_noise if action_noise is not None else self.action_noise
+            why = fused_rollout_unsupported(self, env, replay_buffer, train_freq, noise)
+            if why:
+                if not self._fused_rollout_warned:
+                    warnings.warn(f"fused rollout not used, the reference's collect_rollouts runs instead: {why}", RuntimeWarning, stacklevel=2)
+                    self._fused_rollout_warned = True
+                return super().collect_rollouts(env, callback, train_freq, replay_buffer, action_noise, learning_starts, log_interval)
+            self.policy.set_training_mode(False)
+            n_envs, K = env.num_envs, int(train_freq.frequency)
+            roll = self._fused_rollout_engine(env, replay_buffer, _noise_sigma(noise))
+            stats = self._fused_stats
+            callback.on_rollout_start()
+            remaining = K
+            while remaining > 0:
+                warm = self.num_timesteps < learning_starts  # the reference tests this before every step (:386)
+                k = min(remaining, -(-(learning_starts - self.num_timesteps) // n_envs)) if warm else remaining
+                if not warm:  # the optimiser moved the weights since the last launch: refresh the kernel's copy (device to device)
+                    roll.actor.refresh_from_module(*self._fused_actor_modules()[1])
+                roll.collect(k, warmup=warm, stats=stats)
+                self.fused_rollout_launches += 1
+                self.num_timesteps += n_envs * k
+                remaining -= k
+            num_collected_steps = K
+            callback.update_locals(locals())
+            if not callback.on_step():
+                return RolloutReturn(K * n_envs, 0, continue_training=False)
+            finished = stats.pop()  # (k, 2): return, length of the episodes that ended in this launch
+            num_collected_episodes = int(finished.shape[0])
+            if num_collected_episodes:
+                t = round(time.time() - getattr(self, "_fused_t0", time.time()), 6)
+                keep = finished[-self.ep_info_buffer.maxlen:] if self.ep_info_buffer.maxlen else finished
+                self.ep_info_buffer.extend({"r": float(r), "l": int(l), "t": t} for r, l in keep)
+                before = self._episode_num
+                self._episode_num += num_collected_episodes
+                if log_interval is not None and before // log_interval != self._episode_num // log_interval:
+                    self._dump_logs()
+            self._update_current_progress_remaining(self.num_timesteps, self._total_timesteps)
+            self._on_step()
+            callback.on_rollout_end()
+            return RolloutReturn(K * n_envs, num_collected_episodes, True)
+
+        def learn(self, *args, **kwargs):
+            self._fused_t0 = time.time()
+            out = super().learn(*args, **kwargs)
+            if self._fused_roll is not None:  # `_last_obs` is the host copy the reference's own paths (predict, save) expect
+                self._last_obs = self._fused_roll.env.state.cpu().numpy()
+            return out
+
+        def _excluded_save_params(self):
+            return super()._excluded_save_params() + ["_fused_roll", "_fused_stats"]
+
+    FusedRolloutAlgorithm.__name__ = algo_base.__name__
+    FusedRolloutAlgorithm.__qualname__ = algo_base.__qualname__
+    return FusedRolloutAlgorithm

@@ -1,0 +1,112 @@
+"""-m gpu, needs the reference tree too (``oracle/refload.py``: /root/reference or the staged, git-ignored ``baseline/_ref``; skipped
+otherwise): the reference's OWN ``learn()`` (core/common/off_policy_algorithm.py:309-355) driven by the fused rollout kernel through
+``bind_offpolicy_rollout`` — collect_rollouts is one ``cstr_rollout_fused`` launch, train() is ``cstr_td3_update`` / ``cstr_sac_update``.
+"""
+import numpy as np
+import pytest
+import torch
+
+import refload
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refload.available(), reason="reference tree not staged")]
+
+
+@pytest.fixture(scope="module")
+def ref(pkg):
+    refload.install_shims()
+    core = refload.load_core()
+    from core.common.buffers import ReplayBuffer
+    from core.common.noise import NormalActionNoise
+    from core.common.vec_env import VecEnv
+
+    return dict(core=core, VecEnv=pkg.bind_vec_env_class(VecEnv), Buffer=pkg.bind_replay_buffer_class(ReplayBuffer), Noise=NormalActionNoise,
+                ReplayBuffer=ReplayBuffer)
+
+
+def _td3(pkg, ref, n_envs, actor_mode="fp32", **kw):
+    core = ref["core"]
+    cls = pkg.bind_offpolicy_rollout(pkg.bind_td3_class(core.TD3), actor_mode=actor_mode)
+    env = ref["VecEnv"](num_envs=n_envs, init_mode="random", reset_rng="philox", seed=3)
+    args = dict(action_noise=ref["Noise"](mean=np.zeros(2), sigma=0.1 * np.ones(2)), device="cuda", replay_buffer_class=ref["Buffer"],
+                buffer_size=64 * n_envs, replay_buffer_kwargs=dict(index_mode="philox", seed=1), learning_starts=6 * n_envs, batch_size=128,
+                train_freq=(4, "step"), gradient_steps=2, seed=5, verbose=0)
+    args.update(kw)
+    return cls("MlpPolicy", env, **args), env
+
+
+@pytest.mark.parametrize("actor_mode", ["fp32", "tc"])
+def test_td3_learn_runs_on_the_fused_rollout(pkg, ref, actor_mode):
+    core = ref["core"]
+    n = 512
+    model, env = _td3(pkg, ref, n, actor_mode)
+    assert isinstance(model, core.TD3)
+    dumps, seen = [], []
+
+    class Cb(__import__("core.common.callbacks", fromlist=["BaseCallback"]).BaseCallback):
+        def _on_training_start(self) -> None:  # the reference's Logger clears name_to_value inside dump(): look at it just before
+            logger, orig = self.model.logger, self.model.logger.dump
+
+            def spy(step=0):
+                dumps.append(dict(logger.name_to_value))
+                orig(step)
+
+            logger.dump = spy
+
+        def _on_step(self) -> bool:
+            seen.append((self.model.num_timesteps, self.locals["num_collected_steps"]))
+            return True
+
+    launches_before = env.launches
+    total = n * 4 * 110  # 110 launches of 4 steps: 440 env steps -> every reactor finishes one 400-step episode
+    model.learn(total_timesteps=total, callback=Cb(), log_interval=100)
+    assert model.num_timesteps == total and model.fused_rollout_launches == 110 + 1  # the launch that straddles learning_starts is split in two
+    assert env.launches - launches_before <= 1  # nothing but the reset went through the per-step VecEnv path
+    assert model.replay_buffer.launches <= model._n_updates  # ... and the buffer only served samples (fewer once graphs replay): no add() from Python
+    assert model._n_updates == 2 * 109 and model._fused is not None and model._fused.n_updates == model._n_updates
+    # learning_starts = 6 steps: the first launch (4 steps) and half of the second are warm-up (uniform actions), the rest the actor's
+    rec = model.replay_buffer.records
+    assert model.replay_buffer.pos == (4 * 110) % 64 and model.replay_buffer.full
+    # callbacks: once per launch, with num_timesteps advanced by the whole launch
+    assert len(seen) == 110 and seen[0] == (4 * n, 4) and seen[-1][0] == total
+    # Monitor semantics from the device: every reactor finished exactly one episode of length 400
+    assert model._episode_num == n and len(model.ep_info_buffer) == model.ep_info_buffer.maxlen
+    assert all(e["l"] == 400 and -2000 < e["r"] < 0 for e in model.ep_info_buffer)
+    assert dumps and "rollout/ep_rew_mean" in dumps[-1] and "rollout/ep_len_mean" in dumps[-1] and "time/fps" in dumps[-1]
+    assert dumps[-1]["rollout/ep_len_mean"] == 400 and "train/critic_loss" in dumps[-1]
+    assert isinstance(model._last_obs, np.ndarray) and model._last_obs.shape == (n, 4)
+    # the stored transitions are the strict step of the stored action (spot check on the newest row)
+    import build_oracle as B
+
+    row = (model.replay_buffer.pos - 1) % 64
+    r = rec[row].cpu().numpy()
+    nx, rw, _, _, _ = B.step_f32(r[:, 0:4], r[:, 8:10], np.full(n, 10, np.int32), exp_mode=B.EXP_SHARED, sq_mode=B.SQ_MUL)
+    assert np.array_equal(r[:, 4:8], nx) and np.array_equal(r[:, 10], rw)
+    assert np.abs(r[:, 8:10]).max() <= 1.0
+
+
+def test_sac_learn_runs_on_the_fused_rollout(pkg, ref):
+    core = ref["core"]
+    n = 256
+    cls = pkg.bind_offpolicy_rollout(pkg.bind_sac_class(core.SAC))
+    env = ref["VecEnv"](num_envs=n, init_mode="random", reset_rng="philox", seed=4)
+    model = cls("MlpPolicy", env, device="cuda", replay_buffer_class=ref["Buffer"], buffer_size=64 * n,
+                replay_buffer_kwargs=dict(index_mode="philox", seed=2), learning_starts=8 * n, batch_size=128, train_freq=(8, "step"), gradient_steps=4,
+                seed=1, verbose=0)
+    before = [p.detach().clone() for p in model.actor.parameters()]
+    model.learn(total_timesteps=n * 8 * 12, log_interval=None)
+    assert model.fused_rollout_launches == 12 and model._fused is not None and model._n_updates == 4 * 11
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.actor.parameters()))
+    rec = model.replay_buffer.records[(model.replay_buffer.pos - 1) % 64].cpu().numpy()
+    assert np.abs(rec[:, 8:10]).max() < 1.0  # tanh-squashed Gaussian actions, no extra noise
+
+
+def test_unsupported_models_keep_the_reference_rollout(pkg, ref):
+    core = ref["core"]
+    n = 8
+    cls = pkg.bind_offpolicy_rollout(core.TD3)
+    env = ref["VecEnv"](num_envs=n, init_mode="random", reset_rng="pcg64", seed=3)  # host-RNG resets: not the kernel's stream
+    model = cls("MlpPolicy", env, device="cuda", replay_buffer_class=ref["Buffer"], buffer_size=64 * n, learning_starts=2 * n, batch_size=16,
+                train_freq=(1, "step"), gradient_steps=1, seed=0, verbose=0)
+    with pytest.warns(RuntimeWarning, match="fused rollout not used"):
+        model.learn(total_timesteps=6 * n, log_interval=None)
+    assert model.fused_rollout_launches == 0 and model.num_timesteps == 6 * n and model.replay_buffer.pos == 6
