@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CSTR_B200_ABI_VERSION 15
+#define CSTR_B200_ABI_VERSION 16
 
 #define CSTR_EINVAL (-1)   /* bad argument (null pointer, negative size, unknown mode) */
 #define CSTR_EALIGN (-2)   /* pointer not aligned for the vectorised access the layout implies */
@@ -298,6 +298,72 @@ int64_t cstr_sac_workspace_bytes(const cstr_sac_config *cfg);
 int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *state, const float *obs, const float *actions,
                     const float *next_obs, const float *dones, const float *rewards, const float *eps_pi,
                     const float *eps_next, int64_t n_updates, int64_t adam_step, int32_t phases, void *stream);
+
+/* ---- BCQ gradient step (third algorithm) ----------------------------------------------------------
+ * Replaces one iteration of the loop body of BCQ.train (core/bcq/bcq.py:137-205) after the batch has been sampled, with the
+ * networks of core/bcq/policies.py:21-166 for the CSTR spaces (obs 4, action 2):
+ *   vae_enc   Linear(6, Hv) ReLU Linear(Hv, Hv) ReLU + the two heads stacked as ONE (2L, Hv) matrix [mean; log_std]   (:47-55)
+ *   vae_dec   Linear(4 + L, Hv) ReLU Linear(Hv, Hv) ReLU Linear(Hv, 2) Tanh                                          (:58-65)
+ *   pert      Linear(6, Hp) ReLU Linear(Hp, Hp) ReLU Linear(Hp, 2) Tanh, a + max_perturbation * xi clamped to [-1, 1]  (:147-160)
+ *   critic0/1 create_mlp(6, 1, [h1, h2])                                                       (core/common/policies.py:966)
+ * Steps: VAE (reconstruction MSE + 0.5 KL, Adam over encoder + decoder: :142-155); target from n_candidates latent draws through the
+ * just-updated VAE (the "target VAE" is a plain copy of it, :158-159) and the TARGET perturbation net, twin-min, then the max over the
+ * reference's (B, n_candidates) reshape of the candidate-major column AS WRITTEN (:165-172); twin critics (:174-186); on every
+ * actor_delay-th update the perturbation step -Q1(s, pert(s, dec(s, z))).mean() (only the perturbation optimiser steps, :188-196) and
+ * polyak of the critics and the perturbation net (:198-203).
+ * Flat block (params, targets, grads, adam_m, adam_v) = [vae_enc | vae_dec | pert | critic0 | critic1], each net W1 b1 W2 b2 W3 b3
+ * padded to multiples of 4 floats; cstr_bcq_layout writes 5 x 6 tensor offsets + the block size (31 values).  Of `targets` only the
+ * pert and critic ranges are used.  Random draws: standard normal, UNclamped — eps_vae (B, L) of :76, z_next (n_candidates*B, L) of
+ * sample_action (:122), z_actor (B, L) of the actor step's decode; NULL = Philox (key seed, counter (row, n_updates), streams 6/7/8).
+ * State: cstr_td3_state (losses: 6 floats = vae, critic, actor as {sum, count}; counters as for TD3: critic_step is the Adam step of
+ * the VAE and critic optimisers, actor_step that of the perturbation optimiser).  Counters are the values AFTER this update.
+ * Data-parallel training goes through state->peer (the three Adam kernels average their gradient ranges over the ranks).       */
+typedef struct cstr_bcq_config {
+    int32_t latent;        /* L: vae_latent_dim, multiple of 4 in [4, 64]                       */
+    int32_t vae_hidden;    /* Hv: vae_hidden_dim, multiple of 4                                 */
+    int32_t pert_hidden;   /* Hp: perturbation_hidden_dim, multiple of 4                        */
+    int32_t h1, h2;        /* critic hidden sizes                                               */
+    int32_t batch, actor_delay, n_candidates;
+    float gamma, tau, lr, beta1, beta2, eps, max_perturbation, reserved0;
+    uint64_t seed;
+    int32_t gemm_mode, reserved1;
+} cstr_bcq_config;
+int64_t cstr_bcq_param_count(const cstr_bcq_config *cfg);
+int cstr_bcq_layout(const cstr_bcq_config *cfg, int64_t *offsets /* 31 */);
+int64_t cstr_bcq_workspace_bytes(const cstr_bcq_config *cfg);
+int cstr_bcq_update(const cstr_bcq_config *cfg, const cstr_td3_state *state, const float *obs, const float *actions, const float *next_obs,
+                    const float *dones, const float *rewards, const float *eps_vae, const float *z_next, const float *z_actor,
+                    int64_t n_updates, int64_t critic_step, int64_t actor_step, void *stream);
+
+/* ---- MADDPG / IDDPG gradient step (fourth and fifth algorithm) ---------------------------------------
+ * Replaces one iteration of the loop body shared by MADDPG.train (core/maddpg/maddpg.py:127-185) and IDDPG.train
+ * (core/iddpg/iddpg.py:127-185) for BASELINE config #5: the two reactors as two agents, observation_splits [[0,1],[2,3]],
+ * action_splits [[0],[1]].  Per agent i: an actor create_mlp(2, 1, [h1, h2]) + Tanh on the agent's observation slice
+ * (core/maddpg/policies.py:64-72) and n_critics q-networks — over ALL observations and actions (6 inputs) when centralised
+ * (MADDPG, policies.py:236-241), over the agent's own slices (3 inputs) otherwise (IDDPG).
+ * As written in the reference: the target actions of all agents are formed once, before the agent loop (:132-144); per agent the
+ * critic step, then on every policy_delay-th update the actor step — which evaluates EVERY actor on agent i's observation slice
+ * (:169-171) — and the polyak update of ALL agents' nets INSIDE the agent loop (:181-182).  Learning rates are per optimiser
+ * (actor_lr[i], critic_lr[i]); the reference's _update_learning_rate pairing (base_class.py:1112-1136) makes them
+ * learning_rate_list[0] for every actor and learning_rate_list[1] for every critic.
+ * Flat block = [actor0 | actor1 | critic(0,0) .. critic(0,n_critics-1) | critic(1,0) ..]; cstr_ma_layout writes
+ * (2 + 2 n_critics) x 6 tensor offsets + the block size.  noise: (2, B) N(0, target_policy_noise) draws (agent-major), NULL = Philox
+ * (stream 9).  losses: 8 floats = critic0, actor0, critic1, actor1 as {sum, count}.  Counters as for TD3 (every agent's critic
+ * optimiser has taken critic_step steps, every actor optimiser actor_step).  Data-parallel training goes through state->peer.   */
+typedef struct cstr_ma_config {
+    int32_t centralised;   /* 1 = MADDPG, 0 = IDDPG */
+    int32_t h1, h2, batch, policy_delay, n_critics;
+    float gamma, tau, beta1, beta2, eps, target_policy_noise, target_noise_clip, reserved0;
+    float actor_lr[2], critic_lr[2];
+    uint64_t seed;
+    int32_t gemm_mode, reserved1;
+} cstr_ma_config;
+int64_t cstr_ma_param_count(const cstr_ma_config *cfg);
+int cstr_ma_layout(const cstr_ma_config *cfg, int64_t *offsets /* (2 + 2 n_critics) * 6 + 1 */);
+int64_t cstr_ma_workspace_bytes(const cstr_ma_config *cfg);
+int cstr_ma_update(const cstr_ma_config *cfg, const cstr_td3_state *state, const float *obs, const float *actions, const float *next_obs,
+                   const float *dones, const float *rewards, const float *noise, int64_t n_updates, int64_t critic_step, int64_t actor_step,
+                   void *stream);
 
 /* ---- fused rollout --------------------------------------------------------------------------------
  * Replaces, for K consecutive env steps of N reactors, OffPolicyAlgorithm._sample_action +

@@ -12,6 +12,7 @@ from .buffer import GpuReplayBuffer, ReplayBufferSamples, bind_replay_buffer_cla
 from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
 from .normalize import GpuVecNormalize, bind_vec_normalize_class
 from .update import FusedSACUpdate, FusedTD3Update, bind_sac_class, bind_td3_class
+from .update_ext import FusedBCQUpdate, FusedMultiAgentUpdate, bind_bcq_class, bind_multiagent_class
 from .rollout import ActorWeights, EpisodeStats, FusedRollout, bind_offpolicy_rollout, fused_rollout_unsupported
 
 __all__ = [
@@ -23,6 +24,10 @@ __all__ = [
     "GpuReplayBuffer",
     "GpuVecNormalize",
     "FusedTD3Update",
+    "FusedBCQUpdate",
+    "FusedMultiAgentUpdate",
+    "bind_bcq_class",
+    "bind_multiagent_class",
     "FusedSACUpdate",
     "bind_offpolicy_rollout",
     "bind_sac_class",

@@ -9,7 +9,7 @@ from typing import Optional
 
 from . import _build
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 MATH_STRICT, MATH_FAST = 0, 1
 INIT_RANDOM, INIT_STATIC = 0, 1
 REC_FLOATS = 16
@@ -89,6 +89,24 @@ class SacConfig(Structure):
                 ("seed", c_uint64), ("gemm_mode", c_int32), ("local_step", c_int32)]
 
 
+class BcqConfig(Structure):
+    """struct cstr_bcq_config"""
+
+    _fields_ = [("latent", c_int32), ("vae_hidden", c_int32), ("pert_hidden", c_int32), ("h1", c_int32), ("h2", c_int32), ("batch", c_int32),
+                ("actor_delay", c_int32), ("n_candidates", c_int32), ("gamma", c_float), ("tau", c_float), ("lr", c_float), ("beta1", c_float),
+                ("beta2", c_float), ("eps", c_float), ("max_perturbation", c_float), ("reserved0", c_float), ("seed", c_uint64),
+                ("gemm_mode", c_int32), ("reserved1", c_int32)]
+
+
+class MaConfig(Structure):
+    """struct cstr_ma_config"""
+
+    _fields_ = [("centralised", c_int32), ("h1", c_int32), ("h2", c_int32), ("batch", c_int32), ("policy_delay", c_int32), ("n_critics", c_int32),
+                ("gamma", c_float), ("tau", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("target_policy_noise", c_float),
+                ("target_noise_clip", c_float), ("reserved0", c_float), ("actor_lr", c_float * 2), ("critic_lr", c_float * 2), ("seed", c_uint64),
+                ("gemm_mode", c_int32), ("reserved1", c_int32)]
+
+
 TD3_CRITIC_GRAD, TD3_CRITIC_APPLY, TD3_ACTOR_GRAD, TD3_ACTOR_APPLY, TD3_ALL = 1, 2, 4, 8, 15
 
 P = c_void_p
@@ -117,6 +135,14 @@ _SIGNATURES = {
     "cstr_sac_layout": (c_int, [c_int32, c_int32, POINTER(c_int64)]),
     "cstr_sac_workspace_bytes": (c_int64, [POINTER(SacConfig)]),
     "cstr_sac_update": (c_int, [POINTER(SacConfig), POINTER(Td3State), P, P, P, P, P, P, P, c_int64, c_int64, c_int32, P]),
+    "cstr_bcq_param_count": (c_int64, [POINTER(BcqConfig)]),
+    "cstr_bcq_layout": (c_int, [POINTER(BcqConfig), POINTER(c_int64)]),
+    "cstr_bcq_workspace_bytes": (c_int64, [POINTER(BcqConfig)]),
+    "cstr_bcq_update": (c_int, [POINTER(BcqConfig), POINTER(Td3State), P, P, P, P, P, P, P, P, c_int64, c_int64, c_int64, P]),
+    "cstr_ma_param_count": (c_int64, [POINTER(MaConfig)]),
+    "cstr_ma_layout": (c_int, [POINTER(MaConfig), POINTER(c_int64)]),
+    "cstr_ma_workspace_bytes": (c_int64, [POINTER(MaConfig)]),
+    "cstr_ma_update": (c_int, [POINTER(MaConfig), POINTER(Td3State), P, P, P, P, P, P, c_int64, c_int64, c_int64, P]),
     "cstr_peer_flag_bytes": (c_int64, []),
     "cstr_peer_alloc": (c_int, [c_int64, POINTER(c_void_p), P]),
     "cstr_peer_open": (c_int, [P, POINTER(c_void_p)]),

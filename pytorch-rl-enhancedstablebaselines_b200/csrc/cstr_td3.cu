@@ -818,6 +818,7 @@ struct ApplyArgs {
     int64_t polyak_lo, polyak_hi;  // polyak on [polyak_lo, polyak_hi) (after Adam where the ranges overlap)
     float beta1, beta2, eps, step_size, bc2_sqrt, tau;
     const float *dev_scalars;  // graph mode: {step_size, bc2_sqrt} written by td3_tick_kernel (NULL: the by-value fields)
+    float dev_lr_scale;        // graph mode with several learning rates (multi-agent): the tick kernel runs with lr = 1 and this holds the rate (0: unused)
     const float *loss_partial;
     int n_loss_partial;
     float loss_scale;
@@ -845,7 +846,8 @@ __global__ void __launch_bounds__(256) td3_apply_kernel(ApplyArgs a) {
     }
     float p;
     bool have = false;
-    const float step_size = a.dev_scalars ? a.dev_scalars[0] : a.step_size, bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
+    const float step_size = a.dev_scalars ? a.dev_scalars[0] * (a.dev_lr_scale != 0.f ? a.dev_lr_scale : 1.f) : a.step_size;
+    const float bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
     if (i >= a.adam_lo && i < a.adam_hi) {
         const float g = a.g[i];
         float m = a.m[i], v = a.v[i];
@@ -942,7 +944,8 @@ __global__ void __launch_bounds__(256) td3_apply_peer_kernel(ApplyArgs a, PeerAr
             a.loss_acc[1] += 1.f;
         }
     }
-    const float step_size = a.dev_scalars ? a.dev_scalars[0] : a.step_size, bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
+    const float step_size = a.dev_scalars ? a.dev_scalars[0] * (a.dev_lr_scale != 0.f ? a.dev_lr_scale : 1.f) : a.step_size;
+    const float bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
     const int64_t lo = min(a.adam_lo, a.polyak_lo < a.polyak_hi ? a.polyak_lo : a.adam_lo), hi = max(a.adam_hi, a.polyak_hi);
     if (alive)  // every range boundary is a multiple of 4 floats (pad4 layout): one float4 group per thread and trip
         for (int64_t i = lo + 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 4 * (int64_t)gridDim.x * blockDim.x) {
@@ -994,6 +997,9 @@ __global__ void __launch_bounds__(256) td3_apply_peer_kernel(ApplyArgs a, PeerAr
 }
 
 }  // namespace cstr
+
+#include "cstr_mlp.cuh"
+#include "cstr_bcq_kernels.cuh"
 
 using namespace cstr;
 
@@ -1195,9 +1201,13 @@ int forward_hidden(int B, int H1, int H2, int in, const float *obs, const float 
 }
 
 // given dz2 (and h1, x): dz1 (optional), then every weight gradient of the hidden and input layers into the flat grads
-int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float *act, const Net &n, const Net &gn, int64_t z_stride, int Z,
+template <bool YBIAS>
+int launch_skinny_ny(int ny, SkinnyArgs s, int Z, float *part, cudaStream_t st, const char *what, FinJobs *defer);
+
+int backward_hidden(int B, int H1, int H2, const Src &src, const Net &n, const Net &gn, int64_t z_stride, int Z,
                     const float *h1, const float *dz2, float *dz1, const Workspace &w, bool want_weight_grads, cudaStream_t st,
                     FinJobs *pending = nullptr) {
+    const int in = src.n0 + src.n1;
     GemmArgs g{};
     g.A = dz2, g.Bm = n.w2, g.aux = h1, g.C = dz1;
     g.M = B, g.N = H1, g.K = H2, g.lda = H2, g.ldb = H1, g.ldc = H1, g.ldaux = H1;
@@ -1224,16 +1234,22 @@ int backward_hidden(int B, int H1, int H2, int in, const float *obs, const float
     s.X = dz2, s.x_z = (int64_t)B * H2, s.ldx = H2, s.H = H2, s.B = B;
     s.out_w = nullptr, s.out_b = gn.b2, s.out_z = z_stride;
     if (int rc = launch_skinny<0, false>(s, Z, w.skinny, st, "td3_skinny_wgrad_kernel<b2>", &J)) return rc;
-    // dW1 = dz1^T @ [obs | act], db1 = colsum(dz1)
+    // dW1 = dz1^T @ [x0 | x1] (TD3: [obs | act]), db1 = colsum(dz1)
     SkinnyArgs t{};
     t.X = dz1, t.x_z = (int64_t)B * H1, t.ldx = H1, t.H = H1, t.B = B;
-    t.Y0 = obs, t.n0 = OBS, t.ld0 = OBS, t.Y1 = act, t.n1 = in - OBS, t.ld1 = ACT, t.y_z = 0;
+    t.Y0 = src.x0, t.n0 = src.n0, t.ld0 = src.ld0, t.Y1 = src.x1, t.n1 = src.n1, t.ld1 = src.ld1, t.y_z = 0;
     t.out_w = gn.w1, t.out_b = gn.b1, t.out_z = z_stride;
-    if (in == OBS) {
-        if (int rc = launch_skinny<OBS, false>(t, Z, w.skinny + w.skinny_region, st, "td3_skinny_wgrad_kernel<w1>", &J)) return rc;
-    } else if (int rc = launch_skinny<OBS + ACT, false>(t, Z, w.skinny + w.skinny_region, st, "td3_skinny_wgrad_kernel<w1>", &J)) return rc;
+    if (int rc = launch_skinny_ny<false>(in, t, Z, w.skinny + w.skinny_region, st, "td3_skinny_wgrad_kernel<w1>", &J)) return rc;
     return launch_finalize(J, st);
 }
+
+inline Src td3_src(const float *obs, const float *act, int in) {  // [obs (4) | act (in - 4)]
+    Src s{};
+    s.x0 = obs, s.n0 = OBS, s.ld0 = OBS, s.x0_rows = 0, s.x1 = in > OBS ? act : nullptr, s.n1 = in - OBS, s.ld1 = ACT;
+    return s;
+}
+
+#include "cstr_mlp_host.cuh"
 
 }  // namespace
 
@@ -1312,7 +1328,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         s.out_w = g_critic.w3, s.out_b = g_critic.b3, s.out_z = cz, s.transposed = 1;
         FinJobs J{};
         if (int rc = launch_skinny<1, true>(s, ZC, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<w3>", &J)) return rc;
-        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, ZC, w.h1[0], w.dz2, w.dz1, w, true, st, &J)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, td3_src(obs, actions, OBS + ACT), critic, g_critic, cz, ZC, w.h1[0], w.dz2, w.dz1, w, true, st, &J)) return rc;
     }
     if (phases & CSTR_TD3_CRITIC_APPLY) {
         ApplyArgs a{};
@@ -1334,7 +1350,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         launch_k(td3_critic_head_kernel<true>, dim3(rb, 1), 256, 0, st, B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, nullptr, 0.f, w.dq, w.dz2,
                                                                  w.loss_partial);
         if (int rc = check_launch("td3_critic_head_kernel<policy>")) return rc;
-        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, g_critic, cz, 1, w.h1[0], w.dz2, w.dz1, w, false, st)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, td3_src(obs, w.a_pi, OBS + ACT), critic, g_critic, cz, 1, w.h1[0], w.dz2, w.dz1, w, false, st)) return rc;
         // through the critic's input layer and the tanh into the actor; dz2 of the actor reuses slab 1 of the dz2 buffer
         float *dz2a = w.dz2 + (int64_t)B * H2, *dz1a = w.dz1 + (int64_t)B * H1;
         launch_k(td3_actor_bwd_head_kernel, rb, 256, 0, st, B, H1, H2, w.dz1, critic.w1, (const float2 *)w.a_pi, actor.w3, w.a_h2, (float2 *)w.dpre, dz2a);
@@ -1345,7 +1361,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
         s.out_w = g_actor.w3, s.out_b = g_actor.b3, s.out_z = 0, s.transposed = 1;
         FinJobs J{};
         if (int rc = launch_skinny<ACT, true>(s, 1, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<actor w3>", &J)) return rc;
-        if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, dz2a, dz1a, w, true, st, &J)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, td3_src(obs, nullptr, OBS), actor, g_actor, 0, 1, w.a_h1, dz2a, dz1a, w, true, st, &J)) return rc;
     }
     if (policy_step && (phases & CSTR_TD3_ACTOR_APPLY)) {
         if (actor_step < 1) return fail_arg(CSTR_EINVAL, "td3_update: actor_step must be >= 1 on a policy step");
@@ -1469,7 +1485,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         s.out_w = g_critic.w3, s.out_b = g_critic.b3, s.out_z = cz, s.transposed = 1;
         FinJobs J{};
         if (int rc = launch_skinny<1, true>(s, 2, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<w3>", &J)) return rc;
-        if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, actions, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st, &J)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, td3_src(obs, actions, OBS + ACT), critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, true, st, &J)) return rc;
     }
     }  // CRITIC_GRAD
     if (phases & CSTR_TD3_CRITIC_APPLY) {
@@ -1489,7 +1505,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
     if (int rc = forward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, cz, 2, w.h1[0], w.h2[0], w.tensor, st, w.slabs, w.slab_cap)) return rc;
     launch_k(sac_qmin_head_kernel, rb, 256, 0, st, B, H2, w.h2[0], (int64_t)B * H2, critic.w3, critic.b3, cz, w.logp, w.scalars, w.dz2, w.loss_partial);
     if (int rc = check_launch("sac_qmin_head_kernel")) return rc;
-    if (int rc = backward_hidden(B, H1, H2, OBS + ACT, obs, w.a_pi, critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, false, st)) return rc;
+    if (int rc = backward_hidden(B, H1, H2, td3_src(obs, w.a_pi, OBS + ACT), critic, g_critic, cz, 2, w.h1[0], w.dz2, w.dz1, w, false, st)) return rc;
     // the actor's dz2 / dz1 live in the target-activation slabs (free since the target was formed)
     launch_k(sac_actor_bwd_head_kernel, rb, 256, 0, st, B, H1, H2, w.dz1, (int64_t)B * H1, critic.w1, cz, (const float2 *)w.a_pi, (const float2 *)w.std_eps,
                                                  (const float2 *)w.raw_log_std, w.scalars, actor.w3, w.a_h2, (float4 *)w.dpre4, w.t_h2);
@@ -1501,7 +1517,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         s.out_w = g_actor.w3, s.out_b = g_actor.b3, s.out_z = 0, s.transposed = 1;
         FinJobs J{};
         if (int rc = launch_skinny<2 * ACT, true>(s, 1, w.skinny + 2 * w.skinny_region, st, "td3_skinny_wgrad_kernel<sac head>", &J)) return rc;
-        if (int rc = backward_hidden(B, H1, H2, OBS, obs, nullptr, actor, g_actor, 0, 1, w.a_h1, w.t_h2, w.t_h1, w, true, st, &J)) return rc;
+        if (int rc = backward_hidden(B, H1, H2, td3_src(obs, nullptr, OBS), actor, g_actor, 0, 1, w.a_h1, w.t_h2, w.t_h1, w, true, st, &J)) return rc;
     }
     }  // ACTOR_GRAD
     if (phases & CSTR_TD3_ACTOR_APPLY) {
@@ -1519,6 +1535,11 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
     }
     return 0;
 }
+
+}  // extern "C"
+#include "cstr_bcq.cuh"
+#include "cstr_ma.cuh"
+extern "C" {
 
 // ---- peer memory for the fused gradient all-reduce (include/cstr_b200.h, cstr_peer_comm) ---------------------------------
 int64_t cstr_peer_flag_bytes(void) { return (int64_t)(PEER_FLAG_WORDS + 4) * (int64_t)sizeof(uint32_t); }
