@@ -53,7 +53,7 @@ MaWorkspace ma_carve(float *base, const cstr_ma_config *c) {
     w.h1 = b.take(2 * B * H1), w.h2 = b.take(2 * B * H2), w.dz1 = b.take(2 * B * H1), w.dz2 = b.take(2 * B * H2), w.dq = b.take(2 * B);
     w.n_row_blocks = (int)((B + 7) / 8);
     w.loss_partial = b.take(2 * (int64_t)w.n_row_blocks);
-    w.joint = b.take(B * MA_AGENTS), w.da = b.take(B), w.a_dy = b.take(B), w.a_dz2 = b.take(B * H2), w.a_dz1 = b.take(B * H1), w.scalars = b.take(8);
+    w.joint = b.take(B * MA_AGENTS), w.da = b.take(B), w.a_dy = b.take(B), w.a_dz2 = b.take(B * H2), w.a_dz1 = b.take(B * H1), w.scalars = b.take(16);
     w.sc = mlp_scratch(b, (int)B, (int)std::max(H1, H2), 2, OBS + ACT);
     w.floats = b.o;
     return w;
@@ -109,18 +109,20 @@ int cstr_ma_update(const cstr_ma_config *cfg, const cstr_td3_state *stt, const f
     const bool policy_step = (n_updates % cfg->policy_delay) == 0;
     if (policy_step && actor_step < 1) return fail_arg(CSTR_EINVAL, "ma_update: actor_step must be >= 1 on a policy step");
     const float *dev_sc = stt->counters ? w.scalars : nullptr;
-    if (stt->counters) {  // lr = 1: the per-optimiser learning rates multiply the device-side step size in the apply kernels (dev_lr_scale)
-        launch_k(td3_tick_kernel, 1, 32, 0, st, stt->counters, w.scalars, policy_step ? 1 : 0, 1.0, (double)cfg->beta1, (double)cfg->beta2);
+    if (stt->counters) {  // one {step_size, bc2_sqrt} pair per optimiser: critic 0, actor 0 at scalars[0..3], critic 1, actor 1 at scalars[8..11]
+        launch_k(td3_tick_kernel, 1, 32, 0, st, stt->counters, w.scalars, policy_step ? 1 : 0, (double)cfg->critic_lr[0], (double)cfg->beta1, (double)cfg->beta2,
+                 (double)cfg->actor_lr[0], (double)cfg->critic_lr[1], (double)cfg->actor_lr[1]);
         if (int rc = check_launch("td3_tick_kernel")) return rc;
     }
     Workspace tw = as_workspace(w.sc);
     tw.n_row_blocks = rb;
-    auto adam = [&](ApplyArgs &a, int64_t step, float lr, bool actor_scalars) {
+    for (int i = 0; i < MA_AGENTS; ++i)
+        if (!(cfg->actor_lr[i] > 0.f) || !(cfg->critic_lr[i] > 0.f)) return fail_arg(CSTR_EINVAL, "ma_update: learning rates must be positive");
+    auto adam = [&](ApplyArgs &a, int64_t step, float lr, bool actor_scalars, int agent) {
         a.p = stt->params, a.t = stt->targets, a.g = stt->grads, a.m = stt->adam_m, a.v = stt->adam_v;
         const double bc1 = 1.0 - pow((double)cfg->beta1, (double)step), bc2 = 1.0 - pow((double)cfg->beta2, (double)step);
         a.beta1 = cfg->beta1, a.beta2 = cfg->beta2, a.eps = cfg->eps, a.step_size = (float)((double)lr / bc1), a.bc2_sqrt = (float)sqrt(bc2), a.tau = cfg->tau;
-        a.dev_scalars = dev_sc ? dev_sc + (actor_scalars ? 2 : 0) : nullptr;
-        a.dev_lr_scale = lr;
+        a.dev_scalars = dev_sc ? dev_sc + (agent ? 8 : 0) + (actor_scalars ? 2 : 0) : nullptr;
     };
     // critic input of agent i over (observations X, actions A): all of both (MADDPG) or the agent's own slices (IDDPG)
     auto critic_src = [&](int i, const float *X, const float *A) {
@@ -162,7 +164,7 @@ int cstr_ma_update(const cstr_ma_config *cfg, const cstr_td3_state *stt, const f
             if (int rc = launch_skinny<1, true>(s, ZC, tw.skinny + 2 * tw.skinny_region, st, "td3_skinny_wgrad_kernel<w3>", &J)) return rc;
             if (int rc = backward_hidden(B, H1, H2, s_cur, critic, g_critic, cz, ZC, w.h1, w.dz2, w.dz1, tw, true, st, &J)) return rc;
             ApplyArgs a{};
-            adam(a, critic_step, cfg->critic_lr[i], false);
+            adam(a, critic_step, cfg->critic_lr[i], false, i);
             a.adam_lo = T.critic_off[i], a.adam_hi = T.critic_off[i] + ZC * cz, a.polyak_lo = a.polyak_hi = 0;
             a.loss_partial = w.loss_partial, a.n_loss_partial = ZC * rb, a.loss_scale = 1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 4 * i : nullptr;
             if (int rc = launch_apply(a, stt->peer, stt->grads, st, "td3_apply_kernel<ma critic>")) return rc;
@@ -191,7 +193,7 @@ int cstr_ma_update(const cstr_ma_config *cfg, const cstr_td3_state *stt, const f
                                   w.sc, true, st))
             return rc;
         ApplyArgs a{};
-        adam(a, actor_step, cfg->actor_lr[i], true);
+        adam(a, actor_step, cfg->actor_lr[i], true, i);
         a.adam_lo = T.actor_off[i], a.adam_hi = T.actor_off[i] + az, a.polyak_lo = 0, a.polyak_hi = T.total;  // polyak of ALL nets, inside the agent loop (:181-182)
         a.loss_partial = w.loss_partial, a.n_loss_partial = rb, a.loss_scale = -1.f / (float)B, a.loss_acc = stt->losses ? stt->losses + 4 * i + 2 : nullptr;
         if (int rc = launch_apply(a, stt->peer, stt->grads, st, "td3_apply_kernel<ma actor+polyak>")) return rc;

@@ -793,17 +793,22 @@ __global__ void __launch_bounds__(256) td3_finalize_kernel(FinJobs J) {
 // graph mode: the per-update scalars (Philox counter of the smoothing noise, Adam bias corrections) cannot be baked into a captured
 // launch, so they live on the device.  counters = {n_updates, critic_step, actor_step, sample_draw}; one thread advances them at the
 // start of an update and derives scalars = {step_size_c, bc2_sqrt_c, step_size_a, bc2_sqrt_a, bits(n_updates)} (double math as torch).
-__global__ void td3_tick_kernel(int64_t *counters, float *scalars, int policy_step, double lr, double beta1, double beta2) {
+// lr_c2 / lr_a2 > 0 (multi-agent: a second critic / actor optimiser with its own rate): their {step_size, bc2_sqrt} pairs go to scalars[8..11].
+__global__ void td3_tick_kernel(int64_t *counters, float *scalars, int policy_step, double lr, double beta1, double beta2, double lr_a, double lr_c2,
+                                double lr_a2) {
     pdl_enter();
     if (threadIdx.x || blockIdx.x) return;
     const int64_t n = ++counters[0], cs = ++counters[1];
     const int64_t as = policy_step ? ++counters[2] : counters[2];
     counters[3] += 1;
+    if (lr_a < 0.0) lr_a = lr;
     scalars[0] = (float)(lr / (1.0 - pow(beta1, (double)cs)));
     scalars[1] = (float)sqrt(1.0 - pow(beta2, (double)cs));
+    if (lr_c2 > 0.0) scalars[8] = (float)(lr_c2 / (1.0 - pow(beta1, (double)cs))), scalars[9] = scalars[1];
     if (as > 0) {
-        scalars[2] = (float)(lr / (1.0 - pow(beta1, (double)as)));
+        scalars[2] = (float)(lr_a / (1.0 - pow(beta1, (double)as)));
         scalars[3] = (float)sqrt(1.0 - pow(beta2, (double)as));
+        if (lr_a2 > 0.0) scalars[10] = (float)(lr_a2 / (1.0 - pow(beta1, (double)as))), scalars[11] = scalars[3];
     }
     scalars[4] = __uint_as_float((uint32_t)n);
 }
@@ -818,7 +823,6 @@ struct ApplyArgs {
     int64_t polyak_lo, polyak_hi;  // polyak on [polyak_lo, polyak_hi) (after Adam where the ranges overlap)
     float beta1, beta2, eps, step_size, bc2_sqrt, tau;
     const float *dev_scalars;  // graph mode: {step_size, bc2_sqrt} written by td3_tick_kernel (NULL: the by-value fields)
-    float dev_lr_scale;        // graph mode with several learning rates (multi-agent): the tick kernel runs with lr = 1 and this holds the rate (0: unused)
     const float *loss_partial;
     int n_loss_partial;
     float loss_scale;
@@ -846,8 +850,7 @@ __global__ void __launch_bounds__(256) td3_apply_kernel(ApplyArgs a) {
     }
     float p;
     bool have = false;
-    const float step_size = a.dev_scalars ? a.dev_scalars[0] * (a.dev_lr_scale != 0.f ? a.dev_lr_scale : 1.f) : a.step_size;
-    const float bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
+    const float step_size = a.dev_scalars ? a.dev_scalars[0] : a.step_size, bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
     if (i >= a.adam_lo && i < a.adam_hi) {
         const float g = a.g[i];
         float m = a.m[i], v = a.v[i];
@@ -944,8 +947,7 @@ __global__ void __launch_bounds__(256) td3_apply_peer_kernel(ApplyArgs a, PeerAr
             a.loss_acc[1] += 1.f;
         }
     }
-    const float step_size = a.dev_scalars ? a.dev_scalars[0] * (a.dev_lr_scale != 0.f ? a.dev_lr_scale : 1.f) : a.step_size;
-    const float bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
+    const float step_size = a.dev_scalars ? a.dev_scalars[0] : a.step_size, bc2_sqrt = a.dev_scalars ? a.dev_scalars[1] : a.bc2_sqrt;
     const int64_t lo = min(a.adam_lo, a.polyak_lo < a.polyak_hi ? a.polyak_lo : a.adam_lo), hi = max(a.adam_hi, a.polyak_hi);
     if (alive)  // every range boundary is a multiple of 4 floats (pad4 layout): one float4 group per thread and trip
         for (int64_t i = lo + 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 4 * (int64_t)gridDim.x * blockDim.x) {
@@ -1304,7 +1306,7 @@ int cstr_td3_update(const cstr_td3_config *cfg, const cstr_td3_state *stt, const
     const int ZC = cfg->n_critics == 1 ? 1 : 2;  // DDPG = TD3 with one critic (core/ddpg/ddpg.py:100-109); its block 1 stays unused
     const float *dev_sc = stt->counters ? w.scalars : nullptr;  // graph mode (see td3_tick_kernel)
     if (stt->counters && (phases & CSTR_TD3_CRITIC_GRAD)) {
-        launch_k(td3_tick_kernel, 1, 32, 0, st, stt->counters, w.scalars, policy_step ? 1 : 0, (double)cfg->lr, (double)cfg->beta1, (double)cfg->beta2);
+        launch_k(td3_tick_kernel, 1, 32, 0, st, stt->counters, w.scalars, policy_step ? 1 : 0, (double)cfg->lr, (double)cfg->beta1, (double)cfg->beta2, -1.0, 0.0, 0.0);
         if (int rc = check_launch("td3_tick_kernel")) return rc;
     }
 
@@ -1453,7 +1455,7 @@ int cstr_sac_update(const cstr_sac_config *cfg, const cstr_td3_state *stt, const
         return check_launch("sac_ent_coef_kernel");
     };
     if (stt->counters && (phases & CSTR_TD3_CRITIC_GRAD)) {
-        launch_k(td3_tick_kernel, 1, 32, 0, st, stt->counters, w.scalars, 1, (double)cfg->lr, (double)cfg->beta1, (double)cfg->beta2);
+        launch_k(td3_tick_kernel, 1, 32, 0, st, stt->counters, w.scalars, 1, (double)cfg->lr, (double)cfg->beta1, (double)cfg->beta2, -1.0, 0.0, 0.0);
         if (int rc = check_launch("td3_tick_kernel")) return rc;
     }
     if (phases & CSTR_TD3_CRITIC_GRAD) {
