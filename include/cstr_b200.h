@@ -411,6 +411,18 @@ int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K, int math_
                        int64_t pos0, float *records, double *reward_sum, const cstr_episode_stats *stats /* nullable */,
                        void *stream);
 
+/* Multi-agent variant (BASELINE config #5: the two reactors as two agents).  Replaces OffMultiAgentPolicyAlgorithm._sample_action +
+ * MultiAgentBasePolicy.predict + env.step + _store_transition + ReplayBuffer.add
+ * (core/common/multiagent_policy_algorithm.py:346-394,428-491,547; core/common/multi_agent_policies.py:500-563; core/maddpg/policies.py:88-121).
+ * agent_actors: two cstr_actor_f32 (kind TANH, equal hidden sizes), agent i's 2 -> H1 -> H2 -> 1 net zero-padded to the single-agent shape:
+ * W1 (H1,4) with the columns of the OTHER agent's observations zero, W3 (2,H2) with row i the agent's head and the other row zero, b3[i].
+ * As written in the reference (quirk Q5) neither exploration noise nor per-agent rescaling is applied: the env receives, and the buffer
+ * stores, u_i = low + 0.5 (mu_i + 1)(high - low); warm-up actions are the raw uniform draws.  fp32 CUDA-core actor.              */
+int cstr_rollout_fused_multi(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, const cstr_actor_f32 *agent_actors /* [2] */,
+                             int warmup, uint32_t t_base, float *state, int32_t *step_count, int32_t *episode, double *static_base,
+                             int64_t rows, int64_t pos0, float *records, double *reward_sum, const cstr_episode_stats *stats /* nullable */,
+                             void *stream);
+
 /* Packs W2 (H2,H1) fp32 into the bf16 UMMA shared-memory image the tensor-core path streams with
  * TMA-style bulk copies; returns the required size in bytes when dst == NULL.                      */
 int64_t cstr_actor_pack_bf16(const cstr_actor_f32 *actor, void *dst, void *stream);

@@ -8,7 +8,7 @@ Follows, line by line:
   torch.optim.Adam (defaults)    betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad  (torch/optim/adam.py, single-tensor path)
 Further down: SACUpdateOracle (core/sac/sac.py:199-296) and BCQUpdateOracle (core/bcq/bcq.py:129-205, pinned by
 tests/golden/bcq_update.npz) and MultiAgentDDPGOracle (core/maddpg/maddpg.py, core/iddpg/iddpg.py :131-185, pinned by
-tests/golden/{maddpg,iddpg}_update.npz); their CUDA counterparts are not built yet.
+tests/golden/{maddpg,iddpg}_update.npz); their CUDA counterparts are cstr_bcq_update / cstr_ma_update (tests/test_gpu_bcq_ma.py).
 Everything is float32 NumPy with hand-written backward passes.  Pinned against the unmodified reference running on CPU torch
 (tests/golden/td3_update.npz, made by oracle/make_golden.py::gen_td3_update): weights agree to ~1e-6 after 6 gradient steps
 (GEMM summation order is the only difference), tolerance written in tests/test_golden.py.

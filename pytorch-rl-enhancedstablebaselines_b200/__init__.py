@@ -13,10 +13,11 @@ from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
 from .normalize import GpuVecNormalize, bind_vec_normalize_class
 from .update import FusedSACUpdate, FusedTD3Update, bind_sac_class, bind_td3_class
 from .update_ext import FusedBCQUpdate, FusedMultiAgentUpdate, bind_bcq_class, bind_multiagent_class
-from .rollout import ActorWeights, EpisodeStats, FusedRollout, bind_offpolicy_rollout, fused_rollout_unsupported
+from .rollout import ActorWeights, AgentActorWeights, EpisodeStats, FusedRollout, bind_offpolicy_rollout, fused_rollout_unsupported
 
 __all__ = [
     "ActorWeights",
+    "AgentActorWeights",
     "CstrLibraryError",
     "EpisodeStats",
     "FusedRollout",

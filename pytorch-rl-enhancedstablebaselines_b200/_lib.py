@@ -151,6 +151,8 @@ _SIGNATURES = {
     "cstr_peer_error": (c_int, [POINTER(PeerComm), POINTER(c_uint32), P]),
     "cstr_rollout_fused": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, c_int, POINTER(ActorF32), P, c_float, P, c_int,
                                    c_uint32, P, P, P, P, c_int64, c_int64, P, P, POINTER(EpisodeStatsStruct), P]),
+    "cstr_rollout_fused_multi": (c_int, [POINTER(EnvParams), c_int64, c_int64, c_int, P, c_int, c_uint32, P, P, P, P, c_int64, c_int64, P, P,
+                                         POINTER(EpisodeStatsStruct), P]),
     "cstr_actor_pack_bf16": (c_int64, [POINTER(ActorF32), P, P]),
     "cstr_probe_pipe": (c_int, [c_int, c_int64, c_int, c_int, P, P]),
     "cstr_selftest": (c_int, [c_int, P, P]),

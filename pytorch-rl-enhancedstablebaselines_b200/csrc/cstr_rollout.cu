@@ -31,7 +31,8 @@ constexpr int ROLL_THREADS = ROLL_PARTS * 32;
 
 template <int MODE, int KIND>
 __global__ void __launch_bounds__(ROLL_THREADS, 1)
-rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor, float sigma, const float2 *__restrict__ noise, int warmup,
+rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor_a, cstr_actor_f32 actor_b, int n_agents, float sigma,
+                   const float2 *__restrict__ noise, int warmup,
                    uint32_t t_base, float4 *__restrict__ state, int32_t *__restrict__ step_count, int32_t *__restrict__ episode,
                    double *static_base, int64_t rows, int64_t pos0, float4 *__restrict__ records, double *reward_sum, cstr_episode_stats stats,
                    int has_stats) {
@@ -42,7 +43,10 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
     const int m = part * 32 + lane;         // the owned reactor (owners only)
     const int64_t i = (int64_t)blockIdx.x * ROLL_M + m;
     const bool live = owner && i < n;
-    const int H1 = actor.H1, H2 = actor.H2;
+    // n_agents == 2 (multi-agent, core/common/multiagent_policy_algorithm.py:346-394): the actor pass runs once per agent with that agent's
+    // weights — its 2 -> H1 -> H2 -> 1 net zero-padded to the 4 -> H1 -> H2 -> 2 shape (W1 columns of the other agent's observations and the
+    // other W3 row are zero, which adds exact zeros in the same summation order) — and output component `agent` is kept
+    const int H1 = actor_a.H1, H2 = actor_a.H2;
     const size_t h1_floats = max((size_t)H1 * ROLL_M, (size_t)ROLL_PARTS * 4 * ROLL_M);
     float4 *s_state = reinterpret_cast<float4 *>(h1 + h1_floats);
     float *s_o = h1;
@@ -64,8 +68,12 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
                                     __fadd_rn(__fmul_rn(2.0f, __fmul_rn(__fadd_rn(a.y, 1.0f), 0.5f)), -1.0f));
                 env_a = make_float2(__fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(buf_a.x, 1.0f)), 2.0f)),
                                     __fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(buf_a.y, 1.0f)), 2.0f)));
+                if (n_agents > 1) env_a = buf_a = a;  // quirk Q5: the multi-agent path neither scales nor unscales (:369,390-392)
             }
         } else {
+          float mu_agent[2] = {0.f, 0.f};
+          for (int agent = 0; agent < n_agents; ++agent) {
+            const cstr_actor_f32 &actor = agent ? actor_b : actor_a;
             if (owner) s_state[m] = s;
             __syncthreads();
             float4 sv[ROLL_R];
@@ -162,9 +170,20 @@ rollout_f32_kernel(cstr_env_params p, int64_t n, int64_t K, cstr_actor_f32 actor
                 float mu0, mu1;
                 float2 add;
                 actor_head<KIND>(oo, nz, mu0, mu1, add);
-                action_maps(mu0, add.x, env_a.x, buf_a.x);
-                action_maps(mu1, add.y, env_a.y, buf_a.y);
+                if (n_agents == 1) {
+                    action_maps(mu0, add.x, env_a.x, buf_a.x);
+                    action_maps(mu1, add.y, env_a.y, buf_a.y);
+                } else {
+                    mu_agent[agent] = agent ? mu1 : mu0;
+                    if (agent == n_agents - 1) {  // predict()'s unscale (multi_agent_policies.py:548-550,592) is all that happens: no noise, no rescale (Q5)
+                        env_a = make_float2(__fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(mu_agent[0], 1.0f)), 2.0f)),
+                                            __fadd_rn(-1.0f, __fmul_rn(__fmul_rn(0.5f, __fadd_rn(mu_agent[1], 1.0f)), 2.0f)));
+                        buf_a = env_a;
+                    }
+                }
             }
+            if (agent + 1 < n_agents) __syncthreads();  // the owners are done with the partial heads before the next pass overwrites shared memory
+          }
         }
         if (!owner) continue;  // (every thread has passed this step's barriers by now)
         // ---- env step + transition record
@@ -206,10 +225,37 @@ int cstr_rollout_tc_launch(const cstr_env_params *p, int64_t n, int64_t K, int m
                            int32_t *step_count, int32_t *episode, double *static_base, int64_t rows, int64_t pos0, float *records,
                            double *reward_sum, const cstr_episode_stats *stats, void *stream);
 
+static int rollout_fused_impl(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, int actor_mode, const cstr_actor_f32 *actor,
+                              const cstr_actor_f32 *actor_b, const void *packed_bf16, float sigma, const float *noise, int warmup, uint32_t t_base,
+                              float *state, int32_t *step_count, int32_t *episode, double *static_base, int64_t rows, int64_t pos0, float *records,
+                              double *reward_sum, const cstr_episode_stats *stats, void *stream);
+
 extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, int actor_mode,
                                   const cstr_actor_f32 *actor, const void *packed_bf16, float sigma, const float *noise, int warmup,
                                   uint32_t t_base, float *state, int32_t *step_count, int32_t *episode, double *static_base,
                                   int64_t rows, int64_t pos0, float *records, double *reward_sum, const cstr_episode_stats *stats, void *stream) {
+    return rollout_fused_impl(p, n, K, math_mode, actor_mode, actor, nullptr, packed_bf16, sigma, noise, warmup, t_base, state, step_count, episode,
+                              static_base, rows, pos0, records, reward_sum, stats, stream);
+}
+
+extern "C" int cstr_rollout_fused_multi(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, const cstr_actor_f32 *agent_actors, int warmup,
+                                        uint32_t t_base, float *state, int32_t *step_count, int32_t *episode, double *static_base, int64_t rows,
+                                        int64_t pos0, float *records, double *reward_sum, const cstr_episode_stats *stats, void *stream) {
+    if (!warmup) {
+        if (!agent_actors) return fail_arg(CSTR_EINVAL, "rollout_multi: agent actors missing");
+        if (agent_actors[0].H1 != agent_actors[1].H1 || agent_actors[0].H2 != agent_actors[1].H2 || agent_actors[0].kind != CSTR_ACTOR_TANH ||
+            agent_actors[1].kind != CSTR_ACTOR_TANH)
+            return fail_arg(CSTR_EINVAL, "rollout_multi: both agents need tanh actors of the same hidden sizes");
+    }
+    static const cstr_actor_f32 none = {};
+    return rollout_fused_impl(p, n, K, math_mode, 0, agent_actors ? agent_actors : &none, agent_actors ? agent_actors + 1 : &none, nullptr, 0.0f, nullptr,
+                              warmup, t_base, state, step_count, episode, static_base, rows, pos0, records, reward_sum, stats, stream);
+}
+
+static int rollout_fused_impl(const cstr_env_params *p, int64_t n, int64_t K, int math_mode, int actor_mode, const cstr_actor_f32 *actor,
+                              const cstr_actor_f32 *actor_b, const void *packed_bf16, float sigma, const float *noise, int warmup, uint32_t t_base,
+                              float *state, int32_t *step_count, int32_t *episode, double *static_base, int64_t rows, int64_t pos0, float *records,
+                              double *reward_sum, const cstr_episode_stats *stats, void *stream) {
     if (!p || n < 0 || K < 0 || !state || !step_count || !episode || !records || rows <= 0 || pos0 < 0)
         return fail_arg(CSTR_EINVAL, "rollout: null pointer or bad size");
     if (p->init_mode == CSTR_INIT_STATIC && !static_base) return fail_arg(CSTR_EINVAL, "static init_mode needs static_base");
@@ -224,12 +270,18 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
     }
     if (stats && (!stats->ep_return || !stats->finished || !stats->count)) return fail_arg(CSTR_EINVAL, "rollout: episode stats pointers missing");
     if (n == 0 || K == 0) return 0;
+    if (actor_b && !warmup) {
+        if (!actor_b->W1 || !actor_b->b1 || !actor_b->W2 || !actor_b->b2 || !actor_b->W3 || !actor_b->b3 || !aligned(actor_b->W1, 16) || !aligned(actor_b->W2, 16))
+            return fail_arg(CSTR_EINVAL, "rollout_multi: second agent's weights missing or misaligned");
+    }
     if (actor_mode == 1 && !warmup)
         return cstr_rollout_tc_launch(p, n, K, math_mode, actor, packed_bf16, sigma, noise, warmup, t_base, state, step_count, episode,
                                       static_base, rows, pos0, records, reward_sum, stats, stream);
     if (actor_mode != 0 && actor_mode != 1) return fail_arg(CSTR_EINVAL, "rollout: unknown actor_mode");
-    cstr_actor_f32 a = {};
+    cstr_actor_f32 a = {}, b2nd = {};
     if (actor) a = *actor;
+    if (actor_b) b2nd = *actor_b;
+    const int n_agents = actor_b ? 2 : 1;
     const size_t h1_floats = (size_t)a.H1 * ROLL_M > (size_t)ROLL_PARTS * 4 * ROLL_M ? (size_t)a.H1 * ROLL_M : (size_t)ROLL_PARTS * 4 * ROLL_M;
     const size_t smem = warmup ? 0 : h1_floats * sizeof(float) + ROLL_M * sizeof(float4);
     if (smem > 227 * 1024) return fail_arg(CSTR_EINVAL, "rollout: H1 too large for the fp32 path (max 448)");
@@ -240,7 +292,7 @@ extern "C" int cstr_rollout_fused(const cstr_env_params *p, int64_t n, int64_t K
     do {                                                                                                                                   \
         rc = check_cuda(cudaFuncSetAttribute(rollout_f32_kernel<MODE, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
         if (!rc)                                                                                                                           \
-            rollout_f32_kernel<MODE, KIND><<<grid, ROLL_THREADS, smem, st>>>(*p, n, K, a, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state, \
+            rollout_f32_kernel<MODE, KIND><<<grid, ROLL_THREADS, smem, st>>>(*p, n, K, a, b2nd, n_agents, sigma, (const float2 *)noise, warmup, t_base, (float4 *)state, \
                                                                        step_count, episode, static_base, rows, pos0, (float4 *)records, reward_sum, st_copy, has_stats); \
     } while (0)
     cstr_episode_stats st_copy = {};

@@ -114,6 +114,48 @@ class ActorWeights:
         return self.packed_bf16
 
 
+class AgentActorWeights:
+    """The per-agent actors of the reference's multi-agent policies (``core/maddpg/policies.py:21-121``: ``actor.mu_list[i]`` =
+    ``create_mlp(2, 1, [H1, H2]) + Tanh`` on agent i's observation slice) for the two-reactor agents (observation_splits [[0,1],[2,3]],
+    action_splits [[0],[1]]), each zero-padded to the single-agent shape ``4 -> H1 -> H2 -> 2`` the rollout kernel evaluates: ``W1`` (H1,4)
+    with the other agent's observation columns zero, ``W3`` (2,H2) with row i the agent's head."""
+
+    def __init__(self, agent_modules, device="cuda"):
+        torch = _lib.require_cuda()
+        self.device = torch.device(device)
+        if len(agent_modules) != 2:
+            raise ValueError("the multi-agent rollout is specialised to the two reactors as two agents")
+        self.kind = "agents"
+        self.packed_bf16 = None
+        self._tensors = []
+        for i, module in enumerate(agent_modules):
+            lin = ActorWeights._linears(module)
+            if len(lin) != 3 or tuple(lin[0].weight.shape)[1] != 2 or tuple(lin[2].weight.shape)[0] != 1:
+                raise ValueError("expected per-agent actors 2 -> H1 -> H2 -> 1")
+            H1, H2 = int(lin[0].weight.shape[0]), int(lin[1].weight.shape[0])
+            z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=self.device)  # noqa: E731
+            self._tensors.append(dict(W1=z(H1, 4), b1=z(H1), W2=z(H2, H1), b2=z(H2), W3=z(2, H2), b3=z(2)))
+            self.H1, self.H2 = H1, H2
+        if self.H1 % 4:
+            raise ValueError("H1 must be a multiple of 4")
+        self._structs = (_lib.ActorF32 * 2)()
+        for i, t in enumerate(self._tensors):
+            self._structs[i] = _lib.ActorF32(W1=t["W1"].data_ptr(), b1=t["b1"].data_ptr(), W2=t["W2"].data_ptr(), b2=t["b2"].data_ptr(), W3=t["W3"].data_ptr(),
+                                             b3=t["b3"].data_ptr(), H1=self.H1, H2=self.H2, kind=_lib.ACTOR_TANH, reserved=0)
+        self.refresh_from_modules(agent_modules)
+
+    def refresh_from_modules(self, agent_modules) -> None:
+        """Copy the agents' current parameters into the padded images (device to device)."""
+        for i, (module, t) in enumerate(zip(agent_modules, self._tensors)):
+            lin = ActorWeights._linears(module)
+            t["W1"][:, 2 * i:2 * i + 2].copy_(lin[0].weight.detach(), non_blocking=True)
+            t["b1"].copy_(lin[0].bias.detach(), non_blocking=True)
+            t["W2"].copy_(lin[1].weight.detach(), non_blocking=True)
+            t["b2"].copy_(lin[1].bias.detach(), non_blocking=True)
+            t["W3"][i].copy_(lin[2].weight.detach()[0], non_blocking=True)
+            t["b3"][i:i + 1].copy_(lin[2].bias.detach(), non_blocking=True)
+
+
 class EpisodeStats:
     """Device-side ``Monitor`` for the fused rollout (monitor.py:85-111): running return per reactor and a compact list of
     finished episodes ``(return, length)`` that ``pop()`` hands to the host — the feed of ``ep_info_buffer`` /
@@ -161,6 +203,8 @@ class FusedRollout:
         if actor_mode not in ("fp32", "tc"):
             raise ValueError("actor_mode must be 'fp32' or 'tc'")
         self.env, self.buffer, self.actor, self.sigma = env, buffer, actor, float(sigma)
+        if isinstance(actor, AgentActorWeights) and actor_mode != "fp32":
+            raise ValueError("the multi-agent rollout runs the float32 actor (actor_mode='fp32')")
         self.actor_mode = actor_mode
         self.t = 0  # global step counter: the Philox counter of the noise / warm-up action streams
         self._lib = _lib.load()
@@ -184,6 +228,19 @@ class FusedRollout:
             raise ValueError("an ActorWeights is required unless warmup=True")
         if noise is not None and (tuple(noise.shape) != (K, env.num_envs, 2) or noise.dtype != torch.float32 or not noise.is_contiguous()):
             raise ValueError("noise must be a contiguous float32 tensor of shape (K, N, 2)")
+        if isinstance(self.actor, AgentActorWeights):  # the two reactors as two agents (cstr_rollout_fused_multi): no noise, no rescale (Q5)
+            if noise is not None:
+                raise ValueError("the reference's multi-agent _sample_action never adds noise (quirk Q5)")
+            with torch.cuda.device(env.device):
+                rc = self._lib.cstr_rollout_fused_multi(
+                    byref(env._params), env.num_envs, K, _MATH[env.math], self.actor._structs, int(warmup), self.t & 0xFFFFFFFF, _lib.ptr(env.state),
+                    _lib.ptr(env.step_count), _lib.ptr(env.episode), env._sb_ptr(), buf.buffer_size, buf.pos, _lib.ptr(buf.records),
+                    _lib.ptr(reward_sum), byref(stats._struct) if stats is not None else None, env._stream())
+            _lib.check(rc, "cstr_rollout_fused_multi")
+            self.launches += 1
+            self.t += K
+            buf.advance(K)
+            return
         packed = None
         if self.actor_mode == "tc" and not warmup:
             packed = self.actor.packed_bf16 if self.actor.packed_bf16 is not None else self.actor.pack_bf16()
@@ -233,9 +290,14 @@ def fused_rollout_unsupported(model, env, replay_buffer, train_freq, action_nois
         return "use_sde (state-dependent exploration matrices)"
     if getattr(model, "_vec_normalize_env", None) is not None:
         return "VecNormalize wraps the env (the actor would need normalised observations)"
+    actor = getattr(model, "actor", None)
+    if actor is not None and hasattr(actor, "mu_list"):  # multi-agent (MADDPG / IDDPG): any noise object is ignored by the reference itself (Q5)
+        splits = ([list(s) for s in getattr(model, "observation_splits", [])], [list(s) for s in getattr(model, "action_splits", [])])
+        if len(actor.mu_list) != 2 or splits != ([[0, 1], [2, 3]], [[0], [1]]):
+            return "agents are not the two reactors (observation_splits [[0,1],[2,3]], action_splits [[0],[1]])"
+        return None
     if _noise_sigma(action_noise) is None:
         return f"action noise {action_noise!r} is not a zero-mean NormalActionNoise with one sigma"
-    actor = getattr(model, "actor", None)
     if actor is None or not (hasattr(actor, "mu") and (hasattr(actor.mu, "__len__") or hasattr(actor, "latent_pi"))):
         return "the policy has no TD3/DDPG `actor.mu` Sequential or SAC `actor.latent_pi/mu/log_std`"
     return None
@@ -263,13 +325,13 @@ def bind_offpolicy_rollout(algo_base: type, actor_mode: str = "fp32") -> type:
     import time
     import warnings
 
-    root = algo_base.__module__.split(".")[0]
+    RolloutReturn = None
     for klass in algo_base.__mro__:  # the reference package the algorithm comes from ("core", or upstream "stable_baselines3")
-        mod = klass.__module__.split(".")[0]
-        if klass.__name__ == "OffPolicyAlgorithm":
-            root = mod
+        if klass.__name__ in ("OffPolicyAlgorithm", "OffMultiAgentPolicyAlgorithm"):
+            RolloutReturn = importlib.import_module(klass.__module__.split(".")[0] + ".common.type_aliases").RolloutReturn
             break
-    RolloutReturn = importlib.import_module(root + ".common.type_aliases").RolloutReturn
+    if RolloutReturn is None:
+        raise TypeError(f"{algo_base.__name__} is not an off-policy algorithm of the reference (no OffPolicyAlgorithm base)")
 
     class FusedRolloutAlgorithm(algo_base):  # type: ignore[misc, valid-type]
         _fused_roll: Optional[FusedRollout] = None
@@ -290,6 +352,8 @@ def bind_offpolicy_rollout(algo_base: type, actor_mode: str = "fp32") -> type:
 
         def _fused_actor_modules(self):
             a = self.actor
+            if hasattr(a, "mu_list"):  # MADDPG / IDDPG: one actor per agent
+                return "agents", (list(a.mu_list),)
             if hasattr(a, "latent_pi"):  # SAC
                 return "gaussian", (a.latent_pi, a.mu, a.log_std)
             return "tanh", (a.mu,)
@@ -298,9 +362,10 @@ def bind_offpolicy_rollout(algo_base: type, actor_mode: str = "fp32") -> type:
             kind, modules = self._fused_actor_modules()
             roll = self._fused_roll
             if roll is None or roll.env is not env or roll.buffer is not replay_buffer:
-                actor = (ActorWeights.from_sac_actor(*modules, device=env.device) if kind == "gaussian"
+                actor = (AgentActorWeights(modules[0], device=env.device) if kind == "agents"
+                         else ActorWeights.from_sac_actor(*modules, device=env.device) if kind == "gaussian"
                          else ActorWeights.from_module(modules[0], device=env.device))
-                roll = FusedRollout(env, replay_buffer, actor, sigma=sigma, actor_mode=actor_mode)
+                roll = FusedRollout(env, replay_buffer, actor, sigma=sigma, actor_mode="fp32" if kind == "agents" else actor_mode)
                 roll.t = int(self.num_timesteps // max(env.num_envs, 1))
                 self._fused_roll, self._fused_stats = roll, EpisodeStats(env.num_envs, device=env.device)
             roll.sigma = sigma
@@ -316,7 +381,7 @@ def bind_offpolicy_rollout(algo_base: type, actor_mode: str = "fp32") -> type:
                 return super().collect_rollouts(env, callback, train_freq, replay_buffer, action_noise, learning_starts, log_interval)
             self.policy.set_training_mode(False)
             n_envs, K = env.num_envs, int(train_freq.frequency)
-            roll = self._fused_rollout_engine(env, replay_buffer, _noise_sigma(noise))
+            roll = self._fused_rollout_engine(env, replay_buffer, _noise_sigma(noise) or 0.0)
             stats = self._fused_stats
             callback.on_rollout_start()
             remaining = K
@@ -324,7 +389,10 @@ def bind_offpolicy_rollout(algo_base: type, actor_mode: str = "fp32") -> type:
                 warm = self.num_timesteps < learning_starts  # the reference tests this before every step (:386)
                 k = min(remaining, -(-(learning_starts - self.num_timesteps) // n_envs)) if warm else remaining
                 if not warm:  # the optimiser moved the weights since the last launch: refresh the kernel's copy (device to device)
-                    roll.actor.refresh_from_module(*self._fused_actor_modules()[1])
+                    if isinstance(roll.actor, AgentActorWeights):
+                        roll.actor.refresh_from_modules(self._fused_actor_modules()[1][0])
+                    else:
+                        roll.actor.refresh_from_module(*self._fused_actor_modules()[1])
                 roll.collect(k, warmup=warm, stats=stats)
                 self.fused_rollout_launches += 1
                 self.num_timesteps += n_envs * k

@@ -188,7 +188,7 @@ def test_bcq_update_oracle_vs_reference_fixture(golden):
     """BCQUpdateOracle replays 5 gradient steps of the reference's BCQ.train (bcq.py:129-205): VAE step, candidate target through the
     refreshed target VAE + target perturbation net (with the reference's (B, 10) reshape as written), twin critics, delayed perturbation
     step, polyak — on the recorded batches and the recorded randn / randn_like draws.  This pins the oracle for the BCQ update kernels
-    (SURVEY §8f-1), which are not built yet: there is no CUDA counterpart of this test."""
+    (cstr_bcq_update); the CUDA counterpart of this test is tests/test_gpu_bcq_ma.py."""
     import td3_oracle as T
     import td3_util as U
 
@@ -212,7 +212,7 @@ def test_bcq_update_oracle_vs_reference_fixture(golden):
 def test_multi_agent_update_oracle_vs_reference_fixture(golden, algo, centralised):
     """MultiAgentDDPGOracle replays 4 gradient steps of the reference's MADDPG.train / IDDPG.train (two agents = the two reactors, unequal
     learning rates so the reference's actor/critic learning-rate pairing shows) on the recorded batches and target-noise draws.  Pins the
-    oracle for the multi-agent update kernels, which are not built yet: there is no CUDA counterpart of this test."""
+    oracle for the multi-agent update kernels (cstr_ma_update); the CUDA counterpart is tests/test_gpu_bcq_ma.py."""
     import td3_oracle as T
     import td3_util as U
 

@@ -110,3 +110,29 @@ def test_unsupported_models_keep_the_reference_rollout(pkg, ref):
     with pytest.warns(RuntimeWarning, match="fused rollout not used"):
         model.learn(total_timesteps=6 * n, log_interval=None)
     assert model.fused_rollout_launches == 0 and model.num_timesteps == 6 * n and model.replay_buffer.pos == 6
+
+
+@pytest.mark.parametrize("algo", ["MADDPG", "IDDPG"])
+def test_multi_agent_learn_runs_on_the_fused_rollout_and_update(pkg, ref, algo):
+    """BASELINE config #5 in small: the reference's MADDPG / IDDPG ``learn()`` with ``collect_rollouts`` = cstr_rollout_fused_multi and
+    ``train()`` = cstr_ma_update (bind_offpolicy_rollout(bind_multiagent_class(...)))."""
+    core = ref["core"]
+    n = 256
+    cls = pkg.bind_offpolicy_rollout(pkg.bind_multiagent_class(getattr(core, algo)))
+    env = ref["VecEnv"](num_envs=n, init_mode="random", reset_rng="philox", seed=6)
+    model = cls(policy="MlpPolicy", env=env, n_agents=2, observation_splits=[[0, 1], [2, 3]], action_splits=[[0], [1]], learning_rate_list=[1e-3, 5e-4],
+                device="cuda", replay_buffer_class=ref["Buffer"], buffer_size=64 * n, replay_buffer_kwargs=dict(index_mode="philox", seed=2),
+                learning_starts=8 * n, batch_size=128, train_freq=(8, "step"), gradient_steps=4, seed=1, verbose=0)
+    assert isinstance(model, getattr(core, algo))
+    before = [p.detach().clone() for p in model.actor.mu_list[1].parameters()]
+    launches_before = env.launches
+    model.learn(total_timesteps=n * 8 * 12, log_interval=None)
+    assert model.fused_rollout_launches == 12 and env.launches - launches_before <= 1
+    assert model._fused is not None and model._n_updates == 4 * 11 == model._fused.n_updates
+    assert model._fused.centralised == (algo == "MADDPG")
+    # the reference's learning-rate pairing: every actor at learning_rate_list[0], every critic at learning_rate_list[1]
+    assert model._fused.actor_lrs == [1e-3, 1e-3] and model._fused.critic_lrs == [5e-4, 5e-4]
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.actor.mu_list[1].parameters()))
+    assert model.actor.mu_list[0][0].weight.data_ptr() == model._fused.views("params")["actor0"][0].data_ptr()
+    rec = model.replay_buffer.records[(model.replay_buffer.pos - 1) % 64].cpu().numpy()
+    assert np.abs(rec[:, 8:10]).max() <= 1.0
