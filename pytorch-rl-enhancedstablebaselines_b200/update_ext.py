@@ -478,6 +478,31 @@ class FusedMultiAgentUpdate(_FlatEngine):
                         opt.state[p] = {"step": torch.tensor(float(step)), "exp_avg": m, "exp_avg_sq": v}
 
 
+def _ma_arch(policy):
+    """[h1, h2] shared by every per-agent actor (2 -> h1 -> h2 -> 1) and q-network (3|6 -> h1 -> h2 -> 1) of a reference multi-agent policy —
+    read off the modules themselves (``policy.net_arch`` is a per-agent list of lists or dicts) — or None when they do not fit the kernels."""
+    import torch.nn as nn
+
+    def dims(module):
+        lin = [m for m in module.modules() if isinstance(m, nn.Linear)]
+        acts = [m for m in module.modules() if isinstance(m, (nn.ReLU, nn.Tanh, nn.Sigmoid, nn.ELU, nn.LeakyReLU, nn.GELU, nn.SiLU))]
+        if len(lin) != 3 or sum(isinstance(a, nn.ReLU) for a in acts) != 2:
+            return None
+        return (lin[0].in_features, lin[0].out_features, lin[1].out_features, lin[2].out_features)
+
+    actors = [dims(m) for m in policy.actor.mu_list]
+    critics = [dims(q) for qs in policy.critic.q_networks_list for q in qs]
+    if any(d is None for d in actors + critics):
+        return None
+    h = {(d[1], d[2]) for d in actors + critics}
+    if len(h) != 1 or any(d[0] != 2 or d[3] != 1 for d in actors) or len({d[0] for d in critics}) != 1 or critics[0][0] not in (3, 6):
+        return None
+    h1, h2 = next(iter(h))
+    if h1 % 4 or h2 % 4 or h1 < 4 or h2 < 4:
+        return None
+    return [int(h1), int(h2)]
+
+
 def multiagent_update_unsupported(model) -> Optional[str]:
     import torch.nn as nn
     import torch.optim as optim
@@ -489,14 +514,9 @@ def multiagent_update_unsupported(model) -> Optional[str]:
         return "agents are not the two reactors (observation_splits [[0,1],[2,3]], action_splits [[0],[1]])"
     if getattr(pol, "activation_fn", nn.ReLU) is not nn.ReLU:
         return "activation_fn is not ReLU"
-    arch = pol.net_arch
-    if isinstance(arch, dict):
-        if list(arch.get("pi", [])) != list(arch.get("qf", [])):
-            return "different actor and critic net_arch"
-        arch = arch["pi"]
-    arch = list(arch)
-    if len(arch) != 2 or any(int(h) < 4 or int(h) % 4 for h in arch):
-        return f"net_arch {arch}: two hidden layers, multiples of 4"
+    arch = _ma_arch(pol)
+    if arch is None:
+        return "actors / critics are not two-hidden-layer ReLU MLPs of one common width pair (multiples of 4) with inputs 2 and 3 or 6"
     if not 1 <= pol.critic.n_critics <= 2:
         return f"n_critics={pol.critic.n_critics}"
     for opt in list(pol.actor.optimizer_list) + list(pol.critic.optimizer_list):
@@ -525,12 +545,9 @@ def bind_multiagent_class(algo_base: type) -> type:
             for agent_id in range(self.n_agents):
                 self._update_learning_rate([self.actor.optimizer_list[agent_id], self.critic.optimizer_list[agent_id]])
             if self._fused is None:
-                arch = self.policy.net_arch if isinstance(self.policy.net_arch, (list, tuple)) else self.policy.net_arch["pi"]
+                arch = _ma_arch(self.policy)
                 width = int(next(self.critic.q_networks_list[0][0].parameters()).shape[1])
-                if width not in (3, 6):
-                    _fallback_once(self, f"critic input width {width}")
-                    return super().train(gradient_steps, batch_size)
-                eng = FusedMultiAgentUpdate(list(arch), batch_size, width == 6, self.device, self.gamma, self.tau, policy_delay=self.policy_delay,
+                eng = FusedMultiAgentUpdate(arch, batch_size, width == 6, self.device, self.gamma, self.tau, policy_delay=self.policy_delay,
                                             target_policy_noise=self.target_policy_noise, target_noise_clip=self.target_noise_clip,
                                             n_critics=self.critic.n_critics, seed=int(self.seed or 0), dp_rank=_dist_rank())
                 eng.adopt_policy(self.policy)

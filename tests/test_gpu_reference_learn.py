@@ -136,3 +136,44 @@ def test_multi_agent_learn_runs_on_the_fused_rollout_and_update(pkg, ref, algo):
     assert model.actor.mu_list[0][0].weight.data_ptr() == model._fused.views("params")["actor0"][0].data_ptr()
     rec = model.replay_buffer.records[(model.replay_buffer.pos - 1) % 64].cpu().numpy()
     assert np.abs(rec[:, 8:10]).max() <= 1.0
+
+
+def test_bcq_learn_runs_on_the_fused_update(pkg, ref, tmp_path):
+    """BASELINE config #4 in small: a CSTR dataset produced by the tape kernel, handed to the reference's ``BCQ`` through its pickle path
+    (offline_policy_algorithm.py:196-242, quirk Q7), adopted into a GpuReplayBuffer (Q8), and trained by ``BCQ.learn()`` whose ``train()`` is
+    cstr_bcq_update (bind_bcq_class)."""
+    import pickle
+
+    core, ReplayBuffer = ref["core"], ref["ReplayBuffer"]
+    from core.common.vec_env import DummyVecEnv
+
+    n, T = 64, 100
+    env = pkg.GpuCSTRVecEnv(n, seed=3, monitor=False)
+    env.reset()
+    obs0 = env.state.clone()
+    acts = torch.rand((T, n, 2), device="cuda") * 2 - 1
+    res = env.tape(T, acts, want_obs=True)
+    obs = torch.cat([obs0[None], res["obs"][:-1]], 0)
+    ref_buf = ReplayBuffer(n * T, env.observation_space, env.action_space, device="cpu", n_envs=1)
+    ref_buf.observations[:, 0] = obs.reshape(-1, 4).cpu().numpy()
+    ref_buf.next_observations[:, 0] = res["obs"].reshape(-1, 4).cpu().numpy()
+    ref_buf.actions[:, 0] = acts.reshape(-1, 2).cpu().numpy()
+    ref_buf.rewards[:, 0] = res["rewards"].reshape(-1).cpu().numpy()
+    ref_buf.full, ref_buf.pos = True, 0
+    path = tmp_path / "cstr_dataset.pkl"
+    with open(path, "wb") as fh:
+        pickle.dump(ref_buf, fh)
+    single = DummyVecEnv([lambda: pkg.TwoSeriesCSTREnv(init_mode="static")])
+    FusedBCQ = pkg.bind_bcq_class(core.BCQ)
+    model = FusedBCQ("MlpPolicy", single, dataset=str(path), batch_size=128, device="cuda", seed=0)
+    model.replay_buffer = ref["Buffer"].from_reference(model.replay_buffer, index_mode="philox", seed=1)
+    vae_before = model.actor.vae.decoder[0].weight.detach().clone()
+    model.learn(total_timesteps=60)
+    assert isinstance(model, core.BCQ) and model._fused is not None and model._fused.n_updates == model._n_updates > 0
+    assert model._fused.actor_step == model._n_updates // model.actor_delay
+    assert not torch.equal(vae_before, model.actor.vae.decoder[0].weight)
+    # shared storage: policy modules are views of the flat block, and the target VAE is the VAE
+    assert model.actor.vae.decoder[0].weight.data_ptr() == model._fused.views("params")["vae_dec"][0].data_ptr()
+    assert model.actor_target.vae.mean.weight.data_ptr() == model.actor.vae.mean.weight.data_ptr()
+    a, _ = model.predict(np.zeros((1, 4), np.float32), deterministic=True)
+    assert a.shape == (1, 2) and np.abs(a).max() <= 1.0
