@@ -9,7 +9,7 @@ classes does (the CUDA library has no CPU fallback).
 from . import _build, _lib, dist
 from ._lib import CstrLibraryError
 from .buffer import GpuReplayBuffer, ReplayBufferSamples, bind_replay_buffer_class
-from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_vec_env_class
+from .env import GpuCSTRVecEnv, LazyInfos, TwoSeriesCSTREnv, bind_env_class, bind_vec_env_class
 from .normalize import GpuVecNormalize, bind_vec_normalize_class
 from .update import FusedSACUpdate, FusedTD3Update, bind_sac_class, bind_td3_class
 from .update_ext import FusedBCQUpdate, FusedMultiAgentUpdate, bind_bcq_class, bind_multiagent_class
@@ -30,6 +30,7 @@ __all__ = [
     "bind_bcq_class",
     "bind_multiagent_class",
     "FusedSACUpdate",
+    "bind_env_class",
     "bind_offpolicy_rollout",
     "bind_sac_class",
     "bind_td3_class",

@@ -571,6 +571,21 @@ class GpuCSTRVecEnv:
         return None
 
 
+def bind_env_class(gym_env_base: type) -> type:
+    """Return ``class TwoSeriesCSTREnv(TwoSeriesCSTREnv, <gymnasium.Env>)`` for a ``gymnasium`` that became importable only after this
+    module was imported (a harness that puts it on ``sys.path`` late): the reference's ``_patch_env`` (core/common/vec_env/patch_gym.py:31-35)
+    insists on ``isinstance(env, gymnasium.Env)``.  When gymnasium was importable at import time the façade already is one."""
+    if issubclass(TwoSeriesCSTREnv, gym_env_base):
+        return TwoSeriesCSTREnv
+
+    class BoundTwoSeriesCSTREnv(TwoSeriesCSTREnv, gym_env_base):  # type: ignore[misc, valid-type]
+        pass
+
+    BoundTwoSeriesCSTREnv.__name__ = "TwoSeriesCSTREnv"
+    BoundTwoSeriesCSTREnv.__qualname__ = "TwoSeriesCSTREnv"
+    return BoundTwoSeriesCSTREnv
+
+
 def bind_vec_env_class(vec_env_base: type) -> type:
     """Return ``class GpuCSTRVecEnv(GpuCSTRVecEnv, <reference VecEnv>)`` so the unchanged reference
     accepts the env without wrapping it (``isinstance(env, VecEnv)``, core/common/base_class.py:232).

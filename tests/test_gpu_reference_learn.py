@@ -163,7 +163,10 @@ def test_bcq_learn_runs_on_the_fused_update(pkg, ref, tmp_path):
     path = tmp_path / "cstr_dataset.pkl"
     with open(path, "wb") as fh:
         pickle.dump(ref_buf, fh)
-    single = DummyVecEnv([lambda: pkg.TwoSeriesCSTREnv(init_mode="static")])
+    import gymnasium
+
+    Facade = pkg.bind_env_class(gymnasium.Env)  # the harness put gymnasium on sys.path after the package was imported
+    single = DummyVecEnv([lambda: Facade(init_mode="static")])
     FusedBCQ = pkg.bind_bcq_class(core.BCQ)
     model = FusedBCQ("MlpPolicy", single, dataset=str(path), batch_size=128, device="cuda", seed=0)
     model.replay_buffer = ref["Buffer"].from_reference(model.replay_buffer, index_mode="philox", seed=1)
