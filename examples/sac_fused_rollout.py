@@ -47,8 +47,7 @@ def main():
     env = pkg.dist.make_sharded_env(args.n_envs, rank, world, device=dev, seed=args.seed, monitor=False)
     n = env.num_envs
     buf = pkg.GpuReplayBuffer(args.rows * n, device=dev, n_envs=n, index_mode="philox", seed=args.seed * 1000 + rank)
-    eng = pkg.FusedSACUpdate([256, 256], args.batch, device=dev, seed=args.seed * 7919 + rank)
-    hook = pkg.dist.allreduce_flat if world > 1 else None
+    eng = pkg.FusedSACUpdate([256, 256], args.batch, device=dev, seed=args.seed * 7919, dp_rank=rank)
 
     def mlp(i, o):  # torch nn.Linear default init
         out = []
@@ -58,6 +57,8 @@ def main():
         return out
 
     eng.load_nets({"actor": mlp(4, 4), "critic0": mlp(6, 1), "critic1": mlp(6, 1)})
+    if world > 1:  # the gradient mean over the ranks happens inside the Adam kernels (NVLink peer memory): no collective launch
+        eng.enable_peer_allreduce()
     actor_views = eng.views("params")["actor"]
     weights = pkg.ActorWeights(*actor_views, device=dev, kind="gaussian")
     roll = pkg.FusedRollout(env, buf, weights, sigma=0.0, actor_mode=args.actor_mode)
@@ -70,7 +71,7 @@ def main():
     window = max(1, 400 // args.steps_per_iter)  # iterations per 400-step episode: report whole episodes
     for it in range(args.iters):
         roll.collect(args.steps_per_iter, reward_sum=rsum)
-        eng.train(args.updates_per_iter, buf, args.batch, allreduce=hook, graph=(world == 1))  # 1 GPU: one CUDA-graph replay per update once the ring is full
+        eng.train(args.updates_per_iter, buf, args.batch, graph=True)  # one CUDA-graph replay per update once the ring is full
         weights.refresh_from_tensors(actor_views)  # device-to-device; repacks the bf16 UMMA image of W2
         if (it + 1) % window == 0 or it == args.iters - 1:
             mean_r = pkg.dist.global_sum(float(rsum.item()), device=dev) / (args.n_envs * args.steps_per_iter * ((it % window) + 1))
@@ -86,7 +87,9 @@ def main():
     if rank == 0:
         print(json.dumps({"world_size": world, "n_envs": args.n_envs, "transitions": transitions, "seconds": dt,
                           "transitions_per_s_incl_updates": transitions / dt, "updates": eng.n_updates, "mean_reward_first": log[0],
-                          "mean_reward_last": log[-1], "actor_mode": args.actor_mode}))
+                          "mean_reward_last": log[-1], "actor_mode": args.actor_mode, "steps_per_iter": args.steps_per_iter,
+                          "global_batch": args.batch * world, "peer_error": eng.peer_error()}))
+    eng.close_peer_allreduce()
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -65,6 +65,9 @@ def main():
     ap.add_argument("--sigma", type=float, default=0.1, help="exploration noise of the rollout (NormalActionNoise)")
     ap.add_argument("--update", default="fused", choices=["fused", "torch"])
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor", "bf16"], help="hidden-layer GEMMs of the fused update")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl", "nccl-eager"],
+                    help="multi-GPU gradient mean: peer = inside the Adam kernels over NVLink peer memory (CUDA graph), nccl = ncclAllReduce captured "
+                         "in the graph between the phases, nccl-eager = launch by launch with dist.all_reduce between the phases (round 1)")
     args = ap.parse_args()
 
     pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")
@@ -93,9 +96,11 @@ def main():
     fused = None
     if args.update == "fused":
         fused = pkg.FusedTD3Update([400, 300], args.batch, device=dev, gamma=gamma, tau=tau, learning_rate=args.lr, policy_delay=delay,
-                                   target_policy_noise=tnoise, target_noise_clip=tclip, seed=args.seed * 7919 + rank, gemm=args.gemm)
+                                   target_policy_noise=tnoise, target_noise_clip=tclip, seed=args.seed * 7919, dp_rank=rank, gemm=args.gemm)
         fused.adopt_modules(actor, list(critics), actor_t, list(critics_t))  # module parameters become views of the flat blocks
-        hook = pkg.dist.allreduce_flat if world > 1 else None
+        hook = pkg.dist.allreduce_flat if world > 1 and args.dp != "peer" else None
+        if world > 1 and args.dp == "peer":
+            fused.enable_peer_allreduce()
 
     env.reset()
     roll.collect(args.steps_per_iter, warmup=True)  # learning_starts phase: uniform random actions
@@ -107,8 +112,8 @@ def main():
     window = max(1, 400 // args.steps_per_iter)  # iterations per 400-step episode: rewards depend on the episode phase, so report whole episodes
     for it in range(args.iters):
         roll.collect(args.steps_per_iter, reward_sum=rsum)
-        if fused is not None:  # sample + update on the device; single GPU: whole policy_delay cycles replay from one CUDA graph
-            fused.train(args.updates_per_iter, buf, args.batch, allreduce=hook, graph=(world == 1))
+        if fused is not None:  # sample + update on the device: whole policy_delay cycles (incl. the gradient mean over ranks) replay from one CUDA graph
+            fused.train(args.updates_per_iter, buf, args.batch, allreduce=hook, graph=(args.dp != "nccl-eager"))
             n_updates += args.updates_per_iter
         for _ in range(args.updates_per_iter if fused is None else 0):
             b = buf.sample(args.batch)
@@ -148,7 +153,10 @@ def main():
         print(json.dumps({"world_size": world, "n_envs": args.n_envs, "transitions": transitions, "seconds": dt,
                           "transitions_per_s_incl_updates": transitions / dt, "updates": n_updates,
                           "mean_reward_first": log[0], "mean_reward_last": log[-1], "actor_mode": args.actor_mode, "update": args.update,
-                          "gemm": args.gemm}))
+                          "gemm": args.gemm, "dp": args.dp if world > 1 else None, "global_batch": args.batch * world,
+                          "peer_error": fused.peer_error() if fused is not None else 0}))
+    if fused is not None:
+        fused.close_peer_allreduce()
     if world > 1:
         torch.distributed.destroy_process_group()
     return log

@@ -152,23 +152,45 @@ def test_td3_example_learns_end_to_end():
     assert 400 * res["mean_reward_last"] > 400 * res["mean_reward_first"] + 120, res
 
 
-def test_maddpg_example_runs_on_the_device_path():
-    """examples/maddpg_two_agents.py: two per-agent actors -> step kernel on device tensors (step_tensor) -> replay add -> Philox sample ->
-    the reference's MADDPG loop body in torch.  One launch of the step kernel and one of the add kernel per control interval, one gather
-    per gradient step, whatever the number of env copies."""
+def _run_example(name, *args, timeout=900):
     import json
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "examples", "maddpg_two_agents.py"), "--n-envs", "8192", "--iters", "110", "--batch", "256"],
-                         capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", name), *args], capture_output=True, text=True, timeout=timeout)
     assert out.returncode == 0, out.stderr[-2000:]
-    res = json.loads(out.stdout.strip().splitlines()[-1])
-    assert res["transitions"] == 110 * 4 * 8192 and res["updates"] == 440 and res["agents"] == 2
-    assert res["env_launches"] == 440 + 1 and res["buffer_launches"] == 440 + 440  # (+1: reset)
-    assert -3.0 < res["mean_reward_last"] < 0.0  # rewards are in [-7.2, 0] per step; the reference's MADDPG does not improve on this task (see the example)
+    return json.loads(out.stdout.strip().splitlines()[-1]), out.stdout
+
+
+@pytest.mark.parametrize("flag,algo", [((), "MADDPG"), (("--iddpg",), "IDDPG")])
+def test_multi_agent_example_runs_entirely_on_the_device(flag, algo):
+    """examples/maddpg_two_agents.py: cstr_rollout_fused_multi (two per-agent actors + step + record, 4 steps per launch) and cstr_ma_update
+    (graph-replayed once the ring is full): one rollout launch per iteration whatever the number of env copies, no per-step VecEnv call, no
+    replay add from the host."""
+    res, _ = _run_example("maddpg_two_agents.py", "--n-envs", "8192", "--iters", "110", "--batch", "256", *flag)
+    assert res["algo"] == algo and res["transitions"] == 110 * 4 * 8192 and res["rollout_launches"] == 110
+    assert res["updates"] == 4 * (110 - 2)  # the first two iterations (8 ring rows) are warm-up
+    assert res["env_step_launches"] <= 1 and res["peer_error"] == 0  # (the reset)
+    assert -2000.0 < res["episode_return_last"] < 0.0  # 400 steps of rewards in [-7.2, 0]; the reference's MADDPG does not improve on this task either
+
+
+def test_bcq_example_trains_on_the_device_resident_dataset():
+    """examples/bcq_offline.py at a reduced dataset size: dataset written by the fused rollout kernel, every update cstr_bcq_update; the VAE and
+    critic losses must fall, and the eager-torch twin is timed beside it."""
+    res, _ = _run_example("bcq_offline.py", "--transitions", "1024000", "--updates", "400", "--batch", "256", "--torch")
+    assert res["transitions"] == 1_024_000 and res["updates"] == 400 and res["sizes"]["latent"] == 32
+    assert res["vae_loss_first_last"][1] < res["vae_loss_first_last"][0]
+    assert res["fused_ms_per_update"] < res["torch_eager_ms_per_update"]
+    assert all(np.isfinite(v) for v in res["critic_loss_first_last"])
+
+
+def test_sac_example_learns_end_to_end():
+    """examples/sac_fused_rollout.py: squashed-Gaussian actor on tcgen05 in the fused rollout -> Philox sample -> fused SAC update."""
+    res, _ = _run_example("sac_fused_rollout.py", "--n-envs", "16384", "--iters", "1200")
+    assert res["transitions"] == 1200 * res["steps_per_iter"] * 16384 and res["peer_error"] == 0
+    assert 400 * res["mean_reward_last"] > 400 * res["mean_reward_first"] + 100, res
 
 
 @pytest.mark.parametrize("actor_mode,atol", [("fp32", 3e-6), ("tc", 5e-3)])
