@@ -417,9 +417,10 @@ def run_multi_rank_sections(pkg, torch, device, dist, rank, world, args) -> dict
               ranks; weak: 131,072 reactors per rank.  No collective on this path.  value = transitions of ALL ranks / max-over-ranks time.
     dp_update TD3 [400,300] gradient step, data-parallel over the N ranks, per-rank batch 4096 and 256, replayed from ONE CUDA graph
               per policy_delay cycle (Philox sample -> GRAD -> gradient mean over ranks -> Adam/polyak): "peer" = the mean is taken
-              inside the Adam kernels over NVLink peer memory (cstr_peer_comm), "nccl" = ncclAllReduce(avg) captured between the
-              phases, "nccl_eager" = the round-1 path (launch by launch, dist.all_reduce between the phases), "local" = the same
-              graph without any exchange (what one GPU does alone).  ms per update, max over ranks."""
+              inside the Adam kernels over NVLink peer memory (cstr_peer_comm), "nccl_eager" = the round-1 path (launch by launch,
+              ncclAllReduce(avg) between the phases), "local" = the same graph without any exchange (what one GPU does alone).
+              ms per update, max over ranks.  (ncclAllReduce captured INSIDE the graph ran on 2 GPUs — 0.556 ms at batch 4096, 0.162 at
+              256, profiles/r02_bench_n2_sections.json — but hung on 8 and is therefore opt-in, CSTR_NCCL_GRAPH=1, and not timed here.)"""
     import numpy as np
 
     def max_over_ranks(ms: float) -> float:
@@ -484,7 +485,7 @@ def run_multi_rank_sections(pkg, torch, device, dist, rank, world, args) -> dict
     for B in (4096, 256):
         row = {"per_rank_batch": B, "global_batch": B * world, "net_arch": [400, 300], "gradient_bucket_bytes": None}
         reps = 50 if B == 4096 else 100
-        for mode in ("local", "peer", "nccl", "nccl_eager"):
+        for mode in ("local", "peer", "nccl_eager"):
             if world == 1 and mode != "local":
                 continue
             eng = pkg.FusedTD3Update([400, 300], B, device=device, seed=7, dp_rank=rank)
@@ -492,7 +493,7 @@ def run_multi_rank_sections(pkg, torch, device, dist, rank, world, args) -> dict
             row["gradient_bucket_bytes"] = eng.param_count * 4
             if mode == "peer":
                 eng.enable_peer_allreduce()
-            ar = hook if mode in ("nccl", "nccl_eager") else None
+            ar = hook if mode == "nccl_eager" else None
             graph = mode != "nccl_eager"
             ms = timed(lambda: eng.train(2, buf, B, graph=graph, allreduce=ar), reps=reps, warm=5) / 2
             row[f"{mode}_ms_per_update"] = ms
@@ -502,7 +503,7 @@ def run_multi_rank_sections(pkg, torch, device, dist, rank, world, args) -> dict
             del eng
         if world > 1:
             row["peer_over_local"] = row["peer_ms_per_update"] / row["local_ms_per_update"]
-            row["nccl_graph_over_local"] = row["nccl_ms_per_update"] / row["local_ms_per_update"]
+            row["nccl_eager_over_local"] = row["nccl_eager_ms_per_update"] / row["local_ms_per_update"]
         out["dp_update"][f"per_rank_batch_{B}"] = row
     out["dp_update"]["collective"] = ("gradient mean over ranks: critics' range every update, actor's range on policy steps (the actor loss needs the "
                                       "UPDATED critic, td3.py:189-191, so the two ranges cannot share one exchange)")

@@ -65,9 +65,9 @@ def main():
     ap.add_argument("--sigma", type=float, default=0.1, help="exploration noise of the rollout (NormalActionNoise)")
     ap.add_argument("--update", default="fused", choices=["fused", "torch"])
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "tensor", "bf16"], help="hidden-layer GEMMs of the fused update")
-    ap.add_argument("--dp", default="peer", choices=["peer", "nccl", "nccl-eager"],
-                    help="multi-GPU gradient mean: peer = inside the Adam kernels over NVLink peer memory (CUDA graph), nccl = ncclAllReduce captured "
-                         "in the graph between the phases, nccl-eager = launch by launch with dist.all_reduce between the phases (round 1)")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl-eager"],
+                    help="multi-GPU gradient mean: peer = inside the Adam kernels over NVLink peer memory (the whole update in a CUDA graph), "
+                         "nccl-eager = launch by launch with ncclAllReduce between the phases (round 1)")
     args = ap.parse_args()
 
     pkg = importlib.import_module("pytorch-rl-enhancedstablebaselines_b200")

@@ -5,11 +5,12 @@
 set -u
 OUT=gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-run() { echo "== $*" >> $OUT/r2_multi.log; "$@" 2>>$OUT/r2_multi.err | grep -v "^episode\|^iter\|^update" >> $OUT/r2_multi.log; }
+# every command under its own timeout: a hung collective must cost seconds, not the box (round 2 lost its GPU budget to one that was not)
+run() { echo "== $*" >> $OUT/r2_multi.log; timeout 150 "$@" 2>>$OUT/r2_multi.err | grep -v "^episode\|^iter\|^update" >> $OUT/r2_multi.log; }
 : > $OUT/r2_multi.log; : > $OUT/r2_multi.err
 N=$(nvidia-smi -L | wc -l)
 # config #3: TD3, 1,048,576 reactors over N GPUs, 8 fused-rollout steps + 8 DP updates of batch 4096 per rank and iteration
-for dp in peer nccl nccl-eager; do
+for dp in peer nccl-eager; do
   run $TR --nproc-per-node $N --master-port 29601 examples/td3_fused_rollout.py --n-envs 1048576 --iters 200 --steps-per-iter 8 --updates-per-iter 8 --batch 4096 --dp $dp
 done
 # the single-GPU share of the same job (131,072 reactors)
@@ -22,7 +23,7 @@ run $TR --nproc-per-node $N --master-port 29603 examples/maddpg_two_agents.py --
 run $TR --nproc-per-node $N --master-port 29604 examples/maddpg_two_agents.py --n-envs 262144 --iters 400 --batch 1024 --iddpg
 CUDA_VISIBLE_DEVICES=0 run python examples/maddpg_two_agents.py --n-envs $((262144 / N)) --iters 400 --batch 1024
 # the 2-rank NCCL / peer tests and the bench at N
-python -m pytest tests/test_gpu_dist.py -m gpu -q 2>&1 | tail -3 >> $OUT/r2_multi.log
-$TR --nproc-per-node $N --master-port 29605 bench.py --gpus $N --steps 20 --warmup 3 > $OUT/r2_bench_n$N.json 2> $OUT/r2_bench_n$N.err
+timeout 300 python -m pytest tests/test_gpu_dist.py -m gpu -q 2>&1 | tail -3 >> $OUT/r2_multi.log
+timeout 300 $TR --nproc-per-node $N --master-port 29605 bench.py --gpus $N --steps 20 --warmup 3 > $OUT/r2_bench_n$N.json 2> $OUT/r2_bench_n$N.err
 echo "bench rc=$?" >> $OUT/r2_multi.log
 tail -40 $OUT/r2_multi.log

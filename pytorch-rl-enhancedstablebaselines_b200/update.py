@@ -397,14 +397,15 @@ class FusedTD3Update:
         """``TD3.train(gradient_steps, batch_size)`` (td3.py:154-206): sample + update, ``gradient_steps`` times.
         ``graph=True`` (Philox-index buffer): whole cycles of ``policy_delay`` updates are replayed from ONE captured CUDA graph (24-45
         launches per update become one graph launch per cycle); the remainder runs launch by launch.  Data-parallel training is captured
-        too: with ``enable_peer_allreduce`` the averaging is part of the Adam kernels, and an ``allreduce=`` hook (``dist.all_reduce``
-        over NCCL) is captured between the phases, so GRAD -> all-reduce -> APPLY is one graph on every rank."""
+        too when the averaging is part of the Adam kernels (``enable_peer_allreduce``): sample -> GRAD -> mean over ranks -> APPLY is one
+        graph on every rank.  An ``allreduce=`` hook (``dist.all_reduce`` over NCCL) runs launch by launch between the phases unless
+        ``CSTR_NCCL_GRAPH=1`` (see ``_hook_capturable``)."""
         bs = int(batch_size or self._batch)
         done = 0
         if self._peer is not None:
             allreduce = None
         # a captured cycle bakes the sampling range in: only worth capturing once the ring is full (its range is constant from then on)
-        if graph and getattr(buffer, "index_mode", None) == "philox" and buffer.full and _graph_env_ok(env):
+        if graph and _hook_capturable(allreduce) and getattr(buffer, "index_mode", None) == "philox" and buffer.full and _graph_env_ok(env):
             done = self._train_graph(gradient_steps, buffer, bs, env, allreduce)
         for _ in range(gradient_steps - done):
             self.update(buffer.sample(bs, env=env), allreduce=allreduce)
@@ -433,6 +434,16 @@ def _dist_rank() -> int:
         return int(dist.get_rank()) if dist.is_available() and dist.is_initialized() else 0
     except Exception:
         return 0
+
+
+def _hook_capturable(allreduce) -> bool:
+    """Whether ``train(graph=True)`` may capture the update.  With no host-side hook (single GPU, or the peer-memory all-reduce inside the Adam
+    kernels) always.  A ``dist.all_reduce`` hook captured between the phases worked on 2 GPUs (tests, bench) but HUNG on 8 (ProcessGroupNCCL's
+    watchdog stuck while eight ranks captured; profiles/r02_multi_gpu.log), so it is opt-in (``CSTR_NCCL_GRAPH=1``): by default a hook means
+    launch by launch, as in round 1 — use ``enable_peer_allreduce()`` for a captured data-parallel update."""
+    import os
+
+    return allreduce is None or os.environ.get("CSTR_NCCL_GRAPH", "0") == "1"
 
 
 def _graph_env_ok(env) -> bool:
@@ -711,7 +722,8 @@ class FusedSACUpdate(FusedTD3Update):
         done = 0
         if self._peer is not None:
             allreduce = None
-        if graph and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1 and _graph_env_ok(env):
+        if (graph and _hook_capturable(allreduce) and getattr(buffer, "index_mode", None) == "philox" and buffer.full and self.target_update_interval == 1
+                and _graph_env_ok(env)):
             done = self._train_graph(gradient_steps, buffer, bs, env, allreduce)
         for g in range(done, gradient_steps):  # g = the reference's loop index: the target sync tests `g % target_update_interval` (sac.py:284)
             self.update(buffer.sample(bs, env=env), allreduce=allreduce, gradient_step=g)
