@@ -119,10 +119,88 @@ def cpu_port_rate(n_envs: int, target_seconds: float, seed: int = 0):
     return passes * T_cpu * n_envs / dt, T_cpu * passes, B.num_threads(), dt
 
 
+def reference_python_rates(budget_s: float = 24.0) -> dict:
+    """The UNMODIFIED reference (pure Python) timed on this box's host cores, when its tree is staged (oracle/refload.py: /root/reference in
+    the build container, the git-ignored baseline/_ref on a GPU box): BASELINE.md §3's C1 / C2 / C4 / C5.  Reported beside the C port, never
+    as the arm's value: the port is the strongest CPU statement of the same arithmetic, the Python original is what a user of the reference
+    actually runs.  Bounded to ~budget_s seconds in total."""
+    import numpy as np
+
+    import refload
+
+    if not refload.available():
+        return {"unavailable": "reference tree not staged on this box (baseline/_ref)"}
+    out = {"cpu_count": os.cpu_count(), "reference_root": "staged copy" if "baseline" in (refload.reference_root() or "") else "in place"}
+    try:
+        refload.install_shims()
+        core = refload.load_core()
+        env_mod = refload.load_env_module()
+        from core.common.noise import NormalActionNoise
+        from core.common.vec_env import DummyVecEnv, SubprocVecEnv
+
+        import torch
+
+        share = budget_s / 4.0
+        torch.set_num_threads(max(1, min(os.cpu_count() or 1, 8)))
+        out["torch_threads"] = torch.get_num_threads()
+
+        def step_rate(venv, seconds):
+            venv.reset()
+            n = venv.num_envs
+            acts = np.random.default_rng(0).uniform(-1, 1, (64, n, 2)).astype(np.float32)
+            for t in range(3):
+                venv.step(acts[t])
+            t0, k = time.perf_counter(), 0
+            while time.perf_counter() - t0 < seconds:
+                venv.step(acts[k % 64])
+                k += 1
+            return k * n / (time.perf_counter() - t0)
+
+        # C1: DummyVecEnv of 64 unmodified TwoSeriesCSTREnv, one core (dummy_vec_env.py:56-73)
+        venv = DummyVecEnv([lambda: env_mod.TwoSeriesCSTREnv() for _ in range(64)])
+        out["dummy_vec_env_64_envs_1_core_env_steps_per_s"] = step_rate(venv, share)
+        venv.close()
+        # C4: the reference's rollout loop (collect_rollouts + _store_transition + ReplayBuffer.add), TD3 actor on the CPU, 16 envs, no training
+        venv = DummyVecEnv([lambda: env_mod.TwoSeriesCSTREnv() for _ in range(16)])
+        noise = NormalActionNoise(mean=np.zeros(2), sigma=0.1 * np.ones(2))
+        model = core.TD3("MlpPolicy", venv, action_noise=noise, learning_starts=0, train_freq=(1, "step"), gradient_steps=0, buffer_size=100_000,
+                         device="cpu", seed=0, verbose=0)
+        model.learn(total_timesteps=16 * 8)
+
+        def best_window(fn, units, seconds, windows=3):  # the best of a few windows: host cores of a shared box are noisy, be fair to the reference
+            best = 0.0
+            for _ in range(windows):
+                t0, k = time.perf_counter(), 0
+                while time.perf_counter() - t0 < seconds / windows:
+                    fn()
+                    k += units
+                best = max(best, k / (time.perf_counter() - t0))
+            return best
+
+        out["collect_rollouts_16_envs_transitions_per_s"] = best_window(lambda: model.learn(total_timesteps=16 * 40, reset_num_timesteps=False), 16 * 40, share)
+        # C5: TD3.train on the CPU, batch 256 (td3.py:154-211)
+        model.train(gradient_steps=2, batch_size=256)
+        out["td3_train_batch_256_updates_per_s"] = best_window(lambda: model.train(gradient_steps=4, batch_size=256), 4, share)
+        venv.close()
+        # C2: SubprocVecEnv (subproc_vec_env.py:79-221), one env per worker process, one worker per host core (last: it forks)
+        try:
+            workers = max(2, min(os.cpu_count() or 2, 64))
+            venv = SubprocVecEnv([lambda: env_mod.TwoSeriesCSTREnv() for _ in range(workers)], start_method="fork")
+            out["subproc_vec_env_workers"] = workers
+            out["subproc_vec_env_env_steps_per_s"] = step_rate(venv, share)
+            venv.close()
+        except Exception as exc:
+            out["subproc_vec_env_env_steps_per_s"] = f"failed: {exc!r}"
+    except Exception as exc:
+        out["error"] = repr(exc)
+    return out
+
+
 def run_reference_arm(args) -> None:
     """--impl reference: the reference's CPU implementation of the path, timed on this box's host cores.
-    The reference is pure Python and cannot travel to the GPU box, so this is the oracle's C port of it
-    (kind "port", all host threads) — a much faster stand-in than the Python original (6.8 k steps/s/core)."""
+    The reference is pure Python — there is nothing to compile into oracle/_ref — so the arm's value is the oracle's C port of it
+    (kind "port", all host threads), a far stronger baseline than the Python original; the original itself (DummyVecEnv, SubprocVecEnv,
+    collect_rollouts, TD3.train) is timed beside it when the tree is staged (reference_python)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -130,6 +208,7 @@ def run_reference_arm(args) -> None:
 
     import build_oracle as B
 
+    ref_python = reference_python_rates() if not args.no_extras else None  # before the OpenMP pool of the C port exists (thread oversubscription)
     B.use_all_cores()  # torchrun sets OMP_NUM_THREADS=1; the reference arm uses every host core
     rng = np.random.default_rng(0)
     st, sc, ep, _ = B.reset_f32(N_ENVS, 0, 0, 0)
@@ -161,10 +240,13 @@ def run_reference_arm(args) -> None:
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "TwoSeriesCSTR step-only, 65,536 batched envs, random actions, fp32", "n_envs": N_ENVS,
-                   "control_intervals_per_step": T_ref, "note": "reference is pure Python and absent on this box; timed: its C port (oracle/cstr_oracle.c)"},
+                   "control_intervals_per_step": T_ref,
+                   "note": "the reference is pure Python (nothing to compile into oracle/_ref); the arm's value is its C port (oracle/cstr_oracle.c, all host "
+                           "threads); the unmodified Python original is timed beside it under reference_python when its tree is staged"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": B.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_python": ref_python,
     }
     print(json.dumps(line), flush=True)
 
