@@ -217,7 +217,8 @@ typedef struct cstr_td3_config {
  * Cross-GPU ordering: a per-CTA flag barrier over peer memory before the reads (every peer's backward pass has finished)
  * and after them (nobody overwrites its block while a peer still reads it); flags carry a per-launch epoch kept on the
  * device, so the launches can sit inside a CUDA graph.  A rank that waits longer than ~4 s (a dead peer) stops waiting,
- * raises the error word (cstr_peer_error) and skips the update instead of hanging the GPU.
+ * raises the error word (cstr_peer_error) and skips the update instead of hanging the GPU; every later launch then skips
+ * both the waits and the update at once (one bounded wait per broken group, never a hung stream).
  * cstr_peer_alloc returns device memory (cudaMalloc, zeroed) and its 64-byte IPC handle; cstr_peer_open maps a peer's
  * handle.  Layout of one rank's allocation, chosen by the caller: [grads block | pad to 256 B | cstr_peer_flag_bytes()]. */
 #define CSTR_PEER_MAX_WORLD 8

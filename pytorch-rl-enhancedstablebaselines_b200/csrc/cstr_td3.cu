@@ -931,7 +931,10 @@ __global__ void __launch_bounds__(256) td3_apply_peer_kernel(ApplyArgs a, PeerAr
     pdl_enter();
     uint32_t *my = pa.flags[pa.rank];
     const uint32_t epoch = *(volatile uint32_t *)(my + PEER_EPOCH) + 1u;
-    const bool alive = peer_barrier(pa, 0, epoch);
+    // once a wait has timed out (a peer died or fell out of step) every later launch skips waiting and updating: the cost of a broken
+    // group is ONE bounded wait, after which the host finds the error word (cstr_peer_error) instead of a hung stream
+    const bool broken = *(volatile uint32_t *)(my + PEER_ERROR) != 0u;
+    const bool alive = !broken && peer_barrier(pa, 0, epoch);
     if (blockIdx.x == 0 && a.loss_acc) {  // as td3_apply_kernel: per-CTA loss partials -> running sums (the LOCAL shard's loss)
         __shared__ float sl[256];
         float s = 0.f;
