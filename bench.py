@@ -18,8 +18,18 @@ Keys beyond the base contract:
   cpu_baseline the oracle's C port (oracle/cstr_oracle.c, OpenMP, all host cores) on a bounded sample.
   e2e          same metric through the C-ABI call with HOST (pinned) buffers: H2D of the action tape and
                state, the kernel, D2H of rewards/dones/state, all inside the timed region.
-  extras       other variants (fast math, fp64, in-kernel Philox actions, VecEnv.step loop, replay GB/s,
-               fused rollout transitions/s) — reported, not the headline.
+  rollout      the other half of BASELINE's metric, at every N: fused-rollout transitions/s (config #3, tcgen05 actor), 1,048,576
+               reactors sharded over the N ranks (strong) and 131,072 per rank (weak).
+  dp_update    the only collective of the path, at every N: the TD3 gradient step data-parallel over the ranks (ms per update, max over
+               ranks) — gradient mean inside the Adam kernels over NVLink peer memory, replayed from one CUDA graph, beside eager NCCL.
+  extras       other variants (strict math, fp64, in-kernel Philox actions, VecEnv.step loop, replay GB/s, fused rollout, TD3 / SAC /
+               BCQ / MADDPG update timings) — reported, not the headline; N=1 only.
+  config / run `config` is the workload and is the same dictionary in both arms; `run` holds what varies with the run (math flavour,
+               per-rank times, host placement).
+
+Order: headline -> e2e -> cpu_baseline -> [hard stop armed] rollout / dp_update -> extras -> the ONE JSON line.  The optional sections
+run under a hard stop (CSTR_BENCH_SECTION_LIMIT_S, default 300 s): if one of them hangs, rank 0 prints the line it already has (plus
+"sections_timeout_s") and every rank leaves with exit code 0 — a wedged collective must not cost the headline.
 """
 from __future__ import annotations
 
@@ -43,6 +53,92 @@ T_STEPS = 400
 FLOP_PER_ENV_STEP = 176  # 172 add/mul/div/min/max/abs/cmp + 4 exp, no FMA credit
 METRIC = "CSTR env-steps/sec (TwoSeriesCSTR step-only, 65,536 batched envs per GPU, random actions)"
 UNIT = "env-steps/s"
+
+
+def workload_config(n_gpus: int) -> dict:
+    """The workload both arms run and report under ``config`` — identical dictionaries, so the driver's config comparison of the two
+    arms compares like with like; everything that varies with the run (math flavour, per-rank times, the reference arm's bounded sample)
+    is reported under ``run`` / ``cpu_baseline.sample`` instead."""
+    return {"workload": "TwoSeriesCSTR step-only, 65,536 batched envs, random actions, fp32 (BASELINE.json configs[1])",
+            "n_envs_per_gpu": N_ENVS, "control_intervals_per_step": T_STEPS, "env_steps_per_step_per_gpu": N_ENVS * T_STEPS,
+            "actions": "U(-1,1) float32 tape (400,65536,2)", "outputs_per_interval": "reward f32 + done u8",
+            "parallelism": f"env-shard x{n_gpus}"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# host placement and the hard stop of the optional sections
+# ------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local_rank: int) -> dict:
+    """N>1: run this rank on the host cores of the NUMA node its GPU hangs off, BEFORE the pinned buffers of the e2e leg are allocated
+    (first touch puts them on that node).  Round 1: every rank sat on node 0, the ranks of the far socket pulled their 211 MB action
+    tape across the socket link, and e2e scaled at 0.24 on 8 GPUs.  Pure host placement; any failure leaves the process as it was."""
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        info["gpu_pci"] = bdf
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            info["note"] = "the platform reports no NUMA node for this GPU"
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            info["note"] = "none of the node's cores is in this process's affinity mask"
+            return info
+        os.sched_setaffinity(0, allowed)
+        info.update(bound=True, cores=len(allowed))
+    except Exception as exc:  # placement is an optimisation, never a failure
+        info["note"] = f"not bound: {exc!r}"
+    return info
+
+
+def describe_error(exc: BaseException) -> str:
+    """repr(exc) plus the innermost frames, so that an error key in the JSON line says where it happened."""
+    import traceback
+
+    frames = traceback.extract_tb(exc.__traceback__)[-3:]
+    return repr(exc) + " @ " + " <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in reversed(frames))
+
+
+class HardStop:
+    """The headline numbers are final before the optional sections (multi-rank rollout / data-parallel update, extras) start.  If those
+    sections hang — a rank lost in a collective, a wedged kernel — every rank's timer fires after ``seconds``: rank 0 prints the line it
+    already has (with ``sections_timeout_s``), and the process leaves with exit code 0 instead of holding the box until an outer limit
+    kills the whole run and the headline with it."""
+
+    def __init__(self, seconds: float, rank: int):
+        self.seconds, self.rank, self.line, self.emitted, self.lock = seconds, rank, None, False, threading.Lock()
+        self.timer = threading.Timer(seconds, self._fire)
+        self.timer.daemon = True
+
+    def start(self, line) -> None:
+        self.line = line
+        self.timer.start()
+
+    def emit(self, line) -> None:
+        with self.lock:
+            if not self.emitted and self.rank == 0:
+                print(json.dumps(line), flush=True)
+            self.emitted = True
+
+    def _fire(self) -> None:
+        try:
+            if self.line is not None:
+                self.line["sections_timeout_s"] = self.seconds
+                self.emit(self.line)
+            sys.stdout.flush()
+        finally:
+            os._exit(0)
+
+    def cancel(self) -> None:
+        self.timer.cancel()
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -239,10 +335,12 @@ def run_reference_arm(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "TwoSeriesCSTR step-only, 65,536 batched envs, random actions, fp32", "n_envs": N_ENVS,
-                   "control_intervals_per_step": T_ref,
-                   "note": "the reference is pure Python (nothing to compile into oracle/_ref); the arm's value is its C port (oracle/cstr_oracle.c, all host "
-                           "threads); the unmodified Python original is timed beside it under reference_python when its tree is staged"},
+        "config": workload_config(args.gpus),
+        "run": {"control_intervals_per_step_timed": T_ref,
+                "note": "the reference is pure Python (nothing to compile into oracle/_ref); the arm's value is its C port (oracle/cstr_oracle.c, strict "
+                        "float32 arithmetic with libm expf/powf as NumPy evaluates the reference, all host threads); a step is a bounded sample of the "
+                        "workload when the host cannot finish 400 intervals in ~2 s; the unmodified Python original is timed beside it under "
+                        "reference_python when its tree is staged"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": B.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -308,11 +406,13 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else {"bound": False, "note": "single rank: left where the launcher put it"}
     dist = None
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=device)
+        backend = os.environ.get("CSTR_BENCH_BACKEND", "nccl")  # "gloo": the CPU dry run of this file's control flow (tests/test_bench_dryrun.py)
+        dist.init_process_group(backend, **({"device_id": device} if backend == "nccl" else {}))
     lib = pkg._lib.load()
     from ctypes import byref
 
@@ -405,8 +505,13 @@ def run_ours(args) -> None:
     for _ in range(e2e_reps):
         e2e_step()  # synchronises internally: results are on the host when it returns
     torch.cuda.synchronize(device)
-    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    e2e_local_s = time.perf_counter() - t0
+    e2e_dt = torch.tensor([e2e_local_s], dtype=torch.float64, device=device)
+    e2e_per_rank_s = [e2e_local_s]
     if dist is not None:
+        gathered = [torch.zeros(1, dtype=torch.float64, device=device) for _ in range(world)]
+        dist.all_gather(gathered, e2e_dt.clone())
+        e2e_per_rank_s = [float(g.item()) for g in gathered]
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_reps * n * T / float(e2e_dt.item())
     h2d = T * n * 8 + n * (16 + 4 + 4)
@@ -414,26 +519,7 @@ def run_ours(args) -> None:
     assert int(h_done.sum().item()) == n
     clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
 
-    # ---- the other half of the metric and the only collective, at EVERY N (all ranks take part) -------------------------------
-    multi = {}
-    if not args.no_extras:
-        try:
-            multi = run_multi_rank_sections(pkg, torch, device, dist, rank, world, args)
-        except Exception as exc:  # must never take the headline down
-            multi = {"error": repr(exc)}
-
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- extras (rank 0, N=1 only: variants that explain the headline) ---------------------------------------------
-    extras = {}
-    if world == 1 and not args.no_extras:
-        args._ffma_peak = peaks.get("fp32_ffma_tflops") if peaks else None
-        extras = run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args)
-    # ---- CPU baseline on a bounded sample ----------------------------------------------------------------------------
+    # ---- CPU baseline on a bounded sample (N=1, rank 0; BEFORE the optional sections so that the line below is complete) -------
     cpu = None
     if world == 1:
         try:
@@ -442,53 +528,83 @@ def run_ours(args) -> None:
                    "sample": f"{n} reactors x {T_cpu} control intervals (repeated 400-interval passes), float32, libm expf/powf, OpenMP ({dt:.1f} s of CPU work)"}
         except Exception as exc:  # the baseline must never take the bench down
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
-    kernel_ms = statistics.mean(per)
-    achieved = FLOP_PER_ENV_STEP * n * T / (kernel_ms * 1e-3) / 1e12
-    peak = peaks["fp32_ffma_tflops"]
-    # dram__bytes_read + dram__bytes_write of one launch: STATIC, from the committed ncu --set full capture (ncu cannot run inside the bench)
-    traffic, traffic_source = None, None
-    for name in ("r02_traffic.json", "r01_traffic.json"):
-        tpath = os.path.join(ROOT, "profiles", name)
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                key = "tape_f32_kernel<0, 0, 0, 0>" if args.math == "strict" else "tape_f32_kernel<1, 0, 0, 0>"
-                traffic = tj.get(key, {}).get("dram_bytes")
-                traffic_source = f"static: ncu --set full capture in profiles/{name} (commit {tj.get('_commit', 'unrecorded')}), not measured in this run"
-            except Exception:
-                traffic = None
-            if traffic is not None:
-                break
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "TwoSeriesCSTR step-only, 65,536 batched envs, random actions, fp32 (BASELINE.json configs[1])",
-                   "n_envs_per_gpu": n, "control_intervals_per_step": T, "env_steps_per_step_per_gpu": n * T, "math": args.math,
-                   "actions": "U(-1,1) float32 tape (400,65536,2) streamed from HBM", "outputs_per_interval": "reward f32 + done u8",
-                   "l2": "inputs larger than L2 (210 MB tape vs 126 MB): no flush needed", "parallelism": f"env-shard x{world}", "per_rank_ms_per_step": [round(t / args.steps, 5) for t in per_rank_ms],
-                   "parity": "fast: |dobs|<=2e-6 per step vs the reference arithmetic (tests/test_gpu_step.py); strict: bit-exact vs oracle"},
-        "roofline": {"bound": "fp32-pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": traffic, "traffic_source": traffic_source, "kernel": f"tape_f32_kernel<{args.math}>", "kernel_ms": kernel_ms,
-                     "frac_of_clock_derived_peak": achieved / peaks["fp32_clock_derived_tflops"],
-                     "peak_note": "the FFMA probe (64 FFMA per loop branch, SASS-checked) runs at the SM clock it reports (fp32_ffma_sm_mhz) — "
-                                  "the clock-derived figure assumes the nominal maximum clock",
-                     "flop_per_env_step": FLOP_PER_ENV_STEP, "peak_source": "measured in this run: cstr_probe_pipe FFMA chains (2 flop/FMA)",
-                     "other_peaks": peaks,
-                     "hbm_algorithmic_gbs": n * T * (8 + 4 + 1) / (kernel_ms * 1e-3) / 1e9},
-        "other_math": {"math": other_name, "value": world * n * T / (other_ms * 1e-3), "unit": UNIT, "kernel_ms": other_ms,
-                       "roofline_frac": (FLOP_PER_ENV_STEP * n * T / (other_ms * 1e-3) / 1e12) / peak if peak else None,
-                       "note": "strict = reference association, no FMA contraction, bit-exact vs the oracle; fast = throughput variant, |dobs| <= 2e-6/step"},
-        "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "cstr_tape_f32_host (pinned host buffers -> H2D -> tape kernel -> D2H, synchronous)"},
-        "gpu_launches": args.steps, "clocks": clocks, "rollout": multi.get("rollout"), "dp_update": multi.get("dp_update"),
-        "multi_rank_error": multi.get("error"), "extras": extras,
-    }
-    print(json.dumps(line), flush=True)
+
+    # ---- the line as it stands once the headline, e2e and the CPU baseline are measured --------------------------------------------
+    line = None
+    if rank == 0:
+        kernel_ms = statistics.mean(per)
+        achieved = FLOP_PER_ENV_STEP * n * T / (kernel_ms * 1e-3) / 1e12
+        peak = peaks["fp32_ffma_tflops"]
+        # dram__bytes_read + dram__bytes_write of one launch: STATIC, from the committed ncu --set full capture (ncu cannot run inside the bench)
+        traffic, traffic_source = None, None
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                try:
+                    tj = json.load(open(tpath))
+                    key = "tape_f32_kernel<0, 0, 0, 0>" if args.math == "strict" else "tape_f32_kernel<1, 0, 0, 0>"
+                    traffic = tj.get(key, {}).get("dram_bytes")
+                    traffic_source = f"static: ncu --set full capture in profiles/{name} (commit {tj.get('_commit', 'unrecorded')}), not measured in this run"
+                except Exception:
+                    traffic = None
+                if traffic is not None:
+                    break
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "run": {"math": args.math, "actions": "streamed from HBM", "l2": "inputs larger than L2 (210 MB tape vs 126 MB): no flush needed",
+                    "per_rank_ms_per_step": [round(t / args.steps, 5) for t in per_rank_ms], "host_placement": numa,
+                    "parity": "fast: |dobs|<=2e-6 per step, <=1e-5 over 400 steps, |dreward|<=1e-5, dones equal vs the oracle "
+                              "(tests/test_gpu_step.py::test_fast_tape_hbm_actions_rewards_dones_vs_oracle; |dreward|<=5e-5 over the trajectory); strict: bit-exact vs the oracle"},
+            "roofline": {"bound": "fp32-pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": traffic, "traffic_source": traffic_source, "kernel": f"tape_f32_kernel<{args.math}>", "kernel_ms": kernel_ms,
+                         "frac_of_clock_derived_peak": achieved / peaks["fp32_clock_derived_tflops"],
+                         "peak_note": "the FFMA probe (64 FFMA per loop branch, SASS-checked) runs at the SM clock it reports (fp32_ffma_sm_mhz) — "
+                                      "the clock-derived figure assumes the nominal maximum clock",
+                         "flop_per_env_step": FLOP_PER_ENV_STEP, "peak_source": "measured in this run: cstr_probe_pipe FFMA chains (2 flop/FMA)",
+                         "other_peaks": peaks,
+                         "hbm_algorithmic_gbs": n * T * (8 + 4 + 1) / (kernel_ms * 1e-3) / 1e9},
+            "other_math": {"math": other_name, "value": world * n * T / (other_ms * 1e-3), "unit": UNIT, "kernel_ms": other_ms,
+                           "roofline_frac": (FLOP_PER_ENV_STEP * n * T / (other_ms * 1e-3) / 1e12) / peak if peak else None,
+                           "note": "strict = reference association, no FMA contraction, bit-exact vs the oracle; fast = throughput variant, |dobs| <= 2e-6/step"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "cstr_tape_f32_host (pinned host buffers -> H2D -> tape kernel -> D2H, synchronous)",
+                    "per_rank_h2d_gbs": [round(e2e_reps * h2d / t / 1e9, 2) for t in e2e_per_rank_s],
+                    "per_rank_d2h_gbs": [round(e2e_reps * d2h / t / 1e9, 2) for t in e2e_per_rank_s]},
+            "gpu_launches": args.steps, "clocks": clocks, "rollout": None, "dp_update": None, "multi_rank_error": None, "extras": {},
+        }
+
+    # ---- optional sections under a hard stop: they may fail or hang, the line above may not be lost -------------------------------
+    stop = HardStop(float(os.environ.get("CSTR_BENCH_SECTION_LIMIT_S", "300")), rank)
+    stop.start(line)
+    sticky = False
+    if not args.no_extras:
+        # the other half of the metric and the only collective, at EVERY N (all ranks take part)
+        try:
+            multi = run_multi_rank_sections(pkg, torch, device, dist, rank, world, args)
+        except Exception as exc:  # must never take the headline down
+            multi, sticky = {"error": describe_error(exc)}, True
+        if rank == 0:
+            with stop.lock:
+                line.update(rollout=multi.get("rollout"), dp_update=multi.get("dp_update"), multi_rank_error=multi.get("error"))
+        # extras (rank 0, N=1 only: variants that explain the headline)
+        if rank == 0 and world == 1:
+            args._ffma_peak = peaks.get("fp32_ffma_tflops") if peaks else None
+            extras = run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args)
+            sticky = sticky or any(k.endswith("error") for k in extras) or any(k.endswith("error") for k in extras.get("td3_update", {}))
+            with stop.lock:
+                line["extras"] = extras
+    stop.emit(line)
+    if sticky:  # a failed section may have left a sticky CUDA error or a rank out of step: no teardown that could abort or wait
+        sys.stdout.flush()
+        os._exit(0)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    stop.cancel()
 
 
 def run_multi_rank_sections(pkg, torch, device, dist, rank, world, args) -> dict:
@@ -593,7 +709,8 @@ def run_multi_rank_sections(pkg, torch, device, dist, rank, world, args) -> dict
 
 
 def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict:
-    """Variants that explain the headline; each timed with CUDA events after its own warm-up."""
+    """Variants that explain the headline; each timed with CUDA events after its own warm-up.  Every section runs under its own
+    try/except (`<section>_error` in the result): a section that fails must not take the others — or the headline — down."""
     from ctypes import byref
 
     import numpy as np
@@ -614,7 +731,14 @@ def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict
         e1.synchronize()
         return env_steps / (e0.elapsed_time(e1) / reps * 1e-3)
 
-    try:
+    def section(name, fn):
+        try:
+            fn()
+            torch.cuda.synchronize(device)
+        except Exception as exc:
+            ex[f"{name}_error"] = describe_error(exc)
+
+    def tapes():
         for math, mode in (("strict", 0), ("fast", 1)):
             ex[f"tape_f32_{math}_hbm_actions"] = rate_of(lambda: lib.cstr_tape_f32(
                 byref(env._params), n, T, mode, tape.data_ptr(), 0, env.state.data_ptr(), env.step_count.data_ptr(), env.episode.data_ptr(),
@@ -622,16 +746,18 @@ def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict
             ex[f"tape_f32_{math}_philox_actions"] = rate_of(lambda: lib.cstr_tape_f32(
                 byref(env._params), n, T, mode, None, 0, env.state.data_ptr(), env.step_count.data_ptr(), env.episode.data_ptr(),
                 None, rewards.data_ptr(), dones.data_ptr(), None, None, stream), n * T)
-        # fp64 (north_star: fp64 vs fp32)
+
+    def tape_f64():  # north_star: fp64 vs fp32
         e64 = pkg.GpuCSTRVecEnv(n, device=device, dtype="fp64", seed=1, monitor=False)
         e64.reset()
         r64 = torch.empty((T, n), dtype=torch.float64, device=device)
         ex["tape_f64_philox_actions"] = rate_of(lambda: lib.cstr_tape_f64(
             byref(e64._params), n, T, None, 0, e64.state.data_ptr(), e64.step_count.data_ptr(), e64.episode.data_ptr(), None, r64.data_ptr(),
             dones.data_ptr(), None, None, stream), n * T, reps=3)
-        del e64, r64
-        # 1,048,576 reactors (config #3 batch) — the chip is full at this size
-        nb, Tb = 1 << 20, 100
+
+    nb, Tb = 1 << 20, 100
+
+    def tapes_1m():  # 1,048,576 reactors (config #3 batch) — the chip is full at this size
         eb = pkg.GpuCSTRVecEnv(nb, device=device, math=args.math, seed=2, monitor=False)
         eb.reset()
         rb = torch.empty((Tb, nb), dtype=torch.float32, device=device)
@@ -645,8 +771,8 @@ def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict
         r1 = rate_of(lambda: eb.step_tensor(ab), nb, reps=20)
         ex["vec_step_f32_1M_envs"] = r1
         ex["vec_step_f32_1M_envs_hbm_gbs"] = r1 * 70 / 1e9
-        del eb, rb, db, ab
-        # VecEnv.step() through NumPy buffers (the reference-facing protocol call), 65,536 envs
+
+    def numpy_protocol():  # VecEnv.step() through NumPy buffers (the reference-facing protocol call), 65,536 envs
         ev = pkg.GpuCSTRVecEnv(n, device=device, math=args.math, seed=3, monitor=False)
         ev.reset()
         a_np = np.random.default_rng(0).uniform(-1, 1, (n, 2)).astype(np.float32)
@@ -656,7 +782,8 @@ def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict
         for _ in range(20):
             ev.step(a_np)
         ex["vecenv_step_numpy_protocol"] = 20 * n / (time.perf_counter() - t0)
-        del ev
+
+    def replay_and_rollout():
         # replay buffer: add (52 B/transition algorithmic) and sample (116 B/sample algorithmic), HBM-bound
         rows, ne = 64, 1 << 20
         buf = pkg.GpuReplayBuffer(rows * ne, device=device, n_envs=ne, index_mode="philox")
@@ -672,7 +799,7 @@ def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict
         ex["replay_sample_philox_samples_per_s"] = smp
         ex["replay_sample_algorithmic_gbs"] = smp * 116 / 1e9
         # fused rollout (config #3 shape: TD3 actor 4-400-300-2, sigma 0.1), transitions/s
-        g = torch.Generator().manual_seed(0)
+        torch.manual_seed(0)
         lin = [torch.nn.Linear(4, 400), torch.nn.Linear(400, 300), torch.nn.Linear(300, 2)]
         actor = pkg.ActorWeights(lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias, device=device)
         er = pkg.GpuCSTRVecEnv(ne, device=device, math=args.math, seed=4, monitor=False)
@@ -684,11 +811,17 @@ def run_extras(pkg, torch, device, lib, env, tape, rewards, dones, args) -> dict
                 ex[f"fused_rollout_{mode_name}_transitions_per_s"] = rate_of(lambda: roll.collect(Kr), ne * Kr, reps=3)
             except Exception as exc:
                 ex[f"fused_rollout_{mode_name}_transitions_per_s"] = f"unavailable: {exc}"
-        del roll, er, buf
+
+    def updates():
         ex["td3_update"] = td3_update_extras(pkg, torch, device, peaks_tflops=args._ffma_peak)
-    except Exception as exc:  # extras must never take the headline down
-        ex["error"] = repr(exc)
-    torch.cuda.synchronize(device)
+
+    for name, fn in (("tapes", tapes), ("tape_f64", tape_f64), ("tapes_1M", tapes_1m), ("numpy_protocol", numpy_protocol),
+                     ("replay_and_rollout", replay_and_rollout), ("updates", updates)):
+        section(name, fn)
+    try:
+        torch.cuda.synchronize(device)
+    except Exception as exc:
+        ex["sync_error"] = repr(exc)
     return ex
 
 
@@ -772,7 +905,7 @@ def td3_update_extras(pkg, torch, device, peaks_tflops) -> dict:
                                                "torch_eager_same_gpu_ms_per_update": R.timed(lambda: ref.update(buf.sample(B)), 50)}
                 del eng, ref
     except Exception as exc:  # the TD3 / SAC rows above must survive
-        out["bcq_error"] = repr(exc)
+        out["bcq_error"] = describe_error(exc)
     # MADDPG / IDDPG gradient step (cstr_ma_update), two agents, [400, 300] nets
     try:
         for name, central in (("maddpg", True), ("iddpg", False)):
@@ -784,7 +917,7 @@ def td3_update_extras(pkg, torch, device, peaks_tflops) -> dict:
                                             "cuda_graph_ms_per_update": R.timed(lambda: eng.train(2, buf, B, graph=True), 100) / 2}
                 del eng
     except Exception as exc:
-        out["multi_agent_error"] = repr(exc)
+        out["multi_agent_error"] = describe_error(exc)
     return out
 
 
