@@ -49,21 +49,34 @@ def nvcc_path() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every csrc/*.cu into libcstr_b200.so (cross-compiles without a GPU)."""
+    """Compile every csrc/*.cu into libcstr_b200.so (cross-compiles without a GPU).  Safe when several processes of one job call it
+    at once (``torchrun`` ranks that all find the library stale): one builds under a file lock, the others wait and find it fresh."""
     if not force and not is_stale():
         return LIB_PATH
-    extra = os.environ.get("CSTR_NVCC_EXTRA", "").split()  # e.g. -DCSTR_TC_TIMING / -DCSTR_TD3_TIMING (clock64 phase instrumentation)
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB_PATH + ".tmp", *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    # the image's $CC wrapper is not a usable nvcc host compiler; let nvcc pick the system g++
-    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    if verbose:
-        print(res.stderr)
+    import fcntl
+
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while this one waited
+                return LIB_PATH
+            extra = os.environ.get("CSTR_NVCC_EXTRA", "").split()  # e.g. -DCSTR_TC_TIMING / -DCSTR_TD3_TIMING (clock64 phase instrumentation)
+            tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", tmp, *sources()]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            # the image's $CC wrapper is not a usable nvcc host compiler; let nvcc pick the system g++
+            env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+            res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
