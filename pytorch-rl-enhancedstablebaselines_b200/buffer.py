@@ -52,7 +52,9 @@ class GpuReplayBuffer:
     :param index_mode: ``"numpy"`` — indices come from the reference's two global-RNG draws
         (``np.random.randint``, buffers.py:114,309) so ``np.random.seed(k); sample(B)`` returns the same
         rows as the reference, bit for bit;  ``"philox"`` — indices drawn inside the gather kernel.
-    :param seed: Philox key of the ``"philox"`` index stream.
+    :param seed: Philox key of the ``"philox"`` index stream.  In a ``torch.distributed`` job the rank is folded into the key (rank 0 and
+        single-process runs use ``seed`` itself), so data-parallel ranks that were all given the same seed do not draw the same
+        (row, env) pairs for their shards.
     """
 
     def __init__(
@@ -93,6 +95,7 @@ class GpuReplayBuffer:
         self.handle_timeout_termination = handle_timeout_termination
         self.index_mode = index_mode
         self.seed = int(seed)
+        self._key: Optional[int] = None  # seed with the rank folded in, fixed at the first Philox draw (see _philox_key)
         self._draw = 0
         self._device = _get_device(device)
         with torch.cuda.device(self._device):
@@ -219,13 +222,25 @@ class GpuReplayBuffer:
         torch = self._torch
         obs, act, nobs, dones, rew = self._alloc_out(batch_size)
         with torch.cuda.device(self._device):
-            rc = self._libc.cstr_replay_sample_philox(self.seed & (2**64 - 1), self._draw, self.n_envs, upper_bound, batch_size,
+            rc = self._libc.cstr_replay_sample_philox(self._philox_key(), self._draw, self.n_envs, upper_bound, batch_size,
                                                       _lib.ptr(self.records), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones),
                                                       _lib.ptr(rew), None, None, self._norm_arg(env), self._stream())
         _lib.check(rc, "cstr_replay_sample_philox")
         self._draw += 1
         self.launches += 1
         return self._finish(obs, act, nobs, dones, rew, env)
+
+    def _philox_key(self) -> int:
+        if getattr(self, "_key", None) is None:
+            rank = 0
+            try:
+                import torch.distributed as dist
+
+                rank = int(dist.get_rank()) if dist.is_available() and dist.is_initialized() else 0
+            except Exception:
+                rank = 0
+            self._key = (self.seed + 0x9E3779B97F4A7C15 * rank) & (2**64 - 1)
+        return self._key
 
     def sample_into(self, out, draw_counter, env=None) -> None:
         """Philox sample into caller-owned tensors ``out = (obs, act, next_obs, dones, rewards)`` with the draw counter read from the
@@ -241,7 +256,7 @@ class GpuReplayBuffer:
             raise ValueError("cannot sample from an empty replay buffer")
         obs, act, nobs, dones, rew = out
         with self._torch.cuda.device(self._device):
-            rc = self._libc.cstr_replay_sample_philox_dev(self.seed & (2**64 - 1), _lib.ptr(draw_counter), self.n_envs, upper_bound, obs.shape[0],
+            rc = self._libc.cstr_replay_sample_philox_dev(self._philox_key(), _lib.ptr(draw_counter), self.n_envs, upper_bound, obs.shape[0],
                                                           _lib.ptr(self.records), _lib.ptr(obs), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(dones),
                                                           _lib.ptr(rew), None, None, self._norm_arg(env), self._stream())
         _lib.check(rc, "cstr_replay_sample_philox_dev")
@@ -343,7 +358,7 @@ class GpuReplayBuffer:
         return (_unpickle_buffer, (getattr(base, "__module__", None), getattr(base, "__qualname__", None), self.__getstate__()))
 
     def __getstate__(self):
-        state = {k: v for k, v in self.__dict__.items() if k not in ("records", "_torch", "_libc", "_device", "_norm_keepalive")}
+        state = {k: v for k, v in self.__dict__.items() if k not in ("records", "_torch", "_libc", "_device", "_norm_keepalive", "_key")}
         state.update(self.to_numpy_arrays())
         state["device"] = str(self._device)
         return state
