@@ -248,8 +248,13 @@ def test_two_ranks_one_line(tmp_path):
         "sys.argv = ['bench.py', '--gpus', '2', '--steps', '3', '--warmup', '3']\n"
         "b.main()\n")
     env = dict(os.environ, CSTR_BENCH_BACKEND="gloo", OMP_NUM_THREADS="1")
+    import socket
+
+    with socket.socket() as sock:  # a port that is free right now
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29731", str(worker)], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+                        "--master-port", str(port), str(worker)], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     out = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(out) == 1, r.stdout[-2000:]
